@@ -1,0 +1,120 @@
+/* tulip_b200 -- C ABI of the B200-native TULIP Swin forward/backward path.
+ *
+ * The reference (ethz-asl/TULIP) has no FFI: its hot path is the Python nn.Module in
+ * tulip/model/tulip.py, driven by engine_upsampling.py:77-80 (train), :168-171 (eval), :417-419 (MC).
+ * This header is the boundary the replacement is built behind: plain C, raw device pointers, explicit
+ * sizes and a cudaStream_t -- no torch types.  `tulip_b200/model/tulip.py` binds it with ctypes and
+ * re-exposes the reference's module API (same constructor kwargs, forward signature, state_dict).
+ *
+ * Conventions
+ *   - every function returns 0 (TULIP_OK) or an error code; tulip_last_error() gives the message;
+ *     nothing here calls exit()/abort();
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - activations are bf16 NHWC token-major [B*H*W, C]; parameters and gradients are fp32;
+ *   - kernels are enqueued on `stream` (passed as void* = cudaStream_t) and never synchronise;
+ *   - no function allocates device memory except tulip_net_create (persistent bf16 weight arena).
+ * Each entry cites the reference code it replaces (paths relative to the reference root).
+ */
+#ifndef TULIP_B200_H
+#define TULIP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TULIP_MAX_STAGES 8
+
+typedef struct tulip_config {
+  int img_h, img_w;           /* low-res input, tulip.py:531 img_size            */
+  int tgt_h, tgt_w;           /* high-res target, target_img_size                */
+  int patch_h, patch_w;       /* patch_size (patch_w must be 4: circular conv k=(ph,8), s=(ph,4), tulip.py:41) */
+  int in_chans;               /* must be 1                                       */
+  int embed_dim;              /* 96 in both factories, tulip.py:741,750          */
+  int win_h, win_w;           /* window_size; win_h*win_w must be 16             */
+  int num_layers;             /* len(depths)                                     */
+  int depths[TULIP_MAX_STAGES];
+  int num_heads[TULIP_MAX_STAGES];   /* head_dim = C/heads must be 32            */
+  int mlp_ratio;              /* 4                                               */
+  float ln_eps;               /* 1e-6, tulip.py:744                              */
+  int log_transform;          /* second loss term in expm1 space, tulip.py:695-696 */
+} tulip_config;
+
+typedef struct tulip_net tulip_net;
+
+const char* tulip_last_error(void);
+int tulip_abi_version(void);
+
+/* ---- whole network: TULIP.__init__ / TULIP.forward / autograd backward (tulip.py:531-584, 702-737) ---- */
+int tulip_net_create(const tulip_config* cfg, tulip_net** out);
+void tulip_net_destroy(tulip_net* net);
+/* parameter schema in state_dict order without the int64 index buffers */
+int tulip_net_num_params(const tulip_net* net);
+int tulip_net_param_info(const tulip_net* net, int i, char* name, int name_cap, int64_t shape[4], int* ndim);
+int tulip_net_num_blocks(const tulip_net* net);       /* Swin blocks, encoder then decoder, execution order */
+int tulip_net_block_info(const tulip_net* net, int i, int* stage, int* shifted, int* H, int* W);
+int64_t tulip_net_workspace_bytes(const tulip_net* net, int batch);
+int64_t tulip_net_kernel_launches(const tulip_net* net);   /* kernels launched by this net so far */
+
+/* forward: x_lo [B,1,h,w] fp32, target [B,1,H,W] fp32 or NULL (mc_drop=True, tulip.py:733-734)
+ * params: flat fp32 buffer; param_offsets_host[i] = element offset of parameter i (schema order)
+ * drop_scales: NULL (eval) or [2*num_blocks, B] fp32 per-sample DropPath scales, 0 or 1/keep (tulip.py:25-29)
+ * win_mode_host: per block 0 = configured window, 1 = backup window (1,16)/shift (0,8) (tulip.py:284-287)
+ * outputs: pred [B,1,H,W] fp32; losses[2] = {total L1, pixel L1} (tulip.py:690-700), untouched if target == NULL */
+int tulip_net_forward(tulip_net* net, int batch, const float* params, const int64_t* param_offsets_host,
+                      const float* x_lo, const float* target, const float* drop_scales, const int* win_mode_host,
+                      void* workspace, float* pred, float* losses, void* stream);
+/* backward of total_loss * grad_loss[0] (device scalar; GradScaler's 65536 arrives here, misc.py:294-295).
+ * grads: flat fp32 buffer laid out like params; it is OVERWRITTEN (zeroed, then accumulated).
+ * workspace must be the buffer the matching forward ran on, untouched since. */
+int tulip_net_backward(tulip_net* net, int batch, const float* params, const int64_t* param_offsets_host,
+                       float* grads, const float* x_lo, const float* target, const float* pred, const float* grad_loss,
+                       const float* drop_scales, const int* win_mode_host, void* workspace, void* stream);
+
+/* ---- dense contractions ----
+ * NT: out[M,N] = A[M,K] . W[N,K]^T (+bias) -- every nn.Linear / 1x1 Conv2d on the path
+ *     (tulip.py:298 qkv, :318 proj, :195/:198 fc1/fc2, :105 reduction, :119 expand, :716 skip, :175 conv_expand)
+ * epilogue: 0 store, 1 bias+GELU (out2 = pre-activation), 2 residual: out = aux + row_scale*(acc+bias)
+ * TN: dW[N,K] += dY[M,N]^T . X[M,K]; db[N] += colsum(dY)   (autograd of the above) */
+int tulip_gemm_nt(const void* A, const void* W, const float* bias, void* out, void* out2, const void* aux,
+                  const float* row_scale, int rows_per_sample, int M, int N, int K, int epilogue, int impl, void* stream);
+int tulip_gemm_tn(const void* dY, const void* X, float* dW, float* db, int M, int N, int K, int impl, void* stream);
+
+/* ---- window attention core: tulip.py:289-317 without the two Linears; shift/partition/mask/bias in-kernel ---- */
+int tulip_window_attention_fwd(const void* qkv, const float* bias_table, void* out, int B, int H, int W, int C, int heads,
+                               int Mh, int Mw, int sh, int sw, int masked, int bias_Mh, int bias_Mw, void* stream);
+int tulip_window_attention_bwd(const void* qkv, const float* bias_table, const void* dout, void* dqkv, float* dbias_table,
+                               int B, int H, int W, int C, int heads, int Mh, int Mw, int sh, int sw, int masked,
+                               int bias_Mh, int bias_Mw, void* stream);
+
+/* ---- LayerNorm (tulip.py:330,334,80,569), optional PatchMerging 2x2 gather on the input (tulip.py:92-99) ---- */
+int tulip_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* stats, int rows, int C, float eps,
+                        int merge_gather, int H2, int W2, void* stream);
+int tulip_layernorm_bwd(const void* x, const float* w, const float* stats, const void* dy, const void* dres, void* dx,
+                        float* dw, float* db, int rows, int C, int merge_gather, int H2, int W2, void* stream);
+
+/* ---- PatchEmbedding: circular pad + Conv2d(1->E,(ph,8),(ph,4)) + LayerNorm (tulip.py:59-73) ---- */
+int tulip_patch_embed_fwd(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, void* y,
+                          int B, int Himg, int Wimg, int ph, int E, float eps, void* stream);
+int tulip_patch_embed_bwd(const float* x, const float* w, const float* b, const float* ln_w, const void* dy, float* dw,
+                          float* db, float* dln_w, float* dln_b, int B, int Himg, int Wimg, int ph, int E, float eps,
+                          void* stream);
+
+/* ---- loss (tulip.py:690-700); scratch2 and out2 are 2 floats each ---- */
+int tulip_l1_loss(const float* pred, const float* target, int64_t n, int log_transform, float* scratch2, float* out2,
+                  void* stream);
+
+/* ---- stand-alone index ops (bit-exact; the same device functions the fused kernels use) ----
+ * window_partition (tulip.py:248-252) composed with torch.roll(-sh,-sw) (tulip.py:290); reverse = tulip.py:320,323 */
+int tulip_window_partition(const void* x, void* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, void* stream);
+int tulip_window_reverse(const void* xw, void* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, void* stream);
+int tulip_shift_mask(float* out, int H, int W, int Mh, int Mw, int sh, int sw, void* stream);          /* tulip.py:254-280 */
+int tulip_rel_bias_gather(const float* table, float* out, int heads, int Mh, int Mw, void* stream);  /* tulip.py:304-307 */
+int tulip_merge_gather(const void* x, void* out, int B, int H, int W, int C, void* stream);          /* tulip.py:92-99 */
+int tulip_pixel_shuffle(const void* x, void* out, int B, int H, int W, int Cout, int r, void* stream); /* nn.PixelShuffle, NHWC */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TULIP_B200_H */

@@ -1,0 +1,125 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol the header declares,
+its parameter schema equals the oracle's restatement of the reference state_dict, and the host-side module
+mirrors the reference constructor contract.  No kernels are launched."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.params import TULIP_BASE, TULIP_LARGE, Cfg, param_shapes
+from tulip_b200._lib import SIGNATURES, TulipConfig, load_library
+from tulip_b200.model.tulip import TULIP, WindowAttention, tulip_base, tulip_large
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KW = dict(img_size=(16, 1024), target_img_size=(64, 1024), patch_size=(1, 4), in_chans=1, window_size=[2, 8], swin_v2=False,
+          pixel_shuffle=True, circular_padding=True, log_transform=True, patch_unmerging=True)
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "tulip_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tulip_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = load_library()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"libtulip_b200.so does not export {s}"
+    assert sorted(SIGNATURES) == syms, "ctypes signature table and header disagree"
+    assert lib.tulip_abi_version() == 1
+
+
+def c_schema(cfg: Cfg):
+    lib = load_library()
+    c = TulipConfig()
+    c.img_h, c.img_w = cfg.img_size
+    c.tgt_h, c.tgt_w = cfg.target_img_size
+    c.patch_h, c.patch_w = cfg.patch_size
+    c.in_chans, c.embed_dim = cfg.in_chans, cfg.embed_dim
+    c.win_h, c.win_w = cfg.window_size
+    c.num_layers = cfg.num_layers
+    for i in range(cfg.num_layers):
+        c.depths[i], c.num_heads[i] = cfg.depths[i], cfg.num_heads[i]
+    c.mlp_ratio, c.ln_eps, c.log_transform = cfg.mlp_ratio, cfg.ln_eps, int(cfg.log_transform)
+    h = C.c_void_p()
+    rc = lib.tulip_net_create(C.byref(c), C.byref(h))
+    if rc != 0:
+        return rc, lib.tulip_last_error().decode()
+    out = []
+    buf, shape, nd = C.create_string_buffer(256), (C.c_int64 * 4)(), C.c_int()
+    for i in range(lib.tulip_net_num_params(h)):
+        assert lib.tulip_net_param_info(h, i, buf, 256, shape, C.byref(nd)) == 0
+        out.append((buf.value.decode(), tuple(shape[:nd.value])))
+    ws = lib.tulip_net_workspace_bytes(h, 2)
+    nblk = lib.tulip_net_num_blocks(h)
+    lib.tulip_net_destroy(h)
+    return out, ws, nblk
+
+
+@pytest.mark.parametrize("cfg,nblk", [(TULIP_BASE, 14), (TULIP_LARGE, 18),
+                                      (Cfg(img_size=(32, 2048), target_img_size=(128, 2048)), 14)])
+def test_c_schema_matches_reference_state_dict(cfg, nblk):
+    schema, ws, n = c_schema(cfg)
+    want = [(k, tuple(v)) for k, v in param_shapes(cfg).items() if not k.endswith("relative_position_index")]
+    assert schema == want
+    assert n == nblk and ws > 0
+
+
+def test_c_config_errors_are_reported_not_fatal():
+    bad = Cfg(window_size=(4, 8))
+    rc, msg = c_schema(bad)
+    assert rc != 0 and "16 tokens" in msg
+    rc, msg = c_schema(Cfg(target_img_size=(128, 1024)))          # BASELINE cfg5's 8x head: the reference cannot build it either
+    assert rc != 0 and "upscale_factor" in msg
+
+
+@pytest.mark.parametrize("factory,cfg", [(tulip_base, TULIP_BASE), (tulip_large, TULIP_LARGE)])
+def test_module_state_dict_schema(factory, cfg):
+    m = factory(**KW)
+    sd = m.state_dict()
+    want = param_shapes(cfg)
+    assert list(sd.keys()) == list(want.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(want[k])
+        assert v.dtype == (torch.int64 if k.endswith("relative_position_index") else torch.float32)
+    assert [n for n, _ in m.named_children()] == ["pos_drop", "layers", "layers_up", "first_patch_expanding",
+                                                  "skip_connection_layers", "norm_up", "patch_embed", "decoder_pred", "ps_head"]
+    assert m.upscale_factor == 4
+    m._create_net()                      # C schema check against this module (raises on mismatch)
+
+
+def test_module_contract_details():
+    m = tulip_base(**KW)
+    rates = m._drop_rates()
+    want = [0, .1 / 7, .2 / 7, .3 / 7, .4 / 7, .5 / 7, .6 / 7, .1, .4 / 7, .5 / 7, .2 / 7, .3 / 7, 0, .1 / 7]
+    assert np.allclose(rates, want, atol=1e-6)
+    assert isinstance(m.layers[0].blocks[0].drop_path, torch.nn.Identity)
+    a = WindowAttention(96, [2, 8], 3, shift=True)
+    assert a.shift_size == (1, 4) and a.scale == 32 ** -0.5
+    assert a.window_mode(2) == 0 and a.window_size == (2, 8)
+    assert a.window_mode(1) == 1 and a.window_size == (1, 16) and a.shift_size == (0, 8)
+    assert a.window_mode(4) == 1, "the backup switch is permanent (tulip.py:284-287)"
+    with pytest.raises(NotImplementedError):
+        tulip_base(**{**KW, "swin_v2": True})
+    with pytest.raises(NotImplementedError):
+        tulip_base(**{**KW, "pixel_shuffle": False})
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 1, 16, 1024), torch.zeros(1, 1, 64, 1024))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/tulip/model/tulip.py"), reason="reference tree only exists in the build container")
+def test_init_matches_reference_rng_stream():
+    """Same seed -> bit-identical initial state_dict as the reference (construction order and init calls match)."""
+    from oracle.make_golden import build_reference, import_reference
+    T = import_reference()
+    torch.manual_seed(0)
+    ref = build_reference(T, TULIP_BASE, False).state_dict()
+    torch.manual_seed(0)
+    ours = tulip_base(**KW).state_dict()
+    for k in ref:
+        assert torch.equal(ref[k], ours[k]), k

@@ -1,0 +1,58 @@
+"""world_size-2 gloo test of the data-parallel host logic (shard + single flat all-reduce)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tulip_b200.parallel import allreduce_flat_, shard_range
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 1000
+    g = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    allreduce_flat_(g)
+    want = torch.arange(n, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+    ok = torch.allclose(g, want)
+    # frame sharding: the union of the ranks' ranges is the global batch, disjoint and ordered
+    r = shard_range(32, rank, world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, list(r))
+    flat = [i for part in gathered for i in part]
+    ok = ok and flat == list(range(32))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_flat_allreduce_and_sharding_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_shard_range_rejects_ragged():
+    with pytest.raises(ValueError):
+        shard_range(33, 0, 2)
+    assert list(shard_range(8, 1, 4)) == [2, 3]
+    t = torch.ones(4)
+    assert allreduce_flat_(t) is t          # no process group: identity

@@ -1,0 +1,103 @@
+"""ctypes binding of libtulip_b200.so (C ABI: include/tulip_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MAX_STAGES = 8
+
+
+class TulipLibraryError(RuntimeError):
+    pass
+
+
+class TulipConfig(C.Structure):
+    _fields_ = [
+        ("img_h", C.c_int), ("img_w", C.c_int), ("tgt_h", C.c_int), ("tgt_w", C.c_int),
+        ("patch_h", C.c_int), ("patch_w", C.c_int), ("in_chans", C.c_int), ("embed_dim", C.c_int),
+        ("win_h", C.c_int), ("win_w", C.c_int), ("num_layers", C.c_int),
+        ("depths", C.c_int * MAX_STAGES), ("num_heads", C.c_int * MAX_STAGES),
+        ("mlp_ratio", C.c_int), ("ln_eps", C.c_float), ("log_transform", C.c_int),
+    ]
+
+
+def lib_path() -> str:
+    return os.environ.get("TULIP_B200_LIB", os.path.join(_HERE, "lib", "libtulip_b200.so"))
+
+
+_vp, _fp, _i, _i64 = C.c_void_p, C.c_void_p, C.c_int, C.c_int64
+
+# name -> (restype, argtypes); must list every symbol include/tulip_b200.h declares
+SIGNATURES = {
+    "tulip_last_error": (C.c_char_p, []),
+    "tulip_abi_version": (_i, []),
+    "tulip_net_create": (_i, [C.POINTER(TulipConfig), C.POINTER(_vp)]),
+    "tulip_net_destroy": (None, [_vp]),
+    "tulip_net_num_params": (_i, [_vp]),
+    "tulip_net_param_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_i64), C.POINTER(_i)]),
+    "tulip_net_num_blocks": (_i, [_vp]),
+    "tulip_net_block_info": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "tulip_net_workspace_bytes": (_i64, [_vp, _i]),
+    "tulip_net_kernel_launches": (_i64, [_vp]),
+    "tulip_net_forward": (_i, [_vp, _i, _fp, _vp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _vp]),
+    "tulip_net_backward": (_i, [_vp, _i, _fp, _vp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _vp, _vp]),
+    "tulip_gemm_nt": (_i, [_vp, _vp, _fp, _vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
+    "tulip_gemm_tn": (_i, [_vp, _vp, _fp, _fp, _i, _i, _i, _i, _vp]),
+    "tulip_window_attention_fwd": (_i, [_vp, _fp, _vp] + [_i] * 12 + [_vp]),
+    "tulip_window_attention_bwd": (_i, [_vp, _fp, _vp, _vp, _fp] + [_i] * 12 + [_vp]),
+    "tulip_layernorm_fwd": (_i, [_vp, _fp, _fp, _vp, _fp, _i, _i, C.c_float, _i, _i, _i, _vp]),
+    "tulip_layernorm_bwd": (_i, [_vp, _fp, _fp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
+    "tulip_patch_embed_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, C.c_float, _vp]),
+    "tulip_patch_embed_bwd": (_i, [_fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, C.c_float, _vp]),
+    "tulip_l1_loss": (_i, [_fp, _fp, _i64, _i, _fp, _fp, _vp]),
+    "tulip_window_partition": (_i, [_vp, _vp] + [_i] * 8 + [_vp]),
+    "tulip_window_reverse": (_i, [_vp, _vp] + [_i] * 8 + [_vp]),
+    "tulip_shift_mask": (_i, [_fp] + [_i] * 6 + [_vp]),
+    "tulip_rel_bias_gather": (_i, [_fp, _fp, _i, _i, _i, _vp]),
+    "tulip_merge_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "tulip_pixel_shuffle": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+}
+
+
+def load_library():
+    """dlopen the CUDA library; raises TulipLibraryError (never falls back) if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise TulipLibraryError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C tulip_b200/csrc`). tulip_b200 has no CPU / PyTorch fallback.")
+    try:
+        lib = C.CDLL(path)
+    except OSError as e:  # pragma: no cover
+        raise TulipLibraryError(f"cannot load {path}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise TulipLibraryError(f"{path} does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, what: str = "tulip_b200"):
+    if rc != 0:
+        msg = load_library().tulip_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

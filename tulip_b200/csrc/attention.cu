@@ -1,0 +1,311 @@
+// Window attention core (W-MSA / SW-MSA) forward and backward.
+//
+// Reference: tulip/model/tulip.py:282-324 (WindowAttention.forward) minus the two Linear layers,
+// which are per-token and therefore run as plain GEMMs on the un-partitioned, un-shifted tensor.
+// The cyclic shift (torch.roll, :290/:323), window partition / reverse (:295/:320), the shift mask
+// (create_mask, :254-280, closed form of SURVEY.md App. D) and the relative-position-bias gather
+// (:304-308) are index arithmetic inside these kernels -- no data-movement kernels, no mask tensor.
+//
+// A window is 16 tokens and head_dim is 32 at every stage, so one (window, head) problem is
+// S = Q K^T (16x16x32) and O = P V (16x32x16): far below a tcgen05 tile (M >= 64).  One warp owns
+// one (window, head) and keeps S / P in registers with m16n8k16 warp MMAs; a CTA of 3 warps stages
+// the q|k|v rows of one window and three heads in shared memory with 16-byte cp.async.
+#include "common.cuh"
+#include "kernels.h"
+#include "window_index.cuh"
+
+namespace {
+
+constexpr int L = 16;          // tokens per window
+constexpr int HD = 32;         // head dim
+constexpr int HG = 3;          // heads per CTA
+constexpr int QLD = 3 * HG * HD + 8;   // 296-element rows (592 B): conflict-free ldmatrix
+constexpr int OLD = HG * HD + 8;       // 104-element rows for dO
+constexpr int PLD = 24;                // 16x16 scratch rows (48 B)
+
+__device__ __forceinline__ WinGeom geom(const AttnArgs& a) { return WinGeom{a.H, a.W, a.Mh, a.Mw, a.sh, a.sw}; }
+__device__ __forceinline__ int token_index(const AttnArgs& a, int b, int wh, int ww, int i) {
+  return win_token_index(geom(a), b, wh, ww, i);
+}
+__device__ __forceinline__ int region_id(const AttnArgs& a, int wh, int ww, int i) { return win_region_id(geom(a), wh, ww, i); }
+__device__ __forceinline__ int bias_index(const AttnArgs& a, int i, int j) { return rel_bias_index(a.bMh, a.bMw, i, j); }
+
+// S (two m16n8 accumulators = 16x16) for this warp's head: scale * Q K^T + bias (+ mask)
+__device__ __forceinline__ void scores(const AttnArgs& a, const bf16* sq, int hl, int head, const int* s_rid,
+                                       const float* __restrict__ table, float (&s)[2][4], int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[nt][q] = 0.f;
+  const int mat = lane >> 3;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t af[4], bfr[4];
+    ldmatrix_x4(af, sq + (lane & 15) * QLD + hl * HD + ks * 16 + (lane >> 4) * 8);
+    ldmatrix_x4(bfr, sq + ((mat >> 1) * 8 + (lane & 7)) * QLD + HG * HD + hl * HD + ks * 16 + (mat & 1) * 8);
+    mma_bf16_16816(s[0], af, bfr[0], bfr[1]);
+    mma_bf16_16816(s[1], af, bfr[2], bfr[3]);
+  }
+  const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = gq + (q >> 1) * 8, j = nt * 8 + 2 * tq + (q & 1);
+      float v = s[nt][q] * a.scale + table[bias_index(a, i, j) * a.heads + head];
+      if (a.masked && s_rid[i] != s_rid[j]) v += -100.0f;
+      s[nt][q] = v;
+    }
+}
+
+__device__ __forceinline__ void softmax_rows(float (&s)[2][4]) {
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    float m = fmaxf(fmaxf(s[0][hf * 2], s[0][hf * 2 + 1]), fmaxf(s[1][hf * 2], s[1][hf * 2 + 1]));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    float e[4], sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      e[q] = __expf(s[q >> 1][hf * 2 + (q & 1)] - m);
+      sum += e[q];
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[q >> 1][hf * 2 + (q & 1)] = e[q] * inv;
+  }
+}
+
+__device__ __forceinline__ void load_window_rows(const AttnArgs& a, bf16* sq, const bf16* __restrict__ qkv, int b, int wh,
+                                                 int ww, int hg, int tid) {
+  // 16 tokens x 3 segments (q|k|v) x 96 columns = 576 16-byte chunks over 96 threads
+  for (int ch = tid; ch < L * 3 * 12; ch += 96) {
+    const int i = ch / 36, rem = ch % 36, seg = rem / 12, c = (rem % 12) * 8;
+    const int t = token_index(a, b, wh, ww, i);
+    cp_async16(sq + i * QLD + seg * HG * HD + c, qkv + (long)t * 3 * a.C + seg * a.C + hg * HG * HD + c, 16);
+  }
+}
+
+__global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
+  __shared__ __align__(16) bf16 sq[L * QLD];
+  __shared__ int s_rid[L];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nWh = a.H / a.Mh, nWw = a.W / a.Mw;
+  const int hgn = a.heads / HG;
+  const int items = a.B * nWh * nWw * hgn;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int hg = item % hgn;
+    int win = item / hgn;
+    const int ww = win % nWw; win /= nWw;
+    const int wh = win % nWh;
+    const int b = win / nWh;
+    __syncthreads();                                   // previous item's smem reads are done
+    load_window_rows(a, sq, a.qkv, b, wh, ww, hg, tid);
+    cp_async_commit();
+    if (tid < L) s_rid[tid] = a.masked ? region_id(a, wh, ww, tid) : 0;
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const int head = hg * HG + warp;
+    float s[2][4];
+    scores(a, sq, warp, head, s_rid, a.bias_table, s, lane);
+    softmax_rows(s);
+    uint32_t pf[4] = {pack_bf16(s[0][0], s[0][1]), pack_bf16(s[0][2], s[0][3]), pack_bf16(s[1][0], s[1][1]),
+                      pack_bf16(s[1][2], s[1][3])};
+    float o[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[nt][q] = 0.f;
+    const int mat = lane >> 3;
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bfr[4];
+      ldmatrix_x4_trans(bfr, sq + ((mat & 1) * 8 + (lane & 7)) * QLD + 2 * HG * HD + warp * HD + np * 16 + (mat >> 1) * 8);
+      mma_bf16_16816(o[2 * np], pf, bfr[0], bfr[1]);
+      mma_bf16_16816(o[2 * np + 1], pf, bfr[2], bfr[3]);
+    }
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int t = token_index(a, b, wh, ww, gq + hf * 8);
+      bf16* dst = a.out + (long)t * a.C + head * HD + 2 * tq;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(o[nt][hf * 2], o[nt][hf * 2 + 1]);
+    }
+  }
+}
+
+// Backward of the attention core for one (window, head) per warp.  Recomputes S and P from the saved qkv.
+//   dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(dP o P)), dQ = scale * dS K, dK = scale * dS^T Q,
+//   d bias_table[idx(i,j), head] += dS[i,j]     
+__global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf16* sq = reinterpret_cast<bf16*>(smem_raw);               // [16][QLD]  q|k|v
+  bf16* sdo = sq + L * QLD;                                   // [16][OLD]  dO
+  bf16* sp = sdo + L * OLD;                                   // [3 warps][2][16][PLD]  P and dS scratch
+  float* s_dtab = reinterpret_cast<float*>(sp + 3 * 2 * L * PLD);   // [heads][nbias]
+  __shared__ int s_rid[L];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nWh = a.H / a.Mh, nWw = a.W / a.Mw;
+  const int hgn = a.heads / HG;
+  const int items = a.B * nWh * nWw * hgn;
+  for (int i = tid; i < a.heads * a.nbias; i += 96) s_dtab[i] = 0.f;
+
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int hg = item % hgn;
+    int win = item / hgn;
+    const int ww = win % nWw; win /= nWw;
+    const int wh = win % nWh;
+    const int b = win / nWh;
+    __syncthreads();
+    load_window_rows(a, sq, a.qkv, b, wh, ww, hg, tid);
+    for (int ch = tid; ch < L * 12; ch += 96) {
+      const int i = ch / 12, c = (ch % 12) * 8;
+      const int t = token_index(a, b, wh, ww, i);
+      cp_async16(sdo + i * OLD + c, a.dout + (long)t * a.C + hg * HG * HD + c, 16);
+    }
+    cp_async_commit();
+    if (tid < L) s_rid[tid] = a.masked ? region_id(a, wh, ww, tid) : 0;
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const int head = hg * HG + warp;
+    const int mat = lane >> 3, gq = lane >> 2, tq = lane & 3;
+    float p[2][4];
+    scores(a, sq, warp, head, s_rid, a.bias_table, p, lane);
+    softmax_rows(p);
+
+    // dP = dO V^T
+    float dp[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dp[nt][q] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t af[4], bfr[4];
+      ldmatrix_x4(af, sdo + (lane & 15) * OLD + warp * HD + ks * 16 + (lane >> 4) * 8);
+      ldmatrix_x4(bfr, sq + ((mat >> 1) * 8 + (lane & 7)) * QLD + 2 * HG * HD + warp * HD + ks * 16 + (mat & 1) * 8);
+      mma_bf16_16816(dp[0], af, bfr[0], bfr[1]);
+      mma_bf16_16816(dp[1], af, bfr[2], bfr[3]);
+    }
+    // dS = P o (dP - rowsum(dP o P))
+    float ds[2][4];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float r = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r += dp[q >> 1][hf * 2 + (q & 1)] * p[q >> 1][hf * 2 + (q & 1)];
+      r += __shfl_xor_sync(0xffffffffu, r, 1);
+      r += __shfl_xor_sync(0xffffffffu, r, 2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int nt = q >> 1, e = hf * 2 + (q & 1);
+        ds[nt][e] = p[nt][e] * (dp[nt][e] - r);
+      }
+    }
+    // relative-position-bias gradient (per-CTA shared accumulation, flushed once at the end)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = gq + (q >> 1) * 8, j = nt * 8 + 2 * tq + (q & 1);
+        atomicAdd(&s_dtab[head * a.nbias + bias_index(a, i, j)], ds[nt][q]);
+      }
+    // stash P and dS (bf16, [i][j]) for the transposed operands
+    bf16* wp = sp + warp * 2 * L * PLD;
+    bf16* wds = wp + L * PLD;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int i = gq + hf * 8, j = nt * 8 + 2 * tq;
+        *reinterpret_cast<uint32_t*>(wp + i * PLD + j) = pack_bf16(p[nt][hf * 2], p[nt][hf * 2 + 1]);
+        *reinterpret_cast<uint32_t*>(wds + i * PLD + j) = pack_bf16(ds[nt][hf * 2], ds[nt][hf * 2 + 1]);
+      }
+    __syncwarp();
+
+    float dq[4][4], dk[4][4], dv[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dq[nt][q] = dk[nt][q] = dv[nt][q] = 0.f;
+    uint32_t dsf[4] = {pack_bf16(ds[0][0], ds[0][1]), pack_bf16(ds[0][2], ds[0][3]), pack_bf16(ds[1][0], ds[1][1]),
+                       pack_bf16(ds[1][2], ds[1][3])};
+    uint32_t ptf[4], dstf[4];                                  // P^T and dS^T as A operands (rows j, contraction i)
+    ldmatrix_x4_trans(ptf, wp + ((mat >> 1) * 8 + (lane & 7)) * PLD + (mat & 1) * 8);
+    ldmatrix_x4_trans(dstf, wds + ((mat >> 1) * 8 + (lane & 7)) * PLD + (mat & 1) * 8);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bdo[4], bk[4], bq[4];
+      const int roff = ((mat & 1) * 8 + (lane & 7));
+      const int coff = warp * HD + np * 16 + (mat >> 1) * 8;
+      ldmatrix_x4_trans(bdo, sdo + roff * OLD + coff);                         // B[k=i][n=d] = dO[i][d]
+      ldmatrix_x4_trans(bk, sq + roff * QLD + HG * HD + coff);                 // B[k=j][n=d] = K[j][d]
+      ldmatrix_x4_trans(bq, sq + roff * QLD + coff);                           // B[k=i][n=d] = Q[i][d]
+      mma_bf16_16816(dv[2 * np], ptf, bdo[0], bdo[1]);
+      mma_bf16_16816(dv[2 * np + 1], ptf, bdo[2], bdo[3]);
+      mma_bf16_16816(dq[2 * np], dsf, bk[0], bk[1]);
+      mma_bf16_16816(dq[2 * np + 1], dsf, bk[2], bk[3]);
+      mma_bf16_16816(dk[2 * np], dstf, bq[0], bq[1]);
+      mma_bf16_16816(dk[2 * np + 1], dstf, bq[2], bq[3]);
+    }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int t = token_index(a, b, wh, ww, gq + hf * 8);
+      bf16* dst = a.dqkv + (long)t * 3 * a.C + head * HD + 2 * tq;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(dq[nt][hf * 2] * a.scale, dq[nt][hf * 2 + 1] * a.scale);
+        *reinterpret_cast<uint32_t*>(dst + a.C + nt * 8) = pack_bf16(dk[nt][hf * 2] * a.scale, dk[nt][hf * 2 + 1] * a.scale);
+        *reinterpret_cast<uint32_t*>(dst + 2 * a.C + nt * 8) = pack_bf16(dv[nt][hf * 2], dv[nt][hf * 2 + 1]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < a.heads * a.nbias; i += 96) {
+    const float v = s_dtab[i];
+    if (v != 0.f) atomicAdd(a.dbias_table + (i % a.nbias) * a.heads + i / a.nbias, v);
+  }
+}
+
+int check_attn(const AttnArgs& a) {
+  TULIP_REQUIRE(a.Mh * a.Mw == L, "window attention: windows must hold 16 tokens");
+  TULIP_REQUIRE(a.bMh * a.bMw == L, "window attention: bias window must hold 16 tokens");
+  TULIP_REQUIRE(a.C == a.heads * HD, "window attention: head_dim must be 32");
+  TULIP_REQUIRE(a.heads % HG == 0, "window attention: heads must be a multiple of 3");
+  TULIP_REQUIRE(a.H % a.Mh == 0 && a.W % a.Mw == 0, "H or W is not divisible by window_size");
+  TULIP_REQUIRE(a.nbias == (2 * a.bMh - 1) * (2 * a.bMw - 1), "window attention: bias table size");
+  return TULIP_OK;
+}
+
+}  // namespace
+
+int win_attn_fwd(const AttnArgs& a, cudaStream_t st) {
+  int rc = check_attn(a);
+  if (rc) return rc;
+  const int items = a.B * (a.H / a.Mh) * (a.W / a.Mw) * (a.heads / HG);
+  const int grid = min(items, tulip_num_sms() * 16);
+  win_attn_fwd_kernel<<<grid, 96, 0, st>>>(a);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int win_attn_bwd(const AttnArgs& a, cudaStream_t st) {
+  int rc = check_attn(a);
+  if (rc) return rc;
+  const int items = a.B * (a.H / a.Mh) * (a.W / a.Mw) * (a.heads / HG);
+  const int grid = min(items, tulip_num_sms() * 8);
+  const int smem = (L * QLD + L * OLD + 3 * 2 * L * PLD) * 2 + a.heads * a.nbias * 4;
+  static int configured = 0;
+  if (smem > configured) {
+    TULIP_CUDA(cudaFuncSetAttribute(win_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  win_attn_bwd_kernel<<<grid, 96, smem, st>>>(a);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}

@@ -1,0 +1,227 @@
+// extern "C" surface of libtulip_b200.so (declared in include/tulip_b200.h).
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "net.h"
+
+namespace {
+thread_local std::string g_error;
+int g_num_sms = 0;
+}  // namespace
+
+void tulip_set_error(const char* msg) { g_error = msg ? msg : "unknown error"; }
+
+int tulip_num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static int gemm_impl_env() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TULIP_B200_GEMM");
+    v = (e && strcmp(e, "mma") == 0) ? 1 : 0;
+  }
+  return v;
+}
+
+int gemm_nt(const GemmArgs& g, int epi, cudaStream_t st) {
+  if (!gemm_impl_env()) {
+    const int rc = gemm_nt_tc05(g, epi, st);
+    if (rc != TULIP_ERR_UNSUPPORTED) return rc;
+  }
+  return gemm_nt_mma(g, epi, st);
+}
+
+int gemm_tn(const GemmTNArgs& g, cudaStream_t st) {
+  if (!gemm_impl_env()) {
+    const int rc = gemm_tn_tc05(g, st);
+    if (rc != TULIP_ERR_UNSUPPORTED) return rc;
+  }
+  return gemm_tn_mma(g, st);
+}
+
+extern "C" {
+
+const char* tulip_last_error(void) { return g_error.c_str(); }
+int tulip_abi_version(void) { return 1; }
+
+int tulip_net_create(const tulip_config* cfg, tulip_net** out) {
+  if (!cfg || !out) { tulip_set_error("tulip_net_create: null argument"); return TULIP_ERR_ARG; }
+  tulip_net* n = new tulip_net();
+  n->cfg = *cfg;
+  const int rc = n->build();
+  if (rc != TULIP_OK) { delete n; *out = nullptr; return rc; }
+  *out = n;
+  return TULIP_OK;
+}
+
+void tulip_net_destroy(tulip_net* n) {
+  if (!n) return;
+  if (n->warena) cudaFree(n->warena);
+  if (n->faux) cudaFree(n->faux);
+  if (n->items_dev) cudaFree(n->items_dev);
+  delete n;
+}
+
+int tulip_net_num_params(const tulip_net* n) { return (int)n->params.size(); }
+
+int tulip_net_param_info(const tulip_net* n, int i, char* name, int name_cap, int64_t shape[4], int* ndim) {
+  if (i < 0 || i >= (int)n->params.size()) { tulip_set_error("param index out of range"); return TULIP_ERR_ARG; }
+  const ParamInfo& p = n->params[i];
+  if (name && name_cap > 0) { strncpy(name, p.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  for (int k = 0; k < 4; ++k) shape[k] = p.shape[k];
+  *ndim = p.ndim;
+  return TULIP_OK;
+}
+
+int tulip_net_num_blocks(const tulip_net* n) { return (int)n->blocks.size(); }
+
+int tulip_net_block_info(const tulip_net* n, int i, int* stage, int* shifted, int* H, int* W) {
+  if (i < 0 || i >= (int)n->blocks.size()) { tulip_set_error("block index out of range"); return TULIP_ERR_ARG; }
+  const BlockDef& b = n->blocks[i];
+  *stage = b.stage; *shifted = b.shift; *H = n->H0 >> b.stage; *W = n->W0 >> b.stage;
+  return TULIP_OK;
+}
+
+int64_t tulip_net_workspace_bytes(const tulip_net* n, int batch) { return batch > 0 ? n->plan(batch).total : 0; }
+int64_t tulip_net_kernel_launches(const tulip_net* n) { return n->kernel_launches; }
+
+int tulip_net_forward(tulip_net* n, int batch, const float* params, const int64_t* offs, const float* x_lo, const float* target,
+                      const float* drop_scales, const int* win_mode, void* ws, float* pred, float* losses, void* stream) {
+  if (!n || !params || !offs || !x_lo || !ws || !pred) { tulip_set_error("tulip_net_forward: null argument"); return TULIP_ERR_ARG; }
+  if (target && !losses) { tulip_set_error("tulip_net_forward: losses is null"); return TULIP_ERR_ARG; }
+  return n->forward(batch, params, offs, x_lo, target, drop_scales, win_mode, ws, pred, losses, (cudaStream_t)stream);
+}
+
+int tulip_net_backward(tulip_net* n, int batch, const float* params, const int64_t* offs, float* grads, const float* x_lo,
+                       const float* target, const float* pred, const float* grad_loss, const float* drop_scales,
+                       const int* win_mode, void* ws, void* stream) {
+  if (!n || !params || !offs || !grads || !x_lo || !ws) { tulip_set_error("tulip_net_backward: null argument"); return TULIP_ERR_ARG; }
+  return n->backward(batch, params, offs, grads, x_lo, target, pred, grad_loss, drop_scales, win_mode, ws, (cudaStream_t)stream);
+}
+
+int tulip_gemm_nt(const void* A, const void* W, const float* bias, void* out, void* out2, const void* aux, const float* row_scale,
+                  int rows_per_sample, int M, int N, int K, int epilogue, int impl, void* stream) {
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.A = (const bf16*)A; g.lda = K; g.K1 = K; g.B = (const bf16*)W; g.ldb = K; g.M = M; g.N = N; g.K = K; g.bias = bias;
+  g.out = (bf16*)out; g.ldo = N; g.out2 = (bf16*)out2; g.ldo2 = N; g.aux = (const bf16*)aux; g.ldaux = N;
+  g.row_scale = row_scale; g.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
+  if (epilogue != EPI_STORE && epilogue != EPI_GELU && epilogue != EPI_RESID && epilogue != EPI_DGELU) {
+    tulip_set_error("tulip_gemm_nt: epilogue must be 0 (store), 1 (gelu), 2 (residual) or 5 (dgelu)");
+    return TULIP_ERR_ARG;
+  }
+  if (impl == 1) return gemm_nt_mma(g, epilogue, (cudaStream_t)stream);
+  if (impl == 2) return gemm_nt_tc05(g, epilogue, (cudaStream_t)stream);
+  return gemm_nt(g, epilogue, (cudaStream_t)stream);
+}
+
+int tulip_gemm_tn(const void* dY, const void* X, float* dW, float* db, int M, int N, int K, int impl, void* stream) {
+  GemmTNArgs g;
+  memset(&g, 0, sizeof g);
+  g.dY = (const bf16*)dY; g.ldy = N; g.X = (const bf16*)X; g.ldx = K; g.K1 = K; g.M = M; g.N = N; g.K = K;
+  g.dW = dW; g.lddw = K; g.db = db; g.perm_R2 = 1; g.perm_Cc = 1;
+  const int tiles = (N / 96) * (K / 96);
+  int splits = tiles > 0 ? (2 * tulip_num_sms() + tiles - 1) / tiles : 1;
+  const int max_splits = (M + 255) / 256;
+  g.splits = splits > max_splits ? max_splits : (splits < 1 ? 1 : splits);
+  if (impl == 1) return gemm_tn_mma(g, (cudaStream_t)stream);
+  if (impl == 2) return gemm_tn_tc05(g, (cudaStream_t)stream);
+  return gemm_tn(g, (cudaStream_t)stream);
+}
+
+static AttnArgs make_attn(const void* qkv, const float* table, int B, int H, int W, int C, int heads, int Mh, int Mw, int sh, int sw,
+                          int masked, int bMh, int bMw) {
+  AttnArgs a;
+  memset(&a, 0, sizeof a);
+  a.qkv = (const bf16*)qkv; a.bias_table = table; a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads;
+  a.Mh = Mh; a.Mw = Mw; a.sh = sh; a.sw = sw; a.masked = masked; a.bMh = bMh; a.bMw = bMw;
+  a.nbias = (2 * bMh - 1) * (2 * bMw - 1);
+  a.scale = 1.0f / sqrtf((float)(heads > 0 ? C / heads : 1));
+  return a;
+}
+
+int tulip_window_attention_fwd(const void* qkv, const float* bias_table, void* out, int B, int H, int W, int C, int heads, int Mh,
+                               int Mw, int sh, int sw, int masked, int bias_Mh, int bias_Mw, void* stream) {
+  AttnArgs a = make_attn(qkv, bias_table, B, H, W, C, heads, Mh, Mw, sh, sw, masked, bias_Mh, bias_Mw);
+  a.out = (bf16*)out;
+  return win_attn_fwd(a, (cudaStream_t)stream);
+}
+
+int tulip_window_attention_bwd(const void* qkv, const float* bias_table, const void* dout, void* dqkv, float* dbias_table, int B,
+                               int H, int W, int C, int heads, int Mh, int Mw, int sh, int sw, int masked, int bias_Mh, int bias_Mw,
+                               void* stream) {
+  AttnArgs a = make_attn(qkv, bias_table, B, H, W, C, heads, Mh, Mw, sh, sw, masked, bias_Mh, bias_Mw);
+  a.dout = (const bf16*)dout; a.dqkv = (bf16*)dqkv; a.dbias_table = dbias_table;
+  return win_attn_bwd(a, (cudaStream_t)stream);
+}
+
+int tulip_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* stats, int rows, int C, float eps,
+                        int merge_gather_, int H2, int W2, void* stream) {
+  LnArgs a;
+  memset(&a, 0, sizeof a);
+  a.x = (const bf16*)x; a.w = w; a.b = b; a.y = (bf16*)y; a.stats = stats; a.rows = rows; a.C = C; a.eps = eps;
+  a.gather = merge_gather_; a.H2 = H2; a.W2 = W2;
+  return layernorm_fwd(a, (cudaStream_t)stream);
+}
+
+int tulip_layernorm_bwd(const void* x, const float* w, const float* stats, const void* dy, const void* dres, void* dx, float* dw,
+                        float* db, int rows, int C, int merge_gather_, int H2, int W2, void* stream) {
+  LnArgs a;
+  memset(&a, 0, sizeof a);
+  a.x = (const bf16*)x; a.w = w; a.stats = const_cast<float*>(stats); a.dy = (const bf16*)dy; a.dres = (const bf16*)dres;
+  a.dx = (bf16*)dx; a.dw = dw; a.db = db; a.rows = rows; a.C = C; a.gather = merge_gather_; a.H2 = H2; a.W2 = W2;
+  return layernorm_bwd(a, (cudaStream_t)stream);
+}
+
+int tulip_patch_embed_fwd(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, void* y, int B,
+                          int Himg, int Wimg, int ph, int E, float eps, void* stream) {
+  EmbedArgs e;
+  memset(&e, 0, sizeof e);
+  e.x = x; e.w = w; e.b = b; e.ln_w = ln_w; e.ln_b = ln_b; e.y = (bf16*)y; e.B = B; e.Himg = Himg; e.Wimg = Wimg; e.ph = ph; e.E = E;
+  e.eps = eps;
+  return patch_embed_fwd(e, (cudaStream_t)stream);
+}
+
+int tulip_patch_embed_bwd(const float* x, const float* w, const float* b, const float* ln_w, const void* dy, float* dw, float* db,
+                          float* dln_w, float* dln_b, int B, int Himg, int Wimg, int ph, int E, float eps, void* stream) {
+  EmbedArgs e;
+  memset(&e, 0, sizeof e);
+  e.x = x; e.w = w; e.b = b; e.ln_w = ln_w; e.B = B; e.Himg = Himg; e.Wimg = Wimg; e.ph = ph; e.E = E; e.eps = eps;
+  e.dy = (const bf16*)dy; e.dw = dw; e.db = db; e.dln_w = dln_w; e.dln_b = dln_b;
+  return patch_embed_bwd(e, (cudaStream_t)stream);
+}
+
+int tulip_l1_loss(const float* pred, const float* target, int64_t n, int log_transform, float* scratch2, float* out2, void* stream) {
+  return l1_loss(pred, target, (long)n, log_transform, scratch2, out2, (cudaStream_t)stream);
+}
+
+int tulip_window_partition(const void* x, void* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, void* stream) {
+  return window_gather((const bf16*)x, (bf16*)out, B, H, W, C, Mh, Mw, sh, sw, (cudaStream_t)stream);
+}
+int tulip_window_reverse(const void* xw, void* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, void* stream) {
+  return window_scatter((const bf16*)xw, (bf16*)out, B, H, W, C, Mh, Mw, sh, sw, (cudaStream_t)stream);
+}
+int tulip_shift_mask(float* out, int H, int W, int Mh, int Mw, int sh, int sw, void* stream) {
+  return shift_mask(out, H, W, Mh, Mw, sh, sw, (cudaStream_t)stream);
+}
+int tulip_rel_bias_gather(const float* table, float* out, int heads, int Mh, int Mw, void* stream) {
+  return rel_bias_gather(table, out, heads, Mh, Mw, (cudaStream_t)stream);
+}
+int tulip_merge_gather(const void* x, void* out, int B, int H, int W, int C, void* stream) {
+  return merge_gather((const bf16*)x, (bf16*)out, B, H, W, C, (cudaStream_t)stream);
+}
+int tulip_pixel_shuffle(const void* x, void* out, int B, int H, int W, int Cout, int r, void* stream) {
+  return pixel_shuffle_nhwc((const bf16*)x, (bf16*)out, B, H, W, Cout, r, (cudaStream_t)stream);
+}
+
+}  // extern "C"

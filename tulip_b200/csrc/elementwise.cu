@@ -1,0 +1,672 @@
+// HBM-bound kernels of the TULIP path: LayerNorm (+ PatchMerging gather), PatchEmbed, weight repack,
+// loss, small element-wise helpers and the stand-alone index ops.  All of them move each byte once,
+// with 16-byte vector accesses and grids sized in multiples of the SM count.
+#include "common.cuh"
+#include "kernels.h"
+#include "window_index.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm.  A group of LANES lanes owns one row; each lane holds NCH 16-byte chunks (8 bf16) of it.
+// Reference: nn.LayerNorm(eps=1e-6) at tulip.py:330,334 (block norms), :80,104 (PatchMerging, on the
+// 2x2-gathered 4C vector), :569,720 (norm_up).  Statistics in fp32, two-pass in registers.
+
+template <int LANES>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// source address of 16-byte chunk `ch` of row `row` (plain or PatchMerging gather, tulip.py:94-98)
+__device__ __forceinline__ long ln_src_offset(const LnArgs& a, int row, int ch) {
+  if (!a.gather) return (long)row * a.C + ch * 8;
+  const int Cs = a.C >> 2;                       // source channels
+  const int cps = Cs >> 3;                       // chunks per source token
+  const int qd = ch / cps, cc = ch % cps;
+  const int w2 = row % a.W2;
+  const int bh = row / a.W2;
+  const int h2 = bh % a.H2;
+  const int b = bh / a.H2;
+  const int hs = 2 * h2 + (qd & 1), ws = 2 * w2 + (qd >> 1);
+  return ((long)(b * 2 * a.H2 + hs) * (2 * a.W2) + ws) * Cs + cc * 8;
+}
+
+template <int LANES, int NCH>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const LnArgs a) {
+  const int lane = threadIdx.x % LANES;
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  const int ngroups = (gridDim.x * blockDim.x) / LANES;
+  const int nch = a.C >> 3;
+  const float invC = 1.0f / (float)a.C;
+  for (int row = group; row < a.rows; row += ngroups) {
+    uint4 v[NCH];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int ch = lane + i * LANES;
+      if (ch < nch) {
+        v[i] = *reinterpret_cast<const uint4*>(a.x + ln_src_offset(a, row, ch));
+        const float2 p0 = unpack_bf16(v[i].x), p1 = unpack_bf16(v[i].y), p2 = unpack_bf16(v[i].z), p3 = unpack_bf16(v[i].w);
+        sum += (p0.x + p0.y) + (p1.x + p1.y) + (p2.x + p2.y) + (p3.x + p3.y);
+      }
+    }
+    const float mean = group_sum<LANES>(sum) * invC;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int ch = lane + i * LANES;
+      if (ch < nch) {
+        const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 p = unpack_bf16(u[q]);
+          sq += (p.x - mean) * (p.x - mean) + (p.y - mean) * (p.y - mean);
+        }
+      }
+    }
+    const float rstd = rsqrtf(group_sum<LANES>(sq) * invC + a.eps);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int ch = lane + i * LANES;
+      if (ch < nch) {
+        const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+        uint32_t o[4];
+        const float4 w0 = *reinterpret_cast<const float4*>(a.w + ch * 8), w1 = *reinterpret_cast<const float4*>(a.w + ch * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(a.b + ch * 8), b1 = *reinterpret_cast<const float4*>(a.b + ch * 8 + 4);
+        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 p = unpack_bf16(u[q]);
+          o[q] = pack_bf16((p.x - mean) * rstd * ww[2 * q] + bb[2 * q], (p.y - mean) * rstd * ww[2 * q + 1] + bb[2 * q + 1]);
+        }
+        *reinterpret_cast<uint4*>(a.y + (long)row * a.C + ch * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    if (lane == 0 && a.stats) *reinterpret_cast<float2*>(a.stats + 2 * (long)row) = make_float2(mean, rstd);
+  }
+}
+
+// dx = [dres +] rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w;  dw += dy * xhat; db += dy
+template <int LANES, int NCH, bool REGACC>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnArgs a) {
+  const int lane = threadIdx.x % LANES;
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  const int ngroups = (gridDim.x * blockDim.x) / LANES;
+  const int nch = a.C >> 3;
+  const float invC = 1.0f / (float)a.C;
+  float accw[REGACC ? NCH : 1][8], accb[REGACC ? NCH : 1][8];
+  if (REGACC) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) accw[i][q] = accb[i][q] = 0.f;
+  }
+  for (int row = group; row < a.rows; row += ngroups) {
+    const float2 st = *reinterpret_cast<const float2*>(a.stats + 2 * (long)row);
+    const float mean = st.x, rstd = st.y;
+    uint4 xv[NCH], gv[NCH];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int ch = lane + i * LANES;
+      if (ch < nch) {
+        xv[i] = *reinterpret_cast<const uint4*>(a.x + ln_src_offset(a, row, ch));
+        gv[i] = *reinterpret_cast<const uint4*>(a.dy + (long)row * a.C + ch * 8);
+        const uint32_t xu[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+        const uint32_t gu[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+        const float4 w0 = *reinterpret_cast<const float4*>(a.w + ch * 8), w1 = *reinterpret_cast<const float4*>(a.w + ch * 8 + 4);
+        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 x = unpack_bf16(xu[q]), g = unpack_bf16(gu[q]);
+          const float h0 = (x.x - mean) * rstd, h1 = (x.y - mean) * rstd;
+          const float g0 = g.x * ww[2 * q], g1 = g.y * ww[2 * q + 1];
+          s1 += g0 + g1;
+          s2 += g0 * h0 + g1 * h1;
+          if (REGACC) {
+            accw[i][2 * q] += g.x * h0; accw[i][2 * q + 1] += g.y * h1;
+            accb[i][2 * q] += g.x;      accb[i][2 * q + 1] += g.y;
+          } else {
+            atomicAdd(a.dw + ch * 8 + 2 * q, g.x * h0); atomicAdd(a.dw + ch * 8 + 2 * q + 1, g.y * h1);
+            atomicAdd(a.db + ch * 8 + 2 * q, g.x);      atomicAdd(a.db + ch * 8 + 2 * q + 1, g.y);
+          }
+        }
+      }
+    }
+    const float m1 = group_sum<LANES>(s1) * invC, m2 = group_sum<LANES>(s2) * invC;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int ch = lane + i * LANES;
+      if (ch < nch) {
+        const uint32_t xu[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+        const uint32_t gu[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+        const float4 w0 = *reinterpret_cast<const float4*>(a.w + ch * 8), w1 = *reinterpret_cast<const float4*>(a.w + ch * 8 + 4);
+        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const long off = ln_src_offset(a, row, ch);        // dx has the layout of the LN input (scatter for the merge)
+        uint4 rv = make_uint4(0, 0, 0, 0);
+        if (a.dres) rv = *reinterpret_cast<const uint4*>(a.dres + off);
+        const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 x = unpack_bf16(xu[q]), g = unpack_bf16(gu[q]), r = unpack_bf16(ru[q]);
+          const float h0 = (x.x - mean) * rstd, h1 = (x.y - mean) * rstd;
+          const float d0 = rstd * (g.x * ww[2 * q] - m1 - h0 * m2), d1 = rstd * (g.y * ww[2 * q + 1] - m1 - h1 * m2);
+          o[q] = pack_bf16(r.x + d0, r.y + d1);
+        }
+        *reinterpret_cast<uint4*>(a.dx + off) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  if (REGACC) {
+    // combine the groups of this CTA in shared memory, then one atomic per column per CTA
+    extern __shared__ float s_acc[];                      // [2][C]
+    for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int ch = lane + i * LANES;
+      if (ch < nch) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          atomicAdd(&s_acc[ch * 8 + q], accw[i][q]);
+          atomicAdd(&s_acc[a.C + ch * 8 + q], accb[i][q]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.C; i += blockDim.x) {
+      atomicAdd(a.dw + i, s_acc[i]);
+      atomicAdd(a.db + i, s_acc[a.C + i]);
+    }
+  }
+}
+
+struct LnCfg { int lanes, nch; };
+inline bool ln_config(int C, LnCfg* cfg) {
+  if (C % 8) return false;
+  const int nch = C / 8;
+  if (nch <= 16) *cfg = {16, 1};
+  else if (nch <= 32) *cfg = {16, 2};
+  else if (nch <= 48) *cfg = {16, 3};
+  else if (nch <= 96) *cfg = {32, 3};
+  else if (nch <= 192) *cfg = {32, 6};
+  else if (nch <= 384) *cfg = {32, 12};
+  else return false;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PatchEmbedding: circular pad W by (2,2) -> Conv2d(1 -> E, k=(ph,8), s=(ph,4)) -> NHWC -> LayerNorm.
+// Reference tulip.py:59-73.  One warp per output token, lane l owns channels l, l+32, ...
+template <int EPL>   // channels per lane = E / 32
+__global__ void __launch_bounds__(256) patch_embed_fwd_kernel(const EmbedArgs a) {
+  extern __shared__ float s_w[];                          // [E][ph*8] conv weight
+  const int KW = a.ph * 8;
+  for (int i = threadIdx.x; i < a.E * KW; i += blockDim.x) s_w[i] = a.w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int Ho = a.Himg / a.ph, Wo = a.Wimg / 4;
+  const int tokens = a.B * Ho * Wo;
+  float cb[EPL], lw[EPL], lb[EPL];
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) { cb[q] = a.b[lane + 32 * q]; lw[q] = a.ln_w[lane + 32 * q]; lb[q] = a.ln_b[lane + 32 * q]; }
+  const float invE = 1.0f / (float)a.E;
+  for (int t = warp; t < tokens; t += nwarps) {
+    const int wo = t % Wo;
+    const int bh = t / Wo;
+    const int ho = bh % Ho, b = bh / Ho;
+    float u[EPL];
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) u[q] = cb[q];
+    for (int dh = 0; dh < a.ph; ++dh) {
+      const float* row = a.x + ((long)b * a.Himg + ho * a.ph + dh) * a.Wimg;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int wi = 4 * wo + j - 2;
+        wi = wi < 0 ? wi + a.Wimg : (wi >= a.Wimg ? wi - a.Wimg : wi);
+        const float xv = __ldg(row + wi);
+#pragma unroll
+        for (int q = 0; q < EPL; ++q) u[q] = fmaf(s_w[(lane + 32 * q) * KW + dh * 8 + j], xv, u[q]);
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) s += u[q];
+    const float mean = warp_sum(s) * invE;
+    float sq = 0.f;
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) sq += (u[q] - mean) * (u[q] - mean);
+    const float rstd = rsqrtf(warp_sum(sq) * invE + a.eps);
+#pragma unroll
+    for (int q = 0; q < EPL; ++q)
+      a.y[(long)t * a.E + lane + 32 * q] = __float2bfloat16_rn((u[q] - mean) * rstd * lw[q] + lb[q]);
+  }
+}
+
+// Backward: recompute conv + LN statistics from the input image, then LN backward and the conv
+// weight / bias gradients (no input gradient: the input is data).  ph == 1 only (all shipped configs).
+template <int EPL>
+__global__ void __launch_bounds__(256) patch_embed_bwd_kernel(const EmbedArgs a) {
+  extern __shared__ float s_w[];                          // [E][8] weights, then [E][12] accumulators
+  float* s_acc = s_w + a.E * 8;
+  for (int i = threadIdx.x; i < a.E * 8; i += blockDim.x) s_w[i] = a.w[i];
+  for (int i = threadIdx.x; i < a.E * 12; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int Wo = a.Wimg / 4;
+  const int tokens = a.B * a.Himg * Wo;
+  float cb[EPL], lw[EPL];
+  float gw[EPL][8], gb[EPL], glw[EPL], glb[EPL];
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) {
+    cb[q] = a.b[lane + 32 * q]; lw[q] = a.ln_w[lane + 32 * q];
+    gb[q] = glw[q] = glb[q] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gw[q][j] = 0.f;
+  }
+  const float invE = 1.0f / (float)a.E;
+  for (int t = warp; t < tokens; t += nwarps) {
+    const int wo = t % Wo;
+    const int bh = t / Wo;
+    const float* row = a.x + (long)bh * a.Wimg;
+    float xv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int wi = 4 * wo + j - 2;
+      wi = wi < 0 ? wi + a.Wimg : (wi >= a.Wimg ? wi - a.Wimg : wi);
+      xv[j] = __ldg(row + wi);
+    }
+    float u[EPL], dy[EPL];
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) {
+      u[q] = cb[q];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[q] = fmaf(s_w[(lane + 32 * q) * 8 + j], xv[j], u[q]);
+      s += u[q];
+      dy[q] = __bfloat162float(a.dy[(long)t * a.E + lane + 32 * q]);
+    }
+    const float mean = warp_sum(s) * invE;
+    float sq = 0.f;
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) sq += (u[q] - mean) * (u[q] - mean);
+    const float rstd = rsqrtf(warp_sum(sq) * invE + a.eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) {
+      const float h = (u[q] - mean) * rstd, g = dy[q] * lw[q];
+      s1 += g; s2 += g * h;
+      glw[q] += dy[q] * h; glb[q] += dy[q];
+    }
+    const float m1 = warp_sum(s1) * invE, m2 = warp_sum(s2) * invE;
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) {
+      const float h = (u[q] - mean) * rstd;
+      const float du = rstd * (dy[q] * lw[q] - m1 - h * m2);
+      gb[q] += du;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gw[q][j] = fmaf(du, xv[j], gw[q][j]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) {
+    const int c = lane + 32 * q;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[c * 12 + j], gw[q][j]);
+    atomicAdd(&s_acc[c * 12 + 8], gb[q]);
+    atomicAdd(&s_acc[c * 12 + 9], glw[q]);
+    atomicAdd(&s_acc[c * 12 + 10], glb[q]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.E * 12; i += blockDim.x) {
+    const int c = i / 12, k = i % 12;
+    const float v = s_acc[i];
+    if (k < 8) atomicAdd(a.dw + c * 8 + k, v);
+    else if (k == 8) atomicAdd(a.db + c, v);
+    else if (k == 9) atomicAdd(a.dln_w + c, v);
+    else if (k == 10) atomicAdd(a.dln_b + c, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 weight repack, 32x32 tiles, optional row permutation and transposed copy.
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ flat, bf16* __restrict__ arena,
+                                                           const PackItem* __restrict__ items, int n_items) {
+  __shared__ float tile[32][33];
+  __shared__ int s_item;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_items - 1;                          // last item with tile_begin <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (items[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    s_item = lo;
+  }
+  __syncthreads();
+  const PackItem it = items[s_item];
+  const int tiles_c = (it.cols + 31) / 32;
+  const int tl = blockIdx.x - it.tile_begin;
+  const int r0 = (tl / tiles_c) * 32, c0 = (tl % tiles_c) * 32;      // destination (permuted) row block
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.f;
+    if (r < it.rows && c < it.cols) {
+      const int sr = it.perm_R2 > 1 ? (r % it.perm_Cc) * it.perm_R2 + r / it.perm_Cc : r;
+      v = flat[it.src_off + (long)sr * it.cols + c];
+      arena[it.dst_off + (long)r * it.cols + c] = __float2bfloat16_rn(v);
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  if (it.dstT_off < 0) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (r < it.rows && c < it.cols) arena[it.dstT_off + (long)c * it.rows + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+  }
+}
+
+__global__ void permute_bias_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int R2, int Cc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[(i % Cc) * R2 + i / Cc];
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void add_inplace_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, long n16) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long)gridDim.x * blockDim.x) {
+    const uint4 a = dst[i], b = src[i];
+    const uint32_t au[4] = {a.x, a.y, a.z, a.w}, bu[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 x = unpack_bf16(au[q]), y = unpack_bf16(bu[q]);
+      o[q] = pack_bf16(x.x + y.x, x.y + y.y);
+    }
+    dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void scale_rows_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, const float* __restrict__ row_scale,
+                                  long n16, int chunks_per_row, int rows_per_sample) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long)gridDim.x * blockDim.x) {
+    const float s = row_scale[(i / chunks_per_row) / rows_per_sample];
+    const uint4 a = src[i];
+    const uint32_t au[4] = {a.x, a.y, a.z, a.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 x = unpack_bf16(au[q]);
+      o[q] = pack_bf16(x.x * s, x.y * s);
+    }
+    dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// mean |pred - y| and mean |expm1(pred) - expm1(y)| (tulip.py:690-700); acc2 must be zero on entry
+__global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, long n,
+                                                      int log_transform, float* acc2) {
+  float s0 = 0.f, s1 = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float p = pred[i], y = target[i];
+    s0 += fabsf(p - y);
+    if (log_transform) s1 += fabsf(expm1f(p) - expm1f(y));
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1);
+  __shared__ float sh[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][warp] = s0; sh[1][warp] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
+    atomicAdd(acc2, a);
+    atomicAdd(acc2 + 1, b);
+  }
+}
+__global__ void l1_loss_finalize_kernel(const float* acc2, float* out2, float inv_n, int log_transform) {
+  out2[0] = acc2[0] * inv_n;
+  out2[1] = log_transform ? acc2[1] * inv_n : acc2[0] * inv_n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone index ops (16-byte chunks; C % 8 == 0)
+__global__ void window_copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, WinGeom g, int cpt, bool scatter) {
+  const int L = g.Mh * g.Mw;
+  const int nWh = g.H / g.Mh, nWw = g.W / g.Mw;
+  const long total = (long)B * g.H * g.W * cpt;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = idx % cpt;
+    long wt = idx / cpt;                                   // windowed token index (B Nh Nw) L
+    const int i = wt % L; wt /= L;
+    const int ww = wt % nWw; wt /= nWw;
+    const int wh = wt % nWh;
+    const int b = wt / nWh;
+    const long nat = (long)win_token_index(g, b, wh, ww, i) * cpt + c;
+    if (scatter) dst[nat] = src[idx]; else dst[idx] = src[nat];
+  }
+}
+
+__global__ void shift_mask_kernel(float* out, WinGeom g) {
+  const int L = g.Mh * g.Mw;
+  const int nWw = g.W / g.Mw;
+  const int total = (g.H / g.Mh) * nWw * L * L;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int j = idx % L, i = (idx / L) % L, win = idx / (L * L);
+    const int wh = win / nWw, ww = win % nWw;
+    out[idx] = win_region_id(g, wh, ww, i) != win_region_id(g, wh, ww, j) ? -100.0f : 0.0f;
+  }
+}
+
+__global__ void rel_bias_gather_kernel(const float* table, float* out, int heads, int Mh, int Mw) {
+  const int L = Mh * Mw;
+  const int total = heads * L * L;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int j = idx % L, i = (idx / L) % L, h = idx / (L * L);
+    out[idx] = table[rel_bias_index(Mh, Mw, i, j) * heads + h];
+  }
+}
+
+__global__ void merge_gather_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, LnArgs a, long total) {
+  const int nch = a.C >> 3;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int ch = idx % nch;
+    const int row = idx / nch;
+    out[idx] = x[ln_src_offset(a, row, ch) >> 3];
+  }
+}
+
+__global__ void pixel_shuffle_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int B, int H, int W, int Cout, int r) {
+  // out[b, h*r+i, w*r+j, c] = x[b, h, w, c*r*r + i*r + j]
+  const long total = (long)B * H * W * Cout * r * r;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = idx % Cout;
+    long p = idx / Cout;
+    const int wo = p % (W * r); p /= (W * r);
+    const int ho = p % (H * r);
+    const int b = p / (H * r);
+    const int h = ho / r, i = ho % r, w = wo / r, j = wo % r;
+    out[idx] = x[(((long)b * H + h) * W + w) * (Cout * r * r) + c * r * r + i * r + j];
+  }
+}
+
+inline int ew_grid(long n, int threads) {
+  const long want = (n + threads - 1) / threads;
+  const long cap = (long)tulip_num_sms() * 8;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+
+#define LN_DISPATCH(KERNEL, ...)                                                        \
+  if (cfg.lanes == 16 && cfg.nch == 1) KERNEL<16, 1 __VA_ARGS__>                        \
+  else if (cfg.lanes == 16 && cfg.nch == 2) KERNEL<16, 2 __VA_ARGS__>                   \
+  else if (cfg.lanes == 16 && cfg.nch == 3) KERNEL<16, 3 __VA_ARGS__>                   \
+  else if (cfg.lanes == 32 && cfg.nch == 3) KERNEL<32, 3 __VA_ARGS__>                   \
+  else if (cfg.lanes == 32 && cfg.nch == 6) KERNEL<32, 6 __VA_ARGS__>
+
+int layernorm_fwd(const LnArgs& a, cudaStream_t st) {
+  LnCfg cfg;
+  TULIP_REQUIRE(ln_config(a.C, &cfg), "layernorm: C must be a multiple of 8 and <= 3072");
+  TULIP_REQUIRE(a.rows > 0, "layernorm: empty input");
+  const int rows_per_cta = 256 / cfg.lanes;
+  const int grid = min(ceil_div(a.rows, rows_per_cta), tulip_num_sms() * 8);
+  if (cfg.lanes == 16 && cfg.nch == 1) layernorm_fwd_kernel<16, 1><<<grid, 256, 0, st>>>(a);
+  else if (cfg.lanes == 16 && cfg.nch == 2) layernorm_fwd_kernel<16, 2><<<grid, 256, 0, st>>>(a);
+  else if (cfg.lanes == 16 && cfg.nch == 3) layernorm_fwd_kernel<16, 3><<<grid, 256, 0, st>>>(a);
+  else if (cfg.lanes == 32 && cfg.nch == 3) layernorm_fwd_kernel<32, 3><<<grid, 256, 0, st>>>(a);
+  else if (cfg.lanes == 32 && cfg.nch == 6) layernorm_fwd_kernel<32, 6><<<grid, 256, 0, st>>>(a);
+  else layernorm_fwd_kernel<32, 12><<<grid, 256, 0, st>>>(a);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int layernorm_bwd(const LnArgs& a, cudaStream_t st) {
+  LnCfg cfg;
+  TULIP_REQUIRE(ln_config(a.C, &cfg), "layernorm: C must be a multiple of 8 and <= 3072");
+  TULIP_REQUIRE(a.rows > 0, "layernorm: empty input");
+  const int rows_per_cta = 256 / cfg.lanes;
+  const int grid = min(ceil_div(a.rows, rows_per_cta), tulip_num_sms() * 4);
+  const int smem = 2 * a.C * (int)sizeof(float);
+  if (cfg.lanes == 16 && cfg.nch == 1) layernorm_bwd_kernel<16, 1, true><<<grid, 256, smem, st>>>(a);
+  else if (cfg.lanes == 16 && cfg.nch == 2) layernorm_bwd_kernel<16, 2, true><<<grid, 256, smem, st>>>(a);
+  else if (cfg.lanes == 16 && cfg.nch == 3) layernorm_bwd_kernel<16, 3, true><<<grid, 256, smem, st>>>(a);
+  else if (cfg.lanes == 32 && cfg.nch == 3) layernorm_bwd_kernel<32, 3, true><<<grid, 256, smem, st>>>(a);
+  else if (cfg.lanes == 32 && cfg.nch == 6) layernorm_bwd_kernel<32, 6, true><<<grid, 256, smem, st>>>(a);
+  else layernorm_bwd_kernel<32, 12, false><<<grid, 256, 0, st>>>(a);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int patch_embed_fwd(const EmbedArgs& a, cudaStream_t st) {
+  TULIP_REQUIRE(a.E % 32 == 0 && a.E <= 192, "patch_embed: embed_dim must be a multiple of 32, <= 192");
+  TULIP_REQUIRE(a.Wimg % 4 == 0 && a.Himg % a.ph == 0 && a.Wimg >= 4, "patch_embed: image not divisible by the patch");
+  const int tokens = a.B * (a.Himg / a.ph) * (a.Wimg / 4);
+  const int grid = min(ceil_div(tokens, 8 * 4), tulip_num_sms() * 8);
+  const int smem = a.E * a.ph * 8 * (int)sizeof(float);
+  switch (a.E / 32) {
+    case 1: patch_embed_fwd_kernel<1><<<grid, 256, smem, st>>>(a); break;
+    case 2: patch_embed_fwd_kernel<2><<<grid, 256, smem, st>>>(a); break;
+    case 3: patch_embed_fwd_kernel<3><<<grid, 256, smem, st>>>(a); break;
+    case 4: patch_embed_fwd_kernel<4><<<grid, 256, smem, st>>>(a); break;
+    case 5: patch_embed_fwd_kernel<5><<<grid, 256, smem, st>>>(a); break;
+    default: patch_embed_fwd_kernel<6><<<grid, 256, smem, st>>>(a); break;
+  }
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int patch_embed_bwd(const EmbedArgs& a, cudaStream_t st) {
+  TULIP_REQUIRE(a.E % 32 == 0 && a.E <= 192, "patch_embed: embed_dim must be a multiple of 32, <= 192");
+  TULIP_REQUIRE(a.ph == 1, "patch_embed backward: patch height must be 1");
+  const int tokens = a.B * a.Himg * (a.Wimg / 4);
+  const int grid = min(ceil_div(tokens, 8 * 16), tulip_num_sms() * 2);
+  const int smem = a.E * 20 * (int)sizeof(float);
+  switch (a.E / 32) {
+    case 1: patch_embed_bwd_kernel<1><<<grid, 256, smem, st>>>(a); break;
+    case 2: patch_embed_bwd_kernel<2><<<grid, 256, smem, st>>>(a); break;
+    case 3: patch_embed_bwd_kernel<3><<<grid, 256, smem, st>>>(a); break;
+    case 4: patch_embed_bwd_kernel<4><<<grid, 256, smem, st>>>(a); break;
+    case 5: patch_embed_bwd_kernel<5><<<grid, 256, smem, st>>>(a); break;
+    default: patch_embed_bwd_kernel<6><<<grid, 256, smem, st>>>(a); break;
+  }
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int pack_weights(const float* flat, bf16* arena, const PackItem* items_dev, int n_items, int n_tiles, cudaStream_t st) {
+  if (n_tiles <= 0) return TULIP_OK;
+  pack_weights_kernel<<<n_tiles, 256, 0, st>>>(flat, arena, items_dev, n_items);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int permute_bias(const float* src, float* dst, int n, int R2, int Cc, cudaStream_t st) {
+  permute_bias_kernel<<<ceil_div(n, 256), 256, 0, st>>>(src, dst, n, R2, Cc);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int add_inplace_bf16(bf16* dst, const bf16* src, long n, cudaStream_t st) {
+  TULIP_REQUIRE(n % 8 == 0, "add_inplace: length must be a multiple of 8");
+  add_inplace_kernel<<<ew_grid(n / 8, 256), 256, 0, st>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), n / 8);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int scale_rows_bf16(bf16* dst, const bf16* src, const float* row_scale, int rows, int C, int rows_per_sample, cudaStream_t st) {
+  TULIP_REQUIRE(C % 8 == 0, "scale_rows: C must be a multiple of 8");
+  const long n16 = (long)rows * (C / 8);
+  scale_rows_kernel<<<ew_grid(n16, 256), 256, 0, st>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), row_scale,
+                                                       n16, C / 8, rows_per_sample);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int l1_loss(const float* pred, const float* target, long n, int log_transform, float* acc2, float* out2, cudaStream_t st) {
+  TULIP_CUDA(cudaMemsetAsync(acc2, 0, 2 * sizeof(float), st));
+  l1_loss_kernel<<<ew_grid(n, 256), 256, 0, st>>>(pred, target, n, log_transform, acc2);
+  l1_loss_finalize_kernel<<<1, 1, 0, st>>>(acc2, out2, 1.0f / (float)n, log_transform);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int window_gather(const bf16* x, bf16* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, cudaStream_t st) {
+  TULIP_REQUIRE(C % 8 == 0 && H % Mh == 0 && W % Mw == 0, "H or W is not divisible by window_size");
+  const long n = (long)B * H * W * (C / 8);
+  window_copy_kernel<<<ew_grid(n, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B,
+                                                      WinGeom{H, W, Mh, Mw, sh, sw}, C / 8, false);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int window_scatter(const bf16* xw, bf16* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, cudaStream_t st) {
+  TULIP_REQUIRE(C % 8 == 0 && H % Mh == 0 && W % Mw == 0, "H or W is not divisible by window_size");
+  const long n = (long)B * H * W * (C / 8);
+  window_copy_kernel<<<ew_grid(n, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(xw), reinterpret_cast<uint4*>(out), B,
+                                                      WinGeom{H, W, Mh, Mw, sh, sw}, C / 8, true);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int shift_mask(float* out, int H, int W, int Mh, int Mw, int sh, int sw, cudaStream_t st) {
+  TULIP_REQUIRE(H % Mh == 0 && W % Mw == 0, "H or W is not divisible by window_size");
+  const int L = Mh * Mw;
+  const long n = (long)(H / Mh) * (W / Mw) * L * L;
+  shift_mask_kernel<<<ew_grid(n, 256), 256, 0, st>>>(out, WinGeom{H, W, Mh, Mw, sh, sw});
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int rel_bias_gather(const float* table, float* out, int heads, int Mh, int Mw, cudaStream_t st) {
+  const int L = Mh * Mw;
+  rel_bias_gather_kernel<<<ew_grid((long)heads * L * L, 256), 256, 0, st>>>(table, out, heads, Mh, Mw);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int merge_gather(const bf16* x, bf16* out, int B, int H, int W, int C, cudaStream_t st) {
+  TULIP_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "merge: H, W must be even and C a multiple of 8");
+  LnArgs a = {};
+  a.C = 4 * C; a.gather = 1; a.H2 = H / 2; a.W2 = W / 2;
+  const long total = (long)B * (H / 2) * (W / 2) * (4 * C / 8);
+  merge_gather_kernel<<<ew_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), a, total);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int pixel_shuffle_nhwc(const bf16* x, bf16* out, int B, int H, int W, int Cout, int r, cudaStream_t st) {
+  const long total = (long)B * H * W * Cout * r * r;
+  pixel_shuffle_kernel<<<ew_grid(total, 256), 256, 0, st>>>(x, out, B, H, W, Cout, r);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}

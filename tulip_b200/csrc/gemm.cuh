@@ -1,0 +1,121 @@
+// GEMM argument blocks + epilogue math shared by the tcgen05 (gemm_tc05.cu) and the
+// legacy warp-MMA (gemm_mma.cu) implementations.
+//
+//   NT : out[M,N]  = A[M,K] . B[N,K]^T  (+bias, epilogue)      forward linears, dX = dY . Wt^T
+//   TN : dW[N,K]  += dY[M,N]^T . X[M,K], db[N] += colsum(dY)   weight gradients (split over M, fp32 atomics)
+#pragma once
+#include "common.cuh"
+
+enum GemmEpi : int {
+  EPI_STORE = 0,      // out = acc + bias
+  EPI_GELU = 1,       // out2 = pre (acc+bias), out = gelu(pre)            (Mlp.fc1, tulip.py:195-196)
+  EPI_RESID = 2,      // out = aux + row_scale[sample] * (acc + bias)      (residual + DropPath, tulip.py:343-344,350-351)
+  EPI_PIXSHUF = 3,    // NHWC PixelShuffle(2) scatter of (acc + bias)      (PatchUnmerging, tulip.py:117-123)
+  EPI_SPLIT2 = 4,     // cols < split_col -> out, others -> out2            (skip-Linear backward: d[x | skip])
+  EPI_DGELU = 5,      // out = acc * gelu'(aux)                             (backward through GELU)
+  EPI_HEAD = 6,       // pred[m, ij] (+)= sum_c wd[c] * leaky(acc + bias)   (PixelShuffleHead + decoder_pred, tulip.py:174-178,731)
+  EPI_HEAD_BWD = 7,   // recompute pre; out = dh (bf16), dwd += colsum(dpred * leaky(pre))
+  EPI_ROWSCALE = 8,   // out = row_scale[sample] * acc                      (DropPath backward on a branch dX)
+};
+
+enum GemmAMode : int {
+  A_PLAIN = 0,
+  A_UNSHUFFLE = 1,    // A[m=(b,h,w), k=ij*Cc+c] = src[(b,2h+i,2w+j), c]   (PixelShuffle(2) backward gather)
+};
+
+struct GemmArgs {
+  // operands
+  const bf16* A; long lda;
+  const bf16* A2; long lda2; int K1;     // k >= K1 is read from A2 at column k-K1 (two-source concat); K1 == K when unused
+  const bf16* B; long ldb;
+  int M, N, K;
+  int a_mode; int g_H, g_W, g_Cc;        // gather geometry (input grid H x W, Cc channels per shuffled pixel)
+  const float* bias;
+  // epilogue
+  bf16* out; long ldo;
+  bf16* out2; long ldo2;
+  const bf16* aux; long ldaux;
+  const float* row_scale; int rows_per_sample;
+  int split_col;
+  // head
+  const float* wd; const float* target; float* pred; const float* gscale;
+  float* dwd;
+  int hd_H, hd_W, hd_r, hd_E; float hd_inv_npix;
+};
+
+struct GemmTNArgs {
+  const bf16* dY; long ldy;              // [M, N]
+  const bf16* X; long ldx;               // [M, K1]
+  const bf16* X2; long ldx2; int K1;     // columns >= K1 of the (virtual) X come from X2
+  int M, N, K;
+  int y_mode; int g_H, g_W, g_Cc;        // A_UNSHUFFLE gather on dY
+  float* dW; long lddw;                  // [N, K] fp32, accumulated with atomics
+  float* db;                             // [N] or null
+  int perm_R2, perm_Cc;                  // row n' = ij*Cc + c is written to row c*R2 + ij (R2 == 1: identity)
+  int splits;
+};
+
+int gemm_nt_mma(const GemmArgs& g, int epi, cudaStream_t st);
+int gemm_tn_mma(const GemmTNArgs& g, cudaStream_t st);
+int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st);   // returns TULIP_ERR_UNSUPPORTED for shapes it does not take
+int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st);
+int gemm_nt(const GemmArgs& g, int epi, cudaStream_t st);        // dispatch (env TULIP_B200_GEMM=mma forces the legacy path)
+int gemm_tn(const GemmTNArgs& g, cudaStream_t st);
+
+// ---- epilogue math on a run of NV consecutive columns of one output row (shared by both GEMMs) ----
+
+__device__ __forceinline__ void store_bf16_run2(bf16* p, float a, float b) {
+  *reinterpret_cast<uint32_t*>(p) = pack_bf16(a, b);
+}
+
+// pixel-shuffle destination row for source row m and shuffle slot ij (r = 2)
+__device__ __forceinline__ long pixshuf_row(int m, int ij, int H, int W) {
+  const int w = m % W;
+  const int bh = m / W;
+  const int h = bh % H;
+  const int b = bh / H;
+  return ((long)(b * 2 * H + 2 * h + (ij >> 1)) * (2 * W) + 2 * w + (ij & 1));
+}
+
+// Handles two adjacent columns (n, n+1) of row m. n is even, so both columns share every group boundary used here.
+template <int EPI>
+__device__ __forceinline__ void epi_pair(const GemmArgs& g, int m, int n, float v0, float v1) {
+  if (EPI == EPI_STORE) {
+    if (g.bias) { v0 += g.bias[n]; v1 += g.bias[n + 1]; }
+    store_bf16_run2(g.out + (long)m * g.ldo + n, v0, v1);
+  } else if (EPI == EPI_GELU) {
+    v0 += g.bias[n]; v1 += g.bias[n + 1];
+    if (g.out2) store_bf16_run2(g.out2 + (long)m * g.ldo2 + n, v0, v1);
+    store_bf16_run2(g.out + (long)m * g.ldo + n, gelu_erf(v0), gelu_erf(v1));
+  } else if (EPI == EPI_RESID) {
+    if (g.bias) { v0 += g.bias[n]; v1 += g.bias[n + 1]; }
+    const float s = g.row_scale ? g.row_scale[m / g.rows_per_sample] : 1.0f;
+    const float2 r = unpack_bf16(*reinterpret_cast<const uint32_t*>(g.aux + (long)m * g.ldaux + n));
+    store_bf16_run2(g.out + (long)m * g.ldo + n, r.x + s * v0, r.y + s * v1);
+  } else if (EPI == EPI_PIXSHUF) {
+    if (g.bias) { v0 += g.bias[n]; v1 += g.bias[n + 1]; }
+    const int ij = n / g.g_Cc, c = n % g.g_Cc;
+    store_bf16_run2(g.out + pixshuf_row(m, ij, g.g_H, g.g_W) * g.ldo + c, v0, v1);
+  } else if (EPI == EPI_SPLIT2) {
+    if (n < g.split_col) store_bf16_run2(g.out + (long)m * g.ldo + n, v0, v1);
+    else store_bf16_run2(g.out2 + (long)m * g.ldo2 + (n - g.split_col), v0, v1);
+  } else if (EPI == EPI_DGELU) {
+    const float2 p = unpack_bf16(*reinterpret_cast<const uint32_t*>(g.aux + (long)m * g.ldaux + n));
+    store_bf16_run2(g.out + (long)m * g.ldo + n, v0 * gelu_erf_grad(p.x), v1 * gelu_erf_grad(p.y));
+  } else if (EPI == EPI_ROWSCALE) {
+    const float s = g.row_scale ? g.row_scale[m / g.rows_per_sample] : 1.0f;
+    store_bf16_run2(g.out + (long)m * g.ldo + n, s * v0, s * v1);
+  }
+}
+
+// head geometry: row m = (b, h, w) of the low-res grid, slot ij = i*r + j -> pixel (b, h*r+i, w*r+j)
+__device__ __forceinline__ long head_pixel(const GemmArgs& g, int m, int ij) {
+  const int w = m % g.hd_W;
+  const int bh = m / g.hd_W;
+  const int h = bh % g.hd_H;
+  const int b = bh / g.hd_H;
+  const int r = g.hd_r;
+  return ((long)(b * g.hd_H * r + h * r + ij / r) * (g.hd_W * r) + w * r + (ij % r));
+}
+
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x; }

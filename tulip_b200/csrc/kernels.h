@@ -1,0 +1,68 @@
+// Internal launcher declarations (host side) for the non-GEMM kernels.
+#pragma once
+#include "common.cuh"
+
+struct AttnArgs {
+  const bf16* qkv;            // [B*H*W, 3C] natural NHWC token order, feature f = t*C + head*32 + d (tulip.py:298)
+  bf16* out;                  // fwd: [B*H*W, C] head-major concat (tulip.py:317), natural token order
+  const bf16* dout;           // bwd: grad of `out`
+  bf16* dqkv;                 // bwd: [B*H*W, 3C]
+  const float* bias_table;    // [nbias, heads] fp32 (the nn.Parameter itself)
+  float* dbias_table;         // bwd: [nbias, heads] fp32, accumulated
+  int B, H, W, C, heads;
+  int Mh, Mw;                 // window used for partitioning (backup window when H < win_h)
+  int sh, sw;                 // cyclic shift (0,0 for W-MSA)
+  int masked;                 // 1 for shifted blocks (mask is built even when a shift component is 0)
+  int bMh, bMw, nbias;        // window the bias index buffer was built for (never rebuilt, tulip.py:228-240)
+  float scale;
+};
+int win_attn_fwd(const AttnArgs& a, cudaStream_t st);
+int win_attn_bwd(const AttnArgs& a, cudaStream_t st);
+
+struct LnArgs {
+  const bf16* x;              // LN input rows [rows, C]; with gather: source tensor [B, 2*H2, 2*W2, C/4]
+  const float* w; const float* b;
+  bf16* y;                    // [rows, C]
+  float* stats;               // [rows, 2] (mean, rstd)
+  int rows, C; float eps;
+  int gather; int H2, W2;     // PatchMerging 2x2 gather (tulip.py:92-99): rows = B*H2*W2, C = 4*Csrc
+  // backward
+  const bf16* dy; const bf16* dres; bf16* dx; float* dw; float* db;
+};
+int layernorm_fwd(const LnArgs& a, cudaStream_t st);
+int layernorm_bwd(const LnArgs& a, cudaStream_t st);
+
+struct EmbedArgs {
+  const float* x;             // [B, 1, Himg, Wimg] fp32
+  const float* w; const float* b;       // conv weight [E,1,ph,8], bias [E]
+  const float* ln_w; const float* ln_b;
+  bf16* y;                    // [B, Himg/ph, Wimg/4, E]
+  int B, Himg, Wimg, ph, E; float eps;
+  const bf16* dy; float* dw; float* db; float* dln_w; float* dln_b;
+};
+int patch_embed_fwd(const EmbedArgs& a, cudaStream_t st);
+int patch_embed_bwd(const EmbedArgs& a, cudaStream_t st);
+
+// table-driven fp32 -> bf16 weight repack (one launch for the whole model)
+struct PackItem {
+  long src_off;               // element offset into the fp32 flat parameter buffer
+  long dst_off;               // element offset into the bf16 arena: W' [rows, cols] (rows permuted)
+  long dstT_off;              // element offset of the transposed copy Wt' [cols, rows] or -1
+  int rows, cols;
+  int perm_R2, perm_Cc;       // destination row n' = ij*Cc + c  <-  source row c*R2 + ij   (R2 == 1: identity)
+  int tile_begin;             // first 32x32 tile index of this item
+};
+int pack_weights(const float* flat, bf16* arena, const PackItem* items_dev, int n_items, int n_tiles, cudaStream_t st);
+int permute_bias(const float* src, float* dst, int n, int R2, int Cc, cudaStream_t st);
+
+int add_inplace_bf16(bf16* dst, const bf16* src, long n, cudaStream_t st);
+int scale_rows_bf16(bf16* dst, const bf16* src, const float* row_scale, int rows, int C, int rows_per_sample, cudaStream_t st);
+int l1_loss(const float* pred, const float* target, long n, int log_transform, float* acc2, float* out2, cudaStream_t st);
+
+// stand-alone index ops (bit-exact tests of the index arithmetic used inside the fused kernels)
+int window_gather(const bf16* x, bf16* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, cudaStream_t st);
+int window_scatter(const bf16* xw, bf16* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, cudaStream_t st);
+int shift_mask(float* out, int H, int W, int Mh, int Mw, int sh, int sw, cudaStream_t st);
+int rel_bias_gather(const float* table, float* out, int heads, int Mh, int Mw, cudaStream_t st);
+int merge_gather(const bf16* x, bf16* out, int B, int H, int W, int C, cudaStream_t st);
+int pixel_shuffle_nhwc(const bf16* x, bf16* out, int B, int H, int W, int Cout, int r, cudaStream_t st);

@@ -1,0 +1,657 @@
+// Whole-network executor (see net.h).  Reference orchestration: tulip/model/tulip.py:702-737
+// (TULIP.forward), :431-436 (BasicBlock), :477-481 (BasicBlockUp), :338-352 (SwinTransformerBlock).
+#include "net.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <utility>
+
+namespace {
+
+long align_up(long v, long a) { return (v + a - 1) / a * a; }
+
+struct Bump {
+  long off = 0;
+  long take(long bytes) {
+    const long o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  }
+};
+
+}  // namespace
+
+int tulip_net::build() {
+  const tulip_config& c = cfg;
+  TULIP_REQUIRE(c.num_layers >= 2 && c.num_layers <= TULIP_MAX_STAGES, "tulip: num_layers must be in [2, 8]");
+  TULIP_REQUIRE(c.in_chans == 1, "tulip_b200: in_chans must be 1 (all shipped configurations)");
+  TULIP_REQUIRE(c.patch_w == 4, "tulip_b200: patch width must be 4 (circular-padding conv k=(ph,8), s=(ph,4))");
+  TULIP_REQUIRE(c.patch_h == 1, "tulip_b200: patch height must be 1");
+  TULIP_REQUIRE(c.win_h * c.win_w == 16, "tulip_b200: windows must hold 16 tokens");
+  TULIP_REQUIRE(c.embed_dim % 96 == 0 && c.embed_dim <= 192, "tulip_b200: embed_dim must be 96 or 192");
+  TULIP_REQUIRE(c.mlp_ratio == 4, "tulip_b200: mlp_ratio must be 4");
+  TULIP_REQUIRE(c.img_h % c.patch_h == 0 && c.img_w % c.patch_w == 0, "tulip: image not divisible by the patch size");
+  L = c.num_layers;
+  H0 = c.img_h / c.patch_h;
+  W0 = c.img_w / c.patch_w;
+  // upscale factor exactly as tulip.py:577
+  {
+    const double ratio = ((double)c.tgt_h * c.tgt_w) / ((double)c.img_h * c.img_w);
+    const int a = (int)std::sqrt(ratio);
+    const int b = (int)std::sqrt((double)((c.patch_h * c.patch_w) / 4));
+    r = a * 2 * b;
+  }
+  TULIP_REQUIRE(r >= 1 && H0 * r == c.tgt_h && W0 * r == c.tgt_w,
+                "tulip: upscale_factor (tulip.py:577) does not map the token grid onto target_img_size");
+  for (int s = 0; s < L; ++s) {
+    const int C = c.embed_dim << s;
+    TULIP_REQUIRE(c.num_heads[s] * 32 == C, "tulip_b200: head_dim must be 32 at every stage");
+    TULIP_REQUIRE(c.depths[s] >= 1, "tulip: depths must be positive");
+    if (s < L - 1) TULIP_REQUIRE(((H0 >> s) % 2 == 0) && ((W0 >> s) % 2 == 0), "tulip_b200: odd grid before PatchMerging (zero-pad path not built)");
+  }
+
+  auto add_param = [&](const std::string& name, std::initializer_list<long> shape) {
+    ParamInfo p;
+    p.name = name;
+    p.ndim = (int)shape.size();
+    p.numel = 1;
+    int i = 0;
+    for (long d : shape) { p.shape[i++] = d; p.numel *= d; }
+    for (; i < 4; ++i) p.shape[i] = 1;
+    params.push_back(p);
+    return (int)params.size() - 1;
+  };
+  auto add_linear = [&](int slot_w, int slot_b, int N, int K, int R2, int Cc) {
+    Linear l{slot_w, slot_b, N, K, R2, Cc, 0, 0, -1};
+    linears.push_back(l);
+    return (int)linears.size() - 1;
+  };
+  const int nbias = (2 * c.win_h - 1) * (2 * c.win_w - 1);
+  int running = 0;
+  auto add_block = [&](const std::string& pre, int stage, int bidx) {
+    const long C = c.embed_dim << stage;
+    const long heads = c.num_heads[stage];
+    BlockDef b;
+    b.stage = stage;
+    b.shift = bidx % 2;                                   // tulip.py:417,460
+    b.index = running++;
+    b.n1w = add_param(pre + ".norm1.weight", {C});
+    b.n1b = add_param(pre + ".norm1.bias", {C});
+    b.table = add_param(pre + ".attn.relative_position_bias_table", {nbias, heads});
+    const int qw = add_param(pre + ".attn.qkv.weight", {3 * C, C});
+    const int qb = add_param(pre + ".attn.qkv.bias", {3 * C});
+    const int pw = add_param(pre + ".attn.proj.weight", {C, C});
+    const int pb = add_param(pre + ".attn.proj.bias", {C});
+    b.n2w = add_param(pre + ".norm2.weight", {C});
+    b.n2b = add_param(pre + ".norm2.bias", {C});
+    const int f1w = add_param(pre + ".mlp.fc1.weight", {4 * C, C});
+    const int f1b = add_param(pre + ".mlp.fc1.bias", {4 * C});
+    const int f2w = add_param(pre + ".mlp.fc2.weight", {C, 4 * C});
+    const int f2b = add_param(pre + ".mlp.fc2.bias", {C});
+    b.qkv = add_linear(qw, qb, 3 * C, C, 1, 0);
+    b.proj = add_linear(pw, pb, C, C, 1, 0);
+    b.fc1 = add_linear(f1w, f1b, 4 * C, C, 1, 0);
+    b.fc2 = add_linear(f2w, f2b, C, 4 * C, 1, 0);
+    blocks.push_back(b);
+    return (int)blocks.size() - 1;
+  };
+
+  enc_blocks.assign(L, {});
+  dec_blocks.assign(L - 1, {});
+  merge_nw.assign(L, -1); merge_nb.assign(L, -1); merge_lin.assign(L, -1);
+  up_lin.assign(L - 1, -1);
+  skip_lin.assign(L - 1, -1);
+  char buf[128];
+  for (int s = 0; s < L; ++s) {                           // tulip.py:643-660
+    const long C = c.embed_dim << s;
+    for (int b = 0; b < c.depths[s]; ++b) {
+      snprintf(buf, sizeof buf, "layers.%d.blocks.%d", s, b);
+      enc_blocks[s].push_back(add_block(buf, s, b));
+    }
+    if (s < L - 1) {
+      snprintf(buf, sizeof buf, "layers.%d.downsample", s);
+      merge_nw[s] = add_param(std::string(buf) + ".norm.weight", {4 * C});
+      merge_nb[s] = add_param(std::string(buf) + ".norm.bias", {4 * C});
+      const int w = add_param(std::string(buf) + ".reduction.weight", {2 * C, 4 * C});
+      merge_lin[s] = add_linear(w, -1, 2 * C, 4 * C, 1, 0);
+    }
+  }
+  for (int u = 0; u < L - 1; ++u) {                       // tulip.py:662-680; stage index per :447
+    const int s = L - u - 2;
+    const long C = c.embed_dim << s;
+    for (int b = 0; b < c.depths[s]; ++b) {
+      snprintf(buf, sizeof buf, "layers_up.%d.blocks.%d", u, b);
+      dec_blocks[u].push_back(add_block(buf, s, b));
+    }
+    if (u < L - 2) {
+      snprintf(buf, sizeof buf, "layers_up.%d.upsample.expand", u);
+      const int w = add_param(std::string(buf) + ".weight", {2 * C, C, 1, 1});
+      const int bb = add_param(std::string(buf) + ".bias", {2 * C});
+      up_lin[u] = add_linear(w, bb, 2 * C, C, 4, C / 2);
+    }
+  }
+  {
+    const long C = c.embed_dim << (L - 1);
+    const int w = add_param("first_patch_expanding.expand.weight", {2 * C, C, 1, 1});
+    const int bb = add_param("first_patch_expanding.expand.bias", {2 * C});
+    fpe_lin = add_linear(w, bb, 2 * C, C, 4, C / 2);
+  }
+  for (int u = 0; u < L - 1; ++u) {                       // tulip.py:682-688
+    const long C = c.embed_dim << (L - 2 - u);
+    snprintf(buf, sizeof buf, "skip_connection_layers.%d", u);
+    const int w = add_param(std::string(buf) + ".weight", {C, 2 * C});
+    const int bb = add_param(std::string(buf) + ".bias", {C});
+    skip_lin[u] = add_linear(w, bb, C, 2 * C, 1, 0);
+  }
+  const long E = c.embed_dim;
+  slot_normup_w = add_param("norm_up.weight", {E});
+  slot_normup_b = add_param("norm_up.bias", {E});
+  slot_pe_w = add_param("patch_embed.proj.weight", {E, 1, c.patch_h, 8});
+  slot_pe_b = add_param("patch_embed.proj.bias", {E});
+  slot_pe_nw = add_param("patch_embed.norm.weight", {E});
+  slot_pe_nb = add_param("patch_embed.norm.bias", {E});
+  slot_dec_w = add_param("decoder_pred.weight", {1, E, 1, 1});
+  {
+    const int w = add_param("ps_head.conv_expand.0.weight", {E * r * r, E, 1, 1});
+    const int bb = add_param("ps_head.conv_expand.0.bias", {E * r * r});
+    head_lin = add_linear(w, bb, E * r * r, E, r * r, E);
+  }
+
+  // bf16 weight arena + fp32 aux arena (permuted biases)
+  long woff = 0, foff = 0;
+  for (Linear& l : linears) {
+    l.w_off = woff; woff += align_up((long)l.N * l.K, 128);
+    l.wt_off = woff; woff += align_up((long)l.N * l.K, 128);
+    if (l.perm_R2 > 1 && l.slot_b >= 0) { l.pbias_off = foff; foff += align_up(l.N, 64); }
+  }
+  warena_elems = woff;
+  faux_elems = foff > 0 ? foff : 64;
+  return TULIP_OK;                                        // device buffers are allocated on the first forward
+}
+
+int tulip_net::ensure_device() {
+  if (warena) return TULIP_OK;
+  TULIP_CUDA(cudaMalloc(&warena, warena_elems * sizeof(bf16)));
+  TULIP_CUDA(cudaMalloc(&faux, faux_elems * sizeof(float)));
+  return TULIP_OK;
+}
+
+Plan tulip_net::plan(int B) const {
+  Plan p;
+  Bump bump;
+  const long E = cfg.embed_dim;
+  const long T0 = (long)B * H0 * W0;
+  auto act = [&](long rows, long cols) { return bump.take(rows * cols * 2); };
+  p.pe_out = act(T0, E);
+  p.blocks.resize(blocks.size());
+  auto plan_block = [&](int bi) {
+    const BlockDef& b = blocks[bi];
+    const long T = (long)B * (H0 >> b.stage) * (W0 >> b.stage), C = E << b.stage;
+    BlockBuf& bb = p.blocks[bi];
+    bb.xn1 = act(T, C); bb.st1 = bump.take(T * 8);
+    bb.qkv = act(T, 3 * C); bb.ao = act(T, C); bb.xmid = act(T, C);
+    bb.xn2 = act(T, C); bb.st2 = bump.take(T * 8);
+    bb.hpre = act(T, 4 * C); bb.hact = act(T, 4 * C); bb.xout = act(T, C);
+  };
+  p.xn_m.assign(L, -1); p.st_m.assign(L, -1); p.x_merged.assign(L, -1);
+  for (int s = 0; s < L; ++s) {
+    for (int bi : enc_blocks[s]) plan_block(bi);
+    if (s < L - 1) {
+      const long T = (long)B * (H0 >> s) * (W0 >> s), C = E << s;
+      p.xn_m[s] = act(T / 4, 4 * C); p.st_m[s] = bump.take(T / 4 * 8); p.x_merged[s] = act(T / 4, 2 * C);
+    }
+  }
+  {
+    const long T = (long)B * (H0 >> (L - 1)) * (W0 >> (L - 1)), C = E << (L - 1);
+    p.x_fpe = act(4 * T, C / 2);
+  }
+  p.x_skip.assign(L - 1, -1); p.x_up.assign(L - 1, -1);
+  for (int u = 0; u < L - 1; ++u) {
+    const int s = L - u - 2;
+    const long T = (long)B * (H0 >> s) * (W0 >> s), C = E << s;
+    p.x_skip[u] = act(T, C);
+    for (int bi : dec_blocks[u]) plan_block(bi);
+    if (u < L - 2) p.x_up[u] = act(4 * T, C / 2);
+  }
+  p.xn_up = act(T0, E); p.st_up = bump.take(T0 * 8);
+  // backward scratch (T_s * C_s is largest at stage 0)
+  p.gA = act(T0, E); p.gB = act(T0, E); p.scr_gs = act(T0, E);
+  p.scr_dxn = act(T0, E); p.scr_do = act(T0, E); p.scr_dqkv = act(T0, 3 * E);
+  const long big = (long)E * r * r > 4 * E ? (long)E * r * r : 4 * E;      // head dh [T0, E r^2] or block dh [T0, 4E]
+  p.scr_big = act(T0, big);
+  p.g_save.assign(L, -1);
+  for (int s = 0; s < L - 1; ++s) p.g_save[s] = act((long)B * (H0 >> s) * (W0 >> s), E << s);
+  p.loss_acc = bump.take(256);
+  p.total = bump.off;
+  return p;
+}
+
+int tulip_net::upload_pack_table(const int64_t* offs, cudaStream_t st) {
+  bool same = items_dev != nullptr && items_offsets_cache.size() == params.size();
+  if (same)
+    for (size_t i = 0; i < params.size(); ++i)
+      if (items_offsets_cache[i] != offs[i]) { same = false; break; }
+  if (same) return TULIP_OK;
+  std::vector<PackItem> items;
+  int tiles = 0;
+  for (const Linear& l : linears) {
+    PackItem it;
+    it.src_off = offs[l.slot_w];
+    it.dst_off = l.w_off;
+    it.dstT_off = l.wt_off;
+    it.rows = l.N; it.cols = l.K;
+    it.perm_R2 = l.perm_R2; it.perm_Cc = l.perm_Cc;
+    it.tile_begin = tiles;
+    tiles += ((l.N + 31) / 32) * ((l.K + 31) / 32);
+    items.push_back(it);
+  }
+  if (!items_dev) TULIP_CUDA(cudaMalloc(&items_dev, items.size() * sizeof(PackItem)));
+  TULIP_CUDA(cudaMemcpyAsync(items_dev, items.data(), items.size() * sizeof(PackItem), cudaMemcpyHostToDevice, st));
+  TULIP_CUDA(cudaStreamSynchronize(st));                  // `items` is a stack vector; happens once per parameter layout
+  n_items = (int)items.size();
+  n_tiles = tiles;
+  items_offsets_cache.assign(offs, offs + params.size());
+  return TULIP_OK;
+}
+
+#define RUN(call)                   \
+  do {                              \
+    int rc__ = (call);              \
+    if (rc__ != TULIP_OK) return rc__; \
+    ++kernel_launches;              \
+  } while (0)
+
+namespace {
+
+struct Ctx {
+  tulip_net* net;
+  int B;
+  const float* params; const int64_t* offs; float* grads;
+  const float* drop; const int* win_mode;
+  unsigned char* ws;
+  cudaStream_t st;
+  const float* P(int slot) const { return params + offs[slot]; }
+  float* G(int slot) const { return grads + offs[slot]; }
+  bf16* A(long off) const { return reinterpret_cast<bf16*>(ws + off); }
+  float* F(long off) const { return reinterpret_cast<float*>(ws + off); }
+  const bf16* W(const Linear& l) const { return net->warena + l.w_off; }
+  const bf16* Wt(const Linear& l) const { return net->warena + l.wt_off; }
+  const float* bias(const Linear& l) const {
+    if (l.slot_b < 0) return nullptr;
+    return l.pbias_off >= 0 ? net->faux + l.pbias_off : P(l.slot_b);
+  }
+};
+
+GemmArgs nt_args(const bf16* A, long lda, const bf16* B, long ldb, int M, int N, int K, const float* bias, bf16* out, long ldo) {
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.A = A; g.lda = lda; g.K1 = K; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo;
+  return g;
+}
+
+GemmTNArgs tn_args(const bf16* dY, long ldy, const bf16* X, long ldx, int M, int N, int K, float* dW, float* db) {
+  GemmTNArgs g;
+  memset(&g, 0, sizeof g);
+  g.dY = dY; g.ldy = ldy; g.X = X; g.ldx = ldx; g.K1 = K; g.M = M; g.N = N; g.K = K; g.dW = dW; g.lddw = K; g.db = db;
+  g.perm_R2 = 1; g.perm_Cc = 1;
+  const int tiles = (N / 96) * (K / 96);
+  int splits = (2 * tulip_num_sms() + tiles - 1) / tiles;
+  const int max_splits = (M + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  g.splits = splits;
+  return g;
+}
+
+void window_of(const tulip_net& n, const BlockDef& b, int mode, int* Mh, int* Mw, int* sh, int* sw) {
+  const int L = n.cfg.win_h * n.cfg.win_w;
+  if (mode == 0) { *Mh = n.cfg.win_h; *Mw = n.cfg.win_w; } else { *Mh = 1; *Mw = L; }
+  if (!b.shift) { *sh = 0; *sw = 0; }
+  else if (mode == 0) { *sh = n.cfg.win_h / 2; *sw = n.cfg.win_w / 2; }
+  else { *sh = 0; *sw = L / 2; }
+}
+
+AttnArgs attn_args(const Ctx& c, const BlockDef& b, const bf16* qkv) {
+  const tulip_net& n = *c.net;
+  AttnArgs a;
+  memset(&a, 0, sizeof a);
+  a.qkv = qkv;
+  a.bias_table = c.P(b.table);
+  a.B = c.B; a.H = n.H0 >> b.stage; a.W = n.W0 >> b.stage; a.C = n.cfg.embed_dim << b.stage; a.heads = n.cfg.num_heads[b.stage];
+  window_of(n, b, c.win_mode ? c.win_mode[b.index] : 0, &a.Mh, &a.Mw, &a.sh, &a.sw);
+  a.masked = b.shift;
+  a.bMh = n.cfg.win_h; a.bMw = n.cfg.win_w; a.nbias = (2 * a.bMh - 1) * (2 * a.bMw - 1);
+  a.scale = 1.0f / sqrtf(32.0f);
+  return a;
+}
+
+}  // namespace
+
+int tulip_net::forward(int B, const float* params_, const int64_t* offs, const float* x_lo, const float* target,
+                       const float* drop_scales, const int* win_mode, void* ws, float* pred, float* losses, cudaStream_t st) {
+  TULIP_REQUIRE(B > 0, "tulip: empty batch");
+  int rc = ensure_device();
+  if (rc) return rc;
+  rc = upload_pack_table(offs, st);
+  if (rc) return rc;
+  const Plan p = plan(B);
+  Ctx c{this, B, params_, offs, nullptr, drop_scales, win_mode, reinterpret_cast<unsigned char*>(ws), st};
+  const int E = cfg.embed_dim;
+
+  RUN(pack_weights(params_, warena, items_dev, n_items, n_tiles, st));
+  for (const Linear& l : linears)
+    if (l.pbias_off >= 0) RUN(permute_bias(c.P(l.slot_b), faux + l.pbias_off, l.N, l.perm_R2, l.perm_Cc, st));
+
+  {
+    EmbedArgs e;
+    memset(&e, 0, sizeof e);
+    e.x = x_lo; e.w = c.P(slot_pe_w); e.b = c.P(slot_pe_b); e.ln_w = c.P(slot_pe_nw); e.ln_b = c.P(slot_pe_nb);
+    e.y = c.A(p.pe_out); e.B = B; e.Himg = cfg.img_h; e.Wimg = cfg.img_w; e.ph = cfg.patch_h; e.E = E; e.eps = cfg.ln_eps;
+    RUN(patch_embed_fwd(e, st));
+  }
+
+  auto ln = [&](const bf16* x, int wslot, int bslot, bf16* y, float* stats, int rows, int C, int gather, int H2, int W2) {
+    LnArgs a;
+    memset(&a, 0, sizeof a);
+    a.x = x; a.w = c.P(wslot); a.b = c.P(bslot); a.y = y; a.stats = stats; a.rows = rows; a.C = C; a.eps = cfg.ln_eps;
+    a.gather = gather; a.H2 = H2; a.W2 = W2;
+    return layernorm_fwd(a, st);
+  };
+
+  auto block_fwd = [&](int bi, const bf16* x_in) -> int {
+    const BlockDef& b = blocks[bi];
+    const BlockBuf& bb = p.blocks[bi];
+    const int Hs = H0 >> b.stage, Ws = W0 >> b.stage, C = E << b.stage, T = B * Hs * Ws;
+    const float* ds1 = drop_scales ? drop_scales + (long)(2 * b.index) * B : nullptr;
+    const float* ds2 = drop_scales ? drop_scales + (long)(2 * b.index + 1) * B : nullptr;
+    RUN(ln(x_in, b.n1w, b.n1b, c.A(bb.xn1), c.F(bb.st1), T, C, 0, 0, 0));
+    {
+      const Linear& l = linears[b.qkv];
+      GemmArgs g = nt_args(c.A(bb.xn1), C, c.W(l), C, T, 3 * C, C, c.bias(l), c.A(bb.qkv), 3 * C);
+      RUN(gemm_nt(g, EPI_STORE, st));
+    }
+    {
+      AttnArgs a = attn_args(c, b, c.A(bb.qkv));
+      a.out = c.A(bb.ao);
+      RUN(win_attn_fwd(a, st));
+    }
+    {
+      const Linear& l = linears[b.proj];
+      GemmArgs g = nt_args(c.A(bb.ao), C, c.W(l), C, T, C, C, c.bias(l), c.A(bb.xmid), C);
+      g.aux = x_in; g.ldaux = C; g.row_scale = ds1; g.rows_per_sample = Hs * Ws;
+      RUN(gemm_nt(g, EPI_RESID, st));
+    }
+    RUN(ln(c.A(bb.xmid), b.n2w, b.n2b, c.A(bb.xn2), c.F(bb.st2), T, C, 0, 0, 0));
+    {
+      const Linear& l = linears[b.fc1];
+      GemmArgs g = nt_args(c.A(bb.xn2), C, c.W(l), C, T, 4 * C, C, c.bias(l), c.A(bb.hact), 4 * C);
+      g.out2 = c.A(bb.hpre); g.ldo2 = 4 * C;
+      RUN(gemm_nt(g, EPI_GELU, st));
+    }
+    {
+      const Linear& l = linears[b.fc2];
+      GemmArgs g = nt_args(c.A(bb.hact), 4 * C, c.W(l), 4 * C, T, C, 4 * C, c.bias(l), c.A(bb.xout), C);
+      g.aux = c.A(bb.xmid); g.ldaux = C; g.row_scale = ds2; g.rows_per_sample = Hs * Ws;
+      RUN(gemm_nt(g, EPI_RESID, st));
+    }
+    return TULIP_OK;
+  };
+
+  auto unmerge_fwd = [&](const Linear& l, const bf16* x, bf16* out, int Hs, int Ws, int C) -> int {
+    // 1x1 conv C -> 2C + PixelShuffle(2) as a GEMM with a scatter epilogue (tulip.py:117-123)
+    GemmArgs g = nt_args(x, C, c.W(l), C, B * Hs * Ws, 2 * C, C, c.bias(l), out, C / 2);
+    g.g_H = Hs; g.g_W = Ws; g.g_Cc = C / 2;
+    RUN(gemm_nt(g, EPI_PIXSHUF, st));
+    return TULIP_OK;
+  };
+
+  std::vector<const bf16*> x_save(L);
+  const bf16* x = c.A(p.pe_out);
+  for (int s = 0; s < L; ++s) {
+    x_save[s] = x;
+    for (int bi : enc_blocks[s]) {
+      rc = block_fwd(bi, x);
+      if (rc) return rc;
+      x = c.A(p.blocks[bi].xout);
+    }
+    if (s < L - 1) {
+      const int Hs = H0 >> s, Ws = W0 >> s, C = E << s, T4 = B * Hs * Ws / 4;
+      RUN(ln(x, merge_nw[s], merge_nb[s], c.A(p.xn_m[s]), c.F(p.st_m[s]), T4, 4 * C, 1, Hs / 2, Ws / 2));
+      const Linear& l = linears[merge_lin[s]];
+      GemmArgs g = nt_args(c.A(p.xn_m[s]), 4 * C, c.W(l), 4 * C, T4, 2 * C, 4 * C, nullptr, c.A(p.x_merged[s]), 2 * C);
+      RUN(gemm_nt(g, EPI_STORE, st));
+      x = c.A(p.x_merged[s]);
+    }
+  }
+  rc = unmerge_fwd(linears[fpe_lin], x, c.A(p.x_fpe), H0 >> (L - 1), W0 >> (L - 1), E << (L - 1));
+  if (rc) return rc;
+  x = c.A(p.x_fpe);
+  for (int u = 0; u < L - 1; ++u) {
+    const int s = L - u - 2;
+    const int Hs = H0 >> s, Ws = W0 >> s, C = E << s, T = B * Hs * Ws;
+    {
+      // Linear(2C -> C) on cat([x, x_save[s]], -1) without materialising the concat (tulip.py:715-716)
+      const Linear& l = linears[skip_lin[u]];
+      GemmArgs g = nt_args(x, C, c.W(l), 2 * C, T, C, 2 * C, c.bias(l), c.A(p.x_skip[u]), C);
+      g.A2 = x_save[s]; g.lda2 = C; g.K1 = C;
+      RUN(gemm_nt(g, EPI_STORE, st));
+      x = c.A(p.x_skip[u]);
+    }
+    for (int bi : dec_blocks[u]) {
+      rc = block_fwd(bi, x);
+      if (rc) return rc;
+      x = c.A(p.blocks[bi].xout);
+    }
+    if (u < L - 2) {
+      rc = unmerge_fwd(linears[up_lin[u]], x, c.A(p.x_up[u]), Hs, Ws, C);
+      if (rc) return rc;
+      x = c.A(p.x_up[u]);
+    }
+  }
+  // norm_up -> ps_head -> decoder_pred, fused: the E*r^2-channel tensor never exists (tulip.py:720-731)
+  const int T0 = B * H0 * W0;
+  RUN(ln(x, slot_normup_w, slot_normup_b, c.A(p.xn_up), c.F(p.st_up), T0, E, 0, 0, 0));
+  {
+    const Linear& l = linears[head_lin];
+    if (E != 96) TULIP_CUDA(cudaMemsetAsync(pred, 0, (size_t)T0 * r * r * sizeof(float), st));
+    GemmArgs g = nt_args(c.A(p.xn_up), E, c.W(l), E, T0, E * r * r, E, c.bias(l), nullptr, 0);
+    g.wd = c.P(slot_dec_w); g.pred = pred; g.hd_H = H0; g.hd_W = W0; g.hd_r = r; g.hd_E = E;
+    RUN(gemm_nt(g, EPI_HEAD, st));
+  }
+  if (target) RUN(l1_loss(pred, target, (long)T0 * r * r, cfg.log_transform, c.F(p.loss_acc), losses, st));
+  return TULIP_OK;
+}
+
+int tulip_net::backward(int B, const float* params_, const int64_t* offs, float* grads, const float* x_lo, const float* target,
+                        const float* pred, const float* grad_loss, const float* drop_scales, const int* win_mode, void* ws,
+                        cudaStream_t st) {
+  TULIP_REQUIRE(B > 0 && target && pred && grad_loss, "tulip backward: needs target, pred and grad_loss");
+  TULIP_REQUIRE(warena != nullptr, "tulip backward: no forward has run on this net");
+  const Plan p = plan(B);
+  Ctx c{this, B, params_, offs, grads, drop_scales, win_mode, reinterpret_cast<unsigned char*>(ws), st};
+  const int E = cfg.embed_dim;
+  const int T0 = B * H0 * W0;
+  int rc;
+
+  // zero the whole flat gradient span covered by the parameters
+  {
+    long lo = offs[0], hi = offs[0] + params[0].numel;
+    for (size_t i = 0; i < params.size(); ++i) {
+      if (offs[i] < lo) lo = offs[i];
+      if (offs[i] + params[i].numel > hi) hi = offs[i] + params[i].numel;
+    }
+    TULIP_CUDA(cudaMemsetAsync(grads + lo, 0, (size_t)(hi - lo) * sizeof(float), st));
+  }
+
+  auto ln_bwd = [&](const bf16* x, int wslot, int bslot, const float* stats, const bf16* dy, const bf16* dres, bf16* dx, int rows,
+                    int C, int gather, int H2, int W2) {
+    LnArgs a;
+    memset(&a, 0, sizeof a);
+    a.x = x; a.w = c.P(wslot); a.stats = const_cast<float*>(stats); a.dy = dy; a.dres = dres; a.dx = dx;
+    a.dw = c.G(wslot); a.db = c.G(bslot); a.rows = rows; a.C = C; a.eps = cfg.ln_eps; a.gather = gather; a.H2 = H2; a.W2 = W2;
+    return layernorm_bwd(a, st);
+  };
+  auto dw = [&](const Linear& l, const bf16* dY, const bf16* X, int M) {
+    GemmTNArgs g = tn_args(dY, l.N, X, l.K, M, l.N, l.K, c.G(l.slot_w), l.slot_b >= 0 ? c.G(l.slot_b) : nullptr);
+    g.perm_R2 = l.perm_R2; g.perm_Cc = l.perm_R2 > 1 ? l.perm_Cc : 1;
+    return g;
+  };
+
+  bf16* g_cur = c.A(p.gA);       // gradient w.r.t. the current activation
+  bf16* g_alt = c.A(p.gB);
+
+  // ---- head: dpred -> dh -> (dWe, dbe, dwd), dxn_up -> norm_up ----
+  const bf16* x_last;
+  {
+    const int last_u = L - 2;
+    const int bi = dec_blocks[last_u].back();
+    x_last = c.A(p.blocks[bi].xout);
+  }
+  {
+    const Linear& l = linears[head_lin];
+    bf16* dh = c.A(p.scr_big);
+    GemmArgs g = nt_args(c.A(p.xn_up), E, c.W(l), E, T0, E * r * r, E, c.bias(l), dh, (long)E * r * r);
+    g.wd = c.P(slot_dec_w); g.pred = const_cast<float*>(pred); g.target = target; g.gscale = grad_loss;
+    g.dwd = c.G(slot_dec_w);
+    g.hd_H = H0; g.hd_W = W0; g.hd_r = r; g.hd_E = E; g.hd_inv_npix = 1.0f / ((float)T0 * r * r);
+    RUN(gemm_nt(g, EPI_HEAD_BWD, st));
+    // dxn_up = dh . We'          (A = dh [T0, E r^2], B = We'^T stored as Wt' [E, E r^2])
+    GemmArgs gx = nt_args(dh, (long)E * r * r, c.Wt(l), (long)E * r * r, T0, E, E * r * r, nullptr, c.A(p.scr_dxn), E);
+    RUN(gemm_nt(gx, EPI_STORE, st));
+    // dWe' += dh^T . xn_up (rows un-permuted on store); bias gradient = column sums of dh, same un-permutation
+    GemmTNArgs gw = dw(l, dh, c.A(p.xn_up), T0);
+    RUN(gemm_tn(gw, st));
+    RUN(ln_bwd(x_last, slot_normup_w, slot_normup_b, c.F(p.st_up), c.A(p.scr_dxn), nullptr, g_cur, T0, E, 0, 0, 0));
+  }
+
+  auto block_bwd = [&](int bi, const bf16* x_in, bf16* g_io, bf16* g_tmp) -> int {
+    // g_io holds dL/dx_out on entry and dL/dx_in on exit; g_tmp is a same-sized scratch
+    const BlockDef& b = blocks[bi];
+    const BlockBuf& bb = p.blocks[bi];
+    const int Hs = H0 >> b.stage, Ws = W0 >> b.stage, C = E << b.stage, T = B * Hs * Ws;
+    const float* ds1 = drop_scales ? drop_scales + (long)(2 * b.index) * B : nullptr;
+    const float* ds2 = drop_scales ? drop_scales + (long)(2 * b.index + 1) * B : nullptr;
+    // ---- MLP half: x_out = x_mid + s2 * fc2(gelu(fc1(LN2(x_mid)))) ----
+    const bf16* gy = g_io;
+    if (ds2) {
+      RUN(scale_rows_bf16(c.A(p.scr_gs), g_io, ds2, T, C, Hs * Ws, st));
+      gy = c.A(p.scr_gs);
+    }
+    {
+      const Linear& l2 = linears[b.fc2];
+      GemmArgs g = nt_args(gy, C, c.Wt(l2), C, T, 4 * C, C, nullptr, c.A(p.scr_big), 4 * C);   // dh = (gy . W2) o gelu'(pre)
+      g.aux = c.A(bb.hpre); g.ldaux = 4 * C;
+      RUN(gemm_nt(g, EPI_DGELU, st));
+      RUN(gemm_tn(dw(l2, gy, c.A(bb.hact), T), st));
+      const Linear& l1 = linears[b.fc1];
+      GemmArgs g1 = nt_args(c.A(p.scr_big), 4 * C, c.Wt(l1), 4 * C, T, C, 4 * C, nullptr, c.A(p.scr_dxn), C);
+      RUN(gemm_nt(g1, EPI_STORE, st));
+      RUN(gemm_tn(dw(l1, c.A(p.scr_big), c.A(bb.xn2), T), st));
+    }
+    RUN(ln_bwd(c.A(bb.xmid), b.n2w, b.n2b, c.F(bb.st2), c.A(p.scr_dxn), g_io, g_tmp, T, C, 0, 0, 0));   // g_tmp = dL/dx_mid
+    // ---- attention half: x_mid = x_in + s1 * proj(attn(qkv(LN1(x_in)))) ----
+    gy = g_tmp;
+    if (ds1) {
+      RUN(scale_rows_bf16(c.A(p.scr_gs), g_tmp, ds1, T, C, Hs * Ws, st));
+      gy = c.A(p.scr_gs);
+    }
+    {
+      const Linear& lp = linears[b.proj];
+      GemmArgs g = nt_args(gy, C, c.Wt(lp), C, T, C, C, nullptr, c.A(p.scr_do), C);
+      RUN(gemm_nt(g, EPI_STORE, st));
+      RUN(gemm_tn(dw(lp, gy, c.A(bb.ao), T), st));
+      AttnArgs a = attn_args(c, b, c.A(bb.qkv));
+      a.dout = c.A(p.scr_do); a.dqkv = c.A(p.scr_dqkv); a.dbias_table = c.G(b.table);
+      RUN(win_attn_bwd(a, st));
+      const Linear& lq = linears[b.qkv];
+      GemmArgs gq = nt_args(c.A(p.scr_dqkv), 3 * C, c.Wt(lq), 3 * C, T, C, 3 * C, nullptr, c.A(p.scr_dxn), C);
+      RUN(gemm_nt(gq, EPI_STORE, st));
+      RUN(gemm_tn(dw(lq, c.A(p.scr_dqkv), c.A(bb.xn1), T), st));
+    }
+    RUN(ln_bwd(x_in, b.n1w, b.n1b, c.F(bb.st1), c.A(p.scr_dxn), g_tmp, g_io, T, C, 0, 0, 0));            // g_io = dL/dx_in
+    return TULIP_OK;
+  };
+
+  auto unmerge_bwd = [&](const Linear& l, const bf16* x_in, const bf16* g_out, bf16* g_in, int Hs, int Ws, int C) -> int {
+    // g_out: [B, 2Hs, 2Ws, C/2]; gathered view A[m, ij*C/2 + c] (PixelShuffle backward), then dX and dW
+    const int T = B * Hs * Ws;
+    GemmArgs g = nt_args(g_out, C / 2, c.Wt(l), 2 * C, T, C, 2 * C, nullptr, g_in, C);
+    g.a_mode = A_UNSHUFFLE; g.g_H = Hs; g.g_W = Ws; g.g_Cc = C / 2;
+    RUN(gemm_nt(g, EPI_STORE, st));
+    GemmTNArgs gw = dw(l, g_out, x_in, T);
+    gw.ldy = C / 2; gw.y_mode = A_UNSHUFFLE; gw.g_H = Hs; gw.g_W = Ws; gw.g_Cc = C / 2;
+    RUN(gemm_tn(gw, st));
+    return TULIP_OK;
+  };
+
+  // ---- decoder, last stage first ----
+  for (int u = L - 2; u >= 0; --u) {
+    const int s = L - u - 2;
+    const int Hs = H0 >> s, Ws = W0 >> s, C = E << s, T = B * Hs * Ws;
+    if (u < L - 2) {
+      const bf16* x_before = c.A(p.blocks[dec_blocks[u].back()].xout);
+      rc = unmerge_bwd(linears[up_lin[u]], x_before, g_cur, g_alt, Hs, Ws, C);
+      if (rc) return rc;
+      std::swap(g_cur, g_alt);
+    }
+    for (int k = (int)dec_blocks[u].size() - 1; k >= 0; --k) {
+      const int bi = dec_blocks[u][k];
+      const bf16* x_in = k > 0 ? c.A(p.blocks[dec_blocks[u][k - 1]].xout) : c.A(p.x_skip[u]);
+      rc = block_bwd(bi, x_in, g_cur, g_alt);
+      if (rc) return rc;
+    }
+    {
+      // skip Linear backward: d[x | skip] = g . Wskip ; the skip half is parked until the encoder stage is reached
+      const Linear& l = linears[skip_lin[u]];
+      const bf16* x_prev = (u == 0) ? c.A(p.x_fpe) : c.A(p.x_up[u - 1]);
+      const bf16* x_enc = (s == 0) ? c.A(p.pe_out) : c.A(p.x_merged[s - 1]);
+      GemmArgs g = nt_args(g_cur, C, c.Wt(l), C, T, 2 * C, C, nullptr, g_alt, C);
+      g.out2 = c.A(p.g_save[s]); g.ldo2 = C; g.split_col = C;
+      RUN(gemm_nt(g, EPI_SPLIT2, st));
+      GemmTNArgs gw = dw(l, g_cur, x_prev, T);
+      gw.ldx = C; gw.X2 = x_enc; gw.ldx2 = C; gw.K1 = C;
+      RUN(gemm_tn(gw, st));
+      std::swap(g_cur, g_alt);
+    }
+  }
+  // ---- first_patch_expanding ----
+  {
+    const int s = L - 1;
+    const bf16* x_top = c.A(p.blocks[enc_blocks[s].back()].xout);
+    rc = unmerge_bwd(linears[fpe_lin], x_top, g_cur, g_alt, H0 >> s, W0 >> s, E << s);
+    if (rc) return rc;
+    std::swap(g_cur, g_alt);
+  }
+  // ---- encoder, top stage first ----
+  for (int s = L - 1; s >= 0; --s) {
+    const int Hs = H0 >> s, Ws = W0 >> s, C = E << s, T = B * Hs * Ws;
+    if (s < L - 1) {
+      // PatchMerging backward: g_cur is dL/d(x_merged[s]) [T/4, 2C]
+      const Linear& l = linears[merge_lin[s]];
+      const bf16* x_stage_out = c.A(p.blocks[enc_blocks[s].back()].xout);
+      GemmArgs g = nt_args(g_cur, 2 * C, c.Wt(l), 2 * C, T / 4, 4 * C, 2 * C, nullptr, c.A(p.scr_big), 4 * C);
+      RUN(gemm_nt(g, EPI_STORE, st));
+      RUN(gemm_tn(dw(l, g_cur, c.A(p.xn_m[s]), T / 4), st));
+      RUN(ln_bwd(x_stage_out, merge_nw[s], merge_nb[s], c.F(p.st_m[s]), c.A(p.scr_big), nullptr, g_alt, T / 4, 4 * C, 1, Hs / 2,
+                 Ws / 2));
+      std::swap(g_cur, g_alt);
+    }
+    for (int k = (int)enc_blocks[s].size() - 1; k >= 0; --k) {
+      const int bi = enc_blocks[s][k];
+      const bf16* x_in = k > 0 ? c.A(p.blocks[enc_blocks[s][k - 1]].xout) : (s == 0 ? c.A(p.pe_out) : c.A(p.x_merged[s - 1]));
+      rc = block_bwd(bi, x_in, g_cur, g_alt);
+      if (rc) return rc;
+    }
+    if (s < L - 1) RUN(add_inplace_bf16(g_cur, c.A(p.g_save[s]), (long)T * C, st));     // skip-connection gradient (tulip.py:708,715)
+  }
+  {
+    EmbedArgs e;
+    memset(&e, 0, sizeof e);
+    e.x = x_lo; e.w = c.P(slot_pe_w); e.b = c.P(slot_pe_b); e.ln_w = c.P(slot_pe_nw); e.ln_b = c.P(slot_pe_nb);
+    e.B = B; e.Himg = cfg.img_h; e.Wimg = cfg.img_w; e.ph = cfg.patch_h; e.E = E; e.eps = cfg.ln_eps;
+    e.dy = g_cur; e.dw = c.G(slot_pe_w); e.db = c.G(slot_pe_b); e.dln_w = c.G(slot_pe_nw); e.dln_b = c.G(slot_pe_nb);
+    RUN(patch_embed_bwd(e, st));
+  }
+  return TULIP_OK;
+}

@@ -1,0 +1,77 @@
+// Whole-network executor: plans the activation arena, repacks the weights and launches every kernel
+// of TULIP.forward (tulip/model/tulip.py:702-737) and of its autograd backward
+// from C++, so a training step costs one host call per direction instead of ~11.6k ATen dispatches.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/tulip_b200.h"
+#include "gemm.cuh"
+#include "kernels.h"
+
+struct ParamInfo {
+  std::string name;
+  int ndim;
+  long shape[4];
+  long numel;
+};
+
+struct Linear {            // one GEMM weight: bf16 copy W' [N,K] (rows optionally permuted) and its transpose
+  int slot_w, slot_b;      // parameter slots (slot_b = -1: no bias)
+  int N, K;
+  int perm_R2, perm_Cc;    // row n' = ij*Cc + c holds source row c*R2 + ij (PixelShuffle-friendly order)
+  long w_off, wt_off;      // element offsets into the bf16 weight arena
+  long pbias_off;          // element offset into the fp32 aux arena of the permuted bias, -1 if not permuted
+};
+
+struct BlockDef {
+  int n1w, n1b, table, n2w, n2b;
+  int qkv, proj, fc1, fc2;     // indices into Net::linears
+  int stage, shift, index;     // index = running block number (DropPath scale rows 2*index, 2*index+1)
+};
+
+struct BlockBuf { long xn1, st1, qkv, ao, xmid, xn2, st2, hpre, hact, xout; };
+
+struct Plan {
+  long pe_out;
+  std::vector<BlockBuf> blocks;
+  std::vector<long> xn_m, st_m, x_merged;          // per encoder stage (valid for s < L-1)
+  long x_fpe;
+  std::vector<long> x_skip, x_up;                  // per decoder stage
+  long xn_up, st_up;
+  long gA, gB, scr_gs, scr_big, scr_dxn, scr_do, scr_dqkv;
+  std::vector<long> g_save;
+  long loss_acc;
+  long total;
+};
+
+struct tulip_net {
+  tulip_config cfg;
+  int L;                                           // stages
+  int H0, W0, r;                                   // token grid at stage 0, head upscale factor
+  std::vector<ParamInfo> params;
+  std::vector<Linear> linears;
+  std::vector<BlockDef> blocks;                    // encoder blocks then decoder blocks, execution order
+  std::vector<std::vector<int>> enc_blocks, dec_blocks;
+  std::vector<int> merge_nw, merge_nb, merge_lin;  // per encoder stage
+  std::vector<int> up_lin;                         // per decoder stage (-1: Identity)
+  std::vector<int> skip_lin;
+  int fpe_lin, head_lin;
+  int slot_normup_w, slot_normup_b, slot_pe_w, slot_pe_b, slot_pe_nw, slot_pe_nb, slot_dec_w;
+  // device-side persistent state
+  bf16* warena = nullptr; long warena_elems = 0;
+  float* faux = nullptr; long faux_elems = 0;
+  PackItem* items_dev = nullptr; int n_items = 0, n_tiles = 0;
+  std::vector<long> items_offsets_cache;           // parameter offsets the uploaded pack table was built for
+  long gemm_launches = 0, kernel_launches = 0;
+
+  int build();
+  int ensure_device();
+  Plan plan(int B) const;
+  int upload_pack_table(const int64_t* offs, cudaStream_t st);
+  int forward(int B, const float* params, const int64_t* offs, const float* x_lo, const float* target, const float* drop_scales,
+              const int* win_mode, void* ws, float* pred, float* losses, cudaStream_t st);
+  int backward(int B, const float* params, const int64_t* offs, float* grads, const float* x_lo, const float* target,
+               const float* pred, const float* grad_loss, const float* drop_scales, const int* win_mode, void* ws,
+               cudaStream_t st);
+};

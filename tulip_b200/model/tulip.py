@@ -1,0 +1,491 @@
+"""Drop-in replacement for the reference's `model/tulip.py` (ethz-asl/TULIP, tulip/model/tulip.py).
+
+Same public surface as the reference module:
+
+    tulip_base(**kwargs) / tulip_large(**kwargs)          (reference tulip.py:739-755)
+    TULIP(img_size, target_img_size, patch_size, in_chans, embed_dim, window_size, depths, num_heads, ...)
+    model(x, target, eval=False, mc_drop=False) -> (pred, total_loss, pixel_loss) | pred   (tulip.py:702-737)
+    state_dict(): the reference's 226 keys / shapes / dtypes
+
+but none of the reference's torch modules run.  The nn.Modules below only *own parameters* (fp32
+`nn.Parameter`s, all views into one flat buffer); the whole forward and backward pass is executed by
+the C++/CUDA executor in libtulip_b200.so (include/tulip_b200.h: tulip_net_forward / tulip_net_backward)
+through one `torch.autograd.Function`.  PyTorch supplies device memory, the stream and autograd glue only.
+
+Supported configuration = the one every shipped script uses (bash_scripts/tulip_upsampling_*.sh):
+`--pixel_shuffle --circular_padding --patch_unmerging`, patch (1,4), 16-token windows, in_chans 1,
+head_dim 32.  Anything else raises NotImplementedError -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import collections.abc
+import ctypes as C
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .._lib import MAX_STAGES, TulipConfig, check, current_stream, load_library, ptr
+
+__all__ = ["TULIP", "tulip_base", "tulip_large", "DropPath", "PatchEmbedding", "PatchMerging", "PatchUnmerging",
+           "PixelShuffleHead", "Mlp", "WindowAttention", "SwinTransformerBlock", "BasicBlock", "BasicBlockUp"]
+
+_ALIGN = 64     # parameter offsets in the flat buffer are multiples of 64 floats (256 B)
+
+
+def _no_forward(self, *a, **k):
+    raise RuntimeError(f"{type(self).__name__} only owns parameters in tulip_b200; call TULIP.forward "
+                       "(the fused CUDA executor) or the ops in tulip_b200.ops")
+
+
+class DropPath(nn.Module):
+    """Stochastic depth marker (reference tulip.py:16-30); the per-sample mask is drawn by TULIP.forward."""
+
+    def __init__(self, drop_prob: float = 0.):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    forward = _no_forward
+
+
+class PatchEmbedding(nn.Module):
+    """Parameters of reference PatchEmbedding (tulip.py:33-73): Conv2d(in_c, E, (ph, 8), stride=patch) + LayerNorm."""
+
+    def __init__(self, img_size, patch_size, in_c, embed_dim, norm_layer, circular_padding):
+        super().__init__()
+        self.img_size, self.patch_size, self.circular_padding = img_size, patch_size, circular_padding
+        self.proj = nn.Conv2d(in_c, embed_dim, kernel_size=(patch_size[0], 8), stride=patch_size)
+        self.norm = norm_layer(embed_dim) if norm_layer else nn.Identity()
+        self.grid_size = (img_size[0] // patch_size[0], img_size[1] // patch_size[1])
+        self.num_patches = self.grid_size[0] * self.grid_size[1]
+
+    forward = _no_forward
+
+
+class PatchMerging(nn.Module):
+    """reference tulip.py:76-106: LayerNorm(4C) then Linear(4C, 2C, bias=False)."""
+
+    def __init__(self, dim, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.norm = norm_layer(4 * dim)
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+
+    forward = _no_forward
+
+
+class PatchUnmerging(nn.Module):
+    """reference tulip.py:109-123: Conv2d(C, 2C, 1x1) + PixelShuffle(2)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+        self.expand = nn.Conv2d(in_channels=dim, out_channels=dim * 2, kernel_size=(1, 1))
+
+    forward = _no_forward
+
+
+class PixelShuffleHead(nn.Module):
+    """reference tulip.py:161-178: Sequential(Conv2d(E, E r^2, 1x1), LeakyReLU) + PixelShuffle(r)."""
+
+    def __init__(self, dim, upscale_factor):
+        super().__init__()
+        self.dim = dim
+        self.conv_expand = nn.Sequential(nn.Conv2d(in_channels=dim, out_channels=dim * (upscale_factor ** 2), kernel_size=(1, 1)),
+                                         nn.LeakyReLU(inplace=True))
+
+    forward = _no_forward
+
+
+class Mlp(nn.Module):
+    """reference tulip.py:181-200."""
+
+    def __init__(self, in_features, hidden_features):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.fc2 = nn.Linear(hidden_features, in_features)
+
+    forward = _no_forward
+
+
+class WindowAttention(nn.Module):
+    """Parameters + window state of reference WindowAttention (tulip.py:203-324)."""
+
+    def __init__(self, dim, window_size, num_heads, shift=False):
+        super().__init__()
+        self.window_size = tuple(window_size)
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.shift = shift
+        self.num_windows = window_size[0] * window_size[1]          # tokens per window (reference naming, tulip.py:213)
+        self.backup_window_size = (1, self.num_windows)
+        self.backup_shift_size = (0, self.num_windows // 2)
+        self.shift_size = (window_size[0] // 2, window_size[1] // 2) if shift else 0
+        self.relative_position_bias_table = nn.Parameter(
+            torch.zeros((2 * window_size[0] - 1) * (2 * window_size[1] - 1), num_heads))
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=.02)
+        self.register_buffer("relative_position_index", self.make_index(self.window_size))
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+        self._backup = False
+
+    @staticmethod
+    def make_index(win):
+        """reference tulip.py:228-240 in closed form."""
+        Mh, Mw = win
+        r = torch.arange(Mh * Mw) // Mw
+        c = torch.arange(Mh * Mw) % Mw
+        return (r[:, None] - r[None, :] + Mh - 1) * (2 * Mw - 1) + (c[:, None] - c[None, :] + Mw - 1)
+
+    def window_mode(self, H: int) -> int:
+        """0 = configured window, 1 = backup window; the switch is permanent (reference tulip.py:284-287)."""
+        if not self._backup and H < self.window_size[0]:
+            self._backup = True
+            self.window_size = self.backup_window_size
+            if self.shift:
+                self.shift_size = self.backup_shift_size
+        return 1 if self._backup else 0
+
+    forward = _no_forward
+
+
+class SwinTransformerBlock(nn.Module):
+    """reference tulip.py:326-352."""
+
+    def __init__(self, dim, num_heads, window_size, shift, mlp_ratio, drop_path, norm_layer):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim, window_size=window_size, num_heads=num_heads, shift=shift)
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio))
+
+    forward = _no_forward
+
+
+def _stage_drop_rates(depths, index, drop_path):
+    dpr = [rate.item() for rate in torch.linspace(0, drop_path, sum(depths))]           # reference tulip.py:409-410
+    return dpr[sum(depths[:index]):sum(depths[:index + 1])]
+
+
+class BasicBlock(nn.Module):
+    """reference tulip.py:399-436."""
+
+    def __init__(self, index, embed_dim, window_size, depths, num_heads, mlp_ratio, drop_path, norm_layer, patch_merging):
+        super().__init__()
+        dim = embed_dim * 2 ** index
+        rates = _stage_drop_rates(depths, index, drop_path)
+        self.blocks = nn.ModuleList([
+            SwinTransformerBlock(dim, num_heads[index], window_size, shift=(i % 2 == 1), mlp_ratio=mlp_ratio,
+                                 drop_path=rates[i], norm_layer=norm_layer) for i in range(depths[index])])
+        self.downsample = PatchMerging(dim=dim, norm_layer=norm_layer) if patch_merging else None
+
+    forward = _no_forward
+
+
+class BasicBlockUp(nn.Module):
+    """reference tulip.py:441-481 (stage index mirrored: index = len(depths) - index - 2, :447)."""
+
+    def __init__(self, index, embed_dim, window_size, depths, num_heads, mlp_ratio, drop_path, norm_layer, patch_expanding):
+        super().__init__()
+        index = len(depths) - index - 2
+        dim = embed_dim * 2 ** index
+        rates = _stage_drop_rates(depths, index, drop_path)
+        self.blocks = nn.ModuleList([
+            SwinTransformerBlock(dim, num_heads[index], window_size, shift=(i % 2 == 1), mlp_ratio=mlp_ratio,
+                                 drop_path=rates[i], norm_layer=norm_layer) for i in range(depths[index])])
+        self.upsample = PatchUnmerging(dim=dim) if patch_expanding else nn.Identity()
+
+    forward = _no_forward
+
+
+class _TulipFunction(torch.autograd.Function):
+    """One autograd node for the whole network: forward = tulip_net_forward, backward = tulip_net_backward."""
+
+    @staticmethod
+    def forward(ctx, model, x, target, drop_scales, win_mode, *params):
+        lib = load_library()
+        B = x.shape[0]
+        dev = x.device
+        Ht, Wt = model.target_img_size
+        pred = torch.empty((B, model.in_chans, Ht, Wt), dtype=torch.float32, device=dev)
+        losses = torch.zeros(2, dtype=torch.float32, device=dev)
+        ws = torch.empty(model._workspace_bytes(B), dtype=torch.uint8, device=dev)
+        check(lib.tulip_net_forward(model._net, B, ptr(model._flat), model._offsets_p, ptr(x), ptr(target), ptr(drop_scales),
+                                    win_mode.ctypes.data_as(C.c_void_p), ptr(ws), ptr(pred), ptr(losses), current_stream()),
+              "tulip_net_forward")
+        ctx.model, ctx.B, ctx.win_mode = model, B, win_mode
+        ctx.save_for_backward(x, target, drop_scales, ws, pred)
+        ctx.set_materialize_grads(False)
+        loss, pixel = losses[0], losses[1]
+        ctx.mark_non_differentiable(pixel)
+        return pred, loss, pixel
+
+    @staticmethod
+    def backward(ctx, g_pred, g_loss, g_pixel):
+        model = ctx.model
+        x, target, drop_scales, ws, pred = ctx.saved_tensors
+        if g_pred is not None:
+            raise NotImplementedError("tulip_b200: gradients through `pred` are not implemented; back-propagate total_loss")
+        if target is None:
+            raise RuntimeError("tulip_b200: backward needs the forward to have been given a target")
+        n_fixed = 5
+        if g_loss is None:
+            return (None,) * (n_fixed + len(model._param_list))
+        lib = load_library()
+        g_loss = g_loss.to(torch.float32).reshape(1).contiguous()
+        gbuf = model._grad_buffer()
+        check(lib.tulip_net_backward(model._net, ctx.B, ptr(model._flat), model._offsets_p, ptr(gbuf), ptr(x), ptr(target),
+                                     ptr(pred), ptr(g_loss), ptr(drop_scales), ctx.win_mode.ctypes.data_as(C.c_void_p), ptr(ws),
+                                     current_stream()), "tulip_net_backward")
+        grads = tuple(gbuf[o:o + n].view(s) for o, n, s in model._views)
+        return (None,) * n_fixed + grads
+
+
+class TULIP(nn.Module):
+    """Same constructor signature as the reference TULIP (tulip.py:531-535)."""
+
+    def __init__(self, img_size=(32, 2048), target_img_size=(128, 2048), patch_size=(4, 4), in_chans: int = 1, embed_dim: int = 96,
+                 window_size: int = 4, depths: tuple = (2, 2, 6, 2), num_heads: tuple = (3, 6, 12, 24),
+                 mlp_ratio: float = 4., qkv_bias: bool = True, drop_rate: float = 0., attn_drop_rate: float = 0.,
+                 drop_path_rate: float = 0.1, norm_layer=nn.LayerNorm, patch_norm: bool = True, pixel_shuffle: bool = False,
+                 circular_padding: bool = False, swin_v2: bool = False, log_transform: bool = False,
+                 patch_unmerging: bool = False):
+        super().__init__()
+        if swin_v2:
+            raise NotImplementedError("swin_v2=True is dead code in the reference (AttributeError at tulip.py:602); not built")
+        if not (pixel_shuffle and circular_padding and patch_unmerging):
+            raise NotImplementedError("tulip_b200 builds the shipped configuration only: "
+                                      "pixel_shuffle=True, circular_padding=True, patch_unmerging=True")
+        if drop_rate != 0. or attn_drop_rate != 0. or not qkv_bias or not patch_norm:
+            raise NotImplementedError("tulip_b200: drop_rate/attn_drop_rate must be 0, qkv_bias and patch_norm True (both factories)")
+        if not isinstance(window_size, collections.abc.Iterable):
+            window_size = (window_size, window_size)
+        window_size = [int(v) for v in window_size]
+        probe = norm_layer(8)
+        if not isinstance(probe, nn.LayerNorm):
+            raise NotImplementedError("tulip_b200: norm_layer must build an nn.LayerNorm")
+        self.ln_eps = float(probe.eps)
+
+        self.window_size = window_size
+        self.depths, self.num_heads, self.num_layers = tuple(depths), tuple(num_heads), len(depths)
+        self.embed_dim, self.mlp_ratio, self.qkv_bias = embed_dim, mlp_ratio, qkv_bias
+        self.drop_rate, self.attn_drop_rate, self.drop_path = drop_rate, attn_drop_rate, drop_path_rate
+        self.norm_layer = norm_layer
+        self.img_size, self.target_img_size = tuple(img_size), tuple(target_img_size)
+        self.patch_size, self.in_chans = tuple(patch_size), in_chans
+        self.log_transform, self.patch_unmerging, self.pixel_shuffle = log_transform, patch_unmerging, pixel_shuffle
+
+        # construction order = the reference's (tulip.py:553-580), so torch's RNG is consumed identically at init
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        L = self.num_layers
+        self.layers = nn.ModuleList([
+            BasicBlock(i, embed_dim, window_size, self.depths, self.num_heads, mlp_ratio, drop_path_rate, norm_layer,
+                       patch_merging=(i != L - 1)) for i in range(L)])
+        self.layers_up = nn.ModuleList([
+            BasicBlockUp(i, embed_dim, window_size, self.depths, self.num_heads, mlp_ratio, drop_path_rate, norm_layer,
+                         patch_expanding=(i < L - 2)) for i in range(L - 1)])
+        self.first_patch_expanding = PatchUnmerging(dim=embed_dim * 2 ** (L - 1))
+        self.skip_connection_layers = nn.ModuleList([
+            nn.Linear(embed_dim * 2 ** (L - 2 - i) * 2, embed_dim * 2 ** (L - 2 - i)) for i in range(L - 1)])
+        self.norm_up = norm_layer(embed_dim)
+        self.patch_embed = PatchEmbedding(img_size=self.img_size, patch_size=self.patch_size, in_c=in_chans, embed_dim=embed_dim,
+                                          norm_layer=norm_layer, circular_padding=circular_padding)
+        self.decoder_pred = nn.Conv2d(in_channels=embed_dim, out_channels=in_chans, kernel_size=(1, 1), bias=False)
+        self.upscale_factor = int(((target_img_size[0] * target_img_size[1]) / (img_size[0] * img_size[1])) ** 0.5) * 2 * \
+            int(((patch_size[0] * patch_size[1]) // 4) ** 0.5)                                     # reference tulip.py:577
+        self.ps_head = PixelShuffleHead(dim=embed_dim, upscale_factor=self.upscale_factor)
+        self.apply(self.init_weights)
+
+        self._net = None            # C handle, created lazily on the first CUDA forward
+        self._flat = None           # flat fp32 parameter buffer the nn.Parameters are views of
+        self._grad_bufs = [None, None]
+        self._views = None
+        self._param_list = None
+        self._offsets = None
+        self._ws_bytes = {}
+
+    @staticmethod
+    def init_weights(m):
+        """reference tulip.py:586-594."""
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    # ------------------------------------------------------------------ C executor plumbing
+    def _attention_modules(self):
+        mods = [blk.attn for layer in self.layers for blk in layer.blocks]
+        mods += [blk.attn for layer in self.layers_up for blk in layer.blocks]
+        return mods
+
+    def _drop_rates(self):
+        blks = [blk for layer in self.layers for blk in layer.blocks] + [blk for layer in self.layers_up for blk in layer.blocks]
+        return [float(getattr(b.drop_path, "drop_prob", 0.0)) for b in blks]
+
+    def _config(self) -> TulipConfig:
+        c = TulipConfig()
+        c.img_h, c.img_w = self.img_size
+        c.tgt_h, c.tgt_w = self.target_img_size
+        c.patch_h, c.patch_w = self.patch_size
+        c.in_chans, c.embed_dim = self.in_chans, self.embed_dim
+        c.win_h, c.win_w = self.window_size
+        c.num_layers = self.num_layers
+        if self.num_layers > MAX_STAGES:
+            raise NotImplementedError("tulip_b200: at most 8 stages")
+        for i in range(self.num_layers):
+            c.depths[i], c.num_heads[i] = self.depths[i], self.num_heads[i]
+        c.mlp_ratio = int(self.mlp_ratio)
+        if c.mlp_ratio != self.mlp_ratio:
+            raise NotImplementedError("tulip_b200: mlp_ratio must be an integer")
+        c.ln_eps = self.ln_eps
+        c.log_transform = int(bool(self.log_transform))
+        return c
+
+    def _create_net(self):
+        lib = load_library()
+        handle = C.c_void_p()
+        cfg = self._config()
+        check(lib.tulip_net_create(C.byref(cfg), C.byref(handle)), "tulip_net_create")
+        self._net = handle
+        # the C schema must agree with this module's parameters name-for-name and shape-for-shape
+        named = dict(self.named_parameters())
+        n = lib.tulip_net_num_params(handle)
+        if n != len(named):
+            raise RuntimeError(f"tulip_b200: parameter count mismatch (C {n} vs module {len(named)})")
+        order = []
+        buf = C.create_string_buffer(256)
+        shape = (C.c_int64 * 4)()
+        nd = C.c_int()
+        for i in range(n):
+            check(lib.tulip_net_param_info(handle, i, buf, 256, shape, C.byref(nd)))
+            name = buf.value.decode()
+            if name not in named or tuple(named[name].shape) != tuple(shape[:nd.value]):
+                raise RuntimeError(f"tulip_b200: parameter schema mismatch at {name}")
+            order.append(name)
+        self._schema = order
+        for a in self._attention_modules():           # the kernels compute the index analytically; the buffer must agree
+            if not torch.equal(a.relative_position_index.cpu(), WindowAttention.make_index(tuple(self.window_size))):
+                raise RuntimeError("tulip_b200: relative_position_index buffer differs from the analytic table")
+
+    def __del__(self):
+        try:
+            if self._net is not None:
+                load_library().tulip_net_destroy(self._net)
+        except Exception:
+            pass
+
+    def _is_flat(self, device) -> bool:
+        if self._flat is None or self._flat.device != device:
+            return False
+        base = self._flat.data_ptr()
+        for p, (o, n, _s) in zip(self._param_list, self._views):
+            if p.data_ptr() != base + 4 * o or p.dtype != torch.float32 or not p.is_contiguous():
+                return False
+        return True
+
+    def _ensure_flat(self, device):
+        """(Re)pack every parameter into one flat fp32 buffer and make the nn.Parameters views of it.
+        Survives .to(device), load_state_dict (in-place copy) and DDP's parameter broadcast."""
+        if self._net is None:
+            self._create_net()
+        if self._param_list is not None and self._is_flat(device):
+            return
+        named = dict(self.named_parameters())
+        plist = [named[k] for k in self._schema]
+        views, off = [], 0
+        for p in plist:
+            views.append((off, p.numel(), tuple(p.shape)))
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        flat = torch.zeros(off, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for p, (o, n, s) in zip(plist, views):
+                flat[o:o + n].view(s).copy_(p.detach().to(device=device, dtype=torch.float32))
+                p.data = flat[o:o + n].view(s)
+        self._flat, self._views, self._param_list = flat, views, plist
+        self._grad_bufs = [None, None]
+        self._offsets = np.ascontiguousarray([o for o, _, _ in views], dtype=np.int64)
+        self._offsets_p = self._offsets.ctypes.data_as(C.c_void_p)
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._flat = None           # parameters were re-created by .to()/.cuda()/.float(); re-pack lazily
+        return out
+
+    def _grad_buffer(self):
+        """Flat fp32 gradient buffer that no live `.grad` aliases (so autograd's accumulation stays correct)."""
+        live = self._param_list[0].grad
+        for i in (0, 1):
+            g = self._grad_bufs[i]
+            if g is None:
+                g = self._grad_bufs[i] = torch.empty_like(self._flat)
+            if live is None or live.data_ptr() != g.data_ptr() + 4 * self._views[0][0]:
+                return g
+        raise RuntimeError("tulip_b200: both gradient buffers are aliased by live .grad tensors")
+
+    def _workspace_bytes(self, B):
+        if B not in self._ws_bytes:
+            self._ws_bytes[B] = int(load_library().tulip_net_workspace_bytes(self._net, B))
+        return self._ws_bytes[B]
+
+    def _window_modes(self):
+        lib = load_library()
+        mods = self._attention_modules()
+        out = np.zeros(len(mods), dtype=np.int32)
+        st, sh, H, W = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        for i, a in enumerate(mods):
+            check(lib.tulip_net_block_info(self._net, i, C.byref(st), C.byref(sh), C.byref(H), C.byref(W)))
+            out[i] = a.window_mode(H.value)
+        return out
+
+    def _sample_drop_scales(self, B, device):
+        """Per-sample DropPath scales floor(keep + U[0,1)) / keep for every half-block (reference tulip.py:25-29)."""
+        rates = self._drop_rates()
+        if not self.training or all(r == 0. for r in rates):
+            return None
+        keep = 1.0 - torch.tensor([r for r in rates for _ in (0, 1)], dtype=torch.float32, device=device).unsqueeze(1)
+        u = torch.rand((2 * len(rates), B), dtype=torch.float32, device=device)
+        return (torch.floor(keep + u) / keep).contiguous()
+
+    def kernel_launches(self) -> int:
+        return 0 if self._net is None else int(load_library().tulip_net_kernel_launches(self._net))
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x, target, eval=False, mc_drop=False, _drop_scales=None):
+        """reference tulip.py:702-737.  `eval` is accepted and ignored, exactly like the reference."""
+        if not x.is_cuda:
+            raise RuntimeError("tulip_b200 runs on CUDA (sm_100a) only: no CPU or PyTorch fallback exists")
+        if x.dim() != 4 or tuple(x.shape[1:]) != (self.in_chans, *self.img_size):
+            raise ValueError(f"expected input (B, {self.in_chans}, {self.img_size[0]}, {self.img_size[1]}), got {tuple(x.shape)}")
+        self._ensure_flat(x.device)
+        B = x.shape[0]
+        x = x.detach().to(torch.float32).contiguous()
+        tgt = None
+        if not mc_drop:
+            if tuple(target.shape) != (B, self.in_chans, *self.target_img_size):
+                raise ValueError(f"target must be {(B, self.in_chans, *self.target_img_size)}, got {tuple(target.shape)}")
+            tgt = target.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        drop = _drop_scales if _drop_scales is not None else self._sample_drop_scales(B, x.device)
+        if drop is not None:
+            drop = drop.to(device=x.device, dtype=torch.float32).contiguous()
+        win_mode = self._window_modes()
+        pred, loss, pixel = _TulipFunction.apply(self, x, tgt, drop, win_mode, *self._param_list)
+        if mc_drop:
+            return pred
+        return pred, loss, pixel
+
+
+def tulip_base(**kwargs):
+    """reference tulip.py:739-746."""
+    return TULIP(depths=(2, 2, 2, 2), embed_dim=96, num_heads=(3, 6, 12, 24), qkv_bias=True, mlp_ratio=4,
+                 drop_path_rate=0.1, drop_rate=0, attn_drop_rate=0, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+def tulip_large(**kwargs):
+    """reference tulip.py:748-755."""
+    return TULIP(depths=(2, 2, 2, 2, 2), embed_dim=96, num_heads=(3, 6, 12, 24, 48), qkv_bias=True, mlp_ratio=4,
+                 drop_path_rate=0.1, drop_rate=0, attn_drop_rate=0, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)

@@ -1,0 +1,204 @@
+"""Thin torch-tensor wrappers over the per-kernel C ABI (include/tulip_b200.h).
+
+Every function takes CUDA tensors, enqueues on torch's current stream and returns new tensors.
+Activations are bf16; parameters, statistics and gradients fp32.  No fallbacks: a missing library or
+a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import check, current_stream, load_library, ptr
+
+GEMM_AUTO, GEMM_MMA, GEMM_TC05 = 0, 1, 2
+EPI_STORE, EPI_GELU, EPI_RESID, EPI_DGELU = 0, 1, 2, 5
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("tulip_b200.ops: CUDA tensors only (no CPU fallback)")
+
+
+def _bf16(t):
+    return t.to(torch.bfloat16).contiguous()
+
+
+def _f32(t):
+    return None if t is None else t.to(torch.float32).contiguous()
+
+
+def linear(x, w, bias=None, epilogue=EPI_STORE, aux=None, row_scale=None, rows_per_sample=1, impl=GEMM_AUTO):
+    """x [M,K] bf16, w [N,K] bf16 -> [M,N] bf16; EPI_GELU returns (gelu(pre), pre)."""
+    _cuda(x, w)
+    x, w = _bf16(x), _bf16(w)
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    out2 = torch.empty_like(out) if epilogue == EPI_GELU else None
+    aux = None if aux is None else _bf16(aux)
+    bias, row_scale = _f32(bias), _f32(row_scale)
+    check(load_library().tulip_gemm_nt(ptr(x), ptr(w), ptr(bias), ptr(out), ptr(out2), ptr(aux), ptr(row_scale), rows_per_sample,
+                                       M, N, K, epilogue, impl, current_stream()), "tulip_gemm_nt")
+    return (out, out2) if epilogue == EPI_GELU else out
+
+
+def linear_wgrad(dy, x, want_bias=True, impl=GEMM_AUTO):
+    """dW [N,K] = dy[M,N]^T x[M,K] (fp32), db [N] = colsum(dy)."""
+    _cuda(dy, x)
+    dy, x = _bf16(dy), _bf16(x)
+    M, N = dy.shape
+    K = x.shape[1]
+    dW = torch.zeros((N, K), dtype=torch.float32, device=x.device)
+    db = torch.zeros(N, dtype=torch.float32, device=x.device) if want_bias else None
+    check(load_library().tulip_gemm_tn(ptr(dy), ptr(x), ptr(dW), ptr(db), M, N, K, impl, current_stream()), "tulip_gemm_tn")
+    return dW, db
+
+
+def window_attention(qkv, bias_table, B, H, W, heads, window=(2, 8), shift=(0, 0), masked=False, bias_window=(2, 8)):
+    """qkv [B*H*W, 3C] bf16 (natural token order) -> [B*H*W, C] bf16."""
+    _cuda(qkv, bias_table)
+    qkv, bias_table = _bf16(qkv), _f32(bias_table)
+    C = qkv.shape[1] // 3
+    out = torch.empty((qkv.shape[0], C), dtype=torch.bfloat16, device=qkv.device)
+    check(load_library().tulip_window_attention_fwd(ptr(qkv), ptr(bias_table), ptr(out), B, H, W, C, heads, window[0], window[1],
+                                                    shift[0], shift[1], int(masked), bias_window[0], bias_window[1],
+                                                    current_stream()), "tulip_window_attention_fwd")
+    return out
+
+
+def window_attention_bwd(qkv, bias_table, dout, B, H, W, heads, window=(2, 8), shift=(0, 0), masked=False, bias_window=(2, 8)):
+    _cuda(qkv, bias_table, dout)
+    qkv, bias_table, dout = _bf16(qkv), _f32(bias_table), _bf16(dout)
+    C = qkv.shape[1] // 3
+    dqkv = torch.empty_like(qkv)
+    dtable = torch.zeros_like(bias_table)
+    check(load_library().tulip_window_attention_bwd(ptr(qkv), ptr(bias_table), ptr(dout), ptr(dqkv), ptr(dtable), B, H, W, C, heads,
+                                                    window[0], window[1], shift[0], shift[1], int(masked), bias_window[0],
+                                                    bias_window[1], current_stream()), "tulip_window_attention_bwd")
+    return dqkv, dtable
+
+
+def layernorm(x, w, b, eps=1e-6, merge=None):
+    """x [rows, C] bf16 -> (y bf16, stats [rows,2] fp32).  merge=(B,H,W): x is [B,H,W,Cs] and rows are the
+    2x2-gathered 4*Cs vectors of PatchMerging."""
+    _cuda(x, w, b)
+    x, w, b = _bf16(x), _f32(w), _f32(b)
+    if merge is None:
+        rows, C = x.shape
+        g, H2, W2 = 0, 0, 0
+    else:
+        B, H, W = merge
+        C = 4 * x.shape[-1]
+        rows, g, H2, W2 = B * (H // 2) * (W // 2), 1, H // 2, W // 2
+    y = torch.empty((rows, C), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+    check(load_library().tulip_layernorm_fwd(ptr(x), ptr(w), ptr(b), ptr(y), ptr(stats), rows, C, eps, g, H2, W2, current_stream()),
+          "tulip_layernorm_fwd")
+    return y, stats
+
+
+def layernorm_bwd(x, w, stats, dy, dres=None, merge=None):
+    _cuda(x, w, stats, dy)
+    x, w, dy = _bf16(x), _f32(w), _bf16(dy)
+    rows, C = dy.shape
+    g, H2, W2 = (0, 0, 0) if merge is None else (1, merge[1] // 2, merge[2] // 2)
+    dx = torch.empty_like(x)
+    dw = torch.zeros(C, dtype=torch.float32, device=x.device)
+    db = torch.zeros(C, dtype=torch.float32, device=x.device)
+    dres = None if dres is None else _bf16(dres)
+    check(load_library().tulip_layernorm_bwd(ptr(x), ptr(w), ptr(stats), ptr(dy), ptr(dres), ptr(dx), ptr(dw), ptr(db), rows, C,
+                                             g, H2, W2, current_stream()), "tulip_layernorm_bwd")
+    return dx, dw, db
+
+
+def patch_embed(x, w, b, ln_w, ln_b, eps=1e-6):
+    """x [B,1,H,W] fp32 -> [B, H/ph, W/4, E] bf16."""
+    _cuda(x, w)
+    x, w, b, ln_w, ln_b = _f32(x), _f32(w), _f32(b), _f32(ln_w), _f32(ln_b)
+    B, _, H, W = x.shape
+    E, ph = w.shape[0], w.shape[2]
+    y = torch.empty((B, H // ph, W // 4, E), dtype=torch.bfloat16, device=x.device)
+    check(load_library().tulip_patch_embed_fwd(ptr(x), ptr(w), ptr(b), ptr(ln_w), ptr(ln_b), ptr(y), B, H, W, ph, E, eps,
+                                               current_stream()), "tulip_patch_embed_fwd")
+    return y
+
+
+def patch_embed_bwd(x, w, b, ln_w, dy, eps=1e-6):
+    _cuda(x, w, dy)
+    x, w, b, ln_w, dy = _f32(x), _f32(w), _f32(b), _f32(ln_w), _bf16(dy)
+    B, _, H, W = x.shape
+    E, ph = w.shape[0], w.shape[2]
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    dlw, dlb = torch.zeros_like(ln_w), torch.zeros_like(ln_w)
+    check(load_library().tulip_patch_embed_bwd(ptr(x), ptr(w), ptr(b), ptr(ln_w), ptr(dy), ptr(dw), ptr(db), ptr(dlw), ptr(dlb),
+                                               B, H, W, ph, E, eps, current_stream()), "tulip_patch_embed_bwd")
+    return dw, db, dlw, dlb
+
+
+def l1_loss(pred, target, log_transform=True):
+    _cuda(pred, target)
+    pred, target = _f32(pred), _f32(target)
+    scratch = torch.zeros(2, dtype=torch.float32, device=pred.device)
+    out = torch.zeros(2, dtype=torch.float32, device=pred.device)
+    check(load_library().tulip_l1_loss(ptr(pred), ptr(target), pred.numel(), int(log_transform), ptr(scratch), ptr(out),
+                                       current_stream()), "tulip_l1_loss")
+    return out[0], out[1]
+
+
+def window_partition(x, window=(2, 8), shift=(0, 0)):
+    """(B,H,W,C) bf16 -> ((B Nh Nw), Mh, Mw, C): torch.roll(x, (-sh,-sw)) then the reference's window_partition."""
+    _cuda(x)
+    x = _bf16(x)
+    B, H, W, Cc = x.shape
+    out = torch.empty((B * (H // window[0]) * (W // window[1]), window[0], window[1], Cc), dtype=torch.bfloat16, device=x.device)
+    check(load_library().tulip_window_partition(ptr(x), ptr(out), B, H, W, Cc, window[0], window[1], shift[0], shift[1],
+                                                current_stream()), "tulip_window_partition")
+    return out
+
+
+def window_reverse(xw, B, H, W, window=(2, 8), shift=(0, 0)):
+    _cuda(xw)
+    xw = _bf16(xw)
+    Cc = xw.shape[-1]
+    out = torch.empty((B, H, W, Cc), dtype=torch.bfloat16, device=xw.device)
+    check(load_library().tulip_window_reverse(ptr(xw), ptr(out), B, H, W, Cc, window[0], window[1], shift[0], shift[1],
+                                              current_stream()), "tulip_window_reverse")
+    return out
+
+
+def shift_mask(H, W, window=(2, 8), shift=(1, 4), device="cuda"):
+    L = window[0] * window[1]
+    out = torch.empty(((H // window[0]) * (W // window[1]), L, L), dtype=torch.float32, device=device)
+    check(load_library().tulip_shift_mask(ptr(out), H, W, window[0], window[1], shift[0], shift[1], current_stream()),
+          "tulip_shift_mask")
+    return out
+
+
+def rel_bias_gather(table, window=(2, 8)):
+    _cuda(table)
+    table = _f32(table)
+    L = window[0] * window[1]
+    out = torch.empty((table.shape[1], L, L), dtype=torch.float32, device=table.device)
+    check(load_library().tulip_rel_bias_gather(ptr(table), ptr(out), table.shape[1], window[0], window[1], current_stream()),
+          "tulip_rel_bias_gather")
+    return out
+
+
+def merge_gather(x):
+    _cuda(x)
+    x = _bf16(x)
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, H // 2, W // 2, 4 * Cc), dtype=torch.bfloat16, device=x.device)
+    check(load_library().tulip_merge_gather(ptr(x), ptr(out), B, H, W, Cc, current_stream()), "tulip_merge_gather")
+    return out
+
+
+def pixel_shuffle(x, r):
+    """NHWC PixelShuffle: (B,H,W,Cout*r*r) -> (B,H*r,W*r,Cout)."""
+    _cuda(x)
+    x = _bf16(x)
+    B, H, W, Crr = x.shape
+    out = torch.empty((B, H * r, W * r, Crr // (r * r)), dtype=torch.bfloat16, device=x.device)
+    check(load_library().tulip_pixel_shuffle(ptr(x), ptr(out), B, H, W, Crr // (r * r), r, current_stream()), "tulip_pixel_shuffle")
+    return out
