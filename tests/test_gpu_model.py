@@ -5,7 +5,7 @@ Tolerances.  Activations are bf16 between kernels with fp32 accumulation, so the
 fp32 oracle is bounded by the reference's OWN autocast-bf16 deviation on the same kind of input
 (9.1e-3 rel-L2 on pred with bf16-rounded weights; per-parameter gradient rel-L2 median 9.6e-3,
 worst 0.23 on LayerNorm biases because the L1 loss back-propagates sign()).  The asserts below are:
-pred rel-L2 <= 1.5e-2, losses within 1e-2 relative, per-parameter gradient rel-L2 median <= 2e-2 and
+pred rel-L2 <= 1e-2 (measured 3-4.5e-3), losses within 1e-3 relative, per-parameter gradient rel-L2 median <= 2e-2 and
 every gradient norm within 15 % (LayerNorm / bias vectors 35 %)."""
 import hashlib
 import os
@@ -53,9 +53,9 @@ def test_model_vs_reference_fixture(golden_dir, name, cfg, large):
     print(f"\n[{name}] pred rel-L2 {e_pred:.3e}  loss {loss.item():.6f} vs {float(g['loss']):.6f}  "
           f"pixel {pixel.item():.6f} vs {float(g['pixel_loss']):.6f}")
     assert pred.shape == (int(g["batch"]), 1, *cfg.target_img_size) and pred.dtype == torch.float32
-    assert e_pred <= 1.5e-2
-    assert abs(loss.item() - float(g["loss"])) <= 1e-2 * float(g["loss"])
-    assert abs(pixel.item() - float(g["pixel_loss"])) <= 1e-2 * float(g["pixel_loss"])
+    assert e_pred <= 1e-2
+    assert abs(loss.item() - float(g["loss"])) <= 1e-3 * float(g["loss"])
+    assert abs(pixel.item() - float(g["pixel_loss"])) <= 1e-3 * float(g["pixel_loss"])
     loss.backward()
     names = [str(n) for n in g["grad_names"]]
     grads = dict(model.named_parameters())
@@ -91,7 +91,7 @@ def test_model_vs_oracle_full_gradients():
     worst = max(errs, key=errs.get)
     med = float(np.median(list(errs.values())))
     print(f"\npred rel-L2 {rel_l2(pred, pred_o):.3e}; grad rel-L2 median {med:.3e}, worst {errs[worst]:.3e} ({worst})")
-    assert rel_l2(pred, pred_o) <= 1.5e-2 and med <= 2e-2 and errs[worst] <= 0.3
+    assert rel_l2(pred, pred_o) <= 1e-2 and med <= 2e-2 and errs[worst] <= 0.3
 
 
 def test_train_mode_droppath_and_state_dict_roundtrip():

@@ -95,6 +95,32 @@ int tulip_net_block_info(const tulip_net* n, int i, int* stage, int* shifted, in
 int64_t tulip_net_workspace_bytes(const tulip_net* n, int batch) { return batch > 0 ? n->plan(batch).total : 0; }
 int64_t tulip_net_kernel_launches(const tulip_net* n) { return n->kernel_launches; }
 
+int tulip_net_profile(tulip_net* n, int enable) {
+  if (!n) { tulip_set_error("tulip_net_profile: null net"); return TULIP_ERR_ARG; }
+  n->profiling = enable != 0;
+  n->prof_reset();
+  return TULIP_OK;
+}
+
+int tulip_net_profile_num_tags(void) { return K_COUNT; }
+
+int tulip_net_profile_read(tulip_net* n, int tag_id, char* name, int name_cap, double* ms, double* flops, double* bytes,
+                           int64_t* launches) {
+  if (!n || tag_id < 0 || tag_id >= K_COUNT) { tulip_set_error("tulip_net_profile_read: bad argument"); return TULIP_ERR_ARG; }
+  if (name && name_cap > 0) { strncpy(name, ktag_name(tag_id), name_cap - 1); name[name_cap - 1] = 0; }
+  double t = 0, f = 0, b = 0;
+  int64_t cnt = 0;
+  for (const ProfRec& r : n->recs) {
+    if (r.tag != tag_id) continue;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) { tulip_set_error("profile: event sync failed"); return TULIP_ERR_CUDA; }
+    float dt = 0.f;
+    if (cudaEventElapsedTime(&dt, r.e0, r.e1) != cudaSuccess) { tulip_set_error("profile: elapsed failed"); return TULIP_ERR_CUDA; }
+    t += dt; f += r.flops; b += r.bytes; ++cnt;
+  }
+  *ms = t; *flops = f; *bytes = b; *launches = cnt;
+  return TULIP_OK;
+}
+
 int tulip_net_forward(tulip_net* n, int batch, const float* params, const int64_t* offs, const float* x_lo, const float* target,
                       const float* drop_scales, const int* win_mode, void* ws, float* pred, float* losses, void* stream) {
   if (!n || !params || !offs || !x_lo || !ws || !pred) { tulip_set_error("tulip_net_forward: null argument"); return TULIP_ERR_ARG; }

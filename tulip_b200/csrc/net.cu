@@ -22,6 +22,39 @@ struct Bump {
 
 }  // namespace
 
+const char* ktag_name(int t) {
+  static const char* names[K_COUNT] = {
+      "misc", "gemm_nt<store>", "gemm_nt<gelu>", "gemm_nt<resid>", "gemm_nt<pixshuf>", "gemm_nt<split2>", "gemm_nt<dgelu>",
+      "gemm_nt<head>", "gemm_nt<head_bwd>", "gemm_nt<rowscale>", "gemm_nt<unshuffle>", "gemm_tn", "gemm_tn<unshuffle>",
+      "win_attn_fwd", "win_attn_bwd", "layernorm_fwd", "layernorm_bwd", "patch_embed_fwd", "patch_embed_bwd", "pack_weights",
+      "elementwise", "l1_loss"};
+  return (t >= 0 && t < K_COUNT) ? names[t] : "?";
+}
+
+void tulip_net::prof_begin(cudaStream_t st) {
+  if (!profiling) return;
+  while (ev_pool.size() < ev_used + 2) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ev_pool.push_back(e);
+  }
+  cudaEventRecord(ev_pool[ev_used], st);
+}
+
+void tulip_net::prof_end(cudaStream_t st) {
+  if (profiling) {
+    cudaEventRecord(ev_pool[ev_used + 1], st);
+    recs.push_back(ProfRec{cur_tag, cur_flops, cur_bytes, ev_pool[ev_used], ev_pool[ev_used + 1]});
+    ev_used += 2;
+  }
+  cur_tag = K_MISC; cur_flops = 0; cur_bytes = 0;
+}
+
+void tulip_net::prof_reset() {
+  recs.clear();
+  ev_used = 0;
+}
+
 int tulip_net::build() {
   const tulip_config& c = cfg;
   TULIP_REQUIRE(c.num_layers >= 2 && c.num_layers <= TULIP_MAX_STAGES, "tulip: num_layers must be in [2, 8]");
@@ -257,9 +290,26 @@ int tulip_net::upload_pack_table(const int64_t* offs, cudaStream_t st) {
 
 #define RUN(call)                   \
   do {                              \
+    prof_begin(st);                 \
     int rc__ = (call);              \
     if (rc__ != TULIP_OK) return rc__; \
+    prof_end(st);                   \
     ++kernel_launches;              \
+  } while (0)
+
+// tagged GEMM launches: the tag names the kernel function (template instantiation) that runs
+#define RUN_NT(g, epi)                                                                         \
+  do {                                                                                         \
+    tag((g).a_mode == A_UNSHUFFLE ? K_NT_UNSHUFFLE : nt_tag(epi), 2.0 * (g).M * (g).N * (g).K, \
+        2.0 * ((double)(g).M * (g).K + (double)(g).N * (g).K + (double)(g).M * (g).N));        \
+    RUN(gemm_nt((g), (epi), st));                                                              \
+  } while (0)
+#define RUN_TN(g)                                                                              \
+  do {                                                                                         \
+    const GemmTNArgs& g__ = (g);                                                               \
+    tag(g__.y_mode == A_UNSHUFFLE ? K_TN_UNSHUFFLE : K_TN, 2.0 * g__.M * g__.N * g__.K,        \
+        2.0 * ((double)g__.M * g__.N + (double)g__.M * g__.K) + 4.0 * g__.N * g__.K);          \
+    RUN(gemm_tn(g__, st));                                                                     \
   } while (0)
 
 namespace {
@@ -339,6 +389,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
   Ctx c{this, B, params_, offs, nullptr, drop_scales, win_mode, reinterpret_cast<unsigned char*>(ws), st};
   const int E = cfg.embed_dim;
 
+  tag(K_PACK, 0, 8.0 * warena_elems / 2);
   RUN(pack_weights(params_, warena, items_dev, n_items, n_tiles, st));
   for (const Linear& l : linears)
     if (l.pbias_off >= 0) RUN(permute_bias(c.P(l.slot_b), faux + l.pbias_off, l.N, l.perm_R2, l.perm_Cc, st));
@@ -348,6 +399,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     memset(&e, 0, sizeof e);
     e.x = x_lo; e.w = c.P(slot_pe_w); e.b = c.P(slot_pe_b); e.ln_w = c.P(slot_pe_nw); e.ln_b = c.P(slot_pe_nb);
     e.y = c.A(p.pe_out); e.B = B; e.Himg = cfg.img_h; e.Wimg = cfg.img_w; e.ph = cfg.patch_h; e.E = E; e.eps = cfg.ln_eps;
+    tag(K_EMBED_FWD, 0, 4.0 * B * cfg.img_h * cfg.img_w + 2.0 * B * H0 * W0 * E);
     RUN(patch_embed_fwd(e, st));
   }
 
@@ -356,6 +408,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     memset(&a, 0, sizeof a);
     a.x = x; a.w = c.P(wslot); a.b = c.P(bslot); a.y = y; a.stats = stats; a.rows = rows; a.C = C; a.eps = cfg.ln_eps;
     a.gather = gather; a.H2 = H2; a.W2 = W2;
+    tag(K_LN_FWD, 0, 4.0 * rows * C + 8.0 * rows);
     return layernorm_fwd(a, st);
   };
 
@@ -369,31 +422,32 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     {
       const Linear& l = linears[b.qkv];
       GemmArgs g = nt_args(c.A(bb.xn1), C, c.W(l), C, T, 3 * C, C, c.bias(l), c.A(bb.qkv), 3 * C);
-      RUN(gemm_nt(g, EPI_STORE, st));
+      RUN_NT(g, EPI_STORE);
     }
     {
       AttnArgs a = attn_args(c, b, c.A(bb.qkv));
       a.out = c.A(bb.ao);
+      tag(K_ATTN_FWD, 64.0 * T * C, 8.0 * T * C);
       RUN(win_attn_fwd(a, st));
     }
     {
       const Linear& l = linears[b.proj];
       GemmArgs g = nt_args(c.A(bb.ao), C, c.W(l), C, T, C, C, c.bias(l), c.A(bb.xmid), C);
       g.aux = x_in; g.ldaux = C; g.row_scale = ds1; g.rows_per_sample = Hs * Ws;
-      RUN(gemm_nt(g, EPI_RESID, st));
+      RUN_NT(g, EPI_RESID);
     }
     RUN(ln(c.A(bb.xmid), b.n2w, b.n2b, c.A(bb.xn2), c.F(bb.st2), T, C, 0, 0, 0));
     {
       const Linear& l = linears[b.fc1];
       GemmArgs g = nt_args(c.A(bb.xn2), C, c.W(l), C, T, 4 * C, C, c.bias(l), c.A(bb.hact), 4 * C);
       g.out2 = c.A(bb.hpre); g.ldo2 = 4 * C;
-      RUN(gemm_nt(g, EPI_GELU, st));
+      RUN_NT(g, EPI_GELU);
     }
     {
       const Linear& l = linears[b.fc2];
       GemmArgs g = nt_args(c.A(bb.hact), 4 * C, c.W(l), 4 * C, T, C, 4 * C, c.bias(l), c.A(bb.xout), C);
       g.aux = c.A(bb.xmid); g.ldaux = C; g.row_scale = ds2; g.rows_per_sample = Hs * Ws;
-      RUN(gemm_nt(g, EPI_RESID, st));
+      RUN_NT(g, EPI_RESID);
     }
     return TULIP_OK;
   };
@@ -402,7 +456,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     // 1x1 conv C -> 2C + PixelShuffle(2) as a GEMM with a scatter epilogue (tulip.py:117-123)
     GemmArgs g = nt_args(x, C, c.W(l), C, B * Hs * Ws, 2 * C, C, c.bias(l), out, C / 2);
     g.g_H = Hs; g.g_W = Ws; g.g_Cc = C / 2;
-    RUN(gemm_nt(g, EPI_PIXSHUF, st));
+    RUN_NT(g, EPI_PIXSHUF);
     return TULIP_OK;
   };
 
@@ -420,7 +474,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
       RUN(ln(x, merge_nw[s], merge_nb[s], c.A(p.xn_m[s]), c.F(p.st_m[s]), T4, 4 * C, 1, Hs / 2, Ws / 2));
       const Linear& l = linears[merge_lin[s]];
       GemmArgs g = nt_args(c.A(p.xn_m[s]), 4 * C, c.W(l), 4 * C, T4, 2 * C, 4 * C, nullptr, c.A(p.x_merged[s]), 2 * C);
-      RUN(gemm_nt(g, EPI_STORE, st));
+      RUN_NT(g, EPI_STORE);
       x = c.A(p.x_merged[s]);
     }
   }
@@ -435,7 +489,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
       const Linear& l = linears[skip_lin[u]];
       GemmArgs g = nt_args(x, C, c.W(l), 2 * C, T, C, 2 * C, c.bias(l), c.A(p.x_skip[u]), C);
       g.A2 = x_save[s]; g.lda2 = C; g.K1 = C;
-      RUN(gemm_nt(g, EPI_STORE, st));
+      RUN_NT(g, EPI_STORE);
       x = c.A(p.x_skip[u]);
     }
     for (int bi : dec_blocks[u]) {
@@ -457,8 +511,9 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     if (E != 96) TULIP_CUDA(cudaMemsetAsync(pred, 0, (size_t)T0 * r * r * sizeof(float), st));
     GemmArgs g = nt_args(c.A(p.xn_up), E, c.W(l), E, T0, E * r * r, E, c.bias(l), nullptr, 0);
     g.wd = c.P(slot_dec_w); g.pred = pred; g.hd_H = H0; g.hd_W = W0; g.hd_r = r; g.hd_E = E;
-    RUN(gemm_nt(g, EPI_HEAD, st));
+    RUN_NT(g, EPI_HEAD);
   }
+  tag(K_LOSS, 0, 8.0 * T0 * r * r);
   if (target) RUN(l1_loss(pred, target, (long)T0 * r * r, cfg.log_transform, c.F(p.loss_acc), losses, st));
   return TULIP_OK;
 }
@@ -490,6 +545,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     memset(&a, 0, sizeof a);
     a.x = x; a.w = c.P(wslot); a.stats = const_cast<float*>(stats); a.dy = dy; a.dres = dres; a.dx = dx;
     a.dw = c.G(wslot); a.db = c.G(bslot); a.rows = rows; a.C = C; a.eps = cfg.ln_eps; a.gather = gather; a.H2 = H2; a.W2 = W2;
+    tag(K_LN_BWD, 0, (dres ? 8.0 : 6.0) * rows * C + 8.0 * rows);
     return layernorm_bwd(a, st);
   };
   auto dw = [&](const Linear& l, const bf16* dY, const bf16* X, int M) {
@@ -515,13 +571,13 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     g.wd = c.P(slot_dec_w); g.pred = const_cast<float*>(pred); g.target = target; g.gscale = grad_loss;
     g.dwd = c.G(slot_dec_w);
     g.hd_H = H0; g.hd_W = W0; g.hd_r = r; g.hd_E = E; g.hd_inv_npix = 1.0f / ((float)T0 * r * r);
-    RUN(gemm_nt(g, EPI_HEAD_BWD, st));
+    RUN_NT(g, EPI_HEAD_BWD);
     // dxn_up = dh . We'          (A = dh [T0, E r^2], B = We'^T stored as Wt' [E, E r^2])
     GemmArgs gx = nt_args(dh, (long)E * r * r, c.Wt(l), (long)E * r * r, T0, E, E * r * r, nullptr, c.A(p.scr_dxn), E);
-    RUN(gemm_nt(gx, EPI_STORE, st));
+    RUN_NT(gx, EPI_STORE);
     // dWe' += dh^T . xn_up (rows un-permuted on store); bias gradient = column sums of dh, same un-permutation
     GemmTNArgs gw = dw(l, dh, c.A(p.xn_up), T0);
-    RUN(gemm_tn(gw, st));
+    RUN_TN(gw);
     RUN(ln_bwd(x_last, slot_normup_w, slot_normup_b, c.F(p.st_up), c.A(p.scr_dxn), nullptr, g_cur, T0, E, 0, 0, 0));
   }
 
@@ -535,6 +591,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     // ---- MLP half: x_out = x_mid + s2 * fc2(gelu(fc1(LN2(x_mid)))) ----
     const bf16* gy = g_io;
     if (ds2) {
+      tag(K_ELEMWISE, 0, 4.0 * T * C);
       RUN(scale_rows_bf16(c.A(p.scr_gs), g_io, ds2, T, C, Hs * Ws, st));
       gy = c.A(p.scr_gs);
     }
@@ -542,32 +599,34 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       const Linear& l2 = linears[b.fc2];
       GemmArgs g = nt_args(gy, C, c.Wt(l2), C, T, 4 * C, C, nullptr, c.A(p.scr_big), 4 * C);   // dh = (gy . W2) o gelu'(pre)
       g.aux = c.A(bb.hpre); g.ldaux = 4 * C;
-      RUN(gemm_nt(g, EPI_DGELU, st));
-      RUN(gemm_tn(dw(l2, gy, c.A(bb.hact), T), st));
+      RUN_NT(g, EPI_DGELU);
+      RUN_TN(dw(l2, gy, c.A(bb.hact), T));
       const Linear& l1 = linears[b.fc1];
       GemmArgs g1 = nt_args(c.A(p.scr_big), 4 * C, c.Wt(l1), 4 * C, T, C, 4 * C, nullptr, c.A(p.scr_dxn), C);
-      RUN(gemm_nt(g1, EPI_STORE, st));
-      RUN(gemm_tn(dw(l1, c.A(p.scr_big), c.A(bb.xn2), T), st));
+      RUN_NT(g1, EPI_STORE);
+      RUN_TN(dw(l1, c.A(p.scr_big), c.A(bb.xn2), T));
     }
     RUN(ln_bwd(c.A(bb.xmid), b.n2w, b.n2b, c.F(bb.st2), c.A(p.scr_dxn), g_io, g_tmp, T, C, 0, 0, 0));   // g_tmp = dL/dx_mid
     // ---- attention half: x_mid = x_in + s1 * proj(attn(qkv(LN1(x_in)))) ----
     gy = g_tmp;
     if (ds1) {
+      tag(K_ELEMWISE, 0, 4.0 * T * C);
       RUN(scale_rows_bf16(c.A(p.scr_gs), g_tmp, ds1, T, C, Hs * Ws, st));
       gy = c.A(p.scr_gs);
     }
     {
       const Linear& lp = linears[b.proj];
       GemmArgs g = nt_args(gy, C, c.Wt(lp), C, T, C, C, nullptr, c.A(p.scr_do), C);
-      RUN(gemm_nt(g, EPI_STORE, st));
-      RUN(gemm_tn(dw(lp, gy, c.A(bb.ao), T), st));
+      RUN_NT(g, EPI_STORE);
+      RUN_TN(dw(lp, gy, c.A(bb.ao), T));
       AttnArgs a = attn_args(c, b, c.A(bb.qkv));
       a.dout = c.A(p.scr_do); a.dqkv = c.A(p.scr_dqkv); a.dbias_table = c.G(b.table);
+      tag(K_ATTN_BWD, 160.0 * T * C, 16.0 * T * C);
       RUN(win_attn_bwd(a, st));
       const Linear& lq = linears[b.qkv];
       GemmArgs gq = nt_args(c.A(p.scr_dqkv), 3 * C, c.Wt(lq), 3 * C, T, C, 3 * C, nullptr, c.A(p.scr_dxn), C);
-      RUN(gemm_nt(gq, EPI_STORE, st));
-      RUN(gemm_tn(dw(lq, c.A(p.scr_dqkv), c.A(bb.xn1), T), st));
+      RUN_NT(gq, EPI_STORE);
+      RUN_TN(dw(lq, c.A(p.scr_dqkv), c.A(bb.xn1), T));
     }
     RUN(ln_bwd(x_in, b.n1w, b.n1b, c.F(bb.st1), c.A(p.scr_dxn), g_tmp, g_io, T, C, 0, 0, 0));            // g_io = dL/dx_in
     return TULIP_OK;
@@ -578,10 +637,10 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     const int T = B * Hs * Ws;
     GemmArgs g = nt_args(g_out, C / 2, c.Wt(l), 2 * C, T, C, 2 * C, nullptr, g_in, C);
     g.a_mode = A_UNSHUFFLE; g.g_H = Hs; g.g_W = Ws; g.g_Cc = C / 2;
-    RUN(gemm_nt(g, EPI_STORE, st));
+    RUN_NT(g, EPI_STORE);
     GemmTNArgs gw = dw(l, g_out, x_in, T);
     gw.ldy = C / 2; gw.y_mode = A_UNSHUFFLE; gw.g_H = Hs; gw.g_W = Ws; gw.g_Cc = C / 2;
-    RUN(gemm_tn(gw, st));
+    RUN_TN(gw);
     return TULIP_OK;
   };
 
@@ -608,10 +667,10 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       const bf16* x_enc = (s == 0) ? c.A(p.pe_out) : c.A(p.x_merged[s - 1]);
       GemmArgs g = nt_args(g_cur, C, c.Wt(l), C, T, 2 * C, C, nullptr, g_alt, C);
       g.out2 = c.A(p.g_save[s]); g.ldo2 = C; g.split_col = C;
-      RUN(gemm_nt(g, EPI_SPLIT2, st));
+      RUN_NT(g, EPI_SPLIT2);
       GemmTNArgs gw = dw(l, g_cur, x_prev, T);
       gw.ldx = C; gw.X2 = x_enc; gw.ldx2 = C; gw.K1 = C;
-      RUN(gemm_tn(gw, st));
+      RUN_TN(gw);
       std::swap(g_cur, g_alt);
     }
   }
@@ -631,8 +690,8 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       const Linear& l = linears[merge_lin[s]];
       const bf16* x_stage_out = c.A(p.blocks[enc_blocks[s].back()].xout);
       GemmArgs g = nt_args(g_cur, 2 * C, c.Wt(l), 2 * C, T / 4, 4 * C, 2 * C, nullptr, c.A(p.scr_big), 4 * C);
-      RUN(gemm_nt(g, EPI_STORE, st));
-      RUN(gemm_tn(dw(l, g_cur, c.A(p.xn_m[s]), T / 4), st));
+      RUN_NT(g, EPI_STORE);
+      RUN_TN(dw(l, g_cur, c.A(p.xn_m[s]), T / 4));
       RUN(ln_bwd(x_stage_out, merge_nw[s], merge_nb[s], c.F(p.st_m[s]), c.A(p.scr_big), nullptr, g_alt, T / 4, 4 * C, 1, Hs / 2,
                  Ws / 2));
       std::swap(g_cur, g_alt);
@@ -643,6 +702,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       rc = block_bwd(bi, x_in, g_cur, g_alt);
       if (rc) return rc;
     }
+    tag(K_ELEMWISE, 0, 6.0 * T * C);
     if (s < L - 1) RUN(add_inplace_bf16(g_cur, c.A(p.g_save[s]), (long)T * C, st));     // skip-connection gradient (tulip.py:708,715)
   }
   {
@@ -651,6 +711,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     e.x = x_lo; e.w = c.P(slot_pe_w); e.b = c.P(slot_pe_b); e.ln_w = c.P(slot_pe_nw); e.ln_b = c.P(slot_pe_nb);
     e.B = B; e.Himg = cfg.img_h; e.Wimg = cfg.img_w; e.ph = cfg.patch_h; e.E = E; e.eps = cfg.ln_eps;
     e.dy = g_cur; e.dw = c.G(slot_pe_w); e.db = c.G(slot_pe_b); e.dln_w = c.G(slot_pe_nw); e.dln_b = c.G(slot_pe_nb);
+    tag(K_EMBED_BWD, 0, 4.0 * B * cfg.img_h * cfg.img_w + 2.0 * B * H0 * W0 * E);
     RUN(patch_embed_bwd(e, st));
   }
   return TULIP_OK;

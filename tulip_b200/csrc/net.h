@@ -9,6 +9,24 @@
 #include "gemm.cuh"
 #include "kernels.h"
 
+// kernel-function tags for the built-in per-launch profiler (bench.py roofline section)
+enum KTag : int {
+  K_MISC = 0, K_NT_STORE, K_NT_GELU, K_NT_RESID, K_NT_PIXSHUF, K_NT_SPLIT2, K_NT_DGELU, K_NT_HEAD, K_NT_HEAD_BWD, K_NT_ROWSCALE,
+  K_NT_UNSHUFFLE, K_TN, K_TN_UNSHUFFLE, K_ATTN_FWD, K_ATTN_BWD, K_LN_FWD, K_LN_BWD, K_EMBED_FWD, K_EMBED_BWD, K_PACK,
+  K_ELEMWISE, K_LOSS, K_COUNT
+};
+const char* ktag_name(int tag);
+inline int nt_tag(int epi) {
+  switch (epi) {
+    case EPI_STORE: return K_NT_STORE; case EPI_GELU: return K_NT_GELU; case EPI_RESID: return K_NT_RESID;
+    case EPI_PIXSHUF: return K_NT_PIXSHUF; case EPI_SPLIT2: return K_NT_SPLIT2; case EPI_DGELU: return K_NT_DGELU;
+    case EPI_HEAD: return K_NT_HEAD; case EPI_HEAD_BWD: return K_NT_HEAD_BWD; case EPI_ROWSCALE: return K_NT_ROWSCALE;
+  }
+  return K_MISC;
+}
+
+struct ProfRec { int tag; double flops, bytes; cudaEvent_t e0, e1; };
+
 struct ParamInfo {
   std::string name;
   int ndim;
@@ -63,7 +81,16 @@ struct tulip_net {
   float* faux = nullptr; long faux_elems = 0;
   PackItem* items_dev = nullptr; int n_items = 0, n_tiles = 0;
   std::vector<long> items_offsets_cache;           // parameter offsets the uploaded pack table was built for
-  long gemm_launches = 0, kernel_launches = 0;
+  long kernel_launches = 0;
+  // per-launch profiler (off by default; adds two cudaEventRecord per launch when on)
+  bool profiling = false;
+  int cur_tag = K_MISC; double cur_flops = 0, cur_bytes = 0;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  void tag(int t, double flops, double bytes) { cur_tag = t; cur_flops = flops; cur_bytes = bytes; }
+  void prof_begin(cudaStream_t st);
+  void prof_end(cudaStream_t st);
+  void prof_reset();
 
   int build();
   int ensure_device();
