@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128) gemm_nt_mma_kernel(const GemmArgs g) {
           const int m = m0 + warp * 32 + mt * 16 + hf * 8 + gq;
           if (tq == 0 && m < g.M) {
             float* p = g.pred + head_pixel(g, m, ij);
-            if (g.hd_E == BN) *p = s; else atomicAdd(p, s);
+            if (g.hd_E == BN) *p = s; else atomicAdd(p, s);           // E > 96: pred is zeroed by the caller
           }
         }
     } else {

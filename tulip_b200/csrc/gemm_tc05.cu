@@ -1,4 +1,709 @@
-// tcgen05 / TMEM / TMA GEMMs -- placeholder until the kernels land; every shape falls back to gemm_mma.cu.
+// tcgen05 / TMEM / TMA GEMMs for sm_100a.
+//
+// NT: out[M,N] = A[M,K] . B[N,K]^T with fused epilogues (gemm.cuh).  Persistent, warp-specialised CTA:
+//   warp 0      TMA producer: A (128 x 64) and B (BN x 64) bf16 tiles, 128B-swizzled, mbarrier ring; also prefetches
+//               the epilogue's auxiliary tile (residual / GELU pre-activation) into shared memory
+//   warp 1      MMA issuer: one elected lane, tcgen05.mma cta_group::1 M=128 N=BN K=16, fp32 accumulators in TMEM
+//   warps 2..13 epilogue (12 warps: the erf / exp math of the GELU epilogues needs the issue slots): tcgen05.ld (one
+//               accumulator row per thread, one 32-column box per warp) -> bias / GELU / residual -> bf16 tile in shared
+//               memory (64B-swizzled) -> TMA store.  Scatter epilogues (PixelShuffle, split, head) store directly.
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the loads and MMAs of tile i+1.
+// K is walked in 64-column blocks per *segment*; TMA's out-of-bounds zero fill pads K = 96 / 288 to the block size and
+// makes the two-source concat (skip Linear) and the PixelShuffle-backward gather (5-D tensor map) plain coordinates.
 #include "gemm.cuh"
-int gemm_nt_tc05(const GemmArgs&, int, cudaStream_t) { return TULIP_ERR_UNSUPPORTED; }
-int gemm_tn_tc05(const GemmTNArgs&, cudaStream_t) { return TULIP_ERR_UNSUPPORTED; }
+#include "tc05.cuh"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+constexpr int BM = 128, BK = 64;
+constexpr int EPI_WARPS = 12, EPI_GROUPS = 3, THREADS = 64 + 32 * EPI_WARPS;   // 3 warps per TMEM lane quarter, one column box each
+constexpr int BOXC = 32;                                   // output / aux staging box: 32 bf16 columns (64 B rows, SWIZZLE_64B)
+constexpr int BOX_BYTES = BM * BOXC * 2;                   // 8 KB
+
+struct Segments {
+  int n;                 // K segments (1 plain, 2 concat, 4 unshuffle)
+  int len[4];            // columns of A in the segment
+  int amap[4];           // 0: mapA, 1: mapA2
+  int bcol[4];           // first column of B for the segment
+  int sj[4], si[4];      // (j, i) of the shuffle slot for the 5-D gather map
+  int a5d;               // A map is the 5-D PixelShuffle-backward view
+  int gW;                // 5-D: grid width W
+};
+
+struct Maps {
+  CUtensorMap A, A2, B, out, out2, aux;
+};
+
+__host__ __device__ constexpr bool epi_tma_out(int epi) {
+  return epi == EPI_STORE || epi == EPI_GELU || epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_HEAD_BWD;
+}
+__host__ __device__ constexpr bool epi_has_aux(int epi) { return epi == EPI_RESID || epi == EPI_DGELU; }
+
+template <int BN, int EPI>
+struct Cfg {
+  static constexpr bool TMA_OUT = epi_tma_out(EPI);
+  static constexpr bool HAS_AUX = epi_has_aux(EPI);
+  static constexpr int NBOX = BN / BOXC;
+  static constexpr int TILE_BYTES = NBOX * BOX_BYTES;                       // bf16 [128, BN]
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OUT_BUFS = TMA_OUT ? 2 : 0;                          // GELU uses both per tile (pre, act)
+  static constexpr int AUX_BUFS = HAS_AUX ? (BN <= 96 ? 2 : 1) : 0;
+  static constexpr int STAGES = (BN <= 96) ? 4 : ((OUT_BUFS + AUX_BUFS) * TILE_BYTES > 100 * 1024 ? 2 : 3);
+  static constexpr int OUT_OFF = STAGES * STAGE_BYTES;
+  static constexpr int AUX_OFF = OUT_OFF + OUT_BUFS * TILE_BYTES;
+  static constexpr int RED_OFF = AUX_OFF + AUX_BUFS * TILE_BYTES;           // EPI_HEAD: [2][EPI_GROUPS][128] fp32 partial sums
+  static constexpr int BAR_OFF = RED_OFF + (EPI == EPI_HEAD ? 2 * EPI_GROUPS * BM * 4 : 0);
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;                        // barriers + tmem slot, +1024 manual alignment
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+};
+
+// byte offset of logical 16-byte chunk c (0..3) of row r inside a [128 x 32] bf16 SWIZZLE_64B box
+__device__ __forceinline__ int box_off(int r, int c) { return r * 64 + ((c ^ ((r >> 1) & 3)) << 4); }
+
+__device__ __forceinline__ void store_box_row(unsigned char* box, int r, const float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(box + box_off(r, c)) =
+        make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]), pack_bf16(v[8 * c + 4], v[8 * c + 5]),
+                   pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+}
+__device__ __forceinline__ void load_box_row(const unsigned char* box, int r, float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(box + box_off(r, c));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 f = unpack_bf16(w[q]);
+      v[8 * c + 2 * q] = f.x;
+      v[8 * c + 2 * q + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void add_bias32(const float* __restrict__ bias, int n, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + n + 4 * q);
+    v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+  }
+}
+
+// direct-store epilogues (scatter destinations): 16 consecutive columns of one row
+template <int EPI>
+__device__ __forceinline__ void epi_direct16(const GemmArgs& g, int m, int n, float (&v)[16]) {
+  bf16* dst = nullptr;
+  if (EPI == EPI_PIXSHUF) {
+    if (g.bias) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += g.bias[n + i];
+    }
+    const int ij = n / g.g_Cc, c = n % g.g_Cc;
+    dst = g.out + pixshuf_row(m, ij, g.g_H, g.g_W) * g.ldo + c;
+  } else if (EPI == EPI_SPLIT2) {
+    dst = n < g.split_col ? g.out + (long)m * g.ldo + n : g.out2 + (long)m * g.ldo2 + (n - g.split_col);
+  } else {  // EPI_ROWSCALE
+    const float s = g.row_scale ? g.row_scale[m / g.rows_per_sample] : 1.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= s;
+    dst = g.out + (long)m * g.ldo + n;
+  }
+  uint4* p = reinterpret_cast<uint4*>(dst);
+  p[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  p[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const Segments sg, int tiles_m, int tiles_n) {
+  using CF = Cfg<BN, EPI>;
+  constexpr int STAGES = CF::STAGES;
+  constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + CF::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* afull = tempty + 2;
+  uint64_t* aempty = afull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tfull + b, 1); tc::mbar_init(tempty + b, EPI_WARPS);
+      tc::mbar_init(afull + b, 1); tc::mbar_init(aempty + b, EPI_WARPS);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = tiles_m * tiles_n;
+  int kblocks = 0;
+  for (int s = 0; s < sg.n; ++s) kblocks += (sg.len[s] + BK - 1) / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::prefetch_tensormap(&maps.A);
+      tc::prefetch_tensormap(&maps.B);
+      int stage = 0; uint32_t phase = 0;
+      int abuf = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        if (CF::HAS_AUX) {                                  // residual / pre-activation tile for the epilogue
+          tc::mbar_wait(aempty + abuf, aphase ^ 1);
+          unsigned char* ab = smem + CF::AUX_OFF + abuf * CF::TILE_BYTES;
+          tc::mbar_expect_tx(afull + abuf, CF::TILE_BYTES);
+#pragma unroll
+          for (int j = 0; j < CF::NBOX; ++j) tc::tma_load_2d(ab + j * BOX_BYTES, &maps.aux, afull + abuf, n0 + j * BOXC, m0);
+          if (++abuf == CF::AUX_BUFS) { abuf = 0; aphase ^= 1; }
+        }
+        for (int s = 0; s < sg.n; ++s) {
+          const int nb = (sg.len[s] + BK - 1) / BK;
+          for (int kb = 0; kb < nb; ++kb) {
+            tc::mbar_wait(empty + stage, phase ^ 1);
+            unsigned char* a = smem + stage * CF::STAGE_BYTES;
+            unsigned char* b = a + CF::A_BYTES;
+            tc::mbar_expect_tx(full + stage, CF::STAGE_BYTES);
+            if (sg.a5d) {
+              const int bh0 = m0 / sg.gW, w0 = m0 % sg.gW;
+              tc::tma_load_5d(a, &maps.A, full + stage, kb * BK, sg.sj[s], w0, sg.si[s], bh0);
+            } else {
+              tc::tma_load_2d(a, sg.amap[s] ? &maps.A2 : &maps.A, full + stage, kb * BK, m0);
+            }
+            tc::tma_load_2d(b, &maps.B, full + stage, sg.bcol[s] + kb * BK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(BM, BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int buf = 0; uint32_t tphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        tc::mbar_wait(tempty + buf, tphase ^ 1);             // epilogue has drained this accumulator buffer
+        tc::fence_after_sync();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          tc::mbar_wait(full + stage, phase);
+          tc::fence_after_sync();
+          const unsigned char* a = smem + stage * CF::STAGE_BYTES;
+          const uint64_t da = tc::make_desc_kmajor_sw128(a);
+          const uint64_t db = tc::make_desc_kmajor_sw128(a + CF::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)                   // +32 bytes per K=16 step inside the 128B swizzle atom
+            tc::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          tc::umma_commit(empty + stage);                     // smem slot free once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc::umma_commit(tfull + buf);                         // accumulator complete
+        if (++buf == 2) { buf = 0; tphase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+    const int jgrp = (warp - 2) >> 2;                         // which column boxes of the tile this warp handles
+    const int r = q * 32 + lane;                              // row inside the tile
+    const bool issuer = (threadIdx.x == 64);                  // first epilogue thread drives the TMA stores
+    float cwacc[(CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS][32];   // HEAD_BWD: per-thread column sums for d(decoder_pred.weight)
+    if (EPI == EPI_HEAD_BWD) {
+#pragma unroll
+      for (int a = 0; a < (CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS; ++a)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cwacc[a][i] = 0.f;
+    }
+    int buf = 0; uint32_t tphase = 0;
+    int abuf = 0; uint32_t aphase = 0;
+    int obuf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int m = m0 + r;
+      tc::mbar_wait(tfull + buf, tphase);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+
+      if (CF::TMA_OUT) {
+        // staging buffer(s) must have been read out by the previous TMA store(s)
+        if (issuer) { if (EPI == EPI_GELU) tc::tma_store_wait_read<0>(); else tc::tma_store_wait_read<1>(); }
+        tc::named_bar_sync(1, 32 * EPI_WARPS);
+        unsigned char* ob = smem + CF::OUT_OFF + (EPI == EPI_GELU ? 0 : obuf) * CF::TILE_BYTES;
+        unsigned char* ob2 = smem + CF::OUT_OFF + CF::TILE_BYTES;                     // GELU: activation tile
+        const unsigned char* ab = smem + CF::AUX_OFF + abuf * CF::TILE_BYTES;
+        if (CF::HAS_AUX) tc::mbar_wait(afull + abuf, aphase);
+        float dp = 0.f;
+        int ij = 0, c0 = 0;
+        if (EPI == EPI_HEAD_BWD) {
+          ij = n0 / g.hd_E; c0 = n0 % g.hd_E;
+          if (m < g.M) {
+            const long px = head_pixel(g, m, ij);
+            const float d = g.pred[px] - g.target[px];
+            const float gs = g.gscale[0] * g.hd_inv_npix;
+            dp = d > 0.f ? gs : (d < 0.f ? -gs : 0.f);
+          }
+        }
+        const float rs = (EPI == EPI_RESID && g.row_scale) ? g.row_scale[(m < g.M ? m : g.M - 1) / g.rows_per_sample] : 1.0f;
+#pragma unroll
+        for (int jj = 0; jj < (CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS; ++jj) {
+          const int j = jgrp + jj * EPI_GROUPS;
+          if (j >= CF::NBOX) break;
+          float v[32];
+          tc::tmem_ld32(taddr + j * BOXC, v);
+          const int n = n0 + j * BOXC;
+          if (EPI == EPI_STORE) {
+            if (g.bias) add_bias32(g.bias, n, v);
+          } else if (EPI == EPI_GELU) {
+            add_bias32(g.bias, n, v);
+            if (g.out2) store_box_row(ob + j * BOX_BYTES, r, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          } else if (EPI == EPI_RESID) {
+            if (g.bias) add_bias32(g.bias, n, v);
+            float a[32];
+            load_box_row(ab + j * BOX_BYTES, r, a);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = a[i] + rs * v[i];
+          } else if (EPI == EPI_DGELU) {
+            float a[32];
+            load_box_row(ab + j * BOX_BYTES, r, a);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad(a[i]);
+          } else if (EPI == EPI_HEAD_BWD) {
+            // dh = dpred * wd[c] * leaky'(pre);  dwd[c] += sum_rows dpred * leaky(pre)  (summed per thread across tiles)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float pre = v[i] + g.bias[n + i];
+              cwacc[jj][i] += dp * leaky(pre);
+              v[i] = dp * g.wd[c0 + j * BOXC + i] * (pre > 0.f ? 1.f : 0.01f);
+            }
+          }
+          store_box_row((EPI == EPI_GELU ? ob2 : ob) + j * BOX_BYTES, r, v);
+        }
+        // accumulator and aux tile consumed: release them before the (slower) store path
+        tc::fence_before_sync();
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tc::mbar_arrive(tempty + buf);
+          if (CF::HAS_AUX) tc::mbar_arrive(aempty + abuf);
+        }
+        tc::named_bar_sync(1, 32 * EPI_WARPS);
+        if (issuer) {
+          if (EPI == EPI_GELU) {
+            if (g.out2) {
+#pragma unroll
+              for (int j = 0; j < CF::NBOX; ++j) tc::tma_store_2d(&maps.out2, ob + j * BOX_BYTES, n0 + j * BOXC, m0);
+            }
+#pragma unroll
+            for (int j = 0; j < CF::NBOX; ++j) tc::tma_store_2d(&maps.out, ob2 + j * BOX_BYTES, n0 + j * BOXC, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CF::NBOX; ++j) tc::tma_store_2d(&maps.out, ob + j * BOX_BYTES, n0 + j * BOXC, m0);
+          }
+          tc::tma_store_commit();
+        }
+        obuf ^= 1;
+        if (CF::HAS_AUX) { if (++abuf == CF::AUX_BUFS) { abuf = 0; aphase ^= 1; } }
+      } else if (EPI == EPI_HEAD) {
+        // tile = 128 low-res pixels x 96 expanded channels n' = ij*E + c of one shuffle slot (tulip.py:174-178, 731)
+        const int ij = n0 / g.hd_E, c0 = n0 % g.hd_E;
+        float acc = 0.f;
+#pragma unroll 1
+        for (int j = jgrp; j < CF::NBOX; j += EPI_GROUPS) {
+          float v[32];
+          tc::tmem_ld32(taddr + j * BOXC, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc += g.wd[c0 + j * BOXC + i] * leaky(v[i] + g.bias[n0 + j * BOXC + i]);
+        }
+        // deterministic sum of the 3 column groups of a row through shared memory (double-buffered by tile parity)
+        float* red = reinterpret_cast<float*>(smem + CF::RED_OFF) + obuf * EPI_GROUPS * BM;
+        red[jgrp * BM + r] = acc;
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty + buf);
+        tc::named_bar_sync(1, 32 * EPI_WARPS);
+        if (jgrp == 0 && m < g.M) {
+          float sum = red[r];
+#pragma unroll
+          for (int a = 1; a < EPI_GROUPS; ++a) sum += red[a * BM + r];
+          float* p = g.pred + head_pixel(g, m, ij);
+          if (g.hd_E == BN) *p = sum; else atomicAdd(p, sum);
+        }
+        obuf ^= 1;
+      } else {
+#pragma unroll 1
+        for (int ch = 2 * jgrp; ch < BN / 16; ch += 2 * EPI_GROUPS) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float v[16];
+            tc::tmem_ld16(taddr + (ch + h) * 16, v);
+            if (m < g.M) epi_direct16<EPI>(g, m, n0 + (ch + h) * 16, v);
+          }
+        }
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty + buf);
+      }
+      if (++buf == 2) { buf = 0; tphase ^= 1; }
+    }
+    if (EPI == EPI_HEAD_BWD) {
+      // hd_E == BN on this path (checked by the launcher), so every tile of this CTA covers channels c = 0..95
+#pragma unroll
+      for (int jj = 0; jj < (CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS; ++jj) {
+        const int j = jgrp + jj * EPI_GROUPS;
+        if (j < CF::NBOX) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float cw = warp_sum(cwacc[jj][i]);
+            if (lane == i) atomicAdd(g.dwd + j * BOXC + i, cw);
+          }
+        }
+      }
+    }
+    if (CF::TMA_OUT && issuer) tc::tma_store_wait<0>();       // global writes complete before the CTA retires
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+bool tc05_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TULIP_B200_NO_TC05");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <int BN, int EPI>
+int launch(const Maps& maps, const GemmArgs& g, const Segments& sg, cudaStream_t st) {
+  using CF = Cfg<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    TULIP_CUDA(cudaFuncSetAttribute(gemm_nt_tc05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::TOTAL));
+    configured = true;
+  }
+  const int tiles_m = ceil_div(g.M, BM), tiles_n = g.N / BN;
+  const int grid = min(tiles_m * tiles_n, tulip_num_sms());
+  gemm_nt_tc05_kernel<BN, EPI><<<grid, THREADS, CF::TOTAL, st>>>(maps, g, sg, tiles_m, tiles_n);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+template <int EPI>
+int launch_bn(int bn, const Maps& maps, const GemmArgs& g, const Segments& sg, cudaStream_t st) {
+  if (bn == 192) return launch<192, EPI>(maps, g, sg, st);
+  return launch<96, EPI>(maps, g, sg, st);
+}
+
+int make_io_map(CUtensorMap* map, const void* base, long ld, int M, int N) {
+  // [M, N] bf16 row-major viewed in 32-column boxes of 128 rows, 64B swizzle (epilogue staging layout)
+  const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+  const uint64_t str[1] = {(uint64_t)ld * 2};
+  const uint32_t box[2] = {BOXC, BM};
+  return tulip_make_tmap(map, base, 2, dims, str, box, 64);
+}
+
+}  // namespace
+
+tulip_tmap_encode_fn tulip_tmap_encoder() {
+  static tulip_tmap_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<tulip_tmap_encode_fn>(p);
+  }
+  return fn;
+}
+
+int tulip_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle_bytes) {
+  tulip_tmap_encode_fn enc = tulip_tmap_encoder();
+  TULIP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tulip_set_error("cuTensorMapEncodeTiled failed");
+    return TULIP_ERR_CUDA;
+  }
+  return TULIP_OK;
+}
+
+int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
+  if (tc05_disabled()) return TULIP_ERR_UNSUPPORTED;
+  if (g.N % 96 || g.K % 8 || g.M <= 0) return TULIP_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15) || (g.lda % 8) || (g.ldb % 8))
+    return TULIP_ERR_UNSUPPORTED;
+  const bool head = (epi == EPI_HEAD || epi == EPI_HEAD_BWD);
+  if (epi == EPI_HEAD_BWD && g.hd_E != 96) return TULIP_ERR_UNSUPPORTED;      // per-CTA dwd accumulation assumes one 96-channel group
+  // wide tiles only where the problem is tensor-bound (deep K) and there are enough tiles to fill the chip
+  const int bn = (!head && g.N % 192 == 0 && g.K >= 384 && (long)ceil_div(g.M, BM) * (g.N / 192) >= tulip_num_sms()) ? 192 : 96;
+
+  Segments sg;
+  memset(&sg, 0, sizeof sg);
+  Maps maps;
+  memset(&maps, 0, sizeof maps);
+  int rc;
+  if (g.a_mode == A_UNSHUFFLE) {
+    // A[m=(b,h,w), k=ij*Cc+c] = src[b, 2h+i, 2w+j, c]  as a 5-D view (c, j, w, i, bh) of the [B,2H,2W,Cc] tensor
+    const int W = g.g_W, Cc = g.g_Cc;
+    if (!((W >= BM && W % BM == 0) || (W < BM && BM % W == 0)) || g.M % W || Cc % 8) return TULIP_ERR_UNSUPPORTED;
+    const uint64_t dims[5] = {(uint64_t)Cc, 2, (uint64_t)W, 2, (uint64_t)(g.M / W)};
+    const uint64_t str[4] = {(uint64_t)Cc * 2, (uint64_t)2 * Cc * 2, (uint64_t)2 * W * Cc * 2, (uint64_t)4 * W * Cc * 2};
+    const uint32_t box[5] = {64, 1, (uint32_t)(W >= BM ? BM : W), 1, (uint32_t)(W >= BM ? 1 : BM / W)};
+    rc = tulip_make_tmap(&maps.A, g.A, 5, dims, str, box);
+    if (rc) return rc;
+    maps.A2 = maps.A;
+    sg.n = 4; sg.a5d = 1; sg.gW = W;
+    for (int s = 0; s < 4; ++s) { sg.len[s] = Cc; sg.bcol[s] = s * Cc; sg.sj[s] = s & 1; sg.si[s] = s >> 1; }
+  } else {
+    const int K1 = g.K1 < g.K ? g.K1 : g.K;
+    const uint64_t dims[2] = {(uint64_t)K1, (uint64_t)g.M};
+    const uint64_t str[1] = {(uint64_t)g.lda * 2};
+    const uint32_t box[2] = {64, BM};
+    rc = tulip_make_tmap(&maps.A, g.A, 2, dims, str, box);
+    if (rc) return rc;
+    maps.A2 = maps.A;
+    sg.n = 1; sg.len[0] = K1; sg.amap[0] = 0; sg.bcol[0] = 0;
+    if (K1 < g.K) {
+      if ((reinterpret_cast<uintptr_t>(g.A2) & 15) || (g.lda2 % 8)) return TULIP_ERR_UNSUPPORTED;
+      const uint64_t dims2[2] = {(uint64_t)(g.K - K1), (uint64_t)g.M};
+      const uint64_t str2[1] = {(uint64_t)g.lda2 * 2};
+      rc = tulip_make_tmap(&maps.A2, g.A2, 2, dims2, str2, box);
+      if (rc) return rc;
+      sg.n = 2; sg.len[1] = g.K - K1; sg.amap[1] = 1; sg.bcol[1] = K1;
+    }
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
+    const uint64_t str[1] = {(uint64_t)g.ldb * 2};
+    const uint32_t box[2] = {64, (uint32_t)bn};
+    rc = tulip_make_tmap(&maps.B, g.B, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  maps.out = maps.out2 = maps.aux = maps.B;
+  if (epi_tma_out(epi)) {
+    if ((reinterpret_cast<uintptr_t>(g.out) & 15) || (g.ldo % 8)) return TULIP_ERR_UNSUPPORTED;
+    rc = make_io_map(&maps.out, g.out, g.ldo, g.M, g.N);
+    if (rc) return rc;
+    if (epi == EPI_GELU && g.out2) {
+      if ((reinterpret_cast<uintptr_t>(g.out2) & 15) || (g.ldo2 % 8)) return TULIP_ERR_UNSUPPORTED;
+      rc = make_io_map(&maps.out2, g.out2, g.ldo2, g.M, g.N);
+      if (rc) return rc;
+    }
+    if (epi_has_aux(epi)) {
+      if (!g.aux || (reinterpret_cast<uintptr_t>(g.aux) & 15) || (g.ldaux % 8)) return TULIP_ERR_UNSUPPORTED;
+      rc = make_io_map(&maps.aux, g.aux, g.ldaux, g.M, g.N);
+      if (rc) return rc;
+    }
+  }
+  switch (epi) {
+    case EPI_STORE: return launch_bn<EPI_STORE>(bn, maps, g, sg, st);
+    case EPI_GELU: return launch_bn<EPI_GELU>(bn, maps, g, sg, st);
+    case EPI_RESID: return launch_bn<EPI_RESID>(bn, maps, g, sg, st);
+    case EPI_PIXSHUF: return launch_bn<EPI_PIXSHUF>(bn, maps, g, sg, st);
+    case EPI_SPLIT2: return launch_bn<EPI_SPLIT2>(bn, maps, g, sg, st);
+    case EPI_DGELU: return launch_bn<EPI_DGELU>(bn, maps, g, sg, st);
+    case EPI_ROWSCALE: return launch_bn<EPI_ROWSCALE>(bn, maps, g, sg, st);
+    case EPI_HEAD: return launch<96, EPI_HEAD>(maps, g, sg, st);
+    case EPI_HEAD_BWD: return launch<96, EPI_HEAD_BWD>(maps, g, sg, st);
+  }
+  return TULIP_ERR_UNSUPPORTED;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// TN: dW[N,K] += dY[M,N]^T . X[M,K]  (+ db[N] += colsum(dY)) -- weight gradients.
+// Both operands are MN-major for the tensor core (the contraction runs over tokens, the strided dimension), which
+// tcgen05 takes directly from 128B-swizzled TMA boxes {64 columns, 64 tokens}.  One CTA owns a 128-row x <=192-column
+// block of dW in TMEM for a slice of the tokens; the bias gradient rides along as one extra B block whose first column
+// is all ones.  Slices are combined with vectorised fp32 reductions (red.global.add.v4.f32) into the flat gradient.
+namespace {
+
+constexpr int TN_TOK = 64;                  // tokens per pipeline stage (4 UMMA K-steps)
+constexpr int TN_STAGES = 4;
+constexpr int TN_MAXB = 4;                  // B boxes per stage: up to 3 data boxes (192 columns of X) + the ones box
+constexpr int TN_BOX = 64 * TN_TOK * 2;     // 8 KB
+constexpr int TN_STAGE_BYTES = (2 + 3) * TN_BOX;          // A: 2 boxes (128 dW rows), B: up to 3 boxes
+constexpr int TN_ONES_OFF = TN_STAGES * TN_STAGE_BYTES;
+constexpr int TN_BAR_OFF = TN_ONES_OFF + TN_BOX;
+constexpr int TN_SMEM = TN_BAR_OFF + 256 + 1024;
+constexpr int TN_THREADS = 256;
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(TN_THREADS, 1)
+gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX, const GemmTNArgs g,
+                    int kcols_per_tile, int tok_blocks_per_split) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TN_BAR_OFF);
+  uint64_t* empty = full + TN_STAGES;
+  uint64_t* done = empty + TN_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int n0 = blockIdx.x * 128;                               // first dW row of this CTA
+  const int k0 = blockIdx.y * kcols_per_tile;                    // first dW column
+  const int kvalid = min(kcols_per_tile, g.K - k0);
+  const int nbx = (kvalid + 63) / 64;                            // data boxes of X per stage
+  const bool with_db = (g.db != nullptr) && blockIdx.y == 0;
+  const int nb = nbx + (with_db ? 1 : 0);                        // B blocks per MMA (N_u = 64 * nb)
+  const int tb_total = (g.M + TN_TOK - 1) / TN_TOK;
+  const int tb_begin = blockIdx.z * tok_blocks_per_split;
+  const int tb_end = min(tb_total, tb_begin + tok_blocks_per_split);
+  const int ntb = tb_end - tb_begin;
+  if (ntb <= 0) return;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TN_STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
+    tc::mbar_init(done, 1);
+    tc::fence_barrier_init();
+  }
+  if (with_db) {
+    // ones block: B[k = column 0 of this block, token] = 1, every other column 0 (MN-major, 128B-swizzled rows of 64 columns)
+    uint4* ones = reinterpret_cast<uint4*>(smem + TN_ONES_OFF);
+    for (int i = threadIdx.x; i < TN_BOX / 16; i += TN_THREADS) {
+      const int row = i >> 3, chunk = i & 7;                     // physical 16B chunk `chunk` of token row `row`
+      const int logical = chunk ^ (row & 7);
+      ones[i] = make_uint4(logical == 0 ? 0x00003F80u : 0u, 0u, 0u, 0u);     // bf16(1.0) in element 0
+    }
+    tc::fence_proxy_async();
+  }
+  if (warp == 1) tc::tmem_alloc<256>(tmem_slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tb = tb_begin; tb < tb_end; ++tb) {
+        tc::mbar_wait(empty + stage, phase ^ 1);
+        unsigned char* a = smem + stage * TN_STAGE_BYTES;
+        tc::mbar_expect_tx(full + stage, (2 + nbx) * TN_BOX);
+        tc::tma_load_2d(a, &mapY, full + stage, n0, tb * TN_TOK);
+        tc::tma_load_2d(a + TN_BOX, &mapY, full + stage, n0 + 64, tb * TN_TOK);
+        for (int j = 0; j < nbx; ++j) tc::tma_load_2d(a + (2 + j) * TN_BOX, &mapX, full + stage, k0 + 64 * j, tb * TN_TOK);
+        if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_x = tc::make_idesc(128, 64 * nbx, 1, 1);
+      const uint32_t idesc_1 = tc::make_idesc(128, 64, 1, 1);
+      const uint64_t d_ones = tc::make_desc_mnmajor_sw128(smem + TN_ONES_OFF, TN_BOX);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntb; ++t) {
+        tc::mbar_wait(full + stage, phase);
+        tc::fence_after_sync();
+        const unsigned char* a = smem + stage * TN_STAGE_BYTES;
+        const uint64_t da = tc::make_desc_mnmajor_sw128(a, TN_BOX);
+        const uint64_t db = tc::make_desc_mnmajor_sw128(a + 2 * TN_BOX, TN_BOX);
+#pragma unroll
+        for (int k = 0; k < TN_TOK / 16; ++k) {                   // 16 tokens = 2 groups of 8 rows = 2048 B per K-step
+          const uint32_t acc = (t | k) ? 1u : 0u;
+          tc::umma_bf16(tmem_base, da + 128 * k, db + 128 * k, idesc_x, acc);
+          if (with_db) tc::umma_bf16(tmem_base + 64 * nbx, da + 128 * k, d_ones + 128 * k, idesc_1, acc);
+        }
+        tc::umma_commit(empty + stage);
+        if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc::umma_commit(done);
+    }
+  }
+  // epilogue: every warp drains its TMEM lane quarter; the two warps of a quarter split the columns
+  __syncwarp();
+  tc::mbar_wait(done, 0);
+  tc::fence_after_sync();
+  {
+    const int q = warp & 3, half = warp >> 2;
+    const int n = n0 + q * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool row_ok = n < g.N;
+    const int row = (g.perm_R2 > 1) ? (n % g.perm_Cc) * g.perm_R2 + n / g.perm_Cc : n;
+    float* drow = g.dW + (long)row * g.lddw + k0;
+    const int nchunks = (kvalid + 31) / 32;
+    for (int ch = half; ch < nchunks; ch += 2) {
+      float v[32];
+      tc::tmem_ld32(taddr + ch * 32, v);
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          if (ch * 32 + i < kvalid) red_add_v4(drow + ch * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+    if (with_db && half == 1) {
+      float v[16];
+      tc::tmem_ld16(taddr + 64 * nbx, v);
+      if (row_ok) atomicAdd(g.db + row, v[0]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<256>(tmem_base);
+}
+
+}  // namespace
+
+int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st) {
+  if (tc05_disabled()) return TULIP_ERR_UNSUPPORTED;
+  if (g.y_mode != A_PLAIN || g.K1 < g.K || g.M <= 0) return TULIP_ERR_UNSUPPORTED;
+  if (g.N % 8 || g.K % 8 || (g.ldy % 8) || (g.ldx % 8) || (g.lddw % 4) || (g.K % 4)) return TULIP_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(g.dY) & 15) || (reinterpret_cast<uintptr_t>(g.X) & 15) || (reinterpret_cast<uintptr_t>(g.dW) & 15))
+    return TULIP_ERR_UNSUPPORTED;
+  CUtensorMap mY, mX;
+  {
+    const uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.M};
+    const uint64_t str[1] = {(uint64_t)g.ldy * 2};
+    const uint32_t box[2] = {64, TN_TOK};
+    int rc = tulip_make_tmap(&mY, g.dY, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.M};
+    const uint64_t str[1] = {(uint64_t)g.ldx * 2};
+    const uint32_t box[2] = {64, TN_TOK};
+    int rc = tulip_make_tmap(&mX, g.X, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    TULIP_CUDA(cudaFuncSetAttribute(gemm_tn_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
+    configured = true;
+  }
+  const int kcols = 192;
+  const int n_tiles = ceil_div(g.N, 128), k_tiles = ceil_div(g.K, kcols);
+  const int tb_total = ceil_div(g.M, TN_TOK);
+  int splits = tulip_num_sms() / (n_tiles * k_tiles);
+  if (splits < 1) splits = 1;
+  if (splits > tb_total) splits = tb_total;
+  const int per = ceil_div(tb_total, splits);
+  splits = ceil_div(tb_total, per);
+  dim3 grid(n_tiles, k_tiles, splits);
+  gemm_tn_tc05_kernel<<<grid, TN_THREADS, TN_SMEM, st>>>(mY, mX, g, kcols, per);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}

@@ -508,7 +508,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
   RUN(ln(x, slot_normup_w, slot_normup_b, c.A(p.xn_up), c.F(p.st_up), T0, E, 0, 0, 0));
   {
     const Linear& l = linears[head_lin];
-    if (E != 96) TULIP_CUDA(cudaMemsetAsync(pred, 0, (size_t)T0 * r * r * sizeof(float), st));
+    if (E != 96) TULIP_CUDA(cudaMemsetAsync(pred, 0, (size_t)T0 * r * r * sizeof(float), st));   // partial sums over channel groups
     GemmArgs g = nt_args(c.A(p.xn_up), E, c.W(l), E, T0, E * r * r, E, c.bias(l), nullptr, 0);
     g.wd = c.P(slot_dec_w); g.pred = pred; g.hd_H = H0; g.hd_W = W0; g.hd_r = r; g.hd_E = E;
     RUN_NT(g, EPI_HEAD);
