@@ -180,12 +180,16 @@ def run_ours(args, rank, world, local_rank):
     lo_pin, hi_pin = lo_h.pin_memory(), hi_h.pin_memory()
     lo_d, hi_d = lo_pin.to(dev), hi_pin.to(dev)
 
-    def step(lo, hi):
+    def local_step(lo, hi):
         model.zero_grad(set_to_none=True)
         _, loss, _ = model(lo, hi)
         loss.backward()
+        return loss
+
+    def step(lo, hi):
+        loss = local_step(lo, hi)
         if world > 1:
-            allreduce_gradients(model)
+            allreduce_gradients(model)       # the one exchange step of the path: a single flat NCCL all-reduce
         return loss
 
     def barrier():
@@ -230,8 +234,9 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     # optimizer cost, outside the metric (torch fused AdamW over the 212 parameter views)
+    # (rank 0 only from here on: no collectives)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), fused=True)
-    step(lo_d, hi_d)
+    local_step(lo_d, hi_d)
     for _ in range(2):
         opt.step()
     torch.cuda.synchronize()
@@ -247,7 +252,7 @@ def run_ours(args, rank, world, local_rank):
     prof_steps = 3
     lib.tulip_net_profile(model._net, 1)
     for _ in range(prof_steps):
-        step(lo_d, hi_d)
+        local_step(lo_d, hi_d)
     torch.cuda.synchronize()
     prof = read_profile(model)
     lib.tulip_net_profile(model._net, 0)

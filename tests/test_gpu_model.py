@@ -193,3 +193,34 @@ def test_gradient_accumulation_and_buffer_aliasing():
     before = model._flat.clone()
     opt.step()
     assert not torch.equal(before, model._flat), "optimizer updates must land in the flat parameter buffer"
+
+
+def test_reference_engine_call_pattern_trains():
+    """The call sequence of the unchanged reference engine (engine_upsampling.py:77-100, util/misc.py:292-308): fp16 autocast
+    context, GradScaler (initial scale 65536), unscale_, gradient-norm over p.grad, AdamW with no-decay groups, zero_grad.
+    The loss must fall on a fixed batch and no inf/nan may be reported to the scaler."""
+    cfg = TULIP_BASE
+    torch.manual_seed(0)
+    model = build(cfg).cuda().train()
+    lo, hi = make_inputs(cfg, 4, 52)
+    lo_t, hi_t = torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda()
+    decay = [p for n, p in model.named_parameters() if p.ndim > 1]
+    no_decay = [p for n, p in model.named_parameters() if p.ndim <= 1]
+    opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.01}, {"params": no_decay, "weight_decay": 0.0}], lr=5e-4, betas=(0.9, 0.95))
+    scaler = torch.amp.GradScaler("cuda")
+    losses = []
+    for it in range(12):
+        with torch.autocast("cuda"):
+            _, total_loss, pixel_loss = model(lo_t, hi_t, eval=False)
+        losses.append(total_loss.item())
+        assert np.isfinite(losses[-1]) and np.isfinite(pixel_loss.item())
+        scaler.scale(total_loss).backward()
+        scaler.unscale_(opt)
+        norm = torch.norm(torch.stack([torch.norm(p.grad.detach(), 2.0) for p in model.parameters()]), 2.0)
+        assert torch.isfinite(norm)
+        scaler.step(opt)
+        scaler.update()
+        opt.zero_grad()
+        torch.cuda.synchronize()
+    assert scaler.get_scale() == 65536.0, "a step was skipped: inf/nan gradients"
+    assert losses[-1] < 0.8 * losses[0], losses

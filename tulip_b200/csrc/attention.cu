@@ -30,9 +30,21 @@ __device__ __forceinline__ int token_index(const AttnArgs& a, int b, int wh, int
 __device__ __forceinline__ int region_id(const AttnArgs& a, int wh, int ww, int i) { return win_region_id(geom(a), wh, ww, i); }
 __device__ __forceinline__ int bias_index(const AttnArgs& a, int i, int j) { return rel_bias_index(a.bMh, a.bMw, i, j); }
 
+// this thread's 8 relative-position-bias values (fixed (i,j) fragment positions, fixed head for the whole kernel)
+__device__ __forceinline__ void load_bias(const AttnArgs& a, int head, int lane, float (&bias)[2][4]) {
+  const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = gq + (q >> 1) * 8, j = nt * 8 + 2 * tq + (q & 1);
+      bias[nt][q] = a.bias_table[bias_index(a, i, j) * a.heads + head];
+    }
+}
+
 // S (two m16n8 accumulators = 16x16) for this warp's head: scale * Q K^T + bias (+ mask)
-__device__ __forceinline__ void scores(const AttnArgs& a, const bf16* sq, int hl, int head, const int* s_rid,
-                                       const float* __restrict__ table, float (&s)[2][4], int lane) {
+__device__ __forceinline__ void scores(const AttnArgs& a, const bf16* sq, int hl, const int* s_rid,
+                                       const float (&bias)[2][4], float (&s)[2][4], int lane) {
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
@@ -52,7 +64,7 @@ __device__ __forceinline__ void scores(const AttnArgs& a, const bf16* sq, int hl
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int i = gq + (q >> 1) * 8, j = nt * 8 + 2 * tq + (q & 1);
-      float v = s[nt][q] * a.scale + table[bias_index(a, i, j) * a.heads + head];
+      float v = s[nt][q] * a.scale + bias[nt][q];
       if (a.masked && s_rid[i] != s_rid[j]) v += -100.0f;
       s[nt][q] = v;
     }
@@ -94,10 +106,14 @@ __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nWh = a.H / a.Mh, nWw = a.W / a.Mw;
   const int hgn = a.heads / HG;
-  const int items = a.B * nWh * nWw * hgn;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int hg = item % hgn;
-    int win = item / hgn;
+  const int nwin = a.B * nWh * nWw;
+  // a CTA keeps one head group for its whole life (grid is a multiple of hgn), so bias values live in registers
+  const int hg = blockIdx.x % hgn;
+  const int head = hg * HG + warp;
+  float bias[2][4];
+  load_bias(a, head, lane, bias);
+  for (int widx = blockIdx.x / hgn; widx < nwin; widx += gridDim.x / hgn) {
+    int win = widx;
     const int ww = win % nWw; win /= nWw;
     const int wh = win % nWh;
     const int b = win / nWh;
@@ -108,9 +124,8 @@ __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
     cp_async_wait<0>();
     __syncthreads();
 
-    const int head = hg * HG + warp;
     float s[2][4];
-    scores(a, sq, warp, head, s_rid, a.bias_table, s, lane);
+    scores(a, sq, warp, s_rid, bias, s, lane);
     softmax_rows(s);
     uint32_t pf[4] = {pack_bf16(s[0][0], s[0][1]), pack_bf16(s[0][2], s[0][3]), pack_bf16(s[1][0], s[1][1]),
                       pack_bf16(s[1][2], s[1][3])};
@@ -146,17 +161,24 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
   bf16* sq = reinterpret_cast<bf16*>(smem_raw);               // [16][QLD]  q|k|v
   bf16* sdo = sq + L * QLD;                                   // [16][OLD]  dO
   bf16* sp = sdo + L * OLD;                                   // [3 warps][2][16][PLD]  P and dS scratch
-  float* s_dtab = reinterpret_cast<float*>(sp + 3 * 2 * L * PLD);   // [heads][nbias]
+  float* s_dtab = reinterpret_cast<float*>(sp + 3 * 2 * L * PLD);   // [HG][nbias]
   __shared__ int s_rid[L];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nWh = a.H / a.Mh, nWw = a.W / a.Mw;
   const int hgn = a.heads / HG;
-  const int items = a.B * nWh * nWw * hgn;
-  for (int i = tid; i < a.heads * a.nbias; i += 96) s_dtab[i] = 0.f;
+  const int nwin = a.B * nWh * nWw;
+  const int hg = blockIdx.x % hgn;                              // fixed head group per CTA (grid is a multiple of hgn)
+  const int head = hg * HG + warp;
+  float bias[2][4], dsacc[2][4];                                // bias values and dS sums at this thread's fixed (i,j) positions
+  load_bias(a, head, lane, bias);
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dsacc[nt][q] = 0.f;
+  for (int i = tid; i < HG * a.nbias; i += 96) s_dtab[i] = 0.f;
 
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int hg = item % hgn;
-    int win = item / hgn;
+  for (int widx = blockIdx.x / hgn; widx < nwin; widx += gridDim.x / hgn) {
+    int win = widx;
     const int ww = win % nWw; win /= nWw;
     const int wh = win % nWh;
     const int b = win / nWh;
@@ -172,10 +194,9 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
     cp_async_wait<0>();
     __syncthreads();
 
-    const int head = hg * HG + warp;
     const int mat = lane >> 3, gq = lane >> 2, tq = lane & 3;
     float p[2][4];
-    scores(a, sq, warp, head, s_rid, a.bias_table, p, lane);
+    scores(a, sq, warp, s_rid, bias, p, lane);
     softmax_rows(p);
 
     // dP = dO V^T
@@ -207,14 +228,11 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
         ds[nt][e] = p[nt][e] * (dp[nt][e] - r);
       }
     }
-    // relative-position-bias gradient (per-CTA shared accumulation, flushed once at the end)
+    // relative-position-bias gradient: summed in registers across this CTA's windows, scattered to bins once at the end
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int i = gq + (q >> 1) * 8, j = nt * 8 + 2 * tq + (q & 1);
-        atomicAdd(&s_dtab[head * a.nbias + bias_index(a, i, j)], ds[nt][q]);
-      }
+      for (int q = 0; q < 4; ++q) dsacc[nt][q] += ds[nt][q];
     // stash P and dS (bf16, [i][j]) for the transposed operands
     bf16* wp = sp + warp * 2 * L * PLD;
     bf16* wds = wp + L * PLD;
@@ -266,9 +284,20 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
     }
   }
   __syncthreads();
-  for (int i = tid; i < a.heads * a.nbias; i += 96) {
+  {
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = gq + (q >> 1) * 8, j = nt * 8 + 2 * tq + (q & 1);
+        atomicAdd(&s_dtab[warp * a.nbias + bias_index(a, i, j)], dsacc[nt][q]);
+      }
+  }
+  __syncthreads();
+  for (int i = tid; i < HG * a.nbias; i += 96) {
     const float v = s_dtab[i];
-    if (v != 0.f) atomicAdd(a.dbias_table + (i % a.nbias) * a.heads + i / a.nbias, v);
+    if (v != 0.f) atomicAdd(a.dbias_table + (i % a.nbias) * a.heads + hg * HG + i / a.nbias, v);
   }
 }
 
@@ -287,9 +316,11 @@ int check_attn(const AttnArgs& a) {
 int win_attn_fwd(const AttnArgs& a, cudaStream_t st) {
   int rc = check_attn(a);
   if (rc) return rc;
-  const int items = a.B * (a.H / a.Mh) * (a.W / a.Mw) * (a.heads / HG);
-  const int grid = min(items, tulip_num_sms() * 16);
-  win_attn_fwd_kernel<<<grid, 96, 0, st>>>(a);
+  const int hgn = a.heads / HG, nwin = a.B * (a.H / a.Mh) * (a.W / a.Mw);
+  static int per_sm = 0;
+  if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, win_attn_fwd_kernel, 96, 0) != cudaSuccess || per_sm < 1)) per_sm = 8;
+  const int slots = max(1, min(nwin, per_sm * tulip_num_sms() / hgn));      // one full wave; grid stays a multiple of hgn
+  win_attn_fwd_kernel<<<slots * hgn, 96, 0, st>>>(a);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
@@ -297,15 +328,12 @@ int win_attn_fwd(const AttnArgs& a, cudaStream_t st) {
 int win_attn_bwd(const AttnArgs& a, cudaStream_t st) {
   int rc = check_attn(a);
   if (rc) return rc;
-  const int items = a.B * (a.H / a.Mh) * (a.W / a.Mw) * (a.heads / HG);
-  const int grid = min(items, tulip_num_sms() * 8);
-  const int smem = (L * QLD + L * OLD + 3 * 2 * L * PLD) * 2 + a.heads * a.nbias * 4;
-  static int configured = 0;
-  if (smem > configured) {
-    TULIP_CUDA(cudaFuncSetAttribute(win_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
-  win_attn_bwd_kernel<<<grid, 96, smem, st>>>(a);
+  const int hgn = a.heads / HG, nwin = a.B * (a.H / a.Mh) * (a.W / a.Mw);
+  const int smem = (L * QLD + L * OLD + 3 * 2 * L * PLD) * 2 + HG * a.nbias * 4;
+  static int per_sm = 0;
+  if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, win_attn_bwd_kernel, 96, smem) != cudaSuccess || per_sm < 1)) per_sm = 4;
+  const int slots = max(1, min(nwin, per_sm * tulip_num_sms() / hgn));
+  win_attn_bwd_kernel<<<slots * hgn, 96, smem, st>>>(a);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }

@@ -33,6 +33,8 @@ static int gemm_impl_env() {
   return v;
 }
 
+bool gemm_forced_mma() { return gemm_impl_env() != 0; }
+
 int gemm_nt(const GemmArgs& g, int epi, cudaStream_t st) {
   if (!gemm_impl_env()) {
     const int rc = gemm_nt_tc05(g, epi, st);

@@ -55,12 +55,32 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// exact (erf) GELU and its derivative, as nn.GELU() default (reference tulip.py:183,196)
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-form GELU (nn.GELU() default, reference tulip.py:183,196) and its derivative.
+// erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below a bf16 ulp), evaluated without cancellation:
+//   Phi(x) = 1 - h (x >= 0),  h (x < 0),   h = 0.5 * poly(t) * exp(-x^2/2),  t = 1 / (1 + 0.3275911 |x| / sqrt 2)
+// Two MUFU ops (rcp, ex2) + ~12 FMA-class instructions; the library erff costs ~3x that and made the GELU GEMM
+// epilogues issue-bound.
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& ex) {
+  const float t = fast_rcp(fmaf(0.231641888f, fabsf(x), 1.0f));            // 0.3275911 / sqrt(2)
+  ex = fast_ex2(-0.72134752f * x * x);                                      // exp(-x^2/2)
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float h = 0.5f * p * t * ex;
+  cdf = x >= 0.f ? 1.0f - h : h;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, ex;
+  gelu_parts(x, cdf, ex);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, ex;
+  gelu_parts(x, cdf, ex);
+  return fmaf(x * 0.39894228040143268f, ex, cdf);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

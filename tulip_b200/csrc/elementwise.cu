@@ -107,14 +107,23 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnArgs a) {
   for (int row = group; row < a.rows; row += ngroups) {
     const float2 st = *reinterpret_cast<const float2*>(a.stats + 2 * (long)row);
     const float mean = st.x, rstd = st.y;
-    uint4 xv[NCH], gv[NCH];
+    uint4 xv[NCH], gv[NCH], rv[NCH];
     float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {                       // issue every load of the row before the first use
+      const int ch = lane + i * LANES;
+      rv[i] = make_uint4(0, 0, 0, 0);
+      if (ch < nch) {
+        const long off = ln_src_offset(a, row, ch);
+        xv[i] = *reinterpret_cast<const uint4*>(a.x + off);
+        gv[i] = *reinterpret_cast<const uint4*>(a.dy + (long)row * a.C + ch * 8);
+        if (a.dres) rv[i] = *reinterpret_cast<const uint4*>(a.dres + off);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int ch = lane + i * LANES;
       if (ch < nch) {
-        xv[i] = *reinterpret_cast<const uint4*>(a.x + ln_src_offset(a, row, ch));
-        gv[i] = *reinterpret_cast<const uint4*>(a.dy + (long)row * a.C + ch * 8);
         const uint32_t xu[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
         const uint32_t gu[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
         const float4 w0 = *reinterpret_cast<const float4*>(a.w + ch * 8), w1 = *reinterpret_cast<const float4*>(a.w + ch * 8 + 4);
@@ -146,9 +155,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnArgs a) {
         const float4 w0 = *reinterpret_cast<const float4*>(a.w + ch * 8), w1 = *reinterpret_cast<const float4*>(a.w + ch * 8 + 4);
         const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
         const long off = ln_src_offset(a, row, ch);        // dx has the layout of the LN input (scatter for the merge)
-        uint4 rv = make_uint4(0, 0, 0, 0);
-        if (a.dres) rv = *reinterpret_cast<const uint4*>(a.dres + off);
-        const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+        const uint32_t ru[4] = {rv[i].x, rv[i].y, rv[i].z, rv[i].w};
         uint32_t o[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -162,25 +169,40 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnArgs a) {
     }
   }
   if (REGACC) {
-    // combine the groups of this CTA in shared memory, then one atomic per column per CTA
-    extern __shared__ float s_acc[];                      // [2][C]
-    for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) s_acc[i] = 0.f;
-    __syncthreads();
+    // column sums: shuffle-reduce over the row groups that share a warp, one smem slab per warp, then one global
+    // atomic per column per CTA
+    extern __shared__ float s_acc[];                      // [8 warps][2][C]
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      const int ch = lane + i * LANES;
-      if (ch < nch) {
+    for (int i = 0; i < NCH; ++i)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          atomicAdd(&s_acc[ch * 8 + q], accw[i][q]);
-          atomicAdd(&s_acc[a.C + ch * 8 + q], accb[i][q]);
+      for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int o = LANES; o < 32; o <<= 1) {
+          accw[i][q] += __shfl_xor_sync(0xffffffffu, accw[i][q], o);
+          accb[i][q] += __shfl_xor_sync(0xffffffffu, accb[i][q], o);
+        }
+      }
+    const int wl = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wl < LANES) {
+      float* slab = s_acc + wid * 2 * a.C;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int ch = wl + i * LANES;
+        if (ch < nch) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            slab[ch * 8 + q] = accw[i][q];
+            slab[a.C + ch * 8 + q] = accb[i][q];
+          }
         }
       }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < a.C; i += blockDim.x) {
-      atomicAdd(a.dw + i, s_acc[i]);
-      atomicAdd(a.db + i, s_acc[a.C + i]);
+    for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_acc[w * 2 * a.C + i];
+      atomicAdd((i < a.C ? a.dw : a.db - a.C) + i, t);
     }
   }
 }
@@ -189,6 +211,16 @@ struct LnCfg { int lanes, nch; };
 inline bool ln_config(int C, LnCfg* cfg) {
   if (C % 8) return false;
   const int nch = C / 8;
+  // C = 96 * 2^k (every LayerNorm on the TULIP path): 3 chunks per lane, 4 * 2^k lanes per row -> no idle lanes
+  if (C % 96 == 0) {
+    const int m = C / 96;
+    if (m == 1) { *cfg = {4, 3}; return true; }
+    if (m == 2) { *cfg = {8, 3}; return true; }
+    if (m == 4) { *cfg = {16, 3}; return true; }
+    if (m == 8) { *cfg = {32, 3}; return true; }
+    if (m == 16) { *cfg = {32, 6}; return true; }
+    if (m == 32) { *cfg = {32, 12}; return true; }
+  }
   if (nch <= 16) *cfg = {16, 1};
   else if (nch <= 32) *cfg = {16, 2};
   else if (nch <= 48) *cfg = {16, 3};
@@ -199,14 +231,23 @@ inline bool ln_config(int C, LnCfg* cfg) {
   return true;
 }
 
+// resident CTAs per SM for a grid-stride kernel (so the grid is exactly one full wave)
+template <class K>
+int wave_grid(K kernel, int threads, int smem, long max_ctas) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const long g = (long)per_sm * tulip_num_sms();
+  return (int)(max_ctas < g ? (max_ctas > 0 ? max_ctas : 1) : g);
+}
+
 // ------------------------------------------------------------------------------------------------
 // PatchEmbedding: circular pad W by (2,2) -> Conv2d(1 -> E, k=(ph,8), s=(ph,4)) -> NHWC -> LayerNorm.
 // Reference tulip.py:59-73.  One warp per output token, lane l owns channels l, l+32, ...
 template <int EPL>   // channels per lane = E / 32
 __global__ void __launch_bounds__(256) patch_embed_fwd_kernel(const EmbedArgs a) {
-  extern __shared__ float s_w[];                          // [E][ph*8] conv weight
+  extern __shared__ float s_w[];                          // [ph*8][E] conv weight (transposed: lanes read consecutive channels)
   const int KW = a.ph * 8;
-  for (int i = threadIdx.x; i < a.E * KW; i += blockDim.x) s_w[i] = a.w[i];
+  for (int i = threadIdx.x; i < a.E * KW; i += blockDim.x) s_w[(i % KW) * a.E + i / KW] = a.w[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -232,7 +273,7 @@ __global__ void __launch_bounds__(256) patch_embed_fwd_kernel(const EmbedArgs a)
         wi = wi < 0 ? wi + a.Wimg : (wi >= a.Wimg ? wi - a.Wimg : wi);
         const float xv = __ldg(row + wi);
 #pragma unroll
-        for (int q = 0; q < EPL; ++q) u[q] = fmaf(s_w[(lane + 32 * q) * KW + dh * 8 + j], xv, u[q]);
+        for (int q = 0; q < EPL; ++q) u[q] = fmaf(s_w[(dh * 8 + j) * a.E + lane + 32 * q], xv, u[q]);
       }
     }
     float s = 0.f;
@@ -253,9 +294,9 @@ __global__ void __launch_bounds__(256) patch_embed_fwd_kernel(const EmbedArgs a)
 // weight / bias gradients (no input gradient: the input is data).  ph == 1 only (all shipped configs).
 template <int EPL>
 __global__ void __launch_bounds__(256) patch_embed_bwd_kernel(const EmbedArgs a) {
-  extern __shared__ float s_w[];                          // [E][8] weights, then [E][12] accumulators
+  extern __shared__ float s_w[];                          // [8][E] weights (transposed), then [E][12] accumulators
   float* s_acc = s_w + a.E * 8;
-  for (int i = threadIdx.x; i < a.E * 8; i += blockDim.x) s_w[i] = a.w[i];
+  for (int i = threadIdx.x; i < a.E * 8; i += blockDim.x) s_w[(i % 8) * a.E + i / 8] = a.w[i];
   for (int i = threadIdx.x; i < a.E * 12; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -290,7 +331,7 @@ __global__ void __launch_bounds__(256) patch_embed_bwd_kernel(const EmbedArgs a)
     for (int q = 0; q < EPL; ++q) {
       u[q] = cb[q];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) u[q] = fmaf(s_w[(lane + 32 * q) * 8 + j], xv[j], u[q]);
+      for (int j = 0; j < 8; ++j) u[q] = fmaf(s_w[j * a.E + lane + 32 * q], xv[j], u[q]);
       s += u[q];
       dy[q] = __bfloat162float(a.dy[(long)t * a.E + lane + 32 * q]);
     }
@@ -507,25 +548,23 @@ inline int ew_grid(long n, int threads) {
 
 }  // namespace
 
-#define LN_DISPATCH(KERNEL, ...)                                                        \
-  if (cfg.lanes == 16 && cfg.nch == 1) KERNEL<16, 1 __VA_ARGS__>                        \
-  else if (cfg.lanes == 16 && cfg.nch == 2) KERNEL<16, 2 __VA_ARGS__>                   \
-  else if (cfg.lanes == 16 && cfg.nch == 3) KERNEL<16, 3 __VA_ARGS__>                   \
-  else if (cfg.lanes == 32 && cfg.nch == 3) KERNEL<32, 3 __VA_ARGS__>                   \
-  else if (cfg.lanes == 32 && cfg.nch == 6) KERNEL<32, 6 __VA_ARGS__>
+#define LN_CASE(L, N) (cfg.lanes == L && cfg.nch == N)
 
 int layernorm_fwd(const LnArgs& a, cudaStream_t st) {
   LnCfg cfg;
   TULIP_REQUIRE(ln_config(a.C, &cfg), "layernorm: C must be a multiple of 8 and <= 3072");
   TULIP_REQUIRE(a.rows > 0, "layernorm: empty input");
-  const int rows_per_cta = 256 / cfg.lanes;
-  const int grid = min(ceil_div(a.rows, rows_per_cta), tulip_num_sms() * 8);
-  if (cfg.lanes == 16 && cfg.nch == 1) layernorm_fwd_kernel<16, 1><<<grid, 256, 0, st>>>(a);
-  else if (cfg.lanes == 16 && cfg.nch == 2) layernorm_fwd_kernel<16, 2><<<grid, 256, 0, st>>>(a);
-  else if (cfg.lanes == 16 && cfg.nch == 3) layernorm_fwd_kernel<16, 3><<<grid, 256, 0, st>>>(a);
-  else if (cfg.lanes == 32 && cfg.nch == 3) layernorm_fwd_kernel<32, 3><<<grid, 256, 0, st>>>(a);
-  else if (cfg.lanes == 32 && cfg.nch == 6) layernorm_fwd_kernel<32, 6><<<grid, 256, 0, st>>>(a);
-  else layernorm_fwd_kernel<32, 12><<<grid, 256, 0, st>>>(a);
+  const long want = ceil_div(a.rows, 256 / cfg.lanes);
+#define LN_FWD(L, N) { const int grid = wave_grid(layernorm_fwd_kernel<L, N>, 256, 0, want); layernorm_fwd_kernel<L, N><<<grid, 256, 0, st>>>(a); }
+  if LN_CASE(4, 3) LN_FWD(4, 3)
+  else if LN_CASE(8, 3) LN_FWD(8, 3)
+  else if LN_CASE(16, 1) LN_FWD(16, 1)
+  else if LN_CASE(16, 2) LN_FWD(16, 2)
+  else if LN_CASE(16, 3) LN_FWD(16, 3)
+  else if LN_CASE(32, 3) LN_FWD(32, 3)
+  else if LN_CASE(32, 6) LN_FWD(32, 6)
+  else LN_FWD(32, 12)
+#undef LN_FWD
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
@@ -534,15 +573,21 @@ int layernorm_bwd(const LnArgs& a, cudaStream_t st) {
   LnCfg cfg;
   TULIP_REQUIRE(ln_config(a.C, &cfg), "layernorm: C must be a multiple of 8 and <= 3072");
   TULIP_REQUIRE(a.rows > 0, "layernorm: empty input");
-  const int rows_per_cta = 256 / cfg.lanes;
-  const int grid = min(ceil_div(a.rows, rows_per_cta), tulip_num_sms() * 4);
-  const int smem = 2 * a.C * (int)sizeof(float);
-  if (cfg.lanes == 16 && cfg.nch == 1) layernorm_bwd_kernel<16, 1, true><<<grid, 256, smem, st>>>(a);
-  else if (cfg.lanes == 16 && cfg.nch == 2) layernorm_bwd_kernel<16, 2, true><<<grid, 256, smem, st>>>(a);
-  else if (cfg.lanes == 16 && cfg.nch == 3) layernorm_bwd_kernel<16, 3, true><<<grid, 256, smem, st>>>(a);
-  else if (cfg.lanes == 32 && cfg.nch == 3) layernorm_bwd_kernel<32, 3, true><<<grid, 256, smem, st>>>(a);
-  else if (cfg.lanes == 32 && cfg.nch == 6) layernorm_bwd_kernel<32, 6, true><<<grid, 256, smem, st>>>(a);
-  else layernorm_bwd_kernel<32, 12, false><<<grid, 256, 0, st>>>(a);
+  const long want = ceil_div(a.rows, 256 / cfg.lanes);
+  const int smem = 8 * 2 * a.C * (int)sizeof(float);
+#define LN_BWD(L, N, R) { const int sm = (R) ? smem : 0; \
+    if (sm > 48 * 1024) TULIP_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<L, N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
+    const int grid = wave_grid(layernorm_bwd_kernel<L, N, R>, 256, sm, want); \
+    layernorm_bwd_kernel<L, N, R><<<grid, 256, sm, st>>>(a); }
+  if LN_CASE(4, 3) LN_BWD(4, 3, true)
+  else if LN_CASE(8, 3) LN_BWD(8, 3, true)
+  else if LN_CASE(16, 1) LN_BWD(16, 1, true)
+  else if LN_CASE(16, 2) LN_BWD(16, 2, true)
+  else if LN_CASE(16, 3) LN_BWD(16, 3, true)
+  else if LN_CASE(32, 3) LN_BWD(32, 3, true)
+  else if LN_CASE(32, 6) LN_BWD(32, 6, true)
+  else LN_BWD(32, 12, false)
+#undef LN_BWD
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
@@ -551,8 +596,8 @@ int patch_embed_fwd(const EmbedArgs& a, cudaStream_t st) {
   TULIP_REQUIRE(a.E % 32 == 0 && a.E <= 192, "patch_embed: embed_dim must be a multiple of 32, <= 192");
   TULIP_REQUIRE(a.Wimg % 4 == 0 && a.Himg % a.ph == 0 && a.Wimg >= 4, "patch_embed: image not divisible by the patch");
   const int tokens = a.B * (a.Himg / a.ph) * (a.Wimg / 4);
-  const int grid = min(ceil_div(tokens, 8 * 4), tulip_num_sms() * 8);
   const int smem = a.E * a.ph * 8 * (int)sizeof(float);
+  const int grid = min(ceil_div(tokens, 8 * 4), tulip_num_sms() * 8);
   switch (a.E / 32) {
     case 1: patch_embed_fwd_kernel<1><<<grid, 256, smem, st>>>(a); break;
     case 2: patch_embed_fwd_kernel<2><<<grid, 256, smem, st>>>(a); break;
@@ -569,7 +614,7 @@ int patch_embed_bwd(const EmbedArgs& a, cudaStream_t st) {
   TULIP_REQUIRE(a.E % 32 == 0 && a.E <= 192, "patch_embed: embed_dim must be a multiple of 32, <= 192");
   TULIP_REQUIRE(a.ph == 1, "patch_embed backward: patch height must be 1");
   const int tokens = a.B * a.Himg * (a.Wimg / 4);
-  const int grid = min(ceil_div(tokens, 8 * 16), tulip_num_sms() * 2);
+  const int grid = min(ceil_div(tokens, 8 * 8), tulip_num_sms() * 6);
   const int smem = a.E * 20 * (int)sizeof(float);
   switch (a.E / 32) {
     case 1: patch_embed_bwd_kernel<1><<<grid, 256, smem, st>>>(a); break;

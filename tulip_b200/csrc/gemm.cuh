@@ -16,6 +16,8 @@ enum GemmEpi : int {
   EPI_HEAD = 6,       // pred[m, ij] (+)= sum_c wd[c] * leaky(acc + bias)   (PixelShuffleHead + decoder_pred, tulip.py:174-178,731)
   EPI_HEAD_BWD = 7,   // recompute pre; out = dh (bf16), dwd += colsum(dpred * leaky(pre))
   EPI_ROWSCALE = 8,   // out = row_scale[sample] * acc                      (DropPath backward on a branch dX)
+  EPI_DGELU2 = 9,     // out = (A . B^T) * gelu'(A2 . B2^T + bias): the GELU pre-activation is RECOMPUTED by a second
+                      // accumulator instead of being saved by the forward pass (tcgen05 path only)
 };
 
 enum GemmAMode : int {
@@ -28,6 +30,7 @@ struct GemmArgs {
   const bf16* A; long lda;
   const bf16* A2; long lda2; int K1;     // k >= K1 is read from A2 at column k-K1 (two-source concat); K1 == K when unused
   const bf16* B; long ldb;
+  const bf16* B2; long ldb2; int K2;     // EPI_DGELU2: second product A2[M,K2] . B2[N,K2]^T
   int M, N, K;
   int a_mode; int g_H, g_W, g_Cc;        // gather geometry (input grid H x W, Cc channels per shuffled pixel)
   const float* bias;
@@ -61,6 +64,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st);   // returns TULI
 int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st);
 int gemm_nt(const GemmArgs& g, int epi, cudaStream_t st);        // dispatch (env TULIP_B200_GEMM=mma forces the legacy path)
 int gemm_tn(const GemmTNArgs& g, cudaStream_t st);
+bool gemm_forced_mma();                                          // env TULIP_B200_GEMM=mma
 
 // ---- epilogue math on a run of NV consecutive columns of one output row (shared by both GEMMs) ----
 

@@ -28,17 +28,19 @@ struct Segments {
   int len[4];            // columns of A in the segment
   int amap[4];           // 0: mapA, 1: mapA2
   int bcol[4];           // first column of B for the segment
+  int bmap[4];           // 0: mapB, 1: mapB2
+  int acc[4];            // accumulator the segment feeds (EPI_DGELU2 uses two)
   int sj[4], si[4];      // (j, i) of the shuffle slot for the 5-D gather map
   int a5d;               // A map is the 5-D PixelShuffle-backward view
   int gW;                // 5-D: grid width W
 };
 
 struct Maps {
-  CUtensorMap A, A2, B, out, out2, aux;
+  CUtensorMap A, A2, B, B2, out, out2, aux;
 };
 
 __host__ __device__ constexpr bool epi_tma_out(int epi) {
-  return epi == EPI_STORE || epi == EPI_GELU || epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_HEAD_BWD;
+  return epi == EPI_STORE || epi == EPI_GELU || epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_HEAD_BWD || epi == EPI_DGELU2;
 }
 __host__ __device__ constexpr bool epi_has_aux(int epi) { return epi == EPI_RESID || epi == EPI_DGELU; }
 
@@ -46,13 +48,14 @@ template <int BN, int EPI>
 struct Cfg {
   static constexpr bool TMA_OUT = epi_tma_out(EPI);
   static constexpr bool HAS_AUX = epi_has_aux(EPI);
+  static constexpr int NACC = (EPI == EPI_DGELU2) ? 2 : 1;                  // accumulators per tile
   static constexpr int NBOX = BN / BOXC;
   static constexpr int TILE_BYTES = NBOX * BOX_BYTES;                       // bf16 [128, BN]
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_BUFS = TMA_OUT ? 2 : 0;                          // GELU uses both per tile (pre, act)
   static constexpr int AUX_BUFS = HAS_AUX ? (BN <= 96 ? 2 : 1) : 0;
-  static constexpr int STAGES = (BN <= 96) ? 4 : ((OUT_BUFS + AUX_BUFS) * TILE_BYTES > 100 * 1024 ? 2 : 3);
+  static constexpr int STAGES = (BN <= 96) ? (HAS_AUX ? 4 : 6) : ((OUT_BUFS + AUX_BUFS) * TILE_BYTES > 100 * 1024 ? 2 : 3);
   static constexpr int OUT_OFF = STAGES * STAGE_BYTES;
   static constexpr int AUX_OFF = OUT_OFF + OUT_BUFS * TILE_BYTES;
   static constexpr int RED_OFF = AUX_OFF + AUX_BUFS * TILE_BYTES;           // EPI_HEAD: [2][EPI_GROUPS][128] fp32 partial sums
@@ -121,7 +124,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const Segments sg, int tiles_m, int tiles_n) {
   using CF = Cfg<BN, EPI>;
   constexpr int STAGES = CF::STAGES;
-  constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  constexpr int TMEM_COLS = (2 * CF::NACC * BN <= 128) ? 128 : (2 * CF::NACC * BN <= 256 ? 256 : 512);
+  static_assert(2 * CF::NACC * BN <= 512, "TMEM budget");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + CF::BAR_OFF);
@@ -148,8 +152,6 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_tiles = tiles_m * tiles_n;
-  int kblocks = 0;
-  for (int s = 0; s < sg.n; ++s) kblocks += (sg.len[s] + BK - 1) / BK;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -180,7 +182,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
             } else {
               tc::tma_load_2d(a, sg.amap[s] ? &maps.A2 : &maps.A, full + stage, kb * BK, m0);
             }
-            tc::tma_load_2d(b, &maps.B, full + stage, sg.bcol[s] + kb * BK, n0);
+            tc::tma_load_2d(b, sg.bmap[s] ? &maps.B2 : &maps.B, full + stage, sg.bcol[s] + kb * BK, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -194,18 +196,25 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         tc::mbar_wait(tempty + buf, tphase ^ 1);             // epilogue has drained this accumulator buffer
         tc::fence_after_sync();
-        const uint32_t tmem_d = tmem_base + buf * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          tc::mbar_wait(full + stage, phase);
-          tc::fence_after_sync();
-          const unsigned char* a = smem + stage * CF::STAGE_BYTES;
-          const uint64_t da = tc::make_desc_kmajor_sw128(a);
-          const uint64_t db = tc::make_desc_kmajor_sw128(a + CF::A_BYTES);
+        const uint32_t tmem_d = tmem_base + buf * CF::NACC * BN;
+        uint32_t started = 0;                                 // bit a: accumulator a has received its first MMA
+        for (int s = 0; s < sg.n; ++s) {
+          const int nb = (sg.len[s] + BK - 1) / BK;
+          const int ac = CF::NACC > 1 ? sg.acc[s] : 0;
+          for (int kb = 0; kb < nb; ++kb) {
+            tc::mbar_wait(full + stage, phase);
+            tc::fence_after_sync();
+            const unsigned char* a = smem + stage * CF::STAGE_BYTES;
+            const uint64_t da = tc::make_desc_kmajor_sw128(a);
+            const uint64_t db = tc::make_desc_kmajor_sw128(a + CF::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)                   // +32 bytes per K=16 step inside the 128B swizzle atom
-            tc::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-          tc::umma_commit(empty + stage);                     // smem slot free once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < BK / 16; ++k) {               // +32 bytes per K=16 step inside the 128B swizzle atom
+              tc::umma_bf16(tmem_d + ac * BN, da + 2 * k, db + 2 * k, idesc, (started >> ac) & 1u);
+              started |= 1u << ac;
+            }
+            tc::umma_commit(empty + stage);                   // smem slot free once these MMAs have read it
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
         tc::umma_commit(tfull + buf);                         // accumulator complete
         if (++buf == 2) { buf = 0; tphase ^= 1; }
@@ -229,15 +238,28 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       const int m = m0 + r;
+      // the first box's bias vector is fetched before the accumulator wait so its latency is off the critical path
+      float bias0[32];
+      if ((EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_RESID) && g.bias) {
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8) {
+          const float4 b = *reinterpret_cast<const float4*>(g.bias + n0 + jgrp * BOXC + 4 * q8);
+          bias0[4 * q8] = b.x; bias0[4 * q8 + 1] = b.y; bias0[4 * q8 + 2] = b.z; bias0[4 * q8 + 3] = b.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bias0[i] = 0.f;
+      }
       tc::mbar_wait(tfull + buf, tphase);
       tc::fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * CF::NACC * BN;
 
       if (CF::TMA_OUT) {
         // staging buffer(s) must have been read out by the previous TMA store(s)
-        if (issuer) { if (EPI == EPI_GELU) tc::tma_store_wait_read<0>(); else tc::tma_store_wait_read<1>(); }
+        const bool two_out = (EPI == EPI_GELU) && g.out2 != nullptr;             // pre-activation is saved too: both buffers per tile
+        if (issuer) { if (two_out) tc::tma_store_wait_read<0>(); else tc::tma_store_wait_read<1>(); }
         tc::named_bar_sync(1, 32 * EPI_WARPS);
-        unsigned char* ob = smem + CF::OUT_OFF + (EPI == EPI_GELU ? 0 : obuf) * CF::TILE_BYTES;
+        unsigned char* ob = smem + CF::OUT_OFF + (two_out ? 0 : obuf) * CF::TILE_BYTES;
         unsigned char* ob2 = smem + CF::OUT_OFF + CF::TILE_BYTES;                     // GELU: activation tile
         const unsigned char* ab = smem + CF::AUX_OFF + abuf * CF::TILE_BYTES;
         if (CF::HAS_AUX) tc::mbar_wait(afull + abuf, aphase);
@@ -260,15 +282,20 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
           float v[32];
           tc::tmem_ld32(taddr + j * BOXC, v);
           const int n = n0 + j * BOXC;
+          if (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_RESID) {
+            if (jj == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += bias0[i];
+            } else if (g.bias) {
+              add_bias32(g.bias, n, v);
+            }
+          }
           if (EPI == EPI_STORE) {
-            if (g.bias) add_bias32(g.bias, n, v);
           } else if (EPI == EPI_GELU) {
-            add_bias32(g.bias, n, v);
-            if (g.out2) store_box_row(ob + j * BOX_BYTES, r, v);
+            if (two_out) store_box_row(ob + j * BOX_BYTES, r, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
           } else if (EPI == EPI_RESID) {
-            if (g.bias) add_bias32(g.bias, n, v);
             float a[32];
             load_box_row(ab + j * BOX_BYTES, r, a);
 #pragma unroll
@@ -276,6 +303,12 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
           } else if (EPI == EPI_DGELU) {
             float a[32];
             load_box_row(ab + j * BOX_BYTES, r, a);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad(a[i]);
+          } else if (EPI == EPI_DGELU2) {
+            float a[32];
+            tc::tmem_ld32(taddr + BN + j * BOXC, a);                       // recomputed fc1 pre-activation (second accumulator)
+            if (g.bias) add_bias32(g.bias, n, a);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad(a[i]);
           } else if (EPI == EPI_HEAD_BWD) {
@@ -287,7 +320,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
               v[i] = dp * g.wd[c0 + j * BOXC + i] * (pre > 0.f ? 1.f : 0.01f);
             }
           }
-          store_box_row((EPI == EPI_GELU ? ob2 : ob) + j * BOX_BYTES, r, v);
+          store_box_row((two_out ? ob2 : ob) + j * BOX_BYTES, r, v);
         }
         // accumulator and aux tile consumed: release them before the (slower) store path
         tc::fence_before_sync();
@@ -299,11 +332,9 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
         }
         tc::named_bar_sync(1, 32 * EPI_WARPS);
         if (issuer) {
-          if (EPI == EPI_GELU) {
-            if (g.out2) {
+          if (two_out) {
 #pragma unroll
-              for (int j = 0; j < CF::NBOX; ++j) tc::tma_store_2d(&maps.out2, ob + j * BOX_BYTES, n0 + j * BOXC, m0);
-            }
+            for (int j = 0; j < CF::NBOX; ++j) tc::tma_store_2d(&maps.out2, ob + j * BOX_BYTES, n0 + j * BOXC, m0);
 #pragma unroll
             for (int j = 0; j < CF::NBOX; ++j) tc::tma_store_2d(&maps.out, ob2 + j * BOX_BYTES, n0 + j * BOXC, m0);
           } else {
@@ -456,7 +487,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
   const bool head = (epi == EPI_HEAD || epi == EPI_HEAD_BWD);
   if (epi == EPI_HEAD_BWD && g.hd_E != 96) return TULIP_ERR_UNSUPPORTED;      // per-CTA dwd accumulation assumes one 96-channel group
   // wide tiles only where the problem is tensor-bound (deep K) and there are enough tiles to fill the chip
-  const int bn = (!head && g.N % 192 == 0 && g.K >= 384 && (long)ceil_div(g.M, BM) * (g.N / 192) >= tulip_num_sms()) ? 192 : 96;
+  const int bn = (!head && epi != EPI_DGELU2 && g.N % 192 == 0 && (long)ceil_div(g.M, BM) * (g.N / 192) >= tulip_num_sms()) ? 192 : 96;
 
   Segments sg;
   memset(&sg, 0, sizeof sg);
@@ -500,7 +531,24 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     rc = tulip_make_tmap(&maps.B, g.B, 2, dims, str, box);
     if (rc) return rc;
   }
-  maps.out = maps.out2 = maps.aux = maps.B;
+  maps.B2 = maps.out = maps.out2 = maps.aux = maps.B;
+  if (epi == EPI_DGELU2) {
+    // second product: pre = A2[M,K2] . B2[N,K2]^T feeds accumulator 1
+    if (g.a_mode != A_PLAIN || g.K1 < g.K || !g.A2 || !g.B2 || (g.lda2 % 8) || (g.ldb2 % 8) || (g.K2 % 8) ||
+        (reinterpret_cast<uintptr_t>(g.A2) & 15) || (reinterpret_cast<uintptr_t>(g.B2) & 15))
+      return TULIP_ERR_UNSUPPORTED;
+    const uint64_t dimsA[2] = {(uint64_t)g.K2, (uint64_t)g.M};
+    const uint64_t strA[1] = {(uint64_t)g.lda2 * 2};
+    const uint32_t boxA[2] = {64, BM};
+    rc = tulip_make_tmap(&maps.A2, g.A2, 2, dimsA, strA, boxA);
+    if (rc) return rc;
+    const uint64_t dimsB[2] = {(uint64_t)g.K2, (uint64_t)g.N};
+    const uint64_t strB[1] = {(uint64_t)g.ldb2 * 2};
+    const uint32_t boxB[2] = {64, (uint32_t)bn};
+    rc = tulip_make_tmap(&maps.B2, g.B2, 2, dimsB, strB, boxB);
+    if (rc) return rc;
+    sg.n = 2; sg.len[1] = g.K2; sg.amap[1] = 1; sg.bmap[1] = 1; sg.bcol[1] = 0; sg.acc[1] = 1;
+  }
   if (epi_tma_out(epi)) {
     if ((reinterpret_cast<uintptr_t>(g.out) & 15) || (g.ldo % 8)) return TULIP_ERR_UNSUPPORTED;
     rc = make_io_map(&maps.out, g.out, g.ldo, g.M, g.N);
@@ -523,6 +571,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     case EPI_PIXSHUF: return launch_bn<EPI_PIXSHUF>(bn, maps, g, sg, st);
     case EPI_SPLIT2: return launch_bn<EPI_SPLIT2>(bn, maps, g, sg, st);
     case EPI_DGELU: return launch_bn<EPI_DGELU>(bn, maps, g, sg, st);
+    case EPI_DGELU2: return launch<96, EPI_DGELU2>(maps, g, sg, st);     // two accumulators x two buffers: BN = 96 only
     case EPI_ROWSCALE: return launch_bn<EPI_ROWSCALE>(bn, maps, g, sg, st);
     case EPI_HEAD: return launch<96, EPI_HEAD>(maps, g, sg, st);
     case EPI_HEAD_BWD: return launch<96, EPI_HEAD_BWD>(maps, g, sg, st);
@@ -554,8 +603,9 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 __global__ void __launch_bounds__(TN_THREADS, 1)
-gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX, const GemmTNArgs g,
-                    int kcols_per_tile, int tok_blocks_per_split) {
+gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX,
+                    const __grid_constant__ CUtensorMap mapX2, const GemmTNArgs g, int kcols_per_tile, int tok_blocks_per_split,
+                    int row_seg_len, int row_tiles_per_seg, int y5d) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + TN_BAR_OFF);
@@ -564,8 +614,14 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int n0 = blockIdx.x * 128;                               // first dW row of this CTA
+  // dW rows come in segments of row_seg_len (one segment normally; the 4 shuffle slots of a PixelShuffle-backward
+  // gather otherwise), each tiled by 128 rows with TMA zero fill past the segment end
+  const int seg = blockIdx.x / row_tiles_per_seg;
+  const int c0 = (blockIdx.x % row_tiles_per_seg) * 128;         // first row inside the segment
+  const int n0 = seg * row_seg_len + c0;                         // first dW row (permuted order) of this CTA
+  const int rows_valid = min(128, row_seg_len - c0);
   const int k0 = blockIdx.y * kcols_per_tile;                    // first dW column
+  const bool x2 = k0 >= g.K1;                                    // this column tile reads the second X source (concat)
   const int kvalid = min(kcols_per_tile, g.K - k0);
   const int nbx = (kvalid + 63) / 64;                            // data boxes of X per stage
   const bool with_db = (g.db != nullptr) && blockIdx.y == 0;
@@ -604,9 +660,19 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
         tc::mbar_wait(empty + stage, phase ^ 1);
         unsigned char* a = smem + stage * TN_STAGE_BYTES;
         tc::mbar_expect_tx(full + stage, (2 + nbx) * TN_BOX);
-        tc::tma_load_2d(a, &mapY, full + stage, n0, tb * TN_TOK);
-        tc::tma_load_2d(a + TN_BOX, &mapY, full + stage, n0 + 64, tb * TN_TOK);
-        for (int j = 0; j < nbx; ++j) tc::tma_load_2d(a + (2 + j) * TN_BOX, &mapX, full + stage, k0 + 64 * j, tb * TN_TOK);
+        if (y5d) {
+          // dY'[m=(bh,w), n'=slot*Cc+c] = dOut[bh, 2h+i, 2w+j, c]: 5-D view (c, j, w, i, bh); a 64-token box is a run of w
+          // (W >= 64) or 64/W whole rows
+          const int t0 = tb * TN_TOK;
+          const int bh0 = t0 / g.g_W, w0 = t0 % g.g_W;
+          tc::tma_load_5d(a, &mapY, full + stage, c0, seg & 1, w0, seg >> 1, bh0);
+          tc::tma_load_5d(a + TN_BOX, &mapY, full + stage, c0 + 64, seg & 1, w0, seg >> 1, bh0);
+        } else {
+          tc::tma_load_2d(a, &mapY, full + stage, n0, tb * TN_TOK);
+          tc::tma_load_2d(a + TN_BOX, &mapY, full + stage, n0 + 64, tb * TN_TOK);
+        }
+        for (int j = 0; j < nbx; ++j)
+          tc::tma_load_2d(a + (2 + j) * TN_BOX, x2 ? &mapX2 : &mapX, full + stage, (x2 ? k0 - g.K1 : k0) + 64 * j, tb * TN_TOK);
         if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -642,7 +708,7 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
     const int q = warp & 3, half = warp >> 2;
     const int n = n0 + q * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool row_ok = n < g.N;
+    const bool row_ok = (q * 32 + lane) < rows_valid && n < g.N;
     const int row = (g.perm_R2 > 1) ? (n % g.perm_Cc) * g.perm_R2 + n / g.perm_Cc : n;
     float* drow = g.dW + (long)row * g.lddw + k0;
     const int nchunks = (kvalid + 31) / 32;
@@ -670,12 +736,29 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
 
 int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st) {
   if (tc05_disabled()) return TULIP_ERR_UNSUPPORTED;
-  if (g.y_mode != A_PLAIN || g.K1 < g.K || g.M <= 0) return TULIP_ERR_UNSUPPORTED;
+  if (g.M <= 0) return TULIP_ERR_UNSUPPORTED;
   if (g.N % 8 || g.K % 8 || (g.ldy % 8) || (g.ldx % 8) || (g.lddw % 4) || (g.K % 4)) return TULIP_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(g.dY) & 15) || (reinterpret_cast<uintptr_t>(g.X) & 15) || (reinterpret_cast<uintptr_t>(g.dW) & 15))
     return TULIP_ERR_UNSUPPORTED;
-  CUtensorMap mY, mX;
-  {
+  const bool concat = g.K1 < g.K;
+  int kcols = 192;
+  if (concat) {
+    if (!g.X2 || (reinterpret_cast<uintptr_t>(g.X2) & 15) || (g.ldx2 % 8) || g.K1 % 8) return TULIP_ERR_UNSUPPORTED;
+    if (g.K1 % 192) kcols = (g.K1 % 96 == 0) ? 96 : 0;        // column tiles must not straddle the two sources
+    if (!kcols) return TULIP_ERR_UNSUPPORTED;
+  }
+  CUtensorMap mY, mX, mX2;
+  int row_seg_len = g.N, y5d = 0;
+  if (g.y_mode == A_UNSHUFFLE) {
+    const int W = g.g_W, Cc = g.g_Cc;
+    if (!((W >= TN_TOK && W % TN_TOK == 0) || (W < TN_TOK && TN_TOK % W == 0)) || g.M % W || Cc % 8 || g.N != 4 * Cc) return TULIP_ERR_UNSUPPORTED;
+    const uint64_t dims[5] = {(uint64_t)Cc, 2, (uint64_t)W, 2, (uint64_t)(g.M / W)};
+    const uint64_t str[4] = {(uint64_t)Cc * 2, (uint64_t)2 * Cc * 2, (uint64_t)2 * W * Cc * 2, (uint64_t)4 * W * Cc * 2};
+    const uint32_t box[5] = {64, 1, (uint32_t)(W >= TN_TOK ? TN_TOK : W), 1, (uint32_t)(W >= TN_TOK ? 1 : TN_TOK / W)};
+    int rc = tulip_make_tmap(&mY, g.dY, 5, dims, str, box);
+    if (rc) return rc;
+    row_seg_len = Cc; y5d = 1;
+  } else {
     const uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.M};
     const uint64_t str[1] = {(uint64_t)g.ldy * 2};
     const uint32_t box[2] = {64, TN_TOK};
@@ -683,19 +766,27 @@ int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st) {
     if (rc) return rc;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.M};
+    const uint64_t dims[2] = {(uint64_t)(concat ? g.K1 : g.K), (uint64_t)g.M};
     const uint64_t str[1] = {(uint64_t)g.ldx * 2};
     const uint32_t box[2] = {64, TN_TOK};
     int rc = tulip_make_tmap(&mX, g.X, 2, dims, str, box);
     if (rc) return rc;
+    mX2 = mX;
+    if (concat) {
+      const uint64_t dims2[2] = {(uint64_t)(g.K - g.K1), (uint64_t)g.M};
+      const uint64_t str2[1] = {(uint64_t)g.ldx2 * 2};
+      rc = tulip_make_tmap(&mX2, g.X2, 2, dims2, str2, box);
+      if (rc) return rc;
+    }
   }
   static bool configured = false;
   if (!configured) {
     TULIP_CUDA(cudaFuncSetAttribute(gemm_tn_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
     configured = true;
   }
-  const int kcols = 192;
-  const int n_tiles = ceil_div(g.N, 128), k_tiles = ceil_div(g.K, kcols);
+  const int nseg = g.N / row_seg_len;
+  const int row_tiles_per_seg = ceil_div(row_seg_len, 128);
+  const int n_tiles = nseg * row_tiles_per_seg, k_tiles = ceil_div(g.K, kcols);
   const int tb_total = ceil_div(g.M, TN_TOK);
   int splits = tulip_num_sms() / (n_tiles * k_tiles);
   if (splits < 1) splits = 1;
@@ -703,7 +794,7 @@ int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st) {
   const int per = ceil_div(tb_total, splits);
   splits = ceil_div(tb_total, per);
   dim3 grid(n_tiles, k_tiles, splits);
-  gemm_tn_tc05_kernel<<<grid, TN_THREADS, TN_SMEM, st>>>(mY, mX, g, kcols, per);
+  gemm_tn_tc05_kernel<<<grid, TN_THREADS, TN_SMEM, st>>>(mY, mX, mX2, g, kcols, per, row_seg_len, row_tiles_per_seg, y5d);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }

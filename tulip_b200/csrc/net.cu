@@ -212,6 +212,7 @@ int tulip_net::ensure_device() {
 
 Plan tulip_net::plan(int B) const {
   Plan p;
+  const bool save_pre = gemm_forced_mma();     // the legacy GEMM path keeps the saved-pre-activation GELU backward
   Bump bump;
   const long E = cfg.embed_dim;
   const long T0 = (long)B * H0 * W0;
@@ -225,7 +226,7 @@ Plan tulip_net::plan(int B) const {
     bb.xn1 = act(T, C); bb.st1 = bump.take(T * 8);
     bb.qkv = act(T, 3 * C); bb.ao = act(T, C); bb.xmid = act(T, C);
     bb.xn2 = act(T, C); bb.st2 = bump.take(T * 8);
-    bb.hpre = act(T, 4 * C); bb.hact = act(T, 4 * C); bb.xout = act(T, C);
+    bb.hpre = save_pre ? act(T, 4 * C) : -1; bb.hact = act(T, 4 * C); bb.xout = act(T, C);
   };
   p.xn_m.assign(L, -1); p.st_m.assign(L, -1); p.x_merged.assign(L, -1);
   for (int s = 0; s < L; ++s) {
@@ -440,7 +441,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     {
       const Linear& l = linears[b.fc1];
       GemmArgs g = nt_args(c.A(bb.xn2), C, c.W(l), C, T, 4 * C, C, c.bias(l), c.A(bb.hact), 4 * C);
-      g.out2 = c.A(bb.hpre); g.ldo2 = 4 * C;
+      if (bb.hpre >= 0) { g.out2 = c.A(bb.hpre); g.ldo2 = 4 * C; }      // otherwise the backward recomputes it (EPI_DGELU2)
       RUN_NT(g, EPI_GELU);
     }
     {
@@ -597,9 +598,17 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     }
     {
       const Linear& l2 = linears[b.fc2];
+      const Linear& lf1 = linears[b.fc1];
       GemmArgs g = nt_args(gy, C, c.Wt(l2), C, T, 4 * C, C, nullptr, c.A(p.scr_big), 4 * C);   // dh = (gy . W2) o gelu'(pre)
-      g.aux = c.A(bb.hpre); g.ldaux = 4 * C;
-      RUN_NT(g, EPI_DGELU);
+      if (bb.hpre >= 0) {
+        g.aux = c.A(bb.hpre); g.ldaux = 4 * C;
+        RUN_NT(g, EPI_DGELU);
+      } else {
+        // pre = xn2 . W1^T + b1 is recomputed by a second accumulator of the same kernel: 2x the (cheap, HBM-bound)
+        // MMA work instead of writing and re-reading the [T, 4C] pre-activation
+        g.A2 = c.A(bb.xn2); g.lda2 = C; g.B2 = c.W(lf1); g.ldb2 = C; g.K2 = C; g.bias = c.bias(lf1);
+        RUN_NT(g, EPI_DGELU2);
+      }
       RUN_TN(dw(l2, gy, c.A(bb.hact), T));
       const Linear& l1 = linears[b.fc1];
       GemmArgs g1 = nt_args(c.A(p.scr_big), 4 * C, c.Wt(l1), 4 * C, T, C, 4 * C, nullptr, c.A(p.scr_dxn), C);

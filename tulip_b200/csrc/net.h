@@ -21,6 +21,7 @@ inline int nt_tag(int epi) {
     case EPI_STORE: return K_NT_STORE; case EPI_GELU: return K_NT_GELU; case EPI_RESID: return K_NT_RESID;
     case EPI_PIXSHUF: return K_NT_PIXSHUF; case EPI_SPLIT2: return K_NT_SPLIT2; case EPI_DGELU: return K_NT_DGELU;
     case EPI_HEAD: return K_NT_HEAD; case EPI_HEAD_BWD: return K_NT_HEAD_BWD; case EPI_ROWSCALE: return K_NT_ROWSCALE;
+    case EPI_DGELU2: return K_NT_DGELU;
   }
   return K_MISC;
 }
