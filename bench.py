@@ -261,17 +261,26 @@ def run_ours(args, rank, world, local_rank):
     prof.sort(key=lambda k: -k["ms"])
     top = prof[0]
     per_launch_ms = top["ms"] / top["launches"]
-    is_tensor = top["flops"] > 0 and top["kernel"].startswith("gemm")
-    if is_tensor:
-        achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
-        roof = {"kernel": top["kernel"], "bound": "tensor", "achieved": round(achieved, 2), "peak": pk["tflops_sustained"],
-                "unit": "TFLOP/s", "frac": round(achieved / pk["tflops_sustained"], 4)}
+    ridge = pk["tflops_sustained"] * 1e12 / (pk["hbm_gbs"] * 1e9)
+    ai = top["flops"] / top["bytes"] if top["bytes"] else 0.0
+    tflops = top["flops"] / (top["ms"] * 1e-3) / 1e12
+    gbs = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+    if top["flops"] > 0 and ai >= ridge:
+        roof = {"kernel": top["kernel"], "bound": "tensor", "achieved": round(tflops, 2), "peak": pk["tflops_sustained"],
+                "unit": "TFLOP/s", "frac": round(tflops / pk["tflops_sustained"], 4)}
     else:
-        achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
-        roof = {"kernel": top["kernel"], "bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": round(achieved / pk["hbm_gbs"], 4)}
-    roof.update({"traffic": None, "peak_source": pk["source"] + (", sustained" if is_tensor else ""),
+        # algorithmic intensity below the ridge (%.0f FLOP/B): the kernel is bounded by HBM bytes, not by the tensor pipe
+        roof = {"kernel": top["kernel"], "bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": round(gbs / pk["hbm_gbs"], 4)}
+    roof.update({"arithmetic_intensity_flop_per_byte": round(ai, 1), "ridge_flop_per_byte": round(ridge, 1),
+                 "tflops": round(tflops, 2), "tensor_frac": round(tflops / pk["tflops_sustained"], 4)})
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):                         # dram bytes per launch from a committed ncu capture (scripts/capture_traffic.sh)
+        traffic = json.load(open(tpath)).get(top["kernel"], {}).get("dram_bytes_per_launch")
+    roof.update({"traffic": traffic, "peak_source": pk["source"] + ", sustained figure for the tensor peak",
                  "avg_launch_ms": round(per_launch_ms, 4), "launches_per_step": top["launches"] // prof_steps,
+                 "algorithmic_bytes_per_launch": round(top["bytes"] / top["launches"]),
                  "share_of_step": round(top["ms"] / tot, 4),
                  "kernels": [{"kernel": k["kernel"], "share": round(k["ms"] / tot, 4), "ms_per_step": round(k["ms"] / prof_steps, 4),
                               "launches_per_step": k["launches"] // prof_steps,

@@ -101,6 +101,7 @@ __device__ __forceinline__ void load_window_rows(const AttnArgs& a, bf16* sq, co
 }
 
 __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
+  pdl_sync();
   __shared__ __align__(16) bf16 sq[L * QLD];
   __shared__ int s_rid[L];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
 //   dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(dP o P)), dQ = scale * dS K, dK = scale * dS^T Q,
 //   d bias_table[idx(i,j), head] += dS[i,j]     
 __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* sq = reinterpret_cast<bf16*>(smem_raw);               // [16][QLD]  q|k|v
   bf16* sdo = sq + L * QLD;                                   // [16][OLD]  dO
@@ -320,7 +322,7 @@ int win_attn_fwd(const AttnArgs& a, cudaStream_t st) {
   static int per_sm = 0;
   if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, win_attn_fwd_kernel, 96, 0) != cudaSuccess || per_sm < 1)) per_sm = 8;
   const int slots = max(1, min(nwin, per_sm * tulip_num_sms() / hgn));      // one full wave; grid stays a multiple of hgn
-  win_attn_fwd_kernel<<<slots * hgn, 96, 0, st>>>(a);
+  tulip_launch(win_attn_fwd_kernel, slots * hgn, 96, 0, st, a);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
@@ -333,7 +335,7 @@ int win_attn_bwd(const AttnArgs& a, cudaStream_t st) {
   static int per_sm = 0;
   if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, win_attn_bwd_kernel, 96, smem) != cudaSuccess || per_sm < 1)) per_sm = 4;
   const int slots = max(1, min(nwin, per_sm * tulip_num_sms() / hgn));
-  win_attn_bwd_kernel<<<slots * hgn, 96, smem, st>>>(a);
+  tulip_launch(win_attn_bwd_kernel, slots * hgn, 96, smem, st, a);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }

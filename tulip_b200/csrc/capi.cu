@@ -24,6 +24,15 @@ int tulip_num_sms() {
   return g_num_sms;
 }
 
+bool tulip_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TULIP_B200_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int gemm_impl_env() {
   static int v = -1;
   if (v < 0) {

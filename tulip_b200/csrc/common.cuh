@@ -31,6 +31,27 @@ typedef __nv_bfloat16 bf16;
 
 void tulip_set_error(const char* msg);
 int tulip_num_sms();
+bool tulip_pdl_enabled();          // env TULIP_B200_NO_PDL=1 turns programmatic dependent launch off
+
+// Programmatic dependent launch (PDL): every kernel of the step is launched with the stream-serialization attribute, does
+// its private set-up (barrier init, TMEM allocation, shared-memory tables), then waits for the preceding kernel's memory
+// with griddepcontrol.wait BEFORE its first global access, and immediately lets its own successor start scheduling.
+// The step is ~330 short kernels; overlapping each prologue with the predecessor's tail removes a few us per launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
+template <class... KArgs, class... Args>
+inline void tulip_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tulip_pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);       // errors surface through cudaGetLastError (TULIP_CHECK_LAUNCH)
+}
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -35,6 +35,7 @@ __device__ __forceinline__ long ln_src_offset(const LnArgs& a, int row, int ch) 
 
 template <int LANES, int NCH>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const LnArgs a) {
+  pdl_sync();
   const int lane = threadIdx.x % LANES;
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
   const int ngroups = (gridDim.x * blockDim.x) / LANES;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const LnArgs a) {
 // dx = [dres +] rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w;  dw += dy * xhat; db += dy
 template <int LANES, int NCH, bool REGACC>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnArgs a) {
+  pdl_sync();
   const int lane = threadIdx.x % LANES;
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
   const int ngroups = (gridDim.x * blockDim.x) / LANES;
@@ -245,6 +247,7 @@ int wave_grid(K kernel, int threads, int smem, long max_ctas) {
 // Reference tulip.py:59-73.  One warp per output token, lane l owns channels l, l+32, ...
 template <int EPL>   // channels per lane = E / 32
 __global__ void __launch_bounds__(256) patch_embed_fwd_kernel(const EmbedArgs a) {
+  pdl_sync();
   extern __shared__ float s_w[];                          // [ph*8][E] conv weight (transposed: lanes read consecutive channels)
   const int KW = a.ph * 8;
   for (int i = threadIdx.x; i < a.E * KW; i += blockDim.x) s_w[(i % KW) * a.E + i / KW] = a.w[i];
@@ -294,6 +297,7 @@ __global__ void __launch_bounds__(256) patch_embed_fwd_kernel(const EmbedArgs a)
 // weight / bias gradients (no input gradient: the input is data).  ph == 1 only (all shipped configs).
 template <int EPL>
 __global__ void __launch_bounds__(256) patch_embed_bwd_kernel(const EmbedArgs a) {
+  pdl_sync();
   extern __shared__ float s_w[];                          // [8][E] weights (transposed), then [E][12] accumulators
   float* s_acc = s_w + a.E * 8;
   for (int i = threadIdx.x; i < a.E * 8; i += blockDim.x) s_w[(i % 8) * a.E + i / 8] = a.w[i];
@@ -381,6 +385,7 @@ __global__ void __launch_bounds__(256) patch_embed_bwd_kernel(const EmbedArgs a)
 // fp32 -> bf16 weight repack, 32x32 tiles, optional row permutation and transposed copy.
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ flat, bf16* __restrict__ arena,
                                                            const PackItem* __restrict__ items, int n_items) {
+  pdl_sync();
   __shared__ float tile[32][33];
   __shared__ int s_item;
   if (threadIdx.x == 0) {
@@ -418,12 +423,14 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 }
 
 __global__ void permute_bias_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int R2, int Cc) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[(i % Cc) * R2 + i / Cc];
 }
 
 // ------------------------------------------------------------------------------------------------
 __global__ void add_inplace_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, long n16) {
+  pdl_sync();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long)gridDim.x * blockDim.x) {
     const uint4 a = dst[i], b = src[i];
     const uint32_t au[4] = {a.x, a.y, a.z, a.w}, bu[4] = {b.x, b.y, b.z, b.w};
@@ -439,6 +446,7 @@ __global__ void add_inplace_kernel(uint4* __restrict__ dst, const uint4* __restr
 
 __global__ void scale_rows_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, const float* __restrict__ row_scale,
                                   long n16, int chunks_per_row, int rows_per_sample) {
+  pdl_sync();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long)gridDim.x * blockDim.x) {
     const float s = row_scale[(i / chunks_per_row) / rows_per_sample];
     const uint4 a = src[i];
@@ -456,6 +464,7 @@ __global__ void scale_rows_kernel(uint4* __restrict__ dst, const uint4* __restri
 // mean |pred - y| and mean |expm1(pred) - expm1(y)| (tulip.py:690-700); acc2 must be zero on entry
 __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, long n,
                                                       int log_transform, float* acc2) {
+  pdl_sync();
   float s0 = 0.f, s1 = 0.f;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float p = pred[i], y = target[i];
@@ -475,6 +484,7 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
   }
 }
 __global__ void l1_loss_finalize_kernel(const float* acc2, float* out2, float inv_n, int log_transform) {
+  pdl_sync();
   out2[0] = acc2[0] * inv_n;
   out2[1] = log_transform ? acc2[1] * inv_n : acc2[0] * inv_n;
 }
@@ -482,6 +492,7 @@ __global__ void l1_loss_finalize_kernel(const float* acc2, float* out2, float in
 // ------------------------------------------------------------------------------------------------
 // stand-alone index ops (16-byte chunks; C % 8 == 0)
 __global__ void window_copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, WinGeom g, int cpt, bool scatter) {
+  pdl_sync();
   const int L = g.Mh * g.Mw;
   const int nWh = g.H / g.Mh, nWw = g.W / g.Mw;
   const long total = (long)B * g.H * g.W * cpt;
@@ -498,6 +509,7 @@ __global__ void window_copy_kernel(const uint4* __restrict__ src, uint4* __restr
 }
 
 __global__ void shift_mask_kernel(float* out, WinGeom g) {
+  pdl_sync();
   const int L = g.Mh * g.Mw;
   const int nWw = g.W / g.Mw;
   const int total = (g.H / g.Mh) * nWw * L * L;
@@ -509,6 +521,7 @@ __global__ void shift_mask_kernel(float* out, WinGeom g) {
 }
 
 __global__ void rel_bias_gather_kernel(const float* table, float* out, int heads, int Mh, int Mw) {
+  pdl_sync();
   const int L = Mh * Mw;
   const int total = heads * L * L;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -518,6 +531,7 @@ __global__ void rel_bias_gather_kernel(const float* table, float* out, int heads
 }
 
 __global__ void merge_gather_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, LnArgs a, long total) {
+  pdl_sync();
   const int nch = a.C >> 3;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int ch = idx % nch;
@@ -527,6 +541,7 @@ __global__ void merge_gather_kernel(const uint4* __restrict__ x, uint4* __restri
 }
 
 __global__ void pixel_shuffle_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int B, int H, int W, int Cout, int r) {
+  pdl_sync();
   // out[b, h*r+i, w*r+j, c] = x[b, h, w, c*r*r + i*r + j]
   const long total = (long)B * H * W * Cout * r * r;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -555,7 +570,7 @@ int layernorm_fwd(const LnArgs& a, cudaStream_t st) {
   TULIP_REQUIRE(ln_config(a.C, &cfg), "layernorm: C must be a multiple of 8 and <= 3072");
   TULIP_REQUIRE(a.rows > 0, "layernorm: empty input");
   const long want = ceil_div(a.rows, 256 / cfg.lanes);
-#define LN_FWD(L, N) { const int grid = wave_grid(layernorm_fwd_kernel<L, N>, 256, 0, want); layernorm_fwd_kernel<L, N><<<grid, 256, 0, st>>>(a); }
+#define LN_FWD(L, N) { const int grid = wave_grid(layernorm_fwd_kernel<L, N>, 256, 0, want); tulip_launch(layernorm_fwd_kernel<L, N>, grid, 256, 0, st, a); }
   if LN_CASE(4, 3) LN_FWD(4, 3)
   else if LN_CASE(8, 3) LN_FWD(8, 3)
   else if LN_CASE(16, 1) LN_FWD(16, 1)
@@ -578,7 +593,7 @@ int layernorm_bwd(const LnArgs& a, cudaStream_t st) {
 #define LN_BWD(L, N, R) { const int sm = (R) ? smem : 0; \
     if (sm > 48 * 1024) TULIP_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<L, N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
     const int grid = wave_grid(layernorm_bwd_kernel<L, N, R>, 256, sm, want); \
-    layernorm_bwd_kernel<L, N, R><<<grid, 256, sm, st>>>(a); }
+    tulip_launch(layernorm_bwd_kernel<L, N, R>, grid, 256, sm, st, a); }
   if LN_CASE(4, 3) LN_BWD(4, 3, true)
   else if LN_CASE(8, 3) LN_BWD(8, 3, true)
   else if LN_CASE(16, 1) LN_BWD(16, 1, true)
@@ -599,12 +614,12 @@ int patch_embed_fwd(const EmbedArgs& a, cudaStream_t st) {
   const int smem = a.E * a.ph * 8 * (int)sizeof(float);
   const int grid = min(ceil_div(tokens, 8 * 4), tulip_num_sms() * 8);
   switch (a.E / 32) {
-    case 1: patch_embed_fwd_kernel<1><<<grid, 256, smem, st>>>(a); break;
-    case 2: patch_embed_fwd_kernel<2><<<grid, 256, smem, st>>>(a); break;
-    case 3: patch_embed_fwd_kernel<3><<<grid, 256, smem, st>>>(a); break;
-    case 4: patch_embed_fwd_kernel<4><<<grid, 256, smem, st>>>(a); break;
-    case 5: patch_embed_fwd_kernel<5><<<grid, 256, smem, st>>>(a); break;
-    default: patch_embed_fwd_kernel<6><<<grid, 256, smem, st>>>(a); break;
+    case 1: tulip_launch(patch_embed_fwd_kernel<1>, grid, 256, smem, st, a); break;
+    case 2: tulip_launch(patch_embed_fwd_kernel<2>, grid, 256, smem, st, a); break;
+    case 3: tulip_launch(patch_embed_fwd_kernel<3>, grid, 256, smem, st, a); break;
+    case 4: tulip_launch(patch_embed_fwd_kernel<4>, grid, 256, smem, st, a); break;
+    case 5: tulip_launch(patch_embed_fwd_kernel<5>, grid, 256, smem, st, a); break;
+    default: tulip_launch(patch_embed_fwd_kernel<6>, grid, 256, smem, st, a); break;
   }
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
@@ -617,12 +632,12 @@ int patch_embed_bwd(const EmbedArgs& a, cudaStream_t st) {
   const int grid = min(ceil_div(tokens, 8 * 8), tulip_num_sms() * 6);
   const int smem = a.E * 20 * (int)sizeof(float);
   switch (a.E / 32) {
-    case 1: patch_embed_bwd_kernel<1><<<grid, 256, smem, st>>>(a); break;
-    case 2: patch_embed_bwd_kernel<2><<<grid, 256, smem, st>>>(a); break;
-    case 3: patch_embed_bwd_kernel<3><<<grid, 256, smem, st>>>(a); break;
-    case 4: patch_embed_bwd_kernel<4><<<grid, 256, smem, st>>>(a); break;
-    case 5: patch_embed_bwd_kernel<5><<<grid, 256, smem, st>>>(a); break;
-    default: patch_embed_bwd_kernel<6><<<grid, 256, smem, st>>>(a); break;
+    case 1: tulip_launch(patch_embed_bwd_kernel<1>, grid, 256, smem, st, a); break;
+    case 2: tulip_launch(patch_embed_bwd_kernel<2>, grid, 256, smem, st, a); break;
+    case 3: tulip_launch(patch_embed_bwd_kernel<3>, grid, 256, smem, st, a); break;
+    case 4: tulip_launch(patch_embed_bwd_kernel<4>, grid, 256, smem, st, a); break;
+    case 5: tulip_launch(patch_embed_bwd_kernel<5>, grid, 256, smem, st, a); break;
+    default: tulip_launch(patch_embed_bwd_kernel<6>, grid, 256, smem, st, a); break;
   }
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
@@ -630,20 +645,20 @@ int patch_embed_bwd(const EmbedArgs& a, cudaStream_t st) {
 
 int pack_weights(const float* flat, bf16* arena, const PackItem* items_dev, int n_items, int n_tiles, cudaStream_t st) {
   if (n_tiles <= 0) return TULIP_OK;
-  pack_weights_kernel<<<n_tiles, 256, 0, st>>>(flat, arena, items_dev, n_items);
+  tulip_launch(pack_weights_kernel, n_tiles, 256, 0, st, flat, arena, items_dev, n_items);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
 
 int permute_bias(const float* src, float* dst, int n, int R2, int Cc, cudaStream_t st) {
-  permute_bias_kernel<<<ceil_div(n, 256), 256, 0, st>>>(src, dst, n, R2, Cc);
+  tulip_launch(permute_bias_kernel, ceil_div(n, 256), 256, 0, st, src, dst, n, R2, Cc);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
 
 int add_inplace_bf16(bf16* dst, const bf16* src, long n, cudaStream_t st) {
   TULIP_REQUIRE(n % 8 == 0, "add_inplace: length must be a multiple of 8");
-  add_inplace_kernel<<<ew_grid(n / 8, 256), 256, 0, st>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), n / 8);
+  tulip_launch(add_inplace_kernel, ew_grid(n / 8, 256), 256, 0, st, reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), n / 8);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
@@ -651,7 +666,7 @@ int add_inplace_bf16(bf16* dst, const bf16* src, long n, cudaStream_t st) {
 int scale_rows_bf16(bf16* dst, const bf16* src, const float* row_scale, int rows, int C, int rows_per_sample, cudaStream_t st) {
   TULIP_REQUIRE(C % 8 == 0, "scale_rows: C must be a multiple of 8");
   const long n16 = (long)rows * (C / 8);
-  scale_rows_kernel<<<ew_grid(n16, 256), 256, 0, st>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), row_scale,
+  tulip_launch(scale_rows_kernel, ew_grid(n16, 256), 256, 0, st, reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), row_scale,
                                                        n16, C / 8, rows_per_sample);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
@@ -659,8 +674,8 @@ int scale_rows_bf16(bf16* dst, const bf16* src, const float* row_scale, int rows
 
 int l1_loss(const float* pred, const float* target, long n, int log_transform, float* acc2, float* out2, cudaStream_t st) {
   TULIP_CUDA(cudaMemsetAsync(acc2, 0, 2 * sizeof(float), st));
-  l1_loss_kernel<<<ew_grid(n, 256), 256, 0, st>>>(pred, target, n, log_transform, acc2);
-  l1_loss_finalize_kernel<<<1, 1, 0, st>>>(acc2, out2, 1.0f / (float)n, log_transform);
+  tulip_launch(l1_loss_kernel, ew_grid(n, 256), 256, 0, st, pred, target, n, log_transform, acc2);
+  tulip_launch(l1_loss_finalize_kernel, 1, 1, 0, st, acc2, out2, 1.0f / (float)n, log_transform);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
@@ -668,7 +683,7 @@ int l1_loss(const float* pred, const float* target, long n, int log_transform, f
 int window_gather(const bf16* x, bf16* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, cudaStream_t st) {
   TULIP_REQUIRE(C % 8 == 0 && H % Mh == 0 && W % Mw == 0, "H or W is not divisible by window_size");
   const long n = (long)B * H * W * (C / 8);
-  window_copy_kernel<<<ew_grid(n, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B,
+  tulip_launch(window_copy_kernel, ew_grid(n, 256), 256, 0, st, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B,
                                                       WinGeom{H, W, Mh, Mw, sh, sw}, C / 8, false);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
@@ -677,7 +692,7 @@ int window_gather(const bf16* x, bf16* out, int B, int H, int W, int C, int Mh, 
 int window_scatter(const bf16* xw, bf16* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, cudaStream_t st) {
   TULIP_REQUIRE(C % 8 == 0 && H % Mh == 0 && W % Mw == 0, "H or W is not divisible by window_size");
   const long n = (long)B * H * W * (C / 8);
-  window_copy_kernel<<<ew_grid(n, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(xw), reinterpret_cast<uint4*>(out), B,
+  tulip_launch(window_copy_kernel, ew_grid(n, 256), 256, 0, st, reinterpret_cast<const uint4*>(xw), reinterpret_cast<uint4*>(out), B,
                                                       WinGeom{H, W, Mh, Mw, sh, sw}, C / 8, true);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
@@ -687,14 +702,14 @@ int shift_mask(float* out, int H, int W, int Mh, int Mw, int sh, int sw, cudaStr
   TULIP_REQUIRE(H % Mh == 0 && W % Mw == 0, "H or W is not divisible by window_size");
   const int L = Mh * Mw;
   const long n = (long)(H / Mh) * (W / Mw) * L * L;
-  shift_mask_kernel<<<ew_grid(n, 256), 256, 0, st>>>(out, WinGeom{H, W, Mh, Mw, sh, sw});
+  tulip_launch(shift_mask_kernel, ew_grid(n, 256), 256, 0, st, out, WinGeom{H, W, Mh, Mw, sh, sw});
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
 
 int rel_bias_gather(const float* table, float* out, int heads, int Mh, int Mw, cudaStream_t st) {
   const int L = Mh * Mw;
-  rel_bias_gather_kernel<<<ew_grid((long)heads * L * L, 256), 256, 0, st>>>(table, out, heads, Mh, Mw);
+  tulip_launch(rel_bias_gather_kernel, ew_grid((long)heads * L * L, 256), 256, 0, st, table, out, heads, Mh, Mw);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
@@ -704,14 +719,14 @@ int merge_gather(const bf16* x, bf16* out, int B, int H, int W, int C, cudaStrea
   LnArgs a = {};
   a.C = 4 * C; a.gather = 1; a.H2 = H / 2; a.W2 = W / 2;
   const long total = (long)B * (H / 2) * (W / 2) * (4 * C / 8);
-  merge_gather_kernel<<<ew_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), a, total);
+  tulip_launch(merge_gather_kernel, ew_grid(total, 256), 256, 0, st, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), a, total);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
 
 int pixel_shuffle_nhwc(const bf16* x, bf16* out, int B, int H, int W, int Cout, int r, cudaStream_t st) {
   const long total = (long)B * H * W * Cout * r * r;
-  pixel_shuffle_kernel<<<ew_grid(total, 256), 256, 0, st>>>(x, out, B, H, W, Cout, r);
+  tulip_launch(pixel_shuffle_kernel, ew_grid(total, 256), 256, 0, st, x, out, B, H, W, Cout, r);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }

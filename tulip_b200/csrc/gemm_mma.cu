@@ -22,6 +22,7 @@ __device__ __forceinline__ const bf16* a_src(const GemmArgs& g, int m, int k) {
 
 template <int EPI, int AMODE>
 __global__ void __launch_bounds__(128) gemm_nt_mma_kernel(const GemmArgs g) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* sA = reinterpret_cast<bf16*>(smem_raw);
   bf16* sB = sA + STAGES * BM * LDS;
@@ -181,7 +182,7 @@ int launch_nt(const GemmArgs& g, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(ceil_div(g.M, BM), g.N / BN);
-  gemm_nt_mma_kernel<EPI, AMODE><<<grid, 128, NT_SMEM, st>>>(g);
+  tulip_launch(gemm_nt_mma_kernel<EPI, AMODE>, grid, 128, NT_SMEM, st, g);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
@@ -193,6 +194,7 @@ constexpr int TN_SMEM = STAGES * 2 * TBM * TLD * 2;           // 39,936 B
 
 template <int YMODE>
 __global__ void __launch_bounds__(128) gemm_tn_mma_kernel(const GemmTNArgs g) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* sY = reinterpret_cast<bf16*>(smem_raw);
   bf16* sX = sY + STAGES * TBM * TLD;
@@ -336,8 +338,8 @@ int gemm_tn_mma(const GemmTNArgs& g, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(g.N / TBN, g.K / TBK, g.splits);
-  if (g.y_mode == A_UNSHUFFLE) gemm_tn_mma_kernel<A_UNSHUFFLE><<<grid, 128, TN_SMEM, st>>>(g);
-  else gemm_tn_mma_kernel<A_PLAIN><<<grid, 128, TN_SMEM, st>>>(g);
+  if (g.y_mode == A_UNSHUFFLE) tulip_launch(gemm_tn_mma_kernel<A_UNSHUFFLE>, grid, 128, TN_SMEM, st, g);
+  else tulip_launch(gemm_tn_mma_kernel<A_PLAIN>, grid, 128, TN_SMEM, st, g);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }

@@ -150,6 +150,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();                                               // set-up above overlapped the previous kernel's tail
 
   const int num_tiles = tiles_m * tiles_n;
 
@@ -427,7 +428,7 @@ int launch(const Maps& maps, const GemmArgs& g, const Segments& sg, cudaStream_t
   }
   const int tiles_m = ceil_div(g.M, BM), tiles_n = g.N / BN;
   const int grid = min(tiles_m * tiles_n, tulip_num_sms());
-  gemm_nt_tc05_kernel<BN, EPI><<<grid, THREADS, CF::TOTAL, st>>>(maps, g, sg, tiles_m, tiles_n);
+  tulip_launch(gemm_nt_tc05_kernel<BN, EPI>, grid, THREADS, CF::TOTAL, st, maps, g, sg, tiles_m, tiles_n);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
@@ -630,7 +631,7 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
   const int tb_begin = blockIdx.z * tok_blocks_per_split;
   const int tb_end = min(tb_total, tb_begin + tok_blocks_per_split);
   const int ntb = tb_end - tb_begin;
-  if (ntb <= 0) return;
+  if (ntb <= 0) { pdl_sync(); return; }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TN_STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
@@ -652,6 +653,7 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -794,7 +796,7 @@ int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st) {
   const int per = ceil_div(tb_total, splits);
   splits = ceil_div(tb_total, per);
   dim3 grid(n_tiles, k_tiles, splits);
-  gemm_tn_tc05_kernel<<<grid, TN_THREADS, TN_SMEM, st>>>(mY, mX, mX2, g, kcols, per, row_seg_len, row_tiles_per_seg, y5d);
+  tulip_launch(gemm_tn_tc05_kernel, grid, TN_THREADS, TN_SMEM, st, mY, mX, mX2, g, kcols, per, row_seg_len, row_tiles_per_seg, y5d);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
