@@ -102,8 +102,8 @@ __device__ __forceinline__ void load_window_rows(const AttnArgs& a, bf16* sq, co
 
 __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
   pdl_sync();
-  __shared__ __align__(16) bf16 sq[L * QLD];
-  __shared__ int s_rid[L];
+  __shared__ __align__(16) bf16 sq2[2][L * QLD];       // double buffer: the next window's rows land while this one is computed
+  __shared__ int s_rid2[2][L];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nWh = a.H / a.Mh, nWw = a.W / a.Mw;
   const int hgn = a.heads / HG;
@@ -111,19 +111,37 @@ __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
   // a CTA keeps one head group for its whole life (grid is a multiple of hgn), so bias values live in registers
   const int hg = blockIdx.x % hgn;
   const int head = hg * HG + warp;
+  const int wstep = gridDim.x / hgn;
   float bias[2][4];
   load_bias(a, head, lane, bias);
-  for (int widx = blockIdx.x / hgn; widx < nwin; widx += gridDim.x / hgn) {
-    int win = widx;
-    const int ww = win % nWw; win /= nWw;
-    const int wh = win % nWh;
-    const int b = win / nWh;
-    __syncthreads();                                   // previous item's smem reads are done
-    load_window_rows(a, sq, a.qkv, b, wh, ww, hg, tid);
+
+  auto decode = [&](int widx, int& b, int& wh, int& ww) {
+    ww = widx % nWw;
+    const int t = widx / nWw;
+    wh = t % nWh;
+    b = t / nWh;
+  };
+  auto prefetch = [&](int widx, int buf) {
+    int b, wh, ww;
+    decode(widx, b, wh, ww);
+    load_window_rows(a, sq2[buf], a.qkv, b, wh, ww, hg, tid);
+    if (tid < L) s_rid2[buf][tid] = a.masked ? region_id(a, wh, ww, tid) : 0;
+  };
+
+  int widx = blockIdx.x / hgn;
+  int buf = 0;
+  if (widx < nwin) prefetch(widx, 0);
+  cp_async_commit();
+  for (; widx < nwin; widx += wstep, buf ^= 1) {
+    const int next = widx + wstep;
+    if (next < nwin) prefetch(next, buf ^ 1);
     cp_async_commit();
-    if (tid < L) s_rid[tid] = a.masked ? region_id(a, wh, ww, tid) : 0;
-    cp_async_wait<0>();
+    cp_async_wait<1>();                                 // everything but the newest group (the prefetch) has landed
     __syncthreads();
+    const bf16* sq = sq2[buf];
+    const int* s_rid = s_rid2[buf];
+    int b, wh, ww;
+    decode(widx, b, wh, ww);
 
     float s[2][4];
     scores(a, sq, warp, s_rid, bias, s, lane);
@@ -151,6 +169,7 @@ __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(o[nt][hf * 2], o[nt][hf * 2 + 1]);
     }
+    __syncthreads();                                    // this buffer is overwritten by the prefetch of the next iteration
   }
 }
 
@@ -160,11 +179,11 @@ __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
 __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
   pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* sq = reinterpret_cast<bf16*>(smem_raw);               // [16][QLD]  q|k|v
-  bf16* sdo = sq + L * QLD;                                   // [16][OLD]  dO
-  bf16* sp = sdo + L * OLD;                                   // [3 warps][2][16][PLD]  P and dS scratch
+  bf16* sbuf = reinterpret_cast<bf16*>(smem_raw);             // 2 x { [16][QLD] q|k|v, [16][OLD] dO }: double buffer
+  constexpr int BUF = L * QLD + L * OLD;
+  bf16* sp = sbuf + 2 * BUF;                                  // [3 warps][2][16][PLD]  P and dS scratch
   float* s_dtab = reinterpret_cast<float*>(sp + 3 * 2 * L * PLD);   // [HG][nbias]
-  __shared__ int s_rid[L];
+  __shared__ int s_rid2[2][L];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nWh = a.H / a.Mh, nWw = a.W / a.Mw;
   const int hgn = a.heads / HG;
@@ -179,22 +198,41 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
     for (int q = 0; q < 4; ++q) dsacc[nt][q] = 0.f;
   for (int i = tid; i < HG * a.nbias; i += 96) s_dtab[i] = 0.f;
 
-  for (int widx = blockIdx.x / hgn; widx < nwin; widx += gridDim.x / hgn) {
-    int win = widx;
-    const int ww = win % nWw; win /= nWw;
-    const int wh = win % nWh;
-    const int b = win / nWh;
-    __syncthreads();
-    load_window_rows(a, sq, a.qkv, b, wh, ww, hg, tid);
+  const int wstep = gridDim.x / hgn;
+  auto decode = [&](int widx, int& b, int& wh, int& ww) {
+    ww = widx % nWw;
+    const int t = widx / nWw;
+    wh = t % nWh;
+    b = t / nWh;
+  };
+  auto prefetch = [&](int widx, int buf) {
+    int b, wh, ww;
+    decode(widx, b, wh, ww);
+    bf16* q = sbuf + buf * BUF;
+    bf16* d = q + L * QLD;
+    load_window_rows(a, q, a.qkv, b, wh, ww, hg, tid);
     for (int ch = tid; ch < L * 12; ch += 96) {
       const int i = ch / 12, c = (ch % 12) * 8;
       const int t = token_index(a, b, wh, ww, i);
-      cp_async16(sdo + i * OLD + c, a.dout + (long)t * a.C + hg * HG * HD + c, 16);
+      cp_async16(d + i * OLD + c, a.dout + (long)t * a.C + hg * HG * HD + c, 16);
     }
+    if (tid < L) s_rid2[buf][tid] = a.masked ? region_id(a, wh, ww, tid) : 0;
+  };
+  int widx0 = blockIdx.x / hgn;
+  int buf = 0;
+  if (widx0 < nwin) prefetch(widx0, 0);
+  cp_async_commit();
+  for (int widx = widx0; widx < nwin; widx += wstep, buf ^= 1) {
+    const int next = widx + wstep;
+    if (next < nwin) prefetch(next, buf ^ 1);
     cp_async_commit();
-    if (tid < L) s_rid[tid] = a.masked ? region_id(a, wh, ww, tid) : 0;
-    cp_async_wait<0>();
+    cp_async_wait<1>();
     __syncthreads();
+    const bf16* sq = sbuf + buf * BUF;
+    const bf16* sdo = sq + L * QLD;
+    const int* s_rid = s_rid2[buf];
+    int b, wh, ww;
+    decode(widx, b, wh, ww);
 
     const int mat = lane >> 3, gq = lane >> 2, tq = lane & 3;
     float p[2][4];
@@ -284,6 +322,7 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
         *reinterpret_cast<uint32_t*>(dst + 2 * a.C + nt * 8) = pack_bf16(dv[nt][hf * 2], dv[nt][hf * 2 + 1]);
       }
     }
+    __syncthreads();                                    // buffers and the P/dS scratch are reused by the next iterations
   }
   __syncthreads();
   {
@@ -331,7 +370,7 @@ int win_attn_bwd(const AttnArgs& a, cudaStream_t st) {
   int rc = check_attn(a);
   if (rc) return rc;
   const int hgn = a.heads / HG, nwin = a.B * (a.H / a.Mh) * (a.W / a.Mw);
-  const int smem = (L * QLD + L * OLD + 3 * 2 * L * PLD) * 2 + HG * a.nbias * 4;
+  const int smem = (2 * (L * QLD + L * OLD) + 3 * 2 * L * PLD) * 2 + HG * a.nbias * 4;
   static int per_sm = 0;
   if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, win_attn_bwd_kernel, 96, smem) != cudaSuccess || per_sm < 1)) per_sm = 4;
   const int slots = max(1, min(nwin, per_sm * tulip_num_sms() / hgn));

@@ -39,7 +39,7 @@ bool tulip_pdl_enabled();          // env TULIP_B200_NO_PDL=1 turns programmatic
 // The step is ~330 short kernels; overlapping each prologue with the predecessor's tail removes a few us per launch.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
 
 template <class... KArgs, class... Args>
 inline void tulip_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const LnArgs a) {
 
 // dx = [dres +] rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w;  dw += dy * xhat; db += dy
 template <int LANES, int NCH, bool REGACC>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnArgs a) {
+__global__ void __launch_bounds__(256, (NCH <= 3) ? 2 : 1) layernorm_bwd_kernel(const LnArgs a) {
   pdl_sync();
   const int lane = threadIdx.x % LANES;
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
@@ -167,6 +167,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnArgs a) {
           o[q] = pack_bf16(r.x + d0, r.y + d1);
         }
         *reinterpret_cast<uint4*>(a.dx + off) = make_uint4(o[0], o[1], o[2], o[3]);
+        if (a.dxs) {                                       // same values, scaled per sample (DropPath backward)
+          const float sc = a.row_scale[row / a.rows_per_sample];
+          uint32_t os[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = unpack_bf16(o[q]);
+            os[q] = pack_bf16(f.x * sc, f.y * sc);
+          }
+          *reinterpret_cast<uint4*>(a.dxs + off) = make_uint4(os[0], os[1], os[2], os[3]);
+        }
       }
     }
   }

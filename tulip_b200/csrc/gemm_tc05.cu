@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const Segments sg, int tiles_m, int tiles_n) {
   using CF = Cfg<BN, EPI>;
   constexpr int STAGES = CF::STAGES;
+  pdl_trigger();                                            // successor may start its own set-up right away
   constexpr int TMEM_COLS = (2 * CF::NACC * BN <= 128) ? 128 : (2 * CF::NACC * BN <= 256 ? 256 : 512);
   static_assert(2 * CF::NACC * BN <= 512, "TMEM budget");
   extern __shared__ unsigned char smem_raw[];
@@ -150,7 +151,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();                                               // set-up above overlapped the previous kernel's tail
+  pdl_wait();                                               // set-up above overlapped the previous kernel's tail
 
   const int num_tiles = tiles_m * tiles_n;
 
@@ -314,11 +315,16 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
             for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad(a[i]);
           } else if (EPI == EPI_HEAD_BWD) {
             // dh = dpred * wd[c] * leaky'(pre);  dwd[c] += sum_rows dpred * leaky(pre)  (summed per thread across tiles)
+            add_bias32(g.bias, n, v);
+            float wdv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) wdv[i] = 0.f;
+            add_bias32(g.wd, c0 + j * BOXC, wdv);                          // vector loads of decoder_pred.weight
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float pre = v[i] + g.bias[n + i];
+              const float pre = v[i];
               cwacc[jj][i] += dp * leaky(pre);
-              v[i] = dp * g.wd[c0 + j * BOXC + i] * (pre > 0.f ? 1.f : 0.01f);
+              v[i] = dp * wdv[i] * (pre > 0.f ? 1.f : 0.01f);
             }
           }
           store_box_row((two_out ? ob2 : ob) + j * BOX_BYTES, r, v);
@@ -352,10 +358,14 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
         float acc = 0.f;
 #pragma unroll 1
         for (int j = jgrp; j < CF::NBOX; j += EPI_GROUPS) {
-          float v[32];
+          float v[32], wdv[32];
           tc::tmem_ld32(taddr + j * BOXC, v);
+          add_bias32(g.bias, n0 + j * BOXC, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc += g.wd[c0 + j * BOXC + i] * leaky(v[i] + g.bias[n0 + j * BOXC + i]);
+          for (int i = 0; i < 32; ++i) wdv[i] = 0.f;
+          add_bias32(g.wd, c0 + j * BOXC, wdv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc = fmaf(wdv[i], leaky(v[i]), acc);
         }
         // deterministic sum of the 3 column groups of a row through shared memory (double-buffered by tile parity)
         float* red = reinterpret_cast<float*>(smem + CF::RED_OFF) + obuf * EPI_GROUPS * BM;
@@ -608,6 +618,7 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
                     const __grid_constant__ CUtensorMap mapX2, const GemmTNArgs g, int kcols_per_tile, int tok_blocks_per_split,
                     int row_seg_len, int row_tiles_per_seg, int y5d) {
   extern __shared__ unsigned char smem_raw[];
+  pdl_trigger();
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + TN_BAR_OFF);
   uint64_t* empty = full + TN_STAGES;
@@ -631,7 +642,7 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
   const int tb_begin = blockIdx.z * tok_blocks_per_split;
   const int tb_end = min(tb_total, tb_begin + tok_blocks_per_split);
   const int ntb = tb_end - tb_begin;
-  if (ntb <= 0) { pdl_sync(); return; }
+  if (ntb <= 0) { pdl_wait(); return; }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TN_STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
@@ -653,7 +664,7 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {

@@ -28,6 +28,8 @@ struct LnArgs {
   int gather; int H2, W2;     // PatchMerging 2x2 gather (tulip.py:92-99): rows = B*H2*W2, C = 4*Csrc
   // backward
   const bf16* dy; const bf16* dres; bf16* dx; float* dw; float* db;
+  // optional second output: dxs = row_scale[sample] * dx  (DropPath backward scale for the branch that consumes dx next)
+  bf16* dxs; const float* row_scale; int rows_per_sample;
 };
 int layernorm_fwd(const LnArgs& a, cudaStream_t st);
 int layernorm_bwd(const LnArgs& a, cudaStream_t st);

@@ -250,7 +250,7 @@ Plan tulip_net::plan(int B) const {
   }
   p.xn_up = act(T0, E); p.st_up = bump.take(T0 * 8);
   // backward scratch (T_s * C_s is largest at stage 0)
-  p.gA = act(T0, E); p.gB = act(T0, E); p.scr_gs = act(T0, E);
+  p.gA = act(T0, E); p.gB = act(T0, E); p.scr_gs = act(T0, E); p.scr_gsm = act(T0, E);
   p.scr_dxn = act(T0, E); p.scr_do = act(T0, E); p.scr_dqkv = act(T0, 3 * E);
   const long big = (long)E * r * r > 4 * E ? (long)E * r * r : 4 * E;      // head dh [T0, E r^2] or block dh [T0, 4E]
   p.scr_big = act(T0, big);
@@ -540,13 +540,17 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     TULIP_CUDA(cudaMemsetAsync(grads + lo, 0, (size_t)(hi - lo) * sizeof(float), st));
   }
 
+  // optional fused DropPath scale for the consumer of dx: set before calling ln_bwd, consumed (reset) by it
+  bf16* ln_dxs = nullptr; const float* ln_scale = nullptr; int ln_rps = 1;
   auto ln_bwd = [&](const bf16* x, int wslot, int bslot, const float* stats, const bf16* dy, const bf16* dres, bf16* dx, int rows,
                     int C, int gather, int H2, int W2) {
     LnArgs a;
     memset(&a, 0, sizeof a);
+    a.dxs = ln_dxs; a.row_scale = ln_scale; a.rows_per_sample = ln_rps;
+    ln_dxs = nullptr; ln_scale = nullptr;
     a.x = x; a.w = c.P(wslot); a.stats = const_cast<float*>(stats); a.dy = dy; a.dres = dres; a.dx = dx;
     a.dw = c.G(wslot); a.db = c.G(bslot); a.rows = rows; a.C = C; a.eps = cfg.ln_eps; a.gather = gather; a.H2 = H2; a.W2 = W2;
-    tag(K_LN_BWD, 0, (dres ? 8.0 : 6.0) * rows * C + 8.0 * rows);
+    tag(K_LN_BWD, 0, (dres ? 8.0 : 6.0) * rows * C + 8.0 * rows + (a.dxs ? 2.0 * rows * C : 0.0));
     return layernorm_bwd(a, st);
   };
   auto dw = [&](const Linear& l, const bf16* dY, const bf16* X, int M) {
@@ -557,6 +561,14 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
 
   bf16* g_cur = c.A(p.gA);       // gradient w.r.t. the current activation
   bf16* g_alt = c.A(p.gB);
+  // DropPath backward: the branch gradients are s * g.  Where g is produced by a LayerNorm backward the scaled copy is
+  // written by that kernel (second output); gsM_ready says scr_gsm already holds s2(block) * g for the block about to run.
+  bool gsM_ready = false;
+  auto want_scaled_for = [&](int bi_next, int rows_per_sample) {      // call right before the ln_bwd that produces g for bi_next
+    if (!drop_scales || bi_next < 0) return;
+    ln_dxs = c.A(p.scr_gsm); ln_scale = drop_scales + (long)(2 * blocks[bi_next].index + 1) * B; ln_rps = rows_per_sample;
+    gsM_ready = true;
+  };
 
   // ---- head: dpred -> dh -> (dWe, dbe, dwd), dxn_up -> norm_up ----
   const bf16* x_last;
@@ -579,10 +591,11 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     // dWe' += dh^T . xn_up (rows un-permuted on store); bias gradient = column sums of dh, same un-permutation
     GemmTNArgs gw = dw(l, dh, c.A(p.xn_up), T0);
     RUN_TN(gw);
+    want_scaled_for(dec_blocks[L - 2].back(), H0 * W0);
     RUN(ln_bwd(x_last, slot_normup_w, slot_normup_b, c.F(p.st_up), c.A(p.scr_dxn), nullptr, g_cur, T0, E, 0, 0, 0));
   }
 
-  auto block_bwd = [&](int bi, const bf16* x_in, bf16* g_io, bf16* g_tmp) -> int {
+  auto block_bwd = [&](int bi, const bf16* x_in, bf16* g_io, bf16* g_tmp, int bi_next) -> int {
     // g_io holds dL/dx_out on entry and dL/dx_in on exit; g_tmp is a same-sized scratch
     const BlockDef& b = blocks[bi];
     const BlockBuf& bb = p.blocks[bi];
@@ -592,10 +605,13 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     // ---- MLP half: x_out = x_mid + s2 * fc2(gelu(fc1(LN2(x_mid)))) ----
     const bf16* gy = g_io;
     if (ds2) {
-      tag(K_ELEMWISE, 0, 4.0 * T * C);
-      RUN(scale_rows_bf16(c.A(p.scr_gs), g_io, ds2, T, C, Hs * Ws, st));
-      gy = c.A(p.scr_gs);
+      if (!gsM_ready) {                                   // g came from a GEMM epilogue: scale it here
+        tag(K_ELEMWISE, 0, 4.0 * T * C);
+        RUN(scale_rows_bf16(c.A(p.scr_gsm), g_io, ds2, T, C, Hs * Ws, st));
+      }
+      gy = c.A(p.scr_gsm);
     }
+    gsM_ready = false;
     {
       const Linear& l2 = linears[b.fc2];
       const Linear& lf1 = linears[b.fc1];
@@ -615,14 +631,10 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       RUN_NT(g1, EPI_STORE);
       RUN_TN(dw(l1, c.A(p.scr_big), c.A(bb.xn2), T));
     }
+    if (ds1) { ln_dxs = c.A(p.scr_gs); ln_scale = ds1; ln_rps = Hs * Ws; }       // scaled copy for the attention branch
     RUN(ln_bwd(c.A(bb.xmid), b.n2w, b.n2b, c.F(bb.st2), c.A(p.scr_dxn), g_io, g_tmp, T, C, 0, 0, 0));   // g_tmp = dL/dx_mid
     // ---- attention half: x_mid = x_in + s1 * proj(attn(qkv(LN1(x_in)))) ----
-    gy = g_tmp;
-    if (ds1) {
-      tag(K_ELEMWISE, 0, 4.0 * T * C);
-      RUN(scale_rows_bf16(c.A(p.scr_gs), g_tmp, ds1, T, C, Hs * Ws, st));
-      gy = c.A(p.scr_gs);
-    }
+    gy = ds1 ? c.A(p.scr_gs) : g_tmp;
     {
       const Linear& lp = linears[b.proj];
       GemmArgs g = nt_args(gy, C, c.Wt(lp), C, T, C, C, nullptr, c.A(p.scr_do), C);
@@ -637,6 +649,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       RUN_NT(gq, EPI_STORE);
       RUN_TN(dw(lq, c.A(p.scr_dqkv), c.A(bb.xn1), T));
     }
+    want_scaled_for(bi_next, Hs * Ws);                    // next block in backward order lives on the same grid
     RUN(ln_bwd(x_in, b.n1w, b.n1b, c.F(bb.st1), c.A(p.scr_dxn), g_tmp, g_io, T, C, 0, 0, 0));            // g_io = dL/dx_in
     return TULIP_OK;
   };
@@ -666,7 +679,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     for (int k = (int)dec_blocks[u].size() - 1; k >= 0; --k) {
       const int bi = dec_blocks[u][k];
       const bf16* x_in = k > 0 ? c.A(p.blocks[dec_blocks[u][k - 1]].xout) : c.A(p.x_skip[u]);
-      rc = block_bwd(bi, x_in, g_cur, g_alt);
+      rc = block_bwd(bi, x_in, g_cur, g_alt, k > 0 ? dec_blocks[u][k - 1] : -1);
       if (rc) return rc;
     }
     {
@@ -701,6 +714,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       GemmArgs g = nt_args(g_cur, 2 * C, c.Wt(l), 2 * C, T / 4, 4 * C, 2 * C, nullptr, c.A(p.scr_big), 4 * C);
       RUN_NT(g, EPI_STORE);
       RUN_TN(dw(l, g_cur, c.A(p.xn_m[s]), T / 4));
+      want_scaled_for(enc_blocks[s].back(), (Hs / 2) * (Ws / 2));       // rows here are merged (2x2) tokens
       RUN(ln_bwd(x_stage_out, merge_nw[s], merge_nb[s], c.F(p.st_m[s]), c.A(p.scr_big), nullptr, g_alt, T / 4, 4 * C, 1, Hs / 2,
                  Ws / 2));
       std::swap(g_cur, g_alt);
@@ -708,7 +722,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     for (int k = (int)enc_blocks[s].size() - 1; k >= 0; --k) {
       const int bi = enc_blocks[s][k];
       const bf16* x_in = k > 0 ? c.A(p.blocks[enc_blocks[s][k - 1]].xout) : (s == 0 ? c.A(p.pe_out) : c.A(p.x_merged[s - 1]));
-      rc = block_bwd(bi, x_in, g_cur, g_alt);
+      rc = block_bwd(bi, x_in, g_cur, g_alt, k > 0 ? enc_blocks[s][k - 1] : -1);
       if (rc) return rc;
     }
     tag(K_ELEMWISE, 0, 6.0 * T * C);

@@ -58,7 +58,7 @@ struct Plan {
   long x_fpe;
   std::vector<long> x_skip, x_up;                  // per decoder stage
   long xn_up, st_up;
-  long gA, gB, scr_gs, scr_big, scr_dxn, scr_do, scr_dqkv;
+  long gA, gB, scr_gs, scr_gsm, scr_big, scr_dxn, scr_do, scr_dqkv;
   std::vector<long> g_save;
   long loss_acc;
   long total;
