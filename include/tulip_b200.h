@@ -64,6 +64,9 @@ int tulip_net_profile(tulip_net* net, int enable);
 int tulip_net_profile_num_tags(void);
 int tulip_net_profile_read(tulip_net* net, int tag, char* name, int name_cap, double* ms, double* flops, double* bytes,
                            int64_t* launches);
+/* the same records one launch at a time, in launch order: returns the number of records; if i is in range also fills
+ * tag, device time (ms), algorithmic FLOPs and bytes of launch i */
+int tulip_net_profile_record(tulip_net* net, int i, int* tag, double* ms, double* flops, double* bytes);
 
 /* forward: x_lo [B,1,h,w] fp32, target [B,1,H,W] fp32 or NULL (mc_drop=True, tulip.py:733-734)
  * params: flat fp32 buffer; param_offsets_host[i] = element offset of parameter i (schema order)

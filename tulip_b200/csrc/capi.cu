@@ -132,6 +132,23 @@ int tulip_net_profile_read(tulip_net* n, int tag_id, char* name, int name_cap, d
   return TULIP_OK;
 }
 
+int tulip_net_profile_record(tulip_net* n, int i, int* tag, double* ms, double* flops, double* bytes) {
+  if (!n) { tulip_set_error("tulip_net_profile_record: null net"); return -1; }
+  const int cnt = (int)n->recs.size();
+  if (i < 0 || i >= cnt) return cnt;
+  const ProfRec& r = n->recs[i];
+  float dt = 0.f;
+  if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&dt, r.e0, r.e1) != cudaSuccess) {
+    tulip_set_error("profile: event read failed");
+    return -1;
+  }
+  if (tag) *tag = r.tag;
+  if (ms) *ms = dt;
+  if (flops) *flops = r.flops;
+  if (bytes) *bytes = r.bytes;
+  return cnt;
+}
+
 int tulip_net_forward(tulip_net* n, int batch, const float* params, const int64_t* offs, const float* x_lo, const float* target,
                       const float* drop_scales, const int* win_mode, void* ws, float* pred, float* losses, void* stream) {
   if (!n || !params || !offs || !x_lo || !ws || !pred) { tulip_set_error("tulip_net_forward: null argument"); return TULIP_ERR_ARG; }
