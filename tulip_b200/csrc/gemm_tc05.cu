@@ -121,7 +121,8 @@ __device__ __forceinline__ void epi_direct16(const GemmArgs& g, int m, int n, fl
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const Segments sg, int tiles_m, int tiles_n) {
+gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmArgs g, const __grid_constant__ Segments sg,
+                    int tiles_m, int tiles_n) {
   using CF = Cfg<BN, EPI>;
   constexpr int STAGES = CF::STAGES;
   pdl_trigger();                                            // successor may start its own set-up right away
@@ -137,7 +138,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
   uint64_t* aempty = afull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_idx_sync(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
     for (int b = 0; b < 2; ++b) {
@@ -156,25 +157,31 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
   const int num_tiles = tiles_m * tiles_n;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: the whole warp walks the loop (uniform control flow), one elected lane issues
+    if (tc::elect_one_sync()) {
       tc::prefetch_tensormap(&maps.A);
       tc::prefetch_tensormap(&maps.B);
-      int stage = 0; uint32_t phase = 0;
-      int abuf = 0; uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-        if (CF::HAS_AUX) {                                  // residual / pre-activation tile for the epilogue
-          tc::mbar_wait(aempty + abuf, aphase ^ 1);
+    }
+    int stage = 0; uint32_t phase = 0;
+    int abuf = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      if (CF::HAS_AUX) {                                  // residual / pre-activation tile for the epilogue
+        tc::mbar_wait(aempty + abuf, aphase ^ 1);
+        if (tc::elect_one_sync()) {
           unsigned char* ab = smem + CF::AUX_OFF + abuf * CF::TILE_BYTES;
           tc::mbar_expect_tx(afull + abuf, CF::TILE_BYTES);
 #pragma unroll
           for (int j = 0; j < CF::NBOX; ++j) tc::tma_load_2d(ab + j * BOX_BYTES, &maps.aux, afull + abuf, n0 + j * BOXC, m0);
-          if (++abuf == CF::AUX_BUFS) { abuf = 0; aphase ^= 1; }
         }
-        for (int s = 0; s < sg.n; ++s) {
-          const int nb = (sg.len[s] + BK - 1) / BK;
-          for (int kb = 0; kb < nb; ++kb) {
-            tc::mbar_wait(empty + stage, phase ^ 1);
+        __syncwarp();
+        if (++abuf == CF::AUX_BUFS) { abuf = 0; aphase ^= 1; }
+      }
+      for (int s = 0; s < sg.n; ++s) {
+        const int nb = (sg.len[s] + BK - 1) / BK;
+        for (int kb = 0; kb < nb; ++kb) {
+          tc::mbar_wait(empty + stage, phase ^ 1);
+          if (tc::elect_one_sync()) {
             unsigned char* a = smem + stage * CF::STAGE_BYTES;
             unsigned char* b = a + CF::A_BYTES;
             tc::mbar_expect_tx(full + stage, CF::STAGE_BYTES);
@@ -185,48 +192,51 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
               tc::tma_load_2d(a, sg.amap[s] ? &maps.A2 : &maps.A, full + stage, kb * BK, m0);
             }
             tc::tma_load_2d(b, sg.bmap[s] ? &maps.B2 : &maps.B, full + stage, sg.bcol[s] + kb * BK, n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc(BM, BN, 0, 0);
-      int stage = 0; uint32_t phase = 0;
-      int buf = 0; uint32_t tphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        tc::mbar_wait(tempty + buf, tphase ^ 1);             // epilogue has drained this accumulator buffer
-        tc::fence_after_sync();
-        const uint32_t tmem_d = tmem_base + buf * CF::NACC * BN;
-        uint32_t started = 0;                                 // bit a: accumulator a has received its first MMA
-        for (int s = 0; s < sg.n; ++s) {
-          const int nb = (sg.len[s] + BK - 1) / BK;
-          const int ac = CF::NACC > 1 ? sg.acc[s] : 0;
-          for (int kb = 0; kb < nb; ++kb) {
-            tc::mbar_wait(full + stage, phase);
-            tc::fence_after_sync();
+    // MMA issuer: same scheme; descriptors stay in uniform registers
+    constexpr uint32_t idesc = tc::make_idesc(BM, BN, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int buf = 0; uint32_t tphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      tc::mbar_wait(tempty + buf, tphase ^ 1);             // epilogue has drained this accumulator buffer
+      tc::fence_after_sync();
+      const uint32_t tmem_d = tmem_base + buf * CF::NACC * BN;
+      uint32_t started = 0;                                 // bit a: accumulator a has received its first MMA
+      for (int s = 0; s < sg.n; ++s) {
+        const int nb = (sg.len[s] + BK - 1) / BK;
+        const int ac = CF::NACC > 1 ? sg.acc[s] : 0;
+        for (int kb = 0; kb < nb; ++kb) {
+          tc::mbar_wait(full + stage, phase);
+          tc::fence_after_sync();
+          if (tc::elect_one_sync()) {
             const unsigned char* a = smem + stage * CF::STAGE_BYTES;
             const uint64_t da = tc::make_desc_kmajor_sw128(a);
             const uint64_t db = tc::make_desc_kmajor_sw128(a + CF::A_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {               // +32 bytes per K=16 step inside the 128B swizzle atom
-              tc::umma_bf16(tmem_d + ac * BN, da + 2 * k, db + 2 * k, idesc, (started >> ac) & 1u);
-              started |= 1u << ac;
-            }
-            tc::umma_commit(empty + stage);                   // smem slot free once these MMAs have read it
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < BK / 16; ++k)               // +32 bytes per K=16 step inside the 128B swizzle atom
+              tc::umma_bf16(tmem_d + ac * BN, da + 2 * k, db + 2 * k, idesc, (k > 0) ? 1u : ((started >> ac) & 1u));
+            tc::umma_commit(empty + stage);                 // smem slot free once these MMAs have read it
           }
+          __syncwarp();
+          started |= 1u << ac;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(tfull + buf);                         // accumulator complete
-        if (++buf == 2) { buf = 0; tphase ^= 1; }
       }
+      if (tc::elect_one_sync()) tc::umma_commit(tfull + buf);   // accumulator complete
+      __syncwarp();
+      if (++buf == 2) { buf = 0; tphase ^= 1; }
     }
   } else {
     const int q = warp & 3;                                   // TMEM lane quarter this warp may access
     const int jgrp = (warp - 2) >> 2;                         // which column boxes of the tile this warp handles
     const int r = q * 32 + lane;                              // row inside the tile
-    const bool issuer = (threadIdx.x == 64);                  // first epilogue thread drives the TMA stores
+    const bool issue_warp = (warp == 2);                      // first epilogue warp drives the TMA stores (one elected lane)
     float cwacc[(CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS][32];   // HEAD_BWD: per-thread column sums for d(decoder_pred.weight)
     if (EPI == EPI_HEAD_BWD) {
 #pragma unroll
@@ -259,7 +269,11 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
       if (CF::TMA_OUT) {
         // staging buffer(s) must have been read out by the previous TMA store(s)
         const bool two_out = (EPI == EPI_GELU) && g.out2 != nullptr;             // pre-activation is saved too: both buffers per tile
-        if (issuer) { if (two_out) tc::tma_store_wait_read<0>(); else tc::tma_store_wait_read<1>(); }
+        // bulk-group bookkeeping is per thread: elect.sync picks the same lane for the same (full) mask every time
+        if (issue_warp) {
+          if (tc::elect_one_sync()) { if (two_out) tc::tma_store_wait_read<0>(); else tc::tma_store_wait_read<1>(); }
+          __syncwarp();
+        }
         tc::named_bar_sync(1, 32 * EPI_WARPS);
         unsigned char* ob = smem + CF::OUT_OFF + (two_out ? 0 : obuf) * CF::TILE_BYTES;
         unsigned char* ob2 = smem + CF::OUT_OFF + CF::TILE_BYTES;                     // GELU: activation tile
@@ -338,7 +352,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
           if (CF::HAS_AUX) tc::mbar_arrive(aempty + abuf);
         }
         tc::named_bar_sync(1, 32 * EPI_WARPS);
-        if (issuer) {
+        if (issue_warp && tc::elect_one_sync()) {
           if (two_out) {
 #pragma unroll
             for (int j = 0; j < CF::NBOX; ++j) tc::tma_store_2d(&maps.out2, ob + j * BOX_BYTES, n0 + j * BOXC, m0);
@@ -412,7 +426,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const GemmArgs g, const S
         }
       }
     }
-    if (CF::TMA_OUT && issuer) tc::tma_store_wait<0>();       // global writes complete before the CTA retires
+    if (CF::TMA_OUT && issue_warp && tc::elect_one_sync()) tc::tma_store_wait<0>();   // global writes complete before the CTA retires
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -615,7 +629,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX,
-                    const __grid_constant__ CUtensorMap mapX2, const GemmTNArgs g, int kcols_per_tile, int tok_blocks_per_split,
+                    const __grid_constant__ CUtensorMap mapX2, const __grid_constant__ GemmTNArgs g, int kcols_per_tile, int tok_blocks_per_split,
                     int row_seg_len, int row_tiles_per_seg, int y5d) {
   extern __shared__ unsigned char smem_raw[];
   pdl_trigger();
@@ -624,7 +638,7 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
   uint64_t* empty = full + TN_STAGES;
   uint64_t* done = empty + TN_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_idx_sync(), lane = threadIdx.x & 31;
 
   // dW rows come in segments of row_seg_len (one segment normally; the 4 shuffle slots of a PixelShuffle-backward
   // gather otherwise), each tiled by 128 rows with TMA zero fill past the segment end
@@ -667,10 +681,11 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tb = tb_begin; tb < tb_end; ++tb) {
-        tc::mbar_wait(empty + stage, phase ^ 1);
+    // TMA producer: whole warp walks the loop, one elected lane issues (see tc::elect_one_sync)
+    int stage = 0; uint32_t phase = 0;
+    for (int tb = tb_begin; tb < tb_end; ++tb) {
+      tc::mbar_wait(empty + stage, phase ^ 1);
+      if (tc::elect_one_sync()) {
         unsigned char* a = smem + stage * TN_STAGE_BYTES;
         tc::mbar_expect_tx(full + stage, (2 + nbx) * TN_BOX);
         if (y5d) {
@@ -686,18 +701,19 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
         }
         for (int j = 0; j < nbx; ++j)
           tc::tma_load_2d(a + (2 + j) * TN_BOX, x2 ? &mapX2 : &mapX, full + stage, (x2 ? k0 - g.K1 : k0) + 64 * j, tb * TN_TOK);
-        if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_x = tc::make_idesc(128, 64 * nbx, 1, 1);
-      const uint32_t idesc_1 = tc::make_idesc(128, 64, 1, 1);
-      const uint64_t d_ones = tc::make_desc_mnmajor_sw128(smem + TN_ONES_OFF, TN_BOX);
-      int stage = 0; uint32_t phase = 0;
-      for (int t = 0; t < ntb; ++t) {
-        tc::mbar_wait(full + stage, phase);
-        tc::fence_after_sync();
+    const uint32_t idesc_x = tc::make_idesc(128, 64 * nbx, 1, 1);
+    const uint32_t idesc_1 = tc::make_idesc(128, 64, 1, 1);
+    const uint64_t d_ones = tc::make_desc_mnmajor_sw128(smem + TN_ONES_OFF, TN_BOX);
+    int stage = 0; uint32_t phase = 0;
+    for (int t = 0; t < ntb; ++t) {
+      tc::mbar_wait(full + stage, phase);
+      tc::fence_after_sync();
+      if (tc::elect_one_sync()) {
         const unsigned char* a = smem + stage * TN_STAGE_BYTES;
         const uint64_t da = tc::make_desc_mnmajor_sw128(a, TN_BOX);
         const uint64_t db = tc::make_desc_mnmajor_sw128(a + 2 * TN_BOX, TN_BOX);
@@ -708,10 +724,12 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
           if (with_db) tc::umma_bf16(tmem_base + 64 * nbx, da + 128 * k, d_ones + 128 * k, idesc_1, acc);
         }
         tc::umma_commit(empty + stage);
-        if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
       }
-      tc::umma_commit(done);
+      __syncwarp();
+      if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
     }
+    if (tc::elect_one_sync()) tc::umma_commit(done);
+    __syncwarp();
   }
   // epilogue: every warp drains its TMEM lane quarter; the two warps of a quarter split the columns
   __syncwarp();

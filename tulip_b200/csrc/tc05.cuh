@@ -29,6 +29,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+// One lane of a fully converged warp (CUTLASS elect_one_sync).  The single-thread roles (TMA producer, MMA issuer) run
+// their loops with the WHOLE warp and predicate only the issuing instruction on this: inside an `if (lane == 0)` region
+// the compiler cannot keep descriptors / barrier addresses in uniform registers and wraps every UTMALDG / UTCHMMA in an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall loop (~1400 cycles per 64-column K block, measured: the issue chain, not
+// HBM or the tensor pipe, bounded every GEMM).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %1;\n\t"
+      "@%%px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+// warp index as a value the compiler knows to be warp-uniform
+__device__ __forceinline__ int warp_idx_sync() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
