@@ -43,7 +43,7 @@ __device__ __forceinline__ void load_bias(const AttnArgs& a, int head, int lane,
 }
 
 // S (two m16n8 accumulators = 16x16) for this warp's head: scale * Q K^T + bias (+ mask)
-__device__ __forceinline__ void scores(const AttnArgs& a, const bf16* sq, int hl, const int* s_rid,
+__device__ __forceinline__ void scores(const AttnArgs& a, const bf16* sq, int hl, uint32_t maskbits,
                                        const float (&bias)[2][4], float (&s)[2][4], int lane) {
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt)
@@ -58,16 +58,60 @@ __device__ __forceinline__ void scores(const AttnArgs& a, const bf16* sq, int hl
     mma_bf16_16816(s[0], af, bfr[0], bfr[1]);
     mma_bf16_16816(s[1], af, bfr[2], bfr[3]);
   }
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v = s[nt][q] * a.scale + bias[nt][q];
+      if ((maskbits >> (nt * 4 + q)) & 1u) v += -100.0f;
+      s[nt][q] = v;
+    }
+}
+
+// Per-thread window geometry, computed once per kernel: every runtime division of the partition / shift / mask index
+// arithmetic lives here, so the per-window work is a handful of adds and compares (the kernels were issue-bound on it).
+struct WinThread {
+  int H, W, Mh, Mw, sh, sw, nWh, nWw;
+  int lr[2], lc[2];        // window (row, col) of the two tokens this thread stages (li, li + 8)
+  int orow[2], ocol[2];    // ... and of the two fragment rows it writes (gq, gq + 8)
+  uint32_t diffH, diffW;   // bit nt*4+q: tokens i, j of that score fragment lie on different sides of the shift seam
+};
+__device__ __forceinline__ WinThread win_thread(const AttnArgs& a, int li, int lane) {
+  WinThread t;
+  t.H = a.H; t.W = a.W; t.Mh = a.Mh; t.Mw = a.Mw; t.sh = a.sh; t.sw = a.sw; t.nWh = a.H / a.Mh; t.nWw = a.W / a.Mw;
   const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    t.lr[k] = (li + 8 * k) / a.Mw; t.lc[k] = (li + 8 * k) % a.Mw;
+    t.orow[k] = (gq + 8 * k) / a.Mw; t.ocol[k] = (gq + 8 * k) % a.Mw;
+  }
+  t.diffH = 0; t.diffW = 0;
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int i = gq + (q >> 1) * 8, j = nt * 8 + 2 * tq + (q & 1);
-      float v = s[nt][q] * a.scale + bias[nt][q];
-      if (a.masked && s_rid[i] != s_rid[j]) v += -100.0f;
-      s[nt][q] = v;
+      // create_mask (tulip.py:261-271): inside the last window row the rows >= Mh - sh form their own region, same for columns
+      if (((i / a.Mw) >= a.Mh - a.sh) != ((j / a.Mw) >= a.Mh - a.sh)) t.diffH |= 1u << (nt * 4 + q);
+      if (((i % a.Mw) >= a.Mw - a.sw) != ((j % a.Mw) >= a.Mw - a.sw)) t.diffW |= 1u << (nt * 4 + q);
     }
+  return t;
+}
+// flat NHWC token index of window-local (r, c) in window (b, wh, ww): win_token_index without the divisions
+__device__ __forceinline__ int win_tok(const WinThread& t, int b, int wh, int ww, int r, int c) {
+  int hs = wh * t.Mh + r + t.sh;
+  int ws = ww * t.Mw + c + t.sw;
+  if (hs >= t.H) hs -= t.H;
+  if (ws >= t.W) ws -= t.W;
+  return (b * t.H + hs) * t.W + ws;
+}
+// shift mask of one window as fragment bits (win_region_id differs between i and j)
+__device__ __forceinline__ uint32_t win_maskbits(const AttnArgs& a, const WinThread& t, int wh, int ww) {
+  if (!a.masked) return 0u;
+  uint32_t m = 0;
+  if (t.sh > 0 && wh == t.nWh - 1) m |= t.diffH;
+  if (t.sw > 0 && ww == t.nWw - 1) m |= t.diffW;
+  return m;
 }
 
 __device__ __forceinline__ void softmax_rows(float (&s)[2][4]) {
@@ -90,24 +134,26 @@ __device__ __forceinline__ void softmax_rows(float (&s)[2][4]) {
   }
 }
 
-__device__ __forceinline__ void load_window_rows(const AttnArgs& a, bf16* sq, const bf16* __restrict__ qkv, int b, int wh,
-                                                 int ww, int hg, int tid) {
-  // 16 tokens x 3 segments (q|k|v) x 96 columns = 576 16-byte chunks over 96 threads
-  for (int ch = tid; ch < L * 3 * 12; ch += 96) {
-    const int i = ch / 36, rem = ch % 36, seg = rem / 12, c = (rem % 12) * 8;
-    const int t = token_index(a, b, wh, ww, i);
-    cp_async16(sq + i * QLD + seg * HG * HD + c, qkv + (long)t * 3 * a.C + seg * a.C + hg * HG * HD + c, 16);
+// stage the q|k|v rows of one window for this CTA's head group: thread -> tokens (li, li+8), 16-byte chunk lc8 of each segment
+__device__ __forceinline__ void load_window_rows(const AttnArgs& a, bf16* sq, const bf16* __restrict__ qkv, const int (&tok)[2],
+                                                 int li, int lc8, int hg) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const bf16* src = qkv + (long)tok[k] * 3 * a.C + hg * HG * HD + lc8;
+    bf16* dst = sq + (li + 8 * k) * QLD + lc8;
+#pragma unroll
+    for (int seg = 0; seg < 3; ++seg) cp_async16(dst + seg * HG * HD, src + seg * a.C, 16);
   }
 }
 
 __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
   pdl_sync();
   __shared__ __align__(16) bf16 sq2[2][L * QLD];       // double buffer: the next window's rows land while this one is computed
-  __shared__ int s_rid2[2][L];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nWh = a.H / a.Mh, nWw = a.W / a.Mw;
+  const int li = tid / 12, lc8 = (tid % 12) * 8;
+  const WinThread wt = win_thread(a, li, lane);
   const int hgn = a.heads / HG;
-  const int nwin = a.B * nWh * nWw;
+  const int nwin = a.B * wt.nWh * wt.nWw;
   // a CTA keeps one head group for its whole life (grid is a multiple of hgn), so bias values live in registers
   const int hg = blockIdx.x % hgn;
   const int head = hg * HG + warp;
@@ -116,35 +162,32 @@ __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
   load_bias(a, head, lane, bias);
 
   auto decode = [&](int widx, int& b, int& wh, int& ww) {
-    ww = widx % nWw;
-    const int t = widx / nWw;
-    wh = t % nWh;
-    b = t / nWh;
+    ww = widx % wt.nWw;
+    const int t = widx / wt.nWw;
+    wh = t % wt.nWh;
+    b = t / wt.nWh;
   };
-  auto prefetch = [&](int widx, int buf) {
-    int b, wh, ww;
-    decode(widx, b, wh, ww);
-    load_window_rows(a, sq2[buf], a.qkv, b, wh, ww, hg, tid);
-    if (tid < L) s_rid2[buf][tid] = a.masked ? region_id(a, wh, ww, tid) : 0;
+  auto prefetch = [&](int b, int wh, int ww, int buf) {
+    const int tok[2] = {win_tok(wt, b, wh, ww, wt.lr[0], wt.lc[0]), win_tok(wt, b, wh, ww, wt.lr[1], wt.lc[1])};
+    load_window_rows(a, sq2[buf], a.qkv, tok, li, lc8, hg);
   };
 
   int widx = blockIdx.x / hgn;
   int buf = 0;
-  if (widx < nwin) prefetch(widx, 0);
+  int b = 0, wh = 0, ww = 0;
+  if (widx < nwin) { decode(widx, b, wh, ww); prefetch(b, wh, ww, 0); }
   cp_async_commit();
   for (; widx < nwin; widx += wstep, buf ^= 1) {
     const int next = widx + wstep;
-    if (next < nwin) prefetch(next, buf ^ 1);
+    int nb = 0, nwh = 0, nww = 0;
+    if (next < nwin) { decode(next, nb, nwh, nww); prefetch(nb, nwh, nww, buf ^ 1); }
     cp_async_commit();
     cp_async_wait<1>();                                 // everything but the newest group (the prefetch) has landed
     __syncthreads();
     const bf16* sq = sq2[buf];
-    const int* s_rid = s_rid2[buf];
-    int b, wh, ww;
-    decode(widx, b, wh, ww);
 
     float s[2][4];
-    scores(a, sq, warp, s_rid, bias, s, lane);
+    scores(a, sq, warp, win_maskbits(a, wt, wh, ww), bias, s, lane);
     softmax_rows(s);
     uint32_t pf[4] = {pack_bf16(s[0][0], s[0][1]), pack_bf16(s[0][2], s[0][3]), pack_bf16(s[1][0], s[1][1]),
                       pack_bf16(s[1][2], s[1][3])};
@@ -161,14 +204,15 @@ __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
       mma_bf16_16816(o[2 * np], pf, bfr[0], bfr[1]);
       mma_bf16_16816(o[2 * np + 1], pf, bfr[2], bfr[3]);
     }
-    const int gq = lane >> 2, tq = lane & 3;
+    const int tq = lane & 3;
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      const int t = token_index(a, b, wh, ww, gq + hf * 8);
+      const int t = win_tok(wt, b, wh, ww, wt.orow[hf], wt.ocol[hf]);
       bf16* dst = a.out + (long)t * a.C + head * HD + 2 * tq;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(o[nt][hf * 2], o[nt][hf * 2 + 1]);
     }
+    b = nb; wh = nwh; ww = nww;
     __syncthreads();                                    // this buffer is overwritten by the prefetch of the next iteration
   }
 }
@@ -183,11 +227,11 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
   constexpr int BUF = L * QLD + L * OLD;
   bf16* sp = sbuf + 2 * BUF;                                  // [3 warps][2][16][PLD]  P and dS scratch
   float* s_dtab = reinterpret_cast<float*>(sp + 3 * 2 * L * PLD);   // [HG][nbias]
-  __shared__ int s_rid2[2][L];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nWh = a.H / a.Mh, nWw = a.W / a.Mw;
+  const int li = tid / 12, lc8 = (tid % 12) * 8;
+  const WinThread wt = win_thread(a, li, lane);
   const int hgn = a.heads / HG;
-  const int nwin = a.B * nWh * nWw;
+  const int nwin = a.B * wt.nWh * wt.nWw;
   const int hg = blockIdx.x % hgn;                              // fixed head group per CTA (grid is a multiple of hgn)
   const int head = hg * HG + warp;
   float bias[2][4], dsacc[2][4];                                // bias values and dS sums at this thread's fixed (i,j) positions
@@ -200,43 +244,38 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
 
   const int wstep = gridDim.x / hgn;
   auto decode = [&](int widx, int& b, int& wh, int& ww) {
-    ww = widx % nWw;
-    const int t = widx / nWw;
-    wh = t % nWh;
-    b = t / nWh;
+    ww = widx % wt.nWw;
+    const int t = widx / wt.nWw;
+    wh = t % wt.nWh;
+    b = t / wt.nWh;
   };
-  auto prefetch = [&](int widx, int buf) {
-    int b, wh, ww;
-    decode(widx, b, wh, ww);
+  auto prefetch = [&](int b, int wh, int ww, int buf) {
     bf16* q = sbuf + buf * BUF;
     bf16* d = q + L * QLD;
-    load_window_rows(a, q, a.qkv, b, wh, ww, hg, tid);
-    for (int ch = tid; ch < L * 12; ch += 96) {
-      const int i = ch / 12, c = (ch % 12) * 8;
-      const int t = token_index(a, b, wh, ww, i);
-      cp_async16(d + i * OLD + c, a.dout + (long)t * a.C + hg * HG * HD + c, 16);
-    }
-    if (tid < L) s_rid2[buf][tid] = a.masked ? region_id(a, wh, ww, tid) : 0;
+    const int tok[2] = {win_tok(wt, b, wh, ww, wt.lr[0], wt.lc[0]), win_tok(wt, b, wh, ww, wt.lr[1], wt.lc[1])};
+    load_window_rows(a, q, a.qkv, tok, li, lc8, hg);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      cp_async16(d + (li + 8 * k) * OLD + lc8, a.dout + (long)tok[k] * a.C + hg * HG * HD + lc8, 16);
   };
   int widx0 = blockIdx.x / hgn;
   int buf = 0;
-  if (widx0 < nwin) prefetch(widx0, 0);
+  int b = 0, wh = 0, ww = 0;
+  if (widx0 < nwin) { decode(widx0, b, wh, ww); prefetch(b, wh, ww, 0); }
   cp_async_commit();
   for (int widx = widx0; widx < nwin; widx += wstep, buf ^= 1) {
     const int next = widx + wstep;
-    if (next < nwin) prefetch(next, buf ^ 1);
+    int nb = 0, nwh = 0, nww = 0;
+    if (next < nwin) { decode(next, nb, nwh, nww); prefetch(nb, nwh, nww, buf ^ 1); }
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
     const bf16* sq = sbuf + buf * BUF;
     const bf16* sdo = sq + L * QLD;
-    const int* s_rid = s_rid2[buf];
-    int b, wh, ww;
-    decode(widx, b, wh, ww);
 
     const int mat = lane >> 3, gq = lane >> 2, tq = lane & 3;
     float p[2][4];
-    scores(a, sq, warp, s_rid, bias, p, lane);
+    scores(a, sq, warp, win_maskbits(a, wt, wh, ww), bias, p, lane);
     softmax_rows(p);
 
     // dP = dO V^T
@@ -313,7 +352,7 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
     }
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      const int t = token_index(a, b, wh, ww, gq + hf * 8);
+      const int t = win_tok(wt, b, wh, ww, wt.orow[hf], wt.ocol[hf]);
       bf16* dst = a.dqkv + (long)t * 3 * a.C + head * HD + 2 * tq;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
@@ -322,6 +361,7 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
         *reinterpret_cast<uint32_t*>(dst + 2 * a.C + nt * 8) = pack_bf16(dv[nt][hf * 2], dv[nt][hf * 2 + 1]);
       }
     }
+    b = nb; wh = nwh; ww = nww;
     __syncthreads();                                    // buffers and the P/dS scratch are reused by the next iterations
   }
   __syncthreads();

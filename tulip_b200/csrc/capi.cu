@@ -80,6 +80,9 @@ void tulip_net_destroy(tulip_net* n) {
   if (n->warena) cudaFree(n->warena);
   if (n->faux) cudaFree(n->faux);
   if (n->items_dev) cudaFree(n->items_dev);
+  for (cudaEvent_t e : n->sync_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : n->ev_pool) cudaEventDestroy(e);
+  if (n->side) cudaStreamDestroy(n->side);
   delete n;
 }
 

@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 
@@ -53,6 +54,24 @@ void tulip_net::prof_end(cudaStream_t st) {
 void tulip_net::prof_reset() {
   recs.clear();
   ev_used = 0;
+}
+
+cudaEvent_t tulip_net::next_sync_event() {
+  if (sync_used == sync_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    sync_pool.push_back(e);
+  }
+  return sync_pool[sync_used++];
+}
+
+static bool side_stream_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TULIP_B200_NO_SIDE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 int tulip_net::build() {
@@ -540,6 +559,40 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     TULIP_CUDA(cudaMemsetAsync(grads + lo, 0, (size_t)(hi - lo) * sizeof(float), st));
   }
 
+  // Weight-gradient GEMMs (gemm_tn) are leaves of the backward graph: nothing on the dX chain reads them.  They run on a
+  // side stream, forked after the kernel that produced their dY operand and joined before that buffer is overwritten, so
+  // at the deep stages (few CTAs per kernel) they fill idle SMs and at every stage they leave the critical path.
+  const bool use_side = !profiling && !side_stream_disabled();
+  if (use_side && !side) TULIP_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  sync_used = 0;
+  bool side_pending = false;
+  auto fork = [&]() {                                     // side stream is ordered after everything issued on `st` so far
+    cudaEvent_t e = next_sync_event();
+    cudaEventRecord(e, st);
+    cudaStreamWaitEvent(side, e, 0);
+  };
+  auto join = [&]() {                                     // `st` waits for everything issued on the side stream so far
+    if (!side_pending) return;
+    cudaEvent_t e = next_sync_event();
+    cudaEventRecord(e, side);
+    cudaStreamWaitEvent(st, e, 0);
+    side_pending = false;
+  };
+  auto run_tn = [&](const GemmTNArgs& gw) -> int {        // one weight-gradient GEMM, on the side stream when enabled
+    if (!use_side) { RUN_TN(gw); return TULIP_OK; }
+    fork();
+    const int rc_ = gemm_tn(gw, side);
+    if (rc_ != TULIP_OK) return rc_;
+    ++kernel_launches;
+    side_pending = true;
+    return TULIP_OK;
+  };
+#define TN_SIDE(g)                      \
+  do {                                  \
+    const int rc__ = run_tn(g);         \
+    if (rc__ != TULIP_OK) return rc__;  \
+  } while (0)
+
   // optional fused DropPath scale for the consumer of dx: set before calling ln_bwd, consumed (reset) by it
   bf16* ln_dxs = nullptr; const float* ln_scale = nullptr; int ln_rps = 1;
   auto ln_bwd = [&](const bf16* x, int wslot, int bslot, const float* stats, const bf16* dy, const bf16* dres, bf16* dx, int rows,
@@ -585,12 +638,12 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     g.dwd = c.G(slot_dec_w);
     g.hd_H = H0; g.hd_W = W0; g.hd_r = r; g.hd_E = E; g.hd_inv_npix = 1.0f / ((float)T0 * r * r);
     RUN_NT(g, EPI_HEAD_BWD);
+    // dWe' += dh^T . xn_up (rows un-permuted on store); bias gradient = column sums of dh, same un-permutation
+    GemmTNArgs gw = dw(l, dh, c.A(p.xn_up), T0);
+    TN_SIDE(gw);
     // dxn_up = dh . We'          (A = dh [T0, E r^2], B = We'^T stored as Wt' [E, E r^2])
     GemmArgs gx = nt_args(dh, (long)E * r * r, c.Wt(l), (long)E * r * r, T0, E, E * r * r, nullptr, c.A(p.scr_dxn), E);
     RUN_NT(gx, EPI_STORE);
-    // dWe' += dh^T . xn_up (rows un-permuted on store); bias gradient = column sums of dh, same un-permutation
-    GemmTNArgs gw = dw(l, dh, c.A(p.xn_up), T0);
-    RUN_TN(gw);
     want_scaled_for(dec_blocks[L - 2].back(), H0 * W0);
     RUN(ln_bwd(x_last, slot_normup_w, slot_normup_b, c.F(p.st_up), c.A(p.scr_dxn), nullptr, g_cur, T0, E, 0, 0, 0));
   }
@@ -603,6 +656,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     const float* ds1 = drop_scales ? drop_scales + (long)(2 * b.index) * B : nullptr;
     const float* ds2 = drop_scales ? drop_scales + (long)(2 * b.index + 1) * B : nullptr;
     // ---- MLP half: x_out = x_mid + s2 * fc2(gelu(fc1(LN2(x_mid)))) ----
+    join();                                               // side work issued outside blocks still reads the g buffers
     const bf16* gy = g_io;
     if (ds2) {
       if (!gsM_ready) {                                   // g came from a GEMM epilogue: scale it here
@@ -615,6 +669,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     {
       const Linear& l2 = linears[b.fc2];
       const Linear& lf1 = linears[b.fc1];
+      TN_SIDE(dw(l2, gy, c.A(bb.hact), T));
       GemmArgs g = nt_args(gy, C, c.Wt(l2), C, T, 4 * C, C, nullptr, c.A(p.scr_big), 4 * C);   // dh = (gy . W2) o gelu'(pre)
       if (bb.hpre >= 0) {
         g.aux = c.A(bb.hpre); g.ldaux = 4 * C;
@@ -625,11 +680,10 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
         g.A2 = c.A(bb.xn2); g.lda2 = C; g.B2 = c.W(lf1); g.ldb2 = C; g.K2 = C; g.bias = c.bias(lf1);
         RUN_NT(g, EPI_DGELU2);
       }
-      RUN_TN(dw(l2, gy, c.A(bb.hact), T));
       const Linear& l1 = linears[b.fc1];
+      TN_SIDE(dw(l1, c.A(p.scr_big), c.A(bb.xn2), T));
       GemmArgs g1 = nt_args(c.A(p.scr_big), 4 * C, c.Wt(l1), 4 * C, T, C, 4 * C, nullptr, c.A(p.scr_dxn), C);
       RUN_NT(g1, EPI_STORE);
-      RUN_TN(dw(l1, c.A(p.scr_big), c.A(bb.xn2), T));
     }
     if (ds1) { ln_dxs = c.A(p.scr_gs); ln_scale = ds1; ln_rps = Hs * Ws; }       // scaled copy for the attention branch
     RUN(ln_bwd(c.A(bb.xmid), b.n2w, b.n2b, c.F(bb.st2), c.A(p.scr_dxn), g_io, g_tmp, T, C, 0, 0, 0));   // g_tmp = dL/dx_mid
@@ -637,18 +691,19 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     gy = ds1 ? c.A(p.scr_gs) : g_tmp;
     {
       const Linear& lp = linears[b.proj];
+      TN_SIDE(dw(lp, gy, c.A(bb.ao), T));
       GemmArgs g = nt_args(gy, C, c.Wt(lp), C, T, C, C, nullptr, c.A(p.scr_do), C);
       RUN_NT(g, EPI_STORE);
-      RUN_TN(dw(lp, gy, c.A(bb.ao), T));
       AttnArgs a = attn_args(c, b, c.A(bb.qkv));
       a.dout = c.A(p.scr_do); a.dqkv = c.A(p.scr_dqkv); a.dbias_table = c.G(b.table);
       tag(K_ATTN_BWD, 160.0 * T * C, 16.0 * T * C);
       RUN(win_attn_bwd(a, st));
       const Linear& lq = linears[b.qkv];
+      TN_SIDE(dw(lq, c.A(p.scr_dqkv), c.A(bb.xn1), T));
       GemmArgs gq = nt_args(c.A(p.scr_dqkv), 3 * C, c.Wt(lq), 3 * C, T, C, 3 * C, nullptr, c.A(p.scr_dxn), C);
       RUN_NT(gq, EPI_STORE);
-      RUN_TN(dw(lq, c.A(p.scr_dqkv), c.A(bb.xn1), T));
     }
+    join();                                               // the LayerNorm backward below overwrites g_io / the scaled copies
     want_scaled_for(bi_next, Hs * Ws);                    // next block in backward order lives on the same grid
     RUN(ln_bwd(x_in, b.n1w, b.n1b, c.F(bb.st1), c.A(p.scr_dxn), g_tmp, g_io, T, C, 0, 0, 0));            // g_io = dL/dx_in
     return TULIP_OK;
@@ -657,12 +712,13 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   auto unmerge_bwd = [&](const Linear& l, const bf16* x_in, const bf16* g_out, bf16* g_in, int Hs, int Ws, int C) -> int {
     // g_out: [B, 2Hs, 2Ws, C/2]; gathered view A[m, ij*C/2 + c] (PixelShuffle backward), then dX and dW
     const int T = B * Hs * Ws;
+    join();
+    GemmTNArgs gw = dw(l, g_out, x_in, T);
+    gw.ldy = C / 2; gw.y_mode = A_UNSHUFFLE; gw.g_H = Hs; gw.g_W = Ws; gw.g_Cc = C / 2;
+    TN_SIDE(gw);
     GemmArgs g = nt_args(g_out, C / 2, c.Wt(l), 2 * C, T, C, 2 * C, nullptr, g_in, C);
     g.a_mode = A_UNSHUFFLE; g.g_H = Hs; g.g_W = Ws; g.g_Cc = C / 2;
     RUN_NT(g, EPI_STORE);
-    GemmTNArgs gw = dw(l, g_out, x_in, T);
-    gw.ldy = C / 2; gw.y_mode = A_UNSHUFFLE; gw.g_H = Hs; gw.g_W = Ws; gw.g_Cc = C / 2;
-    RUN_TN(gw);
     return TULIP_OK;
   };
 
@@ -687,12 +743,13 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       const Linear& l = linears[skip_lin[u]];
       const bf16* x_prev = (u == 0) ? c.A(p.x_fpe) : c.A(p.x_up[u - 1]);
       const bf16* x_enc = (s == 0) ? c.A(p.pe_out) : c.A(p.x_merged[s - 1]);
+      join();
+      GemmTNArgs gw = dw(l, g_cur, x_prev, T);
+      gw.ldx = C; gw.X2 = x_enc; gw.ldx2 = C; gw.K1 = C;
+      TN_SIDE(gw);
       GemmArgs g = nt_args(g_cur, C, c.Wt(l), C, T, 2 * C, C, nullptr, g_alt, C);
       g.out2 = c.A(p.g_save[s]); g.ldo2 = C; g.split_col = C;
       RUN_NT(g, EPI_SPLIT2);
-      GemmTNArgs gw = dw(l, g_cur, x_prev, T);
-      gw.ldx = C; gw.X2 = x_enc; gw.ldx2 = C; gw.K1 = C;
-      RUN_TN(gw);
       std::swap(g_cur, g_alt);
     }
   }
@@ -711,9 +768,10 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       // PatchMerging backward: g_cur is dL/d(x_merged[s]) [T/4, 2C]
       const Linear& l = linears[merge_lin[s]];
       const bf16* x_stage_out = c.A(p.blocks[enc_blocks[s].back()].xout);
+      join();
+      TN_SIDE(dw(l, g_cur, c.A(p.xn_m[s]), T / 4));
       GemmArgs g = nt_args(g_cur, 2 * C, c.Wt(l), 2 * C, T / 4, 4 * C, 2 * C, nullptr, c.A(p.scr_big), 4 * C);
       RUN_NT(g, EPI_STORE);
-      RUN_TN(dw(l, g_cur, c.A(p.xn_m[s]), T / 4));
       want_scaled_for(enc_blocks[s].back(), (Hs / 2) * (Ws / 2));       // rows here are merged (2x2) tokens
       RUN(ln_bwd(x_stage_out, merge_nw[s], merge_nb[s], c.F(p.st_m[s]), c.A(p.scr_big), nullptr, g_alt, T / 4, 4 * C, 1, Hs / 2,
                  Ws / 2));
@@ -737,5 +795,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     tag(K_EMBED_BWD, 0, 4.0 * B * cfg.img_h * cfg.img_w + 2.0 * B * H0 * W0 * E);
     RUN(patch_embed_bwd(e, st));
   }
+  join();                                                 // every gradient is complete on `st` when backward returns
+#undef TN_SIDE
   return TULIP_OK;
 }

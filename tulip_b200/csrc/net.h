@@ -88,6 +88,10 @@ struct tulip_net {
   int cur_tag = K_MISC; double cur_flops = 0, cur_bytes = 0;
   std::vector<ProfRec> recs;
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  // side stream for the weight-gradient GEMMs of the backward pass (they are off the dX critical path)
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> sync_pool; size_t sync_used = 0;
+  cudaEvent_t next_sync_event();
   void tag(int t, double flops, double bytes) { cur_tag = t; cur_flops = flops; cur_bytes = bytes; }
   void prof_begin(cudaStream_t st);
   void prof_end(cudaStream_t st);
