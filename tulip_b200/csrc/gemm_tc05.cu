@@ -49,6 +49,7 @@ struct Cfg {
   static constexpr bool TMA_OUT = epi_tma_out(EPI);
   static constexpr bool HAS_AUX = epi_has_aux(EPI);
   static constexpr int NACC = (EPI == EPI_DGELU2) ? 2 : 1;                  // accumulators per tile
+  static constexpr int NBUF = (EPI == EPI_HEAD) ? 3 : 2;                    // accumulator buffers in TMEM (HEAD: one per epilogue group)
   static constexpr int NBOX = BN / BOXC;
   static constexpr int TILE_BYTES = NBOX * BOX_BYTES;                       // bf16 [128, BN]
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
@@ -58,8 +59,7 @@ struct Cfg {
   static constexpr int STAGES = (BN <= 96) ? (HAS_AUX ? 4 : 6) : ((OUT_BUFS + AUX_BUFS) * TILE_BYTES > 100 * 1024 ? 2 : 3);
   static constexpr int OUT_OFF = STAGES * STAGE_BYTES;
   static constexpr int AUX_OFF = OUT_OFF + OUT_BUFS * TILE_BYTES;
-  static constexpr int RED_OFF = AUX_OFF + AUX_BUFS * TILE_BYTES;           // EPI_HEAD: [2][EPI_GROUPS][128] fp32 partial sums
-  static constexpr int BAR_OFF = RED_OFF + (EPI == EPI_HEAD ? 2 * EPI_GROUPS * BM * 4 : 0);
+  static constexpr int BAR_OFF = AUX_OFF + AUX_BUFS * TILE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;                        // barriers + tmem slot, +1024 manual alignment
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
@@ -126,25 +126,26 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
   using CF = Cfg<BN, EPI>;
   constexpr int STAGES = CF::STAGES;
   pdl_trigger();                                            // successor may start its own set-up right away
-  constexpr int TMEM_COLS = (2 * CF::NACC * BN <= 128) ? 128 : (2 * CF::NACC * BN <= 256 ? 256 : 512);
-  static_assert(2 * CF::NACC * BN <= 512, "TMEM budget");
+  constexpr int NBUF = CF::NBUF;
+  constexpr int TMEM_COLS = (NBUF * CF::NACC * BN <= 128) ? 128 : (NBUF * CF::NACC * BN <= 256 ? 256 : 512);
+  static_assert(NBUF * CF::NACC * BN <= 512, "TMEM budget");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + CF::BAR_OFF);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* afull = tempty + 2;
+  uint64_t* tempty = tfull + 3;
+  uint64_t* afull = tempty + 3;
   uint64_t* aempty = afull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
 
   const int warp = tc::warp_idx_sync(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
-    for (int b = 0; b < 2; ++b) {
-      tc::mbar_init(tfull + b, 1); tc::mbar_init(tempty + b, EPI_WARPS);
-      tc::mbar_init(afull + b, 1); tc::mbar_init(aempty + b, EPI_WARPS);
+    for (int b = 0; b < 3; ++b) {                             // HEAD: one epilogue group (4 warps) drains a buffer
+      tc::mbar_init(tfull + b, 1); tc::mbar_init(tempty + b, EPI == EPI_HEAD ? 4 : EPI_WARPS);
     }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(afull + b, 1); tc::mbar_init(aempty + b, EPI_WARPS); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -230,13 +231,12 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       }
       if (tc::elect_one_sync()) tc::umma_commit(tfull + buf);   // accumulator complete
       __syncwarp();
-      if (++buf == 2) { buf = 0; tphase ^= 1; }
+      if (++buf == NBUF) { buf = 0; tphase ^= 1; }
     }
   } else {
     const int q = warp & 3;                                   // TMEM lane quarter this warp may access
     const int jgrp = (warp - 2) >> 2;                         // which column boxes of the tile this warp handles
     const int r = q * 32 + lane;                              // row inside the tile
-    const bool issue_warp = (warp == 2);                      // first epilogue warp drives the TMA stores (one elected lane)
     float cwacc[(CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS][32];   // HEAD_BWD: per-thread column sums for d(decoder_pred.weight)
     if (EPI == EPI_HEAD_BWD) {
 #pragma unroll
@@ -244,10 +244,15 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
 #pragma unroll
         for (int i = 0; i < 32; ++i) cwacc[a][i] = 0.f;
     }
-    int buf = 0; uint32_t tphase = 0;
+    // Every epilogue warp is autonomous: it owns rows [32q, 32q+32) of its column boxes, stages them in its own 2 KB
+    // slices of the output buffers and issues its own 32 x 32 TMA stores.  No CTA-wide barrier sits on the per-tile path;
+    // warps drift apart by up to one tile (two accumulator buffers), which overlaps their latency chains.
+    // EPI_HEAD instead hands whole tiles to groups of 4 warps (group jgrp <-> accumulator buffer jgrp of 3).
+    int buf = (EPI == EPI_HEAD) ? jgrp : 0; uint32_t tphase = 0;
     int abuf = 0; uint32_t aphase = 0;
     int obuf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int tile_step = (EPI == EPI_HEAD) ? EPI_GROUPS * gridDim.x : gridDim.x;
+    for (int tile = blockIdx.x + ((EPI == EPI_HEAD) ? jgrp * gridDim.x : 0); tile < num_tiles; tile += tile_step) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       const int m = m0 + r;
       // the first box's bias vector is fetched before the accumulator wait so its latency is off the critical path
@@ -269,12 +274,10 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       if (CF::TMA_OUT) {
         // staging buffer(s) must have been read out by the previous TMA store(s)
         const bool two_out = (EPI == EPI_GELU) && g.out2 != nullptr;             // pre-activation is saved too: both buffers per tile
-        // bulk-group bookkeeping is per thread: elect.sync picks the same lane for the same (full) mask every time
-        if (issue_warp) {
-          if (tc::elect_one_sync()) { if (two_out) tc::tma_store_wait_read<0>(); else tc::tma_store_wait_read<1>(); }
-          __syncwarp();
-        }
-        tc::named_bar_sync(1, 32 * EPI_WARPS);
+        // bulk-group bookkeeping is per thread: elect.sync picks the same lane for the same (full) mask every time.
+        // One group per tile and warp: the slices of buffer `obuf` were last read by the group committed two tiles ago.
+        if (tc::elect_one_sync()) { if (two_out) tc::tma_store_wait_read<0>(); else tc::tma_store_wait_read<1>(); }
+        __syncwarp();
         unsigned char* ob = smem + CF::OUT_OFF + (two_out ? 0 : obuf) * CF::TILE_BYTES;
         unsigned char* ob2 = smem + CF::OUT_OFF + CF::TILE_BYTES;                     // GELU: activation tile
         const unsigned char* ab = smem + CF::AUX_OFF + abuf * CF::TILE_BYTES;
@@ -351,27 +354,28 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
           tc::mbar_arrive(tempty + buf);
           if (CF::HAS_AUX) tc::mbar_arrive(aempty + abuf);
         }
-        tc::named_bar_sync(1, 32 * EPI_WARPS);
-        if (issue_warp && tc::elect_one_sync()) {
-          if (two_out) {
+        if (tc::elect_one_sync()) {
+          if (m0 + q * 32 < g.M) {                            // rows past M are clipped by the tensor map; skip all-out boxes
 #pragma unroll
-            for (int j = 0; j < CF::NBOX; ++j) tc::tma_store_2d(&maps.out2, ob + j * BOX_BYTES, n0 + j * BOXC, m0);
-#pragma unroll
-            for (int j = 0; j < CF::NBOX; ++j) tc::tma_store_2d(&maps.out, ob2 + j * BOX_BYTES, n0 + j * BOXC, m0);
-          } else {
-#pragma unroll
-            for (int j = 0; j < CF::NBOX; ++j) tc::tma_store_2d(&maps.out, ob + j * BOX_BYTES, n0 + j * BOXC, m0);
+            for (int jj = 0; jj < (CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS; ++jj) {
+              const int j = jgrp + jj * EPI_GROUPS;
+              if (j >= CF::NBOX) break;
+              if (two_out) tc::tma_store_2d(&maps.out2, ob + j * BOX_BYTES + q * 2048, n0 + j * BOXC, m0 + q * 32);
+              tc::tma_store_2d(&maps.out, (two_out ? ob2 : ob) + j * BOX_BYTES + q * 2048, n0 + j * BOXC, m0 + q * 32);
+            }
           }
           tc::tma_store_commit();
         }
+        __syncwarp();
         obuf ^= 1;
         if (CF::HAS_AUX) { if (++abuf == CF::AUX_BUFS) { abuf = 0; aphase ^= 1; } }
       } else if (EPI == EPI_HEAD) {
-        // tile = 128 low-res pixels x 96 expanded channels n' = ij*E + c of one shuffle slot (tulip.py:174-178, 731)
+        // tile = 128 low-res pixels x 96 expanded channels n' = ij*E + c of one shuffle slot (tulip.py:174-178, 731);
+        // this thread sums the whole channel run of its pixel in a fixed order (bitwise reproducible, no cross-warp step)
         const int ij = n0 / g.hd_E, c0 = n0 % g.hd_E;
         float acc = 0.f;
-#pragma unroll 1
-        for (int j = jgrp; j < CF::NBOX; j += EPI_GROUPS) {
+#pragma unroll
+        for (int j = 0; j < CF::NBOX; ++j) {
           float v[32], wdv[32];
           tc::tmem_ld32(taddr + j * BOXC, v);
           add_bias32(g.bias, n0 + j * BOXC, v);
@@ -381,21 +385,15 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc = fmaf(wdv[i], leaky(v[i]), acc);
         }
-        // deterministic sum of the 3 column groups of a row through shared memory (double-buffered by tile parity)
-        float* red = reinterpret_cast<float*>(smem + CF::RED_OFF) + obuf * EPI_GROUPS * BM;
-        red[jgrp * BM + r] = acc;
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tempty + buf);
-        tc::named_bar_sync(1, 32 * EPI_WARPS);
-        if (jgrp == 0 && m < g.M) {
-          float sum = red[r];
-#pragma unroll
-          for (int a = 1; a < EPI_GROUPS; ++a) sum += red[a * BM + r];
+        if (m < g.M) {
           float* p = g.pred + head_pixel(g, m, ij);
-          if (g.hd_E == BN) *p = sum; else atomicAdd(p, sum);
+          if (g.hd_E == BN) *p = acc; else atomicAdd(p, acc);
         }
-        obuf ^= 1;
+        tphase ^= 1;                                          // this group's buffer completes one phase per tile it handles
+        continue;
       } else {
 #pragma unroll 1
         for (int ch = 2 * jgrp; ch < BN / 16; ch += 2 * EPI_GROUPS) {
@@ -410,7 +408,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tempty + buf);
       }
-      if (++buf == 2) { buf = 0; tphase ^= 1; }
+      if (++buf == NBUF) { buf = 0; tphase ^= 1; }
     }
     if (EPI == EPI_HEAD_BWD) {
       // hd_E == BN on this path (checked by the launcher), so every tile of this CTA covers channels c = 0..95
@@ -426,7 +424,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         }
       }
     }
-    if (CF::TMA_OUT && issue_warp && tc::elect_one_sync()) tc::tma_store_wait<0>();   // global writes complete before the CTA retires
+    if (CF::TMA_OUT && tc::elect_one_sync()) tc::tma_store_wait<0>();   // global writes complete before the CTA retires
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -463,11 +461,12 @@ int launch_bn(int bn, const Maps& maps, const GemmArgs& g, const Segments& sg, c
   return launch<96, EPI>(maps, g, sg, st);
 }
 
-int make_io_map(CUtensorMap* map, const void* base, long ld, int M, int N) {
-  // [M, N] bf16 row-major viewed in 32-column boxes of 128 rows, 64B swizzle (epilogue staging layout)
+int make_io_map(CUtensorMap* map, const void* base, long ld, int M, int N, int box_rows) {
+  // [M, N] bf16 row-major viewed in 32-column boxes of box_rows rows, 64B swizzle (epilogue staging layout): 128-row boxes
+  // for the producer's auxiliary-tile loads, 32-row boxes for the per-warp stores
   const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
   const uint64_t str[1] = {(uint64_t)ld * 2};
-  const uint32_t box[2] = {BOXC, BM};
+  const uint32_t box[2] = {BOXC, (uint32_t)box_rows};
   return tulip_make_tmap(map, base, 2, dims, str, box, 64);
 }
 
@@ -576,16 +575,16 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
   }
   if (epi_tma_out(epi)) {
     if ((reinterpret_cast<uintptr_t>(g.out) & 15) || (g.ldo % 8)) return TULIP_ERR_UNSUPPORTED;
-    rc = make_io_map(&maps.out, g.out, g.ldo, g.M, g.N);
+    rc = make_io_map(&maps.out, g.out, g.ldo, g.M, g.N, 32);
     if (rc) return rc;
     if (epi == EPI_GELU && g.out2) {
       if ((reinterpret_cast<uintptr_t>(g.out2) & 15) || (g.ldo2 % 8)) return TULIP_ERR_UNSUPPORTED;
-      rc = make_io_map(&maps.out2, g.out2, g.ldo2, g.M, g.N);
+      rc = make_io_map(&maps.out2, g.out2, g.ldo2, g.M, g.N, 32);
       if (rc) return rc;
     }
     if (epi_has_aux(epi)) {
       if (!g.aux || (reinterpret_cast<uintptr_t>(g.aux) & 15) || (g.ldaux % 8)) return TULIP_ERR_UNSUPPORTED;
-      rc = make_io_map(&maps.aux, g.aux, g.ldaux, g.M, g.N);
+      rc = make_io_map(&maps.aux, g.aux, g.ldaux, g.M, g.N, BM);
       if (rc) return rc;
     }
   }
