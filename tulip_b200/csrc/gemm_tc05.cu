@@ -55,12 +55,12 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_BUFS = TMA_OUT ? 2 : 0;                          // GELU uses both per tile (pre, act)
-  static constexpr int AUX_BUFS = HAS_AUX ? (BN <= 96 ? 2 : 1) : 0;
-  static constexpr int STAGES = (BN <= 96) ? (HAS_AUX ? 4 : 6) : ((OUT_BUFS + AUX_BUFS) * TILE_BYTES > 100 * 1024 ? 2 : 3);
+  // the auxiliary tile (residual / saved pre-activation) is TMA-loaded straight into the output staging slices by the
+  // epilogue warps and transformed in place, so it costs no shared memory of its own
+  static constexpr int STAGES = (BN <= 96) ? 6 : 3;
   static constexpr int OUT_OFF = STAGES * STAGE_BYTES;
-  static constexpr int AUX_OFF = OUT_OFF + OUT_BUFS * TILE_BYTES;
-  static constexpr int BAR_OFF = AUX_OFF + AUX_BUFS * TILE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;                        // barriers + tmem slot, +1024 manual alignment
+  static constexpr int BAR_OFF = OUT_OFF + OUT_BUFS * TILE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;                        // barriers + tmem slot, +1024 manual alignment
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
@@ -135,9 +135,8 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 3;
-  uint64_t* afull = tempty + 3;
-  uint64_t* aempty = afull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
+  uint64_t* auxbar = tempty + 3;                            // [EPI_WARPS][2]: per-warp, per-staging-buffer aux arrival
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxbar + 2 * EPI_WARPS);
 
   const int warp = tc::warp_idx_sync(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -145,7 +144,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
     for (int b = 0; b < 3; ++b) {                             // HEAD: one epilogue group (4 warps) drains a buffer
       tc::mbar_init(tfull + b, 1); tc::mbar_init(tempty + b, EPI == EPI_HEAD ? 4 : EPI_WARPS);
     }
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(afull + b, 1); tc::mbar_init(aempty + b, EPI_WARPS); }
+    for (int b = 0; b < 2 * EPI_WARPS; ++b) tc::mbar_init(auxbar + b, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -164,20 +163,8 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       tc::prefetch_tensormap(&maps.B);
     }
     int stage = 0; uint32_t phase = 0;
-    int abuf = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-      if (CF::HAS_AUX) {                                  // residual / pre-activation tile for the epilogue
-        tc::mbar_wait(aempty + abuf, aphase ^ 1);
-        if (tc::elect_one_sync()) {
-          unsigned char* ab = smem + CF::AUX_OFF + abuf * CF::TILE_BYTES;
-          tc::mbar_expect_tx(afull + abuf, CF::TILE_BYTES);
-#pragma unroll
-          for (int j = 0; j < CF::NBOX; ++j) tc::tma_load_2d(ab + j * BOX_BYTES, &maps.aux, afull + abuf, n0 + j * BOXC, m0);
-        }
-        __syncwarp();
-        if (++abuf == CF::AUX_BUFS) { abuf = 0; aphase ^= 1; }
-      }
       for (int s = 0; s < sg.n; ++s) {
         const int nb = (sg.len[s] + BK - 1) / BK;
         for (int kb = 0; kb < nb; ++kb) {
@@ -249,9 +236,30 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
     // warps drift apart by up to one tile (two accumulator buffers), which overlaps their latency chains.
     // EPI_HEAD instead hands whole tiles to groups of 4 warps (group jgrp <-> accumulator buffer jgrp of 3).
     int buf = (EPI == EPI_HEAD) ? jgrp : 0; uint32_t tphase = 0;
-    int abuf = 0; uint32_t aphase = 0;
     int obuf = 0;
+    uint32_t auxphase = 0;                                    // bit b: parity of this warp's aux barrier for staging buffer b
+    uint64_t* mybar = auxbar + 2 * (warp - 2);
     const int tile_step = (EPI == EPI_HEAD) ? EPI_GROUPS * gridDim.x : gridDim.x;
+    // aux tile slices of this warp for `tile` -> staging buffer ob (rows 32q.. of its column boxes), one elected lane
+    auto issue_aux = [&](int tile_a, int ob_a) {
+      const int m0a = (tile_a / tiles_n) * BM + q * 32, n0a = (tile_a % tiles_n) * BN;
+      if (m0a >= g.M) return;                                 // nothing of this slice is inside the matrix: no load, no wait
+      constexpr int MYBOX = (CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS;
+      int nmine = 0;
+#pragma unroll
+      for (int jj = 0; jj < MYBOX; ++jj) nmine += (jgrp + jj * EPI_GROUPS < CF::NBOX) ? 1 : 0;
+      tc::mbar_expect_tx(mybar + ob_a, nmine * 2048);
+#pragma unroll
+      for (int jj = 0; jj < MYBOX; ++jj) {
+        const int j = jgrp + jj * EPI_GROUPS;
+        if (j < CF::NBOX)
+          tc::tma_load_2d(smem + CF::OUT_OFF + ob_a * CF::TILE_BYTES + j * BOX_BYTES + q * 2048, &maps.aux, mybar + ob_a, n0a + j * BOXC, m0a);
+      }
+    };
+    if (CF::HAS_AUX && blockIdx.x < num_tiles) {
+      if (tc::elect_one_sync()) issue_aux(blockIdx.x, 0);
+      __syncwarp();
+    }
     for (int tile = blockIdx.x + ((EPI == EPI_HEAD) ? jgrp * gridDim.x : 0); tile < num_tiles; tile += tile_step) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       const int m = m0 + r;
@@ -267,33 +275,50 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
 #pragma unroll
         for (int i = 0; i < 32; ++i) bias0[i] = 0.f;
       }
+      // per-row scalars of the epilogue come from global memory: fetch them before the accumulator wait as well
+      float dp = 0.f;
+      int ij = 0, c0 = 0;
+      if (EPI == EPI_HEAD_BWD) {
+        ij = n0 / g.hd_E; c0 = n0 % g.hd_E;
+        if (m < g.M) {
+          const long px = head_pixel(g, m, ij);
+          const float d = g.pred[px] - g.target[px];
+          const float gs = g.gscale[0] * g.hd_inv_npix;
+          dp = d > 0.f ? gs : (d < 0.f ? -gs : 0.f);
+        }
+      }
+      const float rs = (EPI == EPI_RESID && g.row_scale) ? g.row_scale[(m < g.M ? m : g.M - 1) / g.rows_per_sample] : 1.0f;
+      const bool two_out = (EPI == EPI_GELU) && g.out2 != nullptr;               // pre-activation is saved too: both buffers per tile
+      if (CF::TMA_OUT) {
+        // staging slices must have been read out by this warp's earlier TMA stores.  Bulk-group bookkeeping is per thread:
+        // elect.sync picks the same lane for the same (full) mask every time.  One group per tile and warp: the slices of
+        // buffer `obuf` were last read by the group committed two tiles ago.
+        if (tc::elect_one_sync()) {
+          if (CF::HAS_AUX) {
+            // the other buffer's slices were stored by the previous tile: once that store has read them, the NEXT tile's
+            // aux slices are loaded into them, one full tile ahead of their use
+            tc::tma_store_wait_read<0>();
+            if (tile + tile_step < num_tiles) issue_aux(tile + tile_step, obuf ^ 1);
+          } else if (two_out) {
+            tc::tma_store_wait_read<0>();
+          } else {
+            tc::tma_store_wait_read<1>();
+          }
+        }
+        __syncwarp();
+      }
       tc::mbar_wait(tfull + buf, tphase);
       tc::fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * CF::NACC * BN;
 
       if (CF::TMA_OUT) {
-        // staging buffer(s) must have been read out by the previous TMA store(s)
-        const bool two_out = (EPI == EPI_GELU) && g.out2 != nullptr;             // pre-activation is saved too: both buffers per tile
-        // bulk-group bookkeeping is per thread: elect.sync picks the same lane for the same (full) mask every time.
-        // One group per tile and warp: the slices of buffer `obuf` were last read by the group committed two tiles ago.
-        if (tc::elect_one_sync()) { if (two_out) tc::tma_store_wait_read<0>(); else tc::tma_store_wait_read<1>(); }
-        __syncwarp();
         unsigned char* ob = smem + CF::OUT_OFF + (two_out ? 0 : obuf) * CF::TILE_BYTES;
         unsigned char* ob2 = smem + CF::OUT_OFF + CF::TILE_BYTES;                     // GELU: activation tile
-        const unsigned char* ab = smem + CF::AUX_OFF + abuf * CF::TILE_BYTES;
-        if (CF::HAS_AUX) tc::mbar_wait(afull + abuf, aphase);
-        float dp = 0.f;
-        int ij = 0, c0 = 0;
-        if (EPI == EPI_HEAD_BWD) {
-          ij = n0 / g.hd_E; c0 = n0 % g.hd_E;
-          if (m < g.M) {
-            const long px = head_pixel(g, m, ij);
-            const float d = g.pred[px] - g.target[px];
-            const float gs = g.gscale[0] * g.hd_inv_npix;
-            dp = d > 0.f ? gs : (d < 0.f ? -gs : 0.f);
-          }
+        const unsigned char* ab = ob;                                                 // aux slices are transformed in place
+        if (CF::HAS_AUX && m0 + q * 32 < g.M) {
+          tc::mbar_wait(mybar + obuf, (auxphase >> obuf) & 1u);
+          auxphase ^= 1u << obuf;
         }
-        const float rs = (EPI == EPI_RESID && g.row_scale) ? g.row_scale[(m < g.M ? m : g.M - 1) / g.rows_per_sample] : 1.0f;
 #pragma unroll
         for (int jj = 0; jj < (CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS; ++jj) {
           const int j = jgrp + jj * EPI_GROUPS;
@@ -350,10 +375,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         tc::fence_before_sync();
         tc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          tc::mbar_arrive(tempty + buf);
-          if (CF::HAS_AUX) tc::mbar_arrive(aempty + abuf);
-        }
+        if (lane == 0) tc::mbar_arrive(tempty + buf);
         if (tc::elect_one_sync()) {
           if (m0 + q * 32 < g.M) {                            // rows past M are clipped by the tensor map; skip all-out boxes
 #pragma unroll
@@ -368,7 +390,6 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         }
         __syncwarp();
         obuf ^= 1;
-        if (CF::HAS_AUX) { if (++abuf == CF::AUX_BUFS) { abuf = 0; aphase ^= 1; } }
       } else if (EPI == EPI_HEAD) {
         // tile = 128 low-res pixels x 96 expanded channels n' = ij*E + c of one shuffle slot (tulip.py:174-178, 731);
         // this thread sums the whole channel run of its pixel in a fixed order (bitwise reproducible, no cross-warp step)
@@ -584,7 +605,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     }
     if (epi_has_aux(epi)) {
       if (!g.aux || (reinterpret_cast<uintptr_t>(g.aux) & 15) || (g.ldaux % 8)) return TULIP_ERR_UNSUPPORTED;
-      rc = make_io_map(&maps.aux, g.aux, g.ldaux, g.M, g.N, BM);
+      rc = make_io_map(&maps.aux, g.aux, g.ldaux, g.M, g.N, 32);
       if (rc) return rc;
     }
   }
