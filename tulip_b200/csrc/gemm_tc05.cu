@@ -39,6 +39,37 @@ struct Maps {
   CUtensorMap A, A2, B, B2, out, out2, aux;
 };
 
+// How the 128 x BN output tiles are dealt to the persistent CTAs.
+//   panel == 0: tile-major round robin, A and B blocks of every tile streamed through one ring (any shape).
+//   panel == 1: B-stationary row panels.  CTA (chunk, worker) keeps the weight rows of its n-chunk (npc tiles x kb
+//               64-column blocks) resident in shared memory for its whole life and walks the 128-row panels worker,
+//               worker + nworkers, ...; the A blocks of a panel are loaded once and reused by the npc tiles of the chunk.
+//               The SM<->L2 link (~64 GB/s per SM, measured) is what bounds the wide-stage GEMMs: this cuts the bytes a
+//               CTA pulls per output tile from A + B to A / npc.
+struct Sched {
+  int tiles_m, tiles_n;
+  int panel;
+  int n_chunks, npc, nworkers;
+  int kb;            // 64-column K blocks per tile
+  int klast;         // 16-column MMA steps in the last K block (1..4)
+  int nsa;           // A ring stages (panel mode)
+  int bres_bytes;    // resident B region (panel mode), the A ring follows it
+};
+__device__ __forceinline__ bool tile_at(const Sched& sc, int it, int& mt, int& nt) {
+  if (!sc.panel) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    if (tile >= sc.tiles_m * sc.tiles_n) return false;
+    mt = tile / sc.tiles_n; nt = tile - mt * sc.tiles_n;
+    return true;
+  }
+  const int worker = blockIdx.x / sc.n_chunks, chunk = blockIdx.x - worker * sc.n_chunks;
+  const int mi = it / sc.npc, ni = it - mi * sc.npc;
+  mt = worker + mi * sc.nworkers;
+  nt = chunk * sc.npc + ni;
+  return mt < sc.tiles_m;
+}
+constexpr int NSA_MAX = 8;
+
 __host__ __device__ constexpr bool epi_tma_out(int epi) {
   return epi == EPI_STORE || epi == EPI_GELU || epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_HEAD_BWD || epi == EPI_DGELU2;
 }
@@ -122,7 +153,7 @@ __device__ __forceinline__ void epi_direct16(const GemmArgs& g, int m, int n, fl
 template <int BN, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmArgs g, const __grid_constant__ Segments sg,
-                    int tiles_m, int tiles_n) {
+                    const __grid_constant__ Sched sc) {
   using CF = Cfg<BN, EPI>;
   constexpr int STAGES = CF::STAGES;
   pdl_trigger();                                            // successor may start its own set-up right away
@@ -132,15 +163,17 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + CF::BAR_OFF);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* empty = full + NSA_MAX;
+  uint64_t* tfull = empty + NSA_MAX;
   uint64_t* tempty = tfull + 3;
-  uint64_t* auxbar = tempty + 3;                            // [EPI_WARPS][2]: per-warp, per-staging-buffer aux arrival
+  uint64_t* bfull = tempty + 3;                             // panel mode: resident B region has landed
+  uint64_t* auxbar = bfull + 1;                             // [EPI_WARPS][2]: per-warp, per-staging-buffer aux arrival
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxbar + 2 * EPI_WARPS);
 
   const int warp = tc::warp_idx_sync(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
+    for (int s = 0; s < NSA_MAX; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
+    tc::mbar_init(bfull, 1);
     for (int b = 0; b < 3; ++b) {                             // HEAD: one epilogue group (4 warps) drains a buffer
       tc::mbar_init(tfull + b, 1); tc::mbar_init(tempty + b, EPI == EPI_HEAD ? 4 : EPI_WARPS);
     }
@@ -154,17 +187,77 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                                               // set-up above overlapped the previous kernel's tail
 
-  const int num_tiles = tiles_m * tiles_n;
+  const int tiles_n = sc.tiles_n;
 
-  if (warp == 0) {
+  if (warp == 0 && sc.panel) {
+    // ---- TMA producer, B-stationary panels ----
+    const int worker = blockIdx.x / sc.n_chunks, chunk = blockIdx.x - worker * sc.n_chunks;
+    if (tc::elect_one_sync()) {
+      tc::prefetch_tensormap(&maps.A);
+      tc::prefetch_tensormap(&maps.B);
+      tc::mbar_expect_tx(bfull, sc.bres_bytes);
+      for (int ni = 0; ni < sc.npc; ++ni)
+        for (int kbi = 0; kbi < sc.kb; ++kbi)
+          tc::tma_load_2d(smem + (ni * sc.kb + kbi) * CF::B_BYTES, &maps.B, bfull, kbi * BK, (chunk * sc.npc + ni) * BN);
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int mt = worker; mt < sc.tiles_m; mt += sc.nworkers) {
+      for (int kbi = 0; kbi < sc.kb; ++kbi) {
+        tc::mbar_wait(empty + stage, phase ^ 1);
+        if (tc::elect_one_sync()) {
+          tc::mbar_expect_tx(full + stage, CF::A_BYTES);
+          tc::tma_load_2d(smem + sc.bres_bytes + stage * CF::A_BYTES, &maps.A, full + stage, kbi * BK, mt * BM);
+        }
+        __syncwarp();
+        if (++stage == sc.nsa) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && sc.panel) {
+    // ---- MMA issuer, B-stationary panels: the A blocks of a panel are waited for by its first tile and released by its last
+    constexpr uint32_t idesc = tc::make_idesc(BM, BN, 0, 0);
+    const int worker = blockIdx.x / sc.n_chunks;
+    tc::mbar_wait(bfull, 0);
+    int stage = 0; uint32_t phase = 0;
+    int buf = 0; uint32_t tphase = 0;
+    for (int mt = worker; mt < sc.tiles_m; mt += sc.nworkers) {
+      int st = stage; uint32_t ph = phase;
+      for (int ni = 0; ni < sc.npc; ++ni) {
+        tc::mbar_wait(tempty + buf, tphase ^ 1);
+        tc::fence_after_sync();
+        const uint32_t tmem_d = tmem_base + buf * CF::NACC * BN;
+        st = stage; ph = phase;
+        for (int kbi = 0; kbi < sc.kb; ++kbi) {
+          if (ni == 0) tc::mbar_wait(full + st, ph);
+          tc::fence_after_sync();
+          if (tc::elect_one_sync()) {
+            const uint64_t da = tc::make_desc_kmajor_sw128(smem + sc.bres_bytes + st * CF::A_BYTES);
+            const uint64_t db = tc::make_desc_kmajor_sw128(smem + (ni * sc.kb + kbi) * CF::B_BYTES);
+            const int ks = (kbi == sc.kb - 1) ? sc.klast : BK / 16;      // zero-padded K steps of the last block are skipped
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              if (k < ks) tc::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kbi | k) ? 1u : 0u);
+            if (ni == sc.npc - 1) tc::umma_commit(empty + st);
+          }
+          __syncwarp();
+          if (++st == sc.nsa) { st = 0; ph ^= 1; }
+        }
+        if (tc::elect_one_sync()) tc::umma_commit(tfull + buf);
+        __syncwarp();
+        if (++buf == NBUF) { buf = 0; tphase ^= 1; }
+      }
+      stage = st; phase = ph;
+    }
+  } else if (warp == 0) {
     // TMA producer: the whole warp walks the loop (uniform control flow), one elected lane issues
     if (tc::elect_one_sync()) {
       tc::prefetch_tensormap(&maps.A);
       tc::prefetch_tensormap(&maps.B);
     }
     int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+    int mt, nt;
+    for (int it = 0; tile_at(sc, it, mt, nt); ++it) {
+      const int m0 = mt * BM, n0 = nt * BN;
       for (int s = 0; s < sg.n; ++s) {
         const int nb = (sg.len[s] + BK - 1) / BK;
         for (int kb = 0; kb < nb; ++kb) {
@@ -191,7 +284,8 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
     constexpr uint32_t idesc = tc::make_idesc(BM, BN, 0, 0);
     int stage = 0; uint32_t phase = 0;
     int buf = 0; uint32_t tphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int mt, nt;
+    for (int it = 0; tile_at(sc, it, mt, nt); ++it) {
       tc::mbar_wait(tempty + buf, tphase ^ 1);             // epilogue has drained this accumulator buffer
       tc::fence_after_sync();
       const uint32_t tmem_d = tmem_base + buf * CF::NACC * BN;
@@ -239,10 +333,10 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
     int obuf = 0;
     uint32_t auxphase = 0;                                    // bit b: parity of this warp's aux barrier for staging buffer b
     uint64_t* mybar = auxbar + 2 * (warp - 2);
-    const int tile_step = (EPI == EPI_HEAD) ? EPI_GROUPS * gridDim.x : gridDim.x;
-    // aux tile slices of this warp for `tile` -> staging buffer ob (rows 32q.. of its column boxes), one elected lane
-    auto issue_aux = [&](int tile_a, int ob_a) {
-      const int m0a = (tile_a / tiles_n) * BM + q * 32, n0a = (tile_a % tiles_n) * BN;
+    constexpr int it_step = (EPI == EPI_HEAD) ? EPI_GROUPS : 1;
+    // aux tile slices of this warp for tile (mt_a, nt_a) -> staging buffer ob (rows 32q.. of its column boxes), one elected lane
+    auto issue_aux = [&](int mt_a, int nt_a, int ob_a) {
+      const int m0a = mt_a * BM + q * 32, n0a = nt_a * BN;
       if (m0a >= g.M) return;                                 // nothing of this slice is inside the matrix: no load, no wait
       constexpr int MYBOX = (CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS;
       int nmine = 0;
@@ -256,12 +350,13 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
           tc::tma_load_2d(smem + CF::OUT_OFF + ob_a * CF::TILE_BYTES + j * BOX_BYTES + q * 2048, &maps.aux, mybar + ob_a, n0a + j * BOXC, m0a);
       }
     };
-    if (CF::HAS_AUX && blockIdx.x < num_tiles) {
-      if (tc::elect_one_sync()) issue_aux(blockIdx.x, 0);
+    int mt, nt;
+    if (CF::HAS_AUX && tile_at(sc, 0, mt, nt)) {
+      if (tc::elect_one_sync()) issue_aux(mt, nt, 0);
       __syncwarp();
     }
-    for (int tile = blockIdx.x + ((EPI == EPI_HEAD) ? jgrp * gridDim.x : 0); tile < num_tiles; tile += tile_step) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+    for (int it = (EPI == EPI_HEAD) ? jgrp : 0; tile_at(sc, it, mt, nt); it += it_step) {
+      const int m0 = mt * BM, n0 = nt * BN;
       const int m = m0 + r;
       // the first box's bias vector is fetched before the accumulator wait so its latency is off the critical path
       float bias0[32];
@@ -298,7 +393,8 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
             // the other buffer's slices were stored by the previous tile: once that store has read them, the NEXT tile's
             // aux slices are loaded into them, one full tile ahead of their use
             tc::tma_store_wait_read<0>();
-            if (tile + tile_step < num_tiles) issue_aux(tile + tile_step, obuf ^ 1);
+            int mt2, nt2;
+            if (tile_at(sc, it + it_step, mt2, nt2)) issue_aux(mt2, nt2, obuf ^ 1);
           } else if (two_out) {
             tc::tma_store_wait_read<0>();
           } else {
@@ -461,25 +557,62 @@ bool tc05_disabled() {
   return v == 1;
 }
 
+bool panel_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TULIP_B200_NO_PANEL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// Tile schedule for a BN-wide launch: B-stationary panels when the weight rows of an n-chunk fit next to a useful A ring
+// and every worker gets enough row panels to amortise loading them; tile-major round robin otherwise.
+Sched make_sched(int bn, int epi, const GemmArgs& g, const Segments& sg) {
+  Sched sc;
+  memset(&sc, 0, sizeof sc);
+  sc.tiles_m = ceil_div(g.M, BM); sc.tiles_n = g.N / bn;
+  sc.kb = ceil_div(g.K, BK);
+  sc.klast = ceil_div(g.K - BK * (sc.kb - 1), 16);
+  sc.n_chunks = 1; sc.npc = sc.tiles_n; sc.nworkers = 1;
+  if (panel_disabled() || epi == EPI_DGELU2 || sg.n != 1 || sg.a5d) return sc;
+  const int a_bytes = BM * BK * 2, b_bytes = bn * BK * 2;
+  const int area = (bn <= 96 ? 6 : 3) * (a_bytes + b_bytes);            // Cfg::STAGES * Cfg::STAGE_BYTES
+  const int sms = tulip_num_sms();
+  for (int nc = 1; nc <= sc.tiles_n; ++nc) {
+    if (sc.tiles_n % nc) continue;
+    const int npc = sc.tiles_n / nc;
+    const int bres = npc * sc.kb * b_bytes;
+    if (bres + 3 * a_bytes > area) continue;
+    int nsa = (area - bres) / a_bytes;
+    if (nsa > NSA_MAX) nsa = NSA_MAX;
+    if (npc > 1 && nsa < sc.kb + 1) continue;                            // a panel's A blocks stay resident across its tiles
+    const int nworkers = min(sc.tiles_m, sms / nc);
+    if (nworkers < 1 || sc.tiles_m < 4 * nworkers) break;               // too few row panels per worker: B loads would not amortise
+    sc.panel = 1; sc.n_chunks = nc; sc.npc = npc; sc.nworkers = nworkers; sc.nsa = nsa; sc.bres_bytes = bres;
+    break;
+  }
+  return sc;
+}
+
 template <int BN, int EPI>
-int launch(const Maps& maps, const GemmArgs& g, const Segments& sg, cudaStream_t st) {
+int launch(const Maps& maps, const GemmArgs& g, const Segments& sg, const Sched& sc, cudaStream_t st) {
   using CF = Cfg<BN, EPI>;
   static bool configured = false;
   if (!configured) {
     TULIP_CUDA(cudaFuncSetAttribute(gemm_nt_tc05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::TOTAL));
     configured = true;
   }
-  const int tiles_m = ceil_div(g.M, BM), tiles_n = g.N / BN;
-  const int grid = min(tiles_m * tiles_n, tulip_num_sms());
-  tulip_launch(gemm_nt_tc05_kernel<BN, EPI>, grid, THREADS, CF::TOTAL, st, maps, g, sg, tiles_m, tiles_n);
+  const int grid = sc.panel ? sc.n_chunks * sc.nworkers : min(sc.tiles_m * sc.tiles_n, tulip_num_sms());
+  tulip_launch(gemm_nt_tc05_kernel<BN, EPI>, grid, THREADS, CF::TOTAL, st, maps, g, sg, sc);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
 
 template <int EPI>
-int launch_bn(int bn, const Maps& maps, const GemmArgs& g, const Segments& sg, cudaStream_t st) {
-  if (bn == 192) return launch<192, EPI>(maps, g, sg, st);
-  return launch<96, EPI>(maps, g, sg, st);
+int launch_bn(int bn, const Maps& maps, const GemmArgs& g, const Segments& sg, const Sched& sc, cudaStream_t st) {
+  if (bn == 192) return launch<192, EPI>(maps, g, sg, sc, st);
+  return launch<96, EPI>(maps, g, sg, sc, st);
 }
 
 int make_io_map(CUtensorMap* map, const void* base, long ld, int M, int N, int box_rows) {
@@ -532,7 +665,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
   const bool head = (epi == EPI_HEAD || epi == EPI_HEAD_BWD);
   if (epi == EPI_HEAD_BWD && g.hd_E != 96) return TULIP_ERR_UNSUPPORTED;      // per-CTA dwd accumulation assumes one 96-channel group
   // wide tiles only where the problem is tensor-bound (deep K) and there are enough tiles to fill the chip
-  const int bn = (!head && epi != EPI_DGELU2 && g.N % 192 == 0 && (long)ceil_div(g.M, BM) * (g.N / 192) >= tulip_num_sms()) ? 192 : 96;
+  int bn = (!head && epi != EPI_DGELU2 && g.N % 192 == 0 && (long)ceil_div(g.M, BM) * (g.N / 192) >= tulip_num_sms()) ? 192 : 96;
 
   Segments sg;
   memset(&sg, 0, sizeof sg);
@@ -568,6 +701,12 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
       if (rc) return rc;
       sg.n = 2; sg.len[1] = g.K - K1; sg.amap[1] = 1; sg.bcol[1] = K1;
     }
+  }
+  // schedule: prefer the tile width whose whole weight matrix stays resident in one chunk (A is then read exactly once)
+  Sched sc = make_sched(bn, epi, g, sg);
+  if (bn == 192 && !(sc.panel && sc.n_chunks == 1)) {
+    const Sched s96 = make_sched(96, epi, g, sg);
+    if (s96.panel && (s96.n_chunks == 1 || !sc.panel)) { bn = 96; sc = s96; }
   }
   {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
@@ -610,16 +749,16 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     }
   }
   switch (epi) {
-    case EPI_STORE: return launch_bn<EPI_STORE>(bn, maps, g, sg, st);
-    case EPI_GELU: return launch_bn<EPI_GELU>(bn, maps, g, sg, st);
-    case EPI_RESID: return launch_bn<EPI_RESID>(bn, maps, g, sg, st);
-    case EPI_PIXSHUF: return launch_bn<EPI_PIXSHUF>(bn, maps, g, sg, st);
-    case EPI_SPLIT2: return launch_bn<EPI_SPLIT2>(bn, maps, g, sg, st);
-    case EPI_DGELU: return launch_bn<EPI_DGELU>(bn, maps, g, sg, st);
-    case EPI_DGELU2: return launch<96, EPI_DGELU2>(maps, g, sg, st);     // two accumulators x two buffers: BN = 96 only
-    case EPI_ROWSCALE: return launch_bn<EPI_ROWSCALE>(bn, maps, g, sg, st);
-    case EPI_HEAD: return launch<96, EPI_HEAD>(maps, g, sg, st);
-    case EPI_HEAD_BWD: return launch<96, EPI_HEAD_BWD>(maps, g, sg, st);
+    case EPI_STORE: return launch_bn<EPI_STORE>(bn, maps, g, sg, sc, st);
+    case EPI_GELU: return launch_bn<EPI_GELU>(bn, maps, g, sg, sc, st);
+    case EPI_RESID: return launch_bn<EPI_RESID>(bn, maps, g, sg, sc, st);
+    case EPI_PIXSHUF: return launch_bn<EPI_PIXSHUF>(bn, maps, g, sg, sc, st);
+    case EPI_SPLIT2: return launch_bn<EPI_SPLIT2>(bn, maps, g, sg, sc, st);
+    case EPI_DGELU: return launch_bn<EPI_DGELU>(bn, maps, g, sg, sc, st);
+    case EPI_DGELU2: return launch<96, EPI_DGELU2>(maps, g, sg, sc, st);     // two accumulators x two buffers: BN = 96 only
+    case EPI_ROWSCALE: return launch_bn<EPI_ROWSCALE>(bn, maps, g, sg, sc, st);
+    case EPI_HEAD: return launch<96, EPI_HEAD>(maps, g, sg, sc, st);
+    case EPI_HEAD_BWD: return launch<96, EPI_HEAD_BWD>(maps, g, sg, sc, st);
   }
   return TULIP_ERR_UNSUPPORTED;
 }
