@@ -22,6 +22,7 @@ constexpr int HG = 3;          // heads per CTA
 constexpr int QLD = 3 * HG * HD + 8;   // 296-element rows (592 B): conflict-free ldmatrix
 constexpr int OLD = HG * HD + 8;       // 104-element rows for dO
 constexpr int PLD = 24;                // 16x16 scratch rows (48 B)
+constexpr int BWD_NB = 3;              // backward: staging buffers per CTA (windows in flight + 1)
 
 __device__ __forceinline__ WinGeom geom(const AttnArgs& a) { return WinGeom{a.H, a.W, a.Mh, a.Mw, a.sh, a.sw}; }
 __device__ __forceinline__ int token_index(const AttnArgs& a, int b, int wh, int ww, int i) {
@@ -223,9 +224,9 @@ __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
 __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
   pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* sbuf = reinterpret_cast<bf16*>(smem_raw);             // 2 x { [16][QLD] q|k|v, [16][OLD] dO }: double buffer
+  bf16* sbuf = reinterpret_cast<bf16*>(smem_raw);             // NB x { [16][QLD] q|k|v, [16][OLD] dO }: two windows in flight
   constexpr int BUF = L * QLD + L * OLD;
-  bf16* sp = sbuf + 2 * BUF;                                  // [3 warps][2][16][PLD]  P and dS scratch
+  bf16* sp = sbuf + BWD_NB * BUF;                             // [3 warps][2][16][PLD]  P and dS scratch
   float* s_dtab = reinterpret_cast<float*>(sp + 3 * 2 * L * PLD);   // [HG][nbias]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int li = tid / 12, lc8 = (tid % 12) * 8;
@@ -258,18 +259,28 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
     for (int k = 0; k < 2; ++k)
       cp_async16(d + (li + 8 * k) * OLD + lc8, a.dout + (long)tok[k] * a.C + hg * HG * HD + lc8, 16);
   };
+  // The kernel is bound by loads in flight (5 CTAs of ~120 registers per SM): each CTA keeps the rows of the next TWO
+  // windows on their way (cp.async groups) while it works on the current one.
   int widx0 = blockIdx.x / hgn;
   int buf = 0;
   int b = 0, wh = 0, ww = 0;
-  if (widx0 < nwin) { decode(widx0, b, wh, ww); prefetch(b, wh, ww, 0); }
-  cp_async_commit();
-  for (int widx = widx0; widx < nwin; widx += wstep, buf ^= 1) {
-    const int next = widx + wstep;
-    int nb = 0, nwh = 0, nww = 0;
-    if (next < nwin) { decode(next, nb, nwh, nww); prefetch(nb, nwh, nww, buf ^ 1); }
+#pragma unroll
+  for (int k = 0; k < BWD_NB - 1; ++k) {
+    const int w = widx0 + k * wstep;
+    if (w < nwin) { decode(w, b, wh, ww); prefetch(b, wh, ww, k); }
     cp_async_commit();
-    cp_async_wait<1>();
+  }
+  for (int widx = widx0; widx < nwin; widx += wstep, buf = (buf + 1 == BWD_NB ? 0 : buf + 1)) {
+    const int ahead = widx + (BWD_NB - 1) * wstep;
+    if (ahead < nwin) {
+      int nb, nwh, nww;
+      decode(ahead, nb, nwh, nww);
+      prefetch(nb, nwh, nww, buf + BWD_NB - 1 >= BWD_NB ? buf - 1 : buf + BWD_NB - 1);
+    }
+    cp_async_commit();
+    cp_async_wait<BWD_NB - 1>();                         // everything but the newest groups (the windows ahead) has landed
     __syncthreads();
+    decode(widx, b, wh, ww);
     const bf16* sq = sbuf + buf * BUF;
     const bf16* sdo = sq + L * QLD;
 
@@ -350,18 +361,33 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
       mma_bf16_16816(dk[2 * np], dstf, bq[0], bq[1]);
       mma_bf16_16816(dk[2 * np + 1], dstf, bq[2], bq[3]);
     }
+    // dq|dk|dv replace this head's q|k|v columns in the staging buffer (only this warp reads or writes them), then the CTA
+    // writes the window back with the same coalesced 16-byte pattern it was loaded with: 6 stores per thread instead of 24
+    // 4-byte ones (the fragment layout gives each store instruction only 16 contiguous bytes per row)
+    __syncwarp();
+    {
+      bf16* sw = const_cast<bf16*>(sq);
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int t = win_tok(wt, b, wh, ww, wt.orow[hf], wt.ocol[hf]);
-      bf16* dst = a.dqkv + (long)t * 3 * a.C + head * HD + 2 * tq;
+      for (int hf = 0; hf < 2; ++hf) {
+        bf16* dst = sw + (gq + hf * 8) * QLD + warp * HD + 2 * tq;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(dq[nt][hf * 2] * a.scale, dq[nt][hf * 2 + 1] * a.scale);
-        *reinterpret_cast<uint32_t*>(dst + a.C + nt * 8) = pack_bf16(dk[nt][hf * 2] * a.scale, dk[nt][hf * 2 + 1] * a.scale);
-        *reinterpret_cast<uint32_t*>(dst + 2 * a.C + nt * 8) = pack_bf16(dv[nt][hf * 2], dv[nt][hf * 2 + 1]);
+        for (int nt = 0; nt < 4; ++nt) {
+          *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(dq[nt][hf * 2] * a.scale, dq[nt][hf * 2 + 1] * a.scale);
+          *reinterpret_cast<uint32_t*>(dst + HG * HD + nt * 8) = pack_bf16(dk[nt][hf * 2] * a.scale, dk[nt][hf * 2 + 1] * a.scale);
+          *reinterpret_cast<uint32_t*>(dst + 2 * HG * HD + nt * 8) = pack_bf16(dv[nt][hf * 2], dv[nt][hf * 2 + 1]);
+        }
       }
     }
-    b = nb; wh = nwh; ww = nww;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int t = win_tok(wt, b, wh, ww, wt.lr[k], wt.lc[k]);
+      const bf16* src = sq + (li + 8 * k) * QLD + lc8;
+      bf16* dst = a.dqkv + (long)t * 3 * a.C + hg * HG * HD + lc8;
+#pragma unroll
+      for (int seg = 0; seg < 3; ++seg)
+        *reinterpret_cast<uint4*>(dst + seg * a.C) = *reinterpret_cast<const uint4*>(src + seg * HG * HD);
+    }
     __syncthreads();                                    // buffers and the P/dS scratch are reused by the next iterations
   }
   __syncthreads();
@@ -410,7 +436,7 @@ int win_attn_bwd(const AttnArgs& a, cudaStream_t st) {
   int rc = check_attn(a);
   if (rc) return rc;
   const int hgn = a.heads / HG, nwin = a.B * (a.H / a.Mh) * (a.W / a.Mw);
-  const int smem = (2 * (L * QLD + L * OLD) + 3 * 2 * L * PLD) * 2 + HG * a.nbias * 4;
+  const int smem = (BWD_NB * (L * QLD + L * OLD) + 3 * 2 * L * PLD) * 2 + HG * a.nbias * 4;
   static int per_sm = 0;
   if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, win_attn_bwd_kernel, 96, smem) != cudaSuccess || per_sm < 1)) per_sm = 4;
   const int slots = max(1, min(nwin, per_sm * tulip_num_sms() / hgn));

@@ -83,24 +83,27 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // epilogues issue-bound.
 __device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& ex) {
+// h(x) = 0.5 * poly(t) * t * exp(-x^2/2) (the 0.5 is folded into the coefficients) and ex = exp(-x^2/2)
+__device__ __forceinline__ float gelu_tail(float x, float& ex) {
   const float t = fast_rcp(fmaf(0.231641888f, fabsf(x), 1.0f));            // 0.3275911 / sqrt(2)
-  ex = fast_ex2(-0.72134752f * x * x);                                      // exp(-x^2/2)
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float h = 0.5f * p * t * ex;
-  cdf = x >= 0.f ? 1.0f - h : h;
+  ex = fast_ex2((x * -0.72134752f) * x);                                    // exp(-x^2/2)
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  return (p * t) * ex;
 }
+// gelu(x) = x * Phi(x) = max(x, 0) - |x| h   (x >= 0: x (1 - h);  x < 0: x h)
 __device__ __forceinline__ float gelu_erf(float x) {
-  float cdf, ex;
-  gelu_parts(x, cdf, ex);
-  return x * cdf;
+  float ex;
+  const float h = gelu_tail(x, ex);
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
 }
+// gelu'(x) = Phi(x) + x phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf, ex;
-  gelu_parts(x, cdf, ex);
+  float ex;
+  const float h = gelu_tail(x, ex);
+  const float cdf = x >= 0.f ? 1.0f - h : h;
   return fmaf(x * 0.39894228040143268f, ex, cdf);
 }
 

@@ -702,11 +702,10 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
       sg.n = 2; sg.len[1] = g.K - K1; sg.amap[1] = 1; sg.bcol[1] = K1;
     }
   }
-  // schedule: prefer the tile width whose whole weight matrix stays resident in one chunk (A is then read exactly once)
   Sched sc = make_sched(bn, epi, g, sg);
-  if (bn == 192 && !(sc.panel && sc.n_chunks == 1)) {
-    const Sched s96 = make_sched(96, epi, g, sg);
-    if (s96.panel && (s96.n_chunks == 1 || !sc.panel)) { bn = 96; sc = s96; }
+  if (bn == 192 && !sc.panel && epi != EPI_GELU) {                       // narrow tiles if only they allow the resident-B schedule
+    const Sched s96 = make_sched(96, epi, g, sg);                        // (not for GELU: its epilogue wants the wide tile)
+    if (s96.panel) { bn = 96; sc = s96; }
   }
   {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
