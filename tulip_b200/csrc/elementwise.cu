@@ -666,6 +666,25 @@ int permute_bias(const float* src, float* dst, int n, int R2, int Cc, cudaStream
   return TULIP_OK;
 }
 
+namespace {
+__global__ void __launch_bounds__(256) sum_copies_kernel(const __grid_constant__ SumCopiesArgs a) {
+  pdl_sync();
+  const SumCopiesItem it = a.item[blockIdx.x];
+  for (int i = threadIdx.x; i < it.n; i += blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < a.copies; ++c) s += it.src[(long)c * it.n + i];
+    it.dst[i] += s;
+  }
+}
+}  // namespace
+
+int sum_copies(const SumCopiesArgs& a, cudaStream_t st) {
+  if (a.count <= 0) return TULIP_OK;
+  tulip_launch(sum_copies_kernel, a.count, 256, 0, st, a);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
 int add_inplace_bf16(bf16* dst, const bf16* src, long n, cudaStream_t st) {
   TULIP_REQUIRE(n % 8 == 0, "add_inplace: length must be a multiple of 8");
   tulip_launch(add_inplace_kernel, ew_grid(n / 8, 256), 256, 0, st, reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), n / 8);

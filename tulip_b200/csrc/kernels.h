@@ -9,6 +9,7 @@ struct AttnArgs {
   bf16* dqkv;                 // bwd: [B*H*W, 3C]
   const float* bias_table;    // [nbias, heads] fp32 (the nn.Parameter itself)
   float* dbias_table;         // bwd: [nbias, heads] fp32, accumulated
+  int dbias_copies;           // bwd: CTAs spread their atomics over this many copies of the table (stride nbias*heads), >= 1
   int B, H, W, C, heads;
   int Mh, Mw;                 // window used for partitioning (backup window when H < win_h)
   int sh, sw;                 // cyclic shift (0,0 for W-MSA)
@@ -58,6 +59,10 @@ int pack_weights(const float* flat, bf16* arena, const PackItem* items_dev, int 
 int permute_bias(const float* src, float* dst, int n, int R2, int Cc, cudaStream_t st);
 
 int add_inplace_bf16(bf16* dst, const bf16* src, long n, cudaStream_t st);
+// dst_j[i] += sum_c src_j[c * n_j + i] for up to 64 (dst, src, n) triples in one launch
+struct SumCopiesItem { float* dst; const float* src; int n; };
+struct SumCopiesArgs { SumCopiesItem item[64]; int count; int copies; };
+int sum_copies(const SumCopiesArgs& a, cudaStream_t st);
 int scale_rows_bf16(bf16* dst, const bf16* src, const float* row_scale, int rows, int C, int rows_per_sample, cudaStream_t st);
 int l1_loss(const float* pred, const float* target, long n, int log_transform, float* acc2, float* out2, cudaStream_t st);
 

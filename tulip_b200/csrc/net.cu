@@ -276,6 +276,10 @@ Plan tulip_net::plan(int B) const {
   p.g_save.assign(L, -1);
   for (int s = 0; s < L - 1; ++s) p.g_save[s] = act((long)B * (H0 >> s) * (W0 >> s), E << s);
   p.loss_acc = bump.take(256);
+  {
+    const long nbias = (2 * cfg.win_h - 1) * (2 * cfg.win_w - 1);
+    p.dtab_scr = bump.take((long)blocks.size() * DTAB_COPIES * nbias * cfg.num_heads[L - 1] * 4);
+  }
   p.total = bump.off;
   return p;
 }
@@ -593,6 +597,10 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     if (rc__ != TULIP_OK) return rc__;  \
   } while (0)
 
+  // bias-table gradients are accumulated in DTAB_COPIES scratch copies per block (see win_attn_bwd_kernel) and summed once
+  const long dtab_stride = (long)DTAB_COPIES * (2 * cfg.win_h - 1) * (2 * cfg.win_w - 1) * cfg.num_heads[L - 1];
+  TULIP_CUDA(cudaMemsetAsync(c.F(p.dtab_scr), 0, (size_t)blocks.size() * dtab_stride * sizeof(float), st));
+
   // optional fused DropPath scale for the consumer of dx: set before calling ln_bwd, consumed (reset) by it
   bf16* ln_dxs = nullptr; const float* ln_scale = nullptr; int ln_rps = 1;
   auto ln_bwd = [&](const bf16* x, int wslot, int bslot, const float* stats, const bf16* dy, const bf16* dres, bf16* dx, int rows,
@@ -695,7 +703,8 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       GemmArgs g = nt_args(gy, C, c.Wt(lp), C, T, C, C, nullptr, c.A(p.scr_do), C);
       RUN_NT(g, EPI_STORE);
       AttnArgs a = attn_args(c, b, c.A(bb.qkv));
-      a.dout = c.A(p.scr_do); a.dqkv = c.A(p.scr_dqkv); a.dbias_table = c.G(b.table);
+      a.dout = c.A(p.scr_do); a.dqkv = c.A(p.scr_dqkv);
+      a.dbias_table = c.F(p.dtab_scr) + (long)bi * dtab_stride; a.dbias_copies = DTAB_COPIES;
       tag(K_ATTN_BWD, 160.0 * T * C, 16.0 * T * C);
       RUN(win_attn_bwd(a, st));
       const Linear& lq = linears[b.qkv];
@@ -794,6 +803,19 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     e.dy = g_cur; e.dw = c.G(slot_pe_w); e.db = c.G(slot_pe_b); e.dln_w = c.G(slot_pe_nw); e.dln_b = c.G(slot_pe_nb);
     tag(K_EMBED_BWD, 0, 4.0 * B * cfg.img_h * cfg.img_w + 2.0 * B * H0 * W0 * E);
     RUN(patch_embed_bwd(e, st));
+  }
+  {
+    TULIP_REQUIRE(blocks.size() <= 64, "tulip_b200: more than 64 Swin blocks");
+    SumCopiesArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.copies = DTAB_COPIES;
+    for (size_t bi = 0; bi < blocks.size(); ++bi) {
+      const BlockDef& b = blocks[bi];
+      const int n = (2 * cfg.win_h - 1) * (2 * cfg.win_w - 1) * cfg.num_heads[b.stage];
+      sa.item[sa.count++] = SumCopiesItem{c.G(b.table), c.F(p.dtab_scr) + (long)bi * dtab_stride, n};
+    }
+    tag(K_ELEMWISE, 0, 0);
+    RUN(sum_copies(sa, st));
   }
   join();                                                 // every gradient is complete on `st` when backward returns
 #undef TN_SIDE

@@ -61,8 +61,11 @@ struct Plan {
   long gA, gB, scr_gs, scr_gsm, scr_big, scr_dxn, scr_do, scr_dqkv;
   std::vector<long> g_save;
   long loss_acc;
+  long dtab_scr;                                   // [blocks][DTAB_COPIES][nbias * heads] fp32 scratch of the bias-table gradients
   long total;
 };
+
+constexpr int DTAB_COPIES = 32;
 
 struct tulip_net {
   tulip_config cfg;
