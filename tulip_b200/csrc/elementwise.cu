@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(256, (NCH <= 3) ? 2 : 1) layernorm_bwd_kernel(
   const int ngroups = (gridDim.x * blockDim.x) / LANES;
   const int nch = a.C >> 3;
   const float invC = 1.0f / (float)a.C;
+  const int copy_off = a.dcopies > 1 ? (int)(blockIdx.x % a.dcopies) * a.dstride : 0;
+  float* const gdw = a.dw + copy_off;
+  float* const gdb = a.db + copy_off;
   float accw[REGACC ? NCH : 1][8], accb[REGACC ? NCH : 1][8];
   if (REGACC) {
 #pragma unroll
@@ -141,8 +144,8 @@ __global__ void __launch_bounds__(256, (NCH <= 3) ? 2 : 1) layernorm_bwd_kernel(
             accw[i][2 * q] += g.x * h0; accw[i][2 * q + 1] += g.y * h1;
             accb[i][2 * q] += g.x;      accb[i][2 * q + 1] += g.y;
           } else {
-            atomicAdd(a.dw + ch * 8 + 2 * q, g.x * h0); atomicAdd(a.dw + ch * 8 + 2 * q + 1, g.y * h1);
-            atomicAdd(a.db + ch * 8 + 2 * q, g.x);      atomicAdd(a.db + ch * 8 + 2 * q + 1, g.y);
+            atomicAdd(gdw + ch * 8 + 2 * q, g.x * h0); atomicAdd(gdw + ch * 8 + 2 * q + 1, g.y * h1);
+            atomicAdd(gdb + ch * 8 + 2 * q, g.x);      atomicAdd(gdb + ch * 8 + 2 * q + 1, g.y);
           }
         }
       }
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(256, (NCH <= 3) ? 2 : 1) layernorm_bwd_kernel(
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += s_acc[w * 2 * a.C + i];
-      atomicAdd((i < a.C ? a.dw : a.db - a.C) + i, t);
+      atomicAdd((i < a.C ? gdw : gdb - a.C) + i, t);
     }
   }
 }
@@ -384,10 +387,11 @@ __global__ void __launch_bounds__(256) patch_embed_bwd_kernel(const EmbedArgs a)
   for (int i = threadIdx.x; i < a.E * 12; i += blockDim.x) {
     const int c = i / 12, k = i % 12;
     const float v = s_acc[i];
-    if (k < 8) atomicAdd(a.dw + c * 8 + k, v);
-    else if (k == 8) atomicAdd(a.db + c, v);
-    else if (k == 9) atomicAdd(a.dln_w + c, v);
-    else if (k == 10) atomicAdd(a.dln_b + c, v);
+    const int co = a.dcopies > 1 ? (int)(blockIdx.x % a.dcopies) * a.dstride : 0;
+    if (k < 8) atomicAdd(a.dw + co + c * 8 + k, v);
+    else if (k == 8) atomicAdd(a.db + co + c, v);
+    else if (k == 9) atomicAdd(a.dln_w + co + c, v);
+    else if (k == 10) atomicAdd(a.dln_b + co + c, v);
   }
 }
 
@@ -672,7 +676,7 @@ __global__ void __launch_bounds__(256) sum_copies_kernel(const __grid_constant__
   const SumCopiesItem it = a.item[blockIdx.x];
   for (int i = threadIdx.x; i < it.n; i += blockDim.x) {
     float s = 0.f;
-    for (int c = 0; c < a.copies; ++c) s += it.src[(long)c * it.n + i];
+    for (int c = 0; c < a.copies; ++c) s += it.src[(long)c * it.stride + i];
     it.dst[i] += s;
   }
 }

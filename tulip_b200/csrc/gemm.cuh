@@ -42,7 +42,7 @@ struct GemmArgs {
   int split_col;
   // head
   const float* wd; const float* target; float* pred; const float* gscale;
-  float* dwd;
+  float* dwd; int dwd_copies;              // EPI_HEAD_BWD: CTA b adds into copy b % dwd_copies (stride hd_E); 0/1 = in place
   int hd_H, hd_W, hd_r, hd_E; float hd_inv_npix;
 };
 

@@ -536,7 +536,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float cw = warp_sum(cwacc[jj][i]);
-            if (lane == i) atomicAdd(g.dwd + j * BOXC + i, cw);
+            if (lane == i) atomicAdd(g.dwd + (g.dwd_copies > 1 ? (int)(blockIdx.x % g.dwd_copies) * g.hd_E : 0) + j * BOXC + i, cw);
           }
         }
       }

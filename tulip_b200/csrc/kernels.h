@@ -31,6 +31,9 @@ struct LnArgs {
   const bf16* dy; const bf16* dres; bf16* dx; float* dw; float* db;
   // optional second output: dxs = row_scale[sample] * dx  (DropPath backward scale for the branch that consumes dx next)
   bf16* dxs; const float* row_scale; int rows_per_sample;
+  // dw / db may point at `dcopies` scratch copies `dstride` floats apart: CTA b accumulates into copy b % dcopies
+  // (same-address atomics from every CTA of the grid serialise in L2); 0 or 1 = accumulate in place
+  int dcopies; int dstride;
 };
 int layernorm_fwd(const LnArgs& a, cudaStream_t st);
 int layernorm_bwd(const LnArgs& a, cudaStream_t st);
@@ -42,6 +45,7 @@ struct EmbedArgs {
   bf16* y;                    // [B, Himg/ph, Wimg/4, E]
   int B, Himg, Wimg, ph, E; float eps;
   const bf16* dy; float* dw; float* db; float* dln_w; float* dln_b;
+  int dcopies; int dstride;   // as in LnArgs, applied to all four gradient pointers
 };
 int patch_embed_fwd(const EmbedArgs& a, cudaStream_t st);
 int patch_embed_bwd(const EmbedArgs& a, cudaStream_t st);
@@ -60,8 +64,8 @@ int permute_bias(const float* src, float* dst, int n, int R2, int Cc, cudaStream
 
 int add_inplace_bf16(bf16* dst, const bf16* src, long n, cudaStream_t st);
 // dst_j[i] += sum_c src_j[c * n_j + i] for up to 64 (dst, src, n) triples in one launch
-struct SumCopiesItem { float* dst; const float* src; int n; };
-struct SumCopiesArgs { SumCopiesItem item[64]; int count; int copies; };
+struct SumCopiesItem { float* dst; const float* src; int n; int stride; };   // copy c of element i is src[c * stride + i]
+struct SumCopiesArgs { SumCopiesItem item[128]; int count; int copies; };
 int sum_copies(const SumCopiesArgs& a, cudaStream_t st);
 int scale_rows_bf16(bf16* dst, const bf16* src, const float* row_scale, int rows, int C, int rows_per_sample, cudaStream_t st);
 int l1_loss(const float* pred, const float* target, long n, int log_transform, float* acc2, float* out2, cudaStream_t st);

@@ -276,10 +276,7 @@ Plan tulip_net::plan(int B) const {
   p.g_save.assign(L, -1);
   for (int s = 0; s < L - 1; ++s) p.g_save[s] = act((long)B * (H0 >> s) * (W0 >> s), E << s);
   p.loss_acc = bump.take(256);
-  {
-    const long nbias = (2 * cfg.win_h - 1) * (2 * cfg.win_w - 1);
-    p.dtab_scr = bump.take((long)blocks.size() * DTAB_COPIES * nbias * cfg.num_heads[L - 1] * 4);
-  }
+  p.gscr = bump.take(GRAD_SCRATCH_BYTES);
   p.total = bump.off;
   return p;
 }
@@ -597,9 +594,24 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     if (rc__ != TULIP_OK) return rc__;  \
   } while (0)
 
-  // bias-table gradients are accumulated in DTAB_COPIES scratch copies per block (see win_attn_bwd_kernel) and summed once
-  const long dtab_stride = (long)DTAB_COPIES * (2 * cfg.win_h - 1) * (2 * cfg.win_w - 1) * cfg.num_heads[L - 1];
-  TULIP_CUDA(cudaMemsetAsync(c.F(p.dtab_scr), 0, (size_t)blocks.size() * dtab_stride * sizeof(float), st));
+  // gradient copies (net.h GRAD_COPIES): grad_scratch(n) hands out GRAD_COPIES x n zeroed floats; sum_to() registers where
+  // elements [off, off + n) of every copy are finally added
+  TULIP_CUDA(cudaMemsetAsync(c.F(p.gscr), 0, (size_t)GRAD_SCRATCH_BYTES, st));
+  long gscr_used = 0;
+  SumCopiesArgs sum_args;
+  memset(&sum_args, 0, sizeof sum_args);
+  sum_args.copies = GRAD_COPIES;
+  bool gscr_overflow = false;
+  auto grad_scratch = [&](int n) -> float* {
+    float* ptr = c.F(p.gscr) + gscr_used;
+    gscr_used += align_up((long)n * GRAD_COPIES, 64);
+    if (gscr_used * 4 > GRAD_SCRATCH_BYTES) { gscr_overflow = true; return c.F(p.gscr); }
+    return ptr;
+  };
+  auto sum_to = [&](float* dst, const float* scr, int off, int n, int stride) {
+    if (sum_args.count >= 128) { gscr_overflow = true; return; }
+    sum_args.item[sum_args.count++] = SumCopiesItem{dst, scr + off, n, stride};
+  };
 
   // optional fused DropPath scale for the consumer of dx: set before calling ln_bwd, consumed (reset) by it
   bf16* ln_dxs = nullptr; const float* ln_scale = nullptr; int ln_rps = 1;
@@ -610,7 +622,13 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     a.dxs = ln_dxs; a.row_scale = ln_scale; a.rows_per_sample = ln_rps;
     ln_dxs = nullptr; ln_scale = nullptr;
     a.x = x; a.w = c.P(wslot); a.stats = const_cast<float*>(stats); a.dy = dy; a.dres = dres; a.dx = dx;
-    a.dw = c.G(wslot); a.db = c.G(bslot); a.rows = rows; a.C = C; a.eps = cfg.ln_eps; a.gather = gather; a.H2 = H2; a.W2 = W2;
+    a.rows = rows; a.C = C; a.eps = cfg.ln_eps; a.gather = gather; a.H2 = H2; a.W2 = W2;
+    {
+      float* scr = grad_scratch(2 * C);                    // per copy: [dgamma | dbeta]
+      a.dw = scr; a.db = scr + C; a.dcopies = GRAD_COPIES; a.dstride = 2 * C;
+      sum_to(c.G(wslot), scr, 0, C, 2 * C);
+      sum_to(c.G(bslot), scr, C, C, 2 * C);
+    }
     tag(K_LN_BWD, 0, (dres ? 8.0 : 6.0) * rows * C + 8.0 * rows + (a.dxs ? 2.0 * rows * C : 0.0));
     return layernorm_bwd(a, st);
   };
@@ -643,7 +661,11 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     bf16* dh = c.A(p.scr_big);
     GemmArgs g = nt_args(c.A(p.xn_up), E, c.W(l), E, T0, E * r * r, E, c.bias(l), dh, (long)E * r * r);
     g.wd = c.P(slot_dec_w); g.pred = const_cast<float*>(pred); g.target = target; g.gscale = grad_loss;
-    g.dwd = c.G(slot_dec_w);
+    {
+      float* scr = grad_scratch(E);
+      g.dwd = scr; g.dwd_copies = GRAD_COPIES;
+      sum_to(c.G(slot_dec_w), scr, 0, E, E);
+    }
     g.hd_H = H0; g.hd_W = W0; g.hd_r = r; g.hd_E = E; g.hd_inv_npix = 1.0f / ((float)T0 * r * r);
     RUN_NT(g, EPI_HEAD_BWD);
     // dWe' += dh^T . xn_up (rows un-permuted on store); bias gradient = column sums of dh, same un-permutation
@@ -704,7 +726,12 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       RUN_NT(g, EPI_STORE);
       AttnArgs a = attn_args(c, b, c.A(bb.qkv));
       a.dout = c.A(p.scr_do); a.dqkv = c.A(p.scr_dqkv);
-      a.dbias_table = c.F(p.dtab_scr) + (long)bi * dtab_stride; a.dbias_copies = DTAB_COPIES;
+      {
+        const int n = a.nbias * a.heads;
+        float* scr = grad_scratch(n);
+        a.dbias_table = scr; a.dbias_copies = GRAD_COPIES;
+        sum_to(c.G(b.table), scr, 0, n, n);
+      }
       tag(K_ATTN_BWD, 160.0 * T * C, 16.0 * T * C);
       RUN(win_attn_bwd(a, st));
       const Linear& lq = linears[b.qkv];
@@ -800,23 +827,21 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     memset(&e, 0, sizeof e);
     e.x = x_lo; e.w = c.P(slot_pe_w); e.b = c.P(slot_pe_b); e.ln_w = c.P(slot_pe_nw); e.ln_b = c.P(slot_pe_nb);
     e.B = B; e.Himg = cfg.img_h; e.Wimg = cfg.img_w; e.ph = cfg.patch_h; e.E = E; e.eps = cfg.ln_eps;
-    e.dy = g_cur; e.dw = c.G(slot_pe_w); e.db = c.G(slot_pe_b); e.dln_w = c.G(slot_pe_nw); e.dln_b = c.G(slot_pe_nb);
+    e.dy = g_cur;
+    {
+      float* scr = grad_scratch(11 * E);                   // per copy: [dW (E x 8) | db | dgamma | dbeta]
+      e.dw = scr; e.db = scr + 8 * E; e.dln_w = scr + 9 * E; e.dln_b = scr + 10 * E; e.dcopies = GRAD_COPIES; e.dstride = 11 * E;
+      sum_to(c.G(slot_pe_w), scr, 0, 8 * E, 11 * E);
+      sum_to(c.G(slot_pe_b), scr, 8 * E, E, 11 * E);
+      sum_to(c.G(slot_pe_nw), scr, 9 * E, E, 11 * E);
+      sum_to(c.G(slot_pe_nb), scr, 10 * E, E, 11 * E);
+    }
     tag(K_EMBED_BWD, 0, 4.0 * B * cfg.img_h * cfg.img_w + 2.0 * B * H0 * W0 * E);
     RUN(patch_embed_bwd(e, st));
   }
-  {
-    TULIP_REQUIRE(blocks.size() <= 64, "tulip_b200: more than 64 Swin blocks");
-    SumCopiesArgs sa;
-    memset(&sa, 0, sizeof sa);
-    sa.copies = DTAB_COPIES;
-    for (size_t bi = 0; bi < blocks.size(); ++bi) {
-      const BlockDef& b = blocks[bi];
-      const int n = (2 * cfg.win_h - 1) * (2 * cfg.win_w - 1) * cfg.num_heads[b.stage];
-      sa.item[sa.count++] = SumCopiesItem{c.G(b.table), c.F(p.dtab_scr) + (long)bi * dtab_stride, n};
-    }
-    tag(K_ELEMWISE, 0, 0);
-    RUN(sum_copies(sa, st));
-  }
+  TULIP_REQUIRE(!gscr_overflow, "tulip_b200: gradient-copy scratch exhausted (too many blocks for GRAD_SCRATCH_BYTES / 128 items)");
+  tag(K_ELEMWISE, 0, 8.0 * gscr_used);
+  RUN(sum_copies(sum_args, st));
   join();                                                 // every gradient is complete on `st` when backward returns
 #undef TN_SIDE
   return TULIP_OK;
