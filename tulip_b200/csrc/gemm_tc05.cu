@@ -215,38 +215,49 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
     }
   } else if (warp == 1 && sc.panel) {
     // ---- MMA issuer, B-stationary panels: the A blocks of a panel are waited for by its first tile and released by its last
+    // Descriptors are advanced incrementally (the start-address field is the only part that changes and never carries out
+    // of its 14 bits for shared-memory addresses): the issue chain of this warp -- uniform-datapath instructions with long
+    // dependent latencies -- is what paces short-K tiles, so it is kept to a wait, four UTCHMMAs and a commit per K block.
     constexpr uint32_t idesc = tc::make_idesc(BM, BN, 0, 0);
+    constexpr uint32_t A16 = CF::A_BYTES >> 4, B16 = CF::B_BYTES >> 4;
     const int worker = blockIdx.x / sc.n_chunks;
+    const uint64_t dA0 = tc::make_desc_kmajor_sw128(smem + sc.bres_bytes);
+    const uint64_t dB0 = tc::make_desc_kmajor_sw128(smem);
     tc::mbar_wait(bfull, 0);
     int stage = 0; uint32_t phase = 0;
+    uint64_t da_stage = dA0;
     int buf = 0; uint32_t tphase = 0;
+    const int kb = sc.kb, npc = sc.npc, nsa = sc.nsa, klast = sc.klast;
     for (int mt = worker; mt < sc.tiles_m; mt += sc.nworkers) {
-      int st = stage; uint32_t ph = phase;
-      for (int ni = 0; ni < sc.npc; ++ni) {
+      int st = stage; uint32_t ph = phase; uint64_t da = da_stage;
+      uint64_t db = dB0;
+      for (int ni = 0; ni < npc; ++ni) {
         tc::mbar_wait(tempty + buf, tphase ^ 1);
         tc::fence_after_sync();
         const uint32_t tmem_d = tmem_base + buf * CF::NACC * BN;
-        st = stage; ph = phase;
-        for (int kbi = 0; kbi < sc.kb; ++kbi) {
-          if (ni == 0) tc::mbar_wait(full + st, ph);
-          tc::fence_after_sync();
+        st = stage; ph = phase; da = da_stage;
+        for (int kbi = 0; kbi < kb; ++kbi) {
+          if (ni == 0) { tc::mbar_wait(full + st, ph); tc::fence_after_sync(); }
           if (tc::elect_one_sync()) {
-            const uint64_t da = tc::make_desc_kmajor_sw128(smem + sc.bres_bytes + st * CF::A_BYTES);
-            const uint64_t db = tc::make_desc_kmajor_sw128(smem + (ni * sc.kb + kbi) * CF::B_BYTES);
-            const int ks = (kbi == sc.kb - 1) ? sc.klast : BK / 16;      // zero-padded K steps of the last block are skipped
+            if (kbi < kb - 1 || klast == 4) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              if (k < ks) tc::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kbi | k) ? 1u : 0u);
-            if (ni == sc.npc - 1) tc::umma_commit(empty + st);
+              for (int k = 0; k < BK / 16; ++k) tc::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kbi | k) ? 1u : 0u);
+            } else {                                          // zero-padded K steps of the last block are skipped
+#pragma unroll
+              for (int k = 0; k < BK / 16 - 1; ++k)
+                if (k < klast) tc::umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kbi | k) ? 1u : 0u);
+            }
+            if (ni == npc - 1) tc::umma_commit(empty + st);
           }
           __syncwarp();
-          if (++st == sc.nsa) { st = 0; ph ^= 1; }
+          db += B16;
+          if (++st == nsa) { st = 0; ph ^= 1; da = dA0; } else { da += A16; }
         }
         if (tc::elect_one_sync()) tc::umma_commit(tfull + buf);
         __syncwarp();
         if (++buf == NBUF) { buf = 0; tphase ^= 1; }
       }
-      stage = st; phase = ph;
+      stage = st; phase = ph; da_stage = da;
     }
   } else if (warp == 0) {
     // TMA producer: the whole warp walks the loop (uniform control flow), one elected lane issues
@@ -282,6 +293,9 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
   } else if (warp == 1) {
     // MMA issuer: same scheme; descriptors stay in uniform registers
     constexpr uint32_t idesc = tc::make_idesc(BM, BN, 0, 0);
+    constexpr uint32_t S16 = CF::STAGE_BYTES >> 4, A16 = CF::A_BYTES >> 4;
+    const uint64_t d0 = tc::make_desc_kmajor_sw128(smem);
+    uint64_t da = d0;                                       // A descriptor of `stage`; its B block follows A16 further
     int stage = 0; uint32_t phase = 0;
     int buf = 0; uint32_t tphase = 0;
     int mt, nt;
@@ -293,21 +307,19 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       for (int s = 0; s < sg.n; ++s) {
         const int nb = (sg.len[s] + BK - 1) / BK;
         const int ac = CF::NACC > 1 ? sg.acc[s] : 0;
+        const uint32_t tmem_acc = tmem_d + ac * BN;
         for (int kb = 0; kb < nb; ++kb) {
           tc::mbar_wait(full + stage, phase);
           tc::fence_after_sync();
           if (tc::elect_one_sync()) {
-            const unsigned char* a = smem + stage * CF::STAGE_BYTES;
-            const uint64_t da = tc::make_desc_kmajor_sw128(a);
-            const uint64_t db = tc::make_desc_kmajor_sw128(a + CF::A_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)               // +32 bytes per K=16 step inside the 128B swizzle atom
-              tc::umma_bf16(tmem_d + ac * BN, da + 2 * k, db + 2 * k, idesc, (k > 0) ? 1u : ((started >> ac) & 1u));
+              tc::umma_bf16(tmem_acc, da + 2 * k, da + A16 + 2 * k, idesc, (k > 0) ? 1u : ((started >> ac) & 1u));
             tc::umma_commit(empty + stage);                 // smem slot free once these MMAs have read it
           }
           __syncwarp();
           started |= 1u << ac;
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; da = d0; } else { da += S16; }
         }
       }
       if (tc::elect_one_sync()) tc::umma_commit(tfull + buf);   // accumulator complete
@@ -867,24 +879,24 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
     const uint32_t idesc_x = tc::make_idesc(128, 64 * nbx, 1, 1);
     const uint32_t idesc_1 = tc::make_idesc(128, 64, 1, 1);
     const uint64_t d_ones = tc::make_desc_mnmajor_sw128(smem + TN_ONES_OFF, TN_BOX);
+    const uint64_t d0 = tc::make_desc_mnmajor_sw128(smem, TN_BOX);
+    constexpr uint32_t S16 = TN_STAGE_BYTES >> 4, B16 = (2 * TN_BOX) >> 4;
+    uint64_t da = d0;                                         // dY boxes of `stage`; the X boxes follow B16 further
     int stage = 0; uint32_t phase = 0;
     for (int t = 0; t < ntb; ++t) {
       tc::mbar_wait(full + stage, phase);
       tc::fence_after_sync();
       if (tc::elect_one_sync()) {
-        const unsigned char* a = smem + stage * TN_STAGE_BYTES;
-        const uint64_t da = tc::make_desc_mnmajor_sw128(a, TN_BOX);
-        const uint64_t db = tc::make_desc_mnmajor_sw128(a + 2 * TN_BOX, TN_BOX);
 #pragma unroll
         for (int k = 0; k < TN_TOK / 16; ++k) {                   // 16 tokens = 2 groups of 8 rows = 2048 B per K-step
           const uint32_t acc = (t | k) ? 1u : 0u;
-          tc::umma_bf16(tmem_base, da + 128 * k, db + 128 * k, idesc_x, acc);
+          tc::umma_bf16(tmem_base, da + 128 * k, da + B16 + 128 * k, idesc_x, acc);
           if (with_db) tc::umma_bf16(tmem_base + 64 * nbx, da + 128 * k, d_ones + 128 * k, idesc_1, acc);
         }
         tc::umma_commit(empty + stage);
       }
       __syncwarp();
-      if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == TN_STAGES) { stage = 0; phase ^= 1; da = d0; } else { da += S16; }
     }
     if (tc::elect_one_sync()) tc::umma_commit(done);
     __syncwarp();
