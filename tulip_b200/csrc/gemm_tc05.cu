@@ -74,6 +74,18 @@ __host__ __device__ constexpr bool epi_tma_out(int epi) {
   return epi == EPI_STORE || epi == EPI_GELU || epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_HEAD_BWD || epi == EPI_DGELU2;
 }
 __host__ __device__ constexpr bool epi_has_aux(int epi) { return epi == EPI_RESID || epi == EPI_DGELU; }
+// Output staging buffers (each one [128, BN] bf16 tile).  Two let the stores of tile i overlap the epilogue of tile i+1 and,
+// for the aux epilogues, hold the in-place aux tile of the next tile.  The wide tile keeps one where it can: its GEMMs are
+// the deep-K ones, paced by the depth of the operand ring, and a CTA only sees a handful of tiles.
+__host__ __device__ constexpr int cfg_out_bufs(int bn, int epi) {
+  return !epi_tma_out(epi) ? 0 : ((bn > 96 && !epi_has_aux(epi)) ? 1 : 2);
+}
+// operand ring stages: whatever fits next to the staging buffers (227 KB - barriers - alignment slack), at most 8
+__host__ __device__ constexpr int cfg_stages(int bn, int epi) {
+  const int stage = (128 + bn) * 64 * 2;
+  const int n = (227 * 1024 - 512 - 1024 - cfg_out_bufs(bn, epi) * 128 * bn * 2) / stage;
+  return n > 8 ? 8 : n;
+}
 
 template <int BN, int EPI>
 struct Cfg {
@@ -85,10 +97,10 @@ struct Cfg {
   static constexpr int TILE_BYTES = NBOX * BOX_BYTES;                       // bf16 [128, BN]
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_BUFS = TMA_OUT ? 2 : 0;                          // GELU uses both per tile (pre, act)
+  static constexpr int OUT_BUFS = cfg_out_bufs(BN, EPI);                    // GELU with a saved pre-activation uses both per tile
   // the auxiliary tile (residual / saved pre-activation) is TMA-loaded straight into the output staging slices by the
   // epilogue warps and transformed in place, so it costs no shared memory of its own
-  static constexpr int STAGES = (BN <= 96) ? 6 : 3;
+  static constexpr int STAGES = cfg_stages(BN, EPI);
   static constexpr int OUT_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = OUT_OFF + OUT_BUFS * TILE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 512 + 1024;                        // barriers + tmem slot, +1024 manual alignment
@@ -407,7 +419,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
             tc::tma_store_wait_read<0>();
             int mt2, nt2;
             if (tile_at(sc, it + it_step, mt2, nt2)) issue_aux(mt2, nt2, obuf ^ 1);
-          } else if (two_out) {
+          } else if (two_out || CF::OUT_BUFS == 1) {
             tc::tma_store_wait_read<0>();
           } else {
             tc::tma_store_wait_read<1>();
@@ -420,8 +432,8 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * CF::NACC * BN;
 
       if (CF::TMA_OUT) {
-        unsigned char* ob = smem + CF::OUT_OFF + (two_out ? 0 : obuf) * CF::TILE_BYTES;
-        unsigned char* ob2 = smem + CF::OUT_OFF + CF::TILE_BYTES;                     // GELU: activation tile
+        unsigned char* ob = smem + CF::OUT_OFF + ((two_out || CF::OUT_BUFS == 1) ? 0 : obuf) * CF::TILE_BYTES;
+        unsigned char* ob2 = smem + CF::OUT_OFF + (CF::OUT_BUFS - 1) * CF::TILE_BYTES; // GELU: activation tile (two_out only)
         const unsigned char* ab = ob;                                                 // aux slices are transformed in place
         if (CF::HAS_AUX && m0 + q * 32 < g.M) {
           tc::mbar_wait(mybar + obuf, (auxphase >> obuf) & 1u);
@@ -589,7 +601,7 @@ Sched make_sched(int bn, int epi, const GemmArgs& g, const Segments& sg) {
   sc.n_chunks = 1; sc.npc = sc.tiles_n; sc.nworkers = 1;
   if (panel_disabled() || epi == EPI_DGELU2 || sg.n != 1 || sg.a5d) return sc;
   const int a_bytes = BM * BK * 2, b_bytes = bn * BK * 2;
-  const int area = (bn <= 96 ? 6 : 3) * (a_bytes + b_bytes);            // Cfg::STAGES * Cfg::STAGE_BYTES
+  const int area = cfg_stages(bn, epi) * (a_bytes + b_bytes);          // Cfg::STAGES * Cfg::STAGE_BYTES
   const int sms = tulip_num_sms();
   for (int nc = 1; nc <= sc.tiles_n; ++nc) {
     if (sc.tiles_n % nc) continue;
@@ -714,6 +726,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
       sg.n = 2; sg.len[1] = g.K - K1; sg.amap[1] = 1; sg.bcol[1] = K1;
     }
   }
+  if (epi == EPI_GELU && g.out2 != nullptr) bn = 96;                     // saving the pre-activation needs both staging buffers
   Sched sc = make_sched(bn, epi, g, sg);
   if (bn == 192 && !sc.panel && epi != EPI_GELU) {                       // narrow tiles if only they allow the resident-B schedule
     const Sched s96 = make_sched(96, epi, g, sg);                        // (not for GELU: its epilogue wants the wide tile)
