@@ -20,7 +20,7 @@ def tag(name):
     for k, t in (("gemm_tn_", "gemm_tn"), ("win_attn_fwd", "win_attn_fwd"), ("win_attn_bwd", "win_attn_bwd"),
                  ("layernorm_fwd", "layernorm_fwd"), ("layernorm_bwd", "layernorm_bwd"), ("patch_embed_fwd", "patch_embed_fwd"),
                  ("patch_embed_bwd", "patch_embed_bwd"), ("pack_weights", "pack_weights"), ("l1_loss", "l1_loss"),
-                 ("scale_rows", "elementwise"), ("add_inplace", "elementwise"), ("permute_bias", "misc")):
+                 ("scale_rows", "elementwise"), ("add_inplace", "elementwise"), ("sum_copies", "elementwise"), ("permute_bias", "misc")):
         if k in n:
             return t
     return None
