@@ -72,6 +72,37 @@ def test_gemm_nt_gelu_resid_dgelu(ops, impl):
     assert rel_l2(got, bf16r(want)) <= 1e-3
 
 
+@pytest.mark.parametrize("M,N,K,epi", [(76001, 288, 96, "store"), (76001, 96, 384, "resid"), (76001, 384, 96, "gelu"),
+                                         (38000, 576, 192, "store"), (76001, 96, 288, "dgelu")])
+def test_gemm_nt_resident_weight_schedule(ops, M, N, K, epi):
+    """Shapes of the wide stages at full batch: enough 128-row panels per CTA for the B-stationary schedule (weights
+    resident in shared memory, A blocks shared by the tiles of a panel), ragged M, every TMA-store epilogue."""
+    x, w, b = rnd(M, K, seed=11), rnd(N, K, seed=12, scale=K ** -0.5), rnd(N, seed=13)
+    pre = F.linear(x, w, b)
+    if epi == "store":
+        got = ops.linear(x.cuda(), w.cuda(), b.cuda()).float().cpu()
+        want = pre
+    elif epi == "gelu":
+        got = ops.linear(x.cuda(), w.cuda(), b.cuda(), epilogue=ops.EPI_GELU, save_pre=False)[0].float().cpu()   # wide tile
+        got2 = ops.linear(x.cuda(), w.cuda(), b.cuda(), epilogue=ops.EPI_GELU)                                # narrow, two outputs
+        want = F.gelu(pre)
+        assert torch.equal(got2[0].float().cpu(), got) and rel_l2(got2[1].float().cpu(), bf16r(pre)) <= 1e-3
+    elif epi == "resid":
+        res = rnd(M, N, seed=14)
+        rows_per = 1000
+        scale = (torch.arange(-(-M // rows_per)) % 3).float() * 0.55
+        want = res + scale.repeat_interleave(rows_per)[:M, None] * pre
+        got = ops.linear(x.cuda(), w.cuda(), b.cuda(), epilogue=ops.EPI_RESID, aux=res.cuda(), row_scale=scale.cuda(),
+                         rows_per_sample=rows_per).float().cpu()
+    else:
+        aux = rnd(M, N, seed=15)
+        a = aux.clone().requires_grad_(True)
+        F.gelu(a).sum().backward()
+        want = F.linear(x, w) * a.grad
+        got = ops.linear(x.cuda(), w.cuda(), None, epilogue=ops.EPI_DGELU, aux=aux.cuda()).float().cpu()
+    assert rel_l2(got, bf16r(want)) <= 1e-3 and ulp_frac(got, bf16r(want)) >= 0.99
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("M,N,K", [(4096, 288, 96), (1000, 96, 384), (64, 768, 3072), (8192, 1536, 96)])
 def test_gemm_tn_wgrad(ops, impl, M, N, K):

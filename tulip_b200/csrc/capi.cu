@@ -5,6 +5,7 @@
 #include <string>
 
 #include "net.h"
+#include <vector>
 
 namespace {
 thread_local std::string g_error;
@@ -60,6 +61,62 @@ int gemm_tn(const GemmTNArgs& g, cudaStream_t st) {
   return gemm_tn_mma(g, st);
 }
 
+static bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TULIP_B200_GRAPHS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static uint64_t hash_words(const void* p, size_t bytes) {          // FNV-1a over small host arrays (offsets, window modes)
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+template <class F>
+int tulip_net::run_graphed(GraphSlot& slot, const std::vector<uint64_t>& key, cudaStream_t st, F&& body) {
+  if (!graphs_enabled() || profiling) return body();
+  if (slot.exec && slot.key == key) {
+    TULIP_CUDA(cudaGraphLaunch(slot.exec, st));
+    kernel_launches += slot.launches;
+    return TULIP_OK;
+  }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return body();   // caller captures already
+  if (slot.last != key) {                                  // first sighting of this call: run it eagerly (also warms every
+    slot.last = key;                                       // one-time initialisation: attributes, occupancy queries, allocations)
+    return body();
+  }
+  if (slot.exec) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+  const long before = kernel_launches;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return body(); }
+  const int rc = body();
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != TULIP_OK || ce != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    kernel_launches = before;
+    if (rc != TULIP_OK) return rc;
+    slot.last.clear();
+    return body();                                         // capture refused: fall back to plain launches
+  }
+  const cudaError_t ie = cudaGraphInstantiate(&slot.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) { slot.exec = nullptr; cudaGetLastError(); kernel_launches = before; slot.last.clear(); return body(); }
+  slot.key = key;
+  slot.launches = kernel_launches - before;
+  kernel_launches = before;
+  TULIP_CUDA(cudaGraphLaunch(slot.exec, st));
+  kernel_launches += slot.launches;
+  return TULIP_OK;
+}
+
+
 extern "C" {
 
 const char* tulip_last_error(void) { return g_error.c_str(); }
@@ -83,6 +140,8 @@ void tulip_net_destroy(tulip_net* n) {
   for (cudaEvent_t e : n->sync_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : n->ev_pool) cudaEventDestroy(e);
   if (n->side) cudaStreamDestroy(n->side);
+  if (n->graph_fwd.exec) cudaGraphExecDestroy(n->graph_fwd.exec);
+  if (n->graph_bwd.exec) cudaGraphExecDestroy(n->graph_bwd.exec);
   delete n;
 }
 
@@ -156,14 +215,34 @@ int tulip_net_forward(tulip_net* n, int batch, const float* params, const int64_
                       const float* drop_scales, const int* win_mode, void* ws, float* pred, float* losses, void* stream) {
   if (!n || !params || !offs || !x_lo || !ws || !pred) { tulip_set_error("tulip_net_forward: null argument"); return TULIP_ERR_ARG; }
   if (target && !losses) { tulip_set_error("tulip_net_forward: losses is null"); return TULIP_ERR_ARG; }
-  return n->forward(batch, params, offs, x_lo, target, drop_scales, win_mode, ws, pred, losses, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  // one-time device allocations and the (synchronising) pack-table upload must not happen inside a capture
+  int rc = n->ensure_device();
+  if (rc) return rc;
+  rc = n->upload_pack_table(offs, st);
+  if (rc) return rc;
+  const std::vector<uint64_t> key = {
+      (uint64_t)batch, (uint64_t)(uintptr_t)params, hash_words(offs, n->params.size() * sizeof(int64_t)), (uint64_t)(uintptr_t)x_lo,
+      (uint64_t)(uintptr_t)target, (uint64_t)(uintptr_t)drop_scales, win_mode ? hash_words(win_mode, n->blocks.size() * sizeof(int)) : 0,
+      (uint64_t)(uintptr_t)ws, (uint64_t)(uintptr_t)pred, (uint64_t)(uintptr_t)losses, (uint64_t)(uintptr_t)stream};
+  return n->run_graphed(n->graph_fwd, key, st, [&]() {
+    return n->forward(batch, params, offs, x_lo, target, drop_scales, win_mode, ws, pred, losses, st);
+  });
 }
 
 int tulip_net_backward(tulip_net* n, int batch, const float* params, const int64_t* offs, float* grads, const float* x_lo,
                        const float* target, const float* pred, const float* grad_loss, const float* drop_scales,
                        const int* win_mode, void* ws, void* stream) {
   if (!n || !params || !offs || !grads || !x_lo || !ws) { tulip_set_error("tulip_net_backward: null argument"); return TULIP_ERR_ARG; }
-  return n->backward(batch, params, offs, grads, x_lo, target, pred, grad_loss, drop_scales, win_mode, ws, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const std::vector<uint64_t> key = {
+      (uint64_t)batch, (uint64_t)(uintptr_t)params, hash_words(offs, n->params.size() * sizeof(int64_t)), (uint64_t)(uintptr_t)grads,
+      (uint64_t)(uintptr_t)x_lo, (uint64_t)(uintptr_t)target, (uint64_t)(uintptr_t)pred, (uint64_t)(uintptr_t)grad_loss,
+      (uint64_t)(uintptr_t)drop_scales, win_mode ? hash_words(win_mode, n->blocks.size() * sizeof(int)) : 0, (uint64_t)(uintptr_t)ws,
+      (uint64_t)(uintptr_t)stream};
+  return n->run_graphed(n->graph_bwd, key, st, [&]() {
+    return n->backward(batch, params, offs, grads, x_lo, target, pred, grad_loss, drop_scales, win_mode, ws, st);
+  });
 }
 
 int tulip_gemm_nt(const void* A, const void* W, const float* bias, void* out, void* out2, const void* aux, const float* row_scale,

@@ -95,6 +95,18 @@ struct tulip_net {
   int cur_tag = K_MISC; double cur_flops = 0, cur_bytes = 0;
   std::vector<ProfRec> recs;
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  // CUDA-graph replay of a whole direction (forward or backward): once the same call (same batch, same pointers) has been
+  // seen twice in a row its ~150 launches are captured -- PDL edges, side-stream fork/joins and memsets included -- and later
+  // calls are one cudaGraphLaunch.  TULIP_B200_GRAPHS=0 turns it off; the per-launch profiler bypasses it.
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<uint64_t> key;          // key of `exec` (valid when exec != nullptr)
+    std::vector<uint64_t> last;         // key of the previous call
+    long launches = 0;                  // kernels per replay
+  };
+  GraphSlot graph_fwd, graph_bwd;
+  template <class F>
+  int run_graphed(GraphSlot& slot, const std::vector<uint64_t>& key, cudaStream_t st, F&& body);
   // side stream for the weight-gradient GEMMs of the backward pass (they are off the dX critical path)
   cudaStream_t side = nullptr;
   std::vector<cudaEvent_t> sync_pool; size_t sync_used = 0;

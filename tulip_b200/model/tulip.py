@@ -22,6 +22,8 @@ import collections.abc
 import ctypes as C
 from functools import partial
 
+import weakref
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -209,14 +211,38 @@ class _TulipFunction(torch.autograd.Function):
         B = x.shape[0]
         dev = x.device
         Ht, Wt = model.target_img_size
-        pred = torch.empty((B, model.in_chans, Ht, Wt), dtype=torch.float32, device=dev)
-        losses = torch.zeros(2, dtype=torch.float32, device=dev)
-        ws = torch.empty(model._workspace_bytes(B), dtype=torch.uint8, device=dev)
-        check(lib.tulip_net_forward(model._net, B, ptr(model._flat), model._offsets_p, ptr(x), ptr(target), ptr(drop_scales),
-                                    win_mode.ctypes.data_as(C.c_void_p), ptr(ws), ptr(pred), ptr(losses), current_stream()),
+        # Stable addresses let the executor replay the whole direction as one CUDA graph (tulip_net::run_graphed): the step
+        # runs on the module's persistent buffers (inputs copied in, pred / losses copied out: ~45 MB of device copies, ~15 us)
+        # unless an earlier forward on those buffers still waits for its backward -- then this call gets buffers of its own.
+        pers = model._step_buffers(B, dev) if model._persistent_free() else None
+        if pers is not None:
+            ws, xin, pred_w, losses_w = pers["ws"], pers["lo"], pers["pred"], pers["losses"]
+            xin.copy_(x)
+            tin = None
+            if target is not None:
+                tin = pers["hi"]
+                tin.copy_(target)
+            din = None
+            if drop_scales is not None:
+                din = pers["drop"]
+                din.copy_(drop_scales)
+        else:
+            ws = torch.empty(model._workspace_bytes(B), dtype=torch.uint8, device=dev)
+            xin, tin, din = x, target, drop_scales
+            pred_w = torch.empty((B, model.in_chans, Ht, Wt), dtype=torch.float32, device=dev)
+            losses_w = torch.zeros(2, dtype=torch.float32, device=dev)
+        check(lib.tulip_net_forward(model._net, B, ptr(model._flat), model._offsets_p, ptr(xin), ptr(tin), ptr(din),
+                                    win_mode.ctypes.data_as(C.c_void_p), ptr(ws), ptr(pred_w), ptr(losses_w), current_stream()),
               "tulip_net_forward")
-        ctx.model, ctx.B, ctx.win_mode = model, B, win_mode
-        ctx.save_for_backward(x, target, drop_scales, ws, pred)
+        if pers is not None:
+            pred = pred_w.clone()
+            losses = losses_w.clone() if target is not None else torch.zeros(2, dtype=torch.float32, device=dev)
+            if target is not None and model._grad_mode_hint:    # (grad mode is always off inside Function.forward)
+                model._persistent_owner = weakref.ref(ctx)      # released by backward (or when the autograd graph dies)
+        else:
+            pred, losses = pred_w, losses_w
+        ctx.model, ctx.B, ctx.win_mode, ctx.pers = model, B, win_mode, pers
+        ctx.save_for_backward(xin, tin, din, ws, pred_w)
         ctx.set_materialize_grads(False)
         loss, pixel = losses[0], losses[1]
         ctx.mark_non_differentiable(pixel)
@@ -234,11 +260,19 @@ class _TulipFunction(torch.autograd.Function):
         if g_loss is None:
             return (None,) * (n_fixed + len(model._param_list))
         lib = load_library()
-        g_loss = g_loss.to(torch.float32).reshape(1).contiguous()
+        if ctx.pers is not None:
+            gl = ctx.pers["gloss"]
+            gl.copy_(g_loss.reshape(1))
+            g_loss = gl
+        else:
+            g_loss = g_loss.to(torch.float32).reshape(1).contiguous()
         gbuf = model._grad_buffer()
         check(lib.tulip_net_backward(model._net, ctx.B, ptr(model._flat), model._offsets_p, ptr(gbuf), ptr(x), ptr(target),
                                      ptr(pred), ptr(g_loss), ptr(drop_scales), ctx.win_mode.ctypes.data_as(C.c_void_p), ptr(ws),
                                      current_stream()), "tulip_net_backward")
+        if ctx.pers is not None:
+            model._persistent_owner = None
+        # fresh views every time: autograd only adopts an incoming gradient as `.grad` (no copy) if nothing else references it
         grads = tuple(gbuf[o:o + n].view(s) for o, n, s in model._views)
         return (None,) * n_fixed + grads
 
@@ -393,8 +427,13 @@ class TULIP(nn.Module):
         Survives .to(device), load_state_dict (in-place copy) and DDP's parameter broadcast."""
         if self._net is None:
             self._create_net()
-        if self._param_list is not None and self._is_flat(device):
-            return
+        if self._param_list is not None and self._flat is not None and self._flat.device == device:
+            # hot path: spot-check three parameters every call, all 212 only now and then (a full scan costs ~60 us of host time)
+            self._flat_checks = getattr(self, "_flat_checks", 0) + 1
+            base, pl, vw = self._flat.data_ptr(), self._param_list, self._views
+            quick = all(pl[i].data_ptr() == base + 4 * vw[i][0] for i in (0, len(pl) // 2, len(pl) - 1))
+            if quick and (self._flat_checks % 64 or self._is_flat(device)):
+                return
         named = dict(self.named_parameters())
         plist = [named[k] for k in self._schema]
         views, off = [], 0
@@ -427,12 +466,65 @@ class TULIP(nn.Module):
                 return g
         raise RuntimeError("tulip_b200: both gradient buffers are aliased by live .grad tensors")
 
+    def _persistent_free(self) -> bool:
+        owner = getattr(self, "_persistent_owner", None)
+        return owner is None or owner() is None
+
+    def _step_buffers(self, B, device):
+        """Persistent per-(batch, device) buffers of one training step: workspace, inputs, pred, losses, DropPath scales."""
+        cache = self.__dict__.setdefault("_step_bufs", {})
+        key = (B, str(device), id(self._net))
+        b = cache.get(key)
+        if b is None:
+            if len(cache) >= 2:                                  # keep at most two batch sizes (train / eval) resident
+                cache.pop(next(iter(cache)))
+            Ht, Wt = self.target_img_size
+            f32 = dict(dtype=torch.float32, device=device)
+            b = cache[key] = {
+                "ws": torch.empty(self._workspace_bytes(B), dtype=torch.uint8, device=device),
+                "lo": torch.empty((B, self.in_chans, *self.img_size), **f32),
+                "hi": torch.empty((B, self.in_chans, Ht, Wt), **f32),
+                "pred": torch.empty((B, self.in_chans, Ht, Wt), **f32),
+                "losses": torch.zeros(2, **f32),
+                "drop": torch.empty((2 * len(self._attention_modules()), B), **f32),
+                "gloss": torch.empty(1, **f32),
+            }
+        return b
+
+    def zero_grad(self, set_to_none: bool = True):
+        """nn.Module.zero_grad walks the module tree (~0.5 ms for 212 parameters, with the GPU idle when the training loop
+        reads the loss every step); the parameters are known here, and zeroing is one fill of the flat buffer."""
+        plist = self._param_list
+        if plist is None:
+            return super().zero_grad(set_to_none=set_to_none)
+        if set_to_none:
+            for p in plist:
+                p.grad = None
+            return
+        live = plist[0].grad
+        if live is None:
+            return
+        for buf in self._grad_bufs:
+            if buf is not None and live.data_ptr() == buf.data_ptr() + 4 * self._views[0][0] and \
+                    all(p.grad is not None and p.grad.data_ptr() == buf.data_ptr() + 4 * o for p, (o, _n, _s) in zip(plist, self._views)):
+                buf.zero_()
+                return
+        super().zero_grad(set_to_none=False)
+
     def _workspace_bytes(self, B):
         if B not in self._ws_bytes:
             self._ws_bytes[B] = int(load_library().tulip_net_workspace_bytes(self._net, B))
         return self._ws_bytes[B]
 
     def _window_modes(self):
+        cached = getattr(self, "_win_modes_cache", None)
+        if cached is not None and cached[0] is self._net:
+            return cached[1]
+        out = self._window_modes_uncached()
+        self._win_modes_cache = (self._net, out)
+        return out
+
+    def _window_modes_uncached(self):
         lib = load_library()
         mods = self._attention_modules()
         out = np.zeros(len(mods), dtype=np.int32)
@@ -444,12 +536,19 @@ class TULIP(nn.Module):
 
     def _sample_drop_scales(self, B, device):
         """Per-sample DropPath scales floor(keep + U[0,1)) / keep for every half-block (reference tulip.py:25-29)."""
-        rates = self._drop_rates()
-        if not self.training or all(r == 0. for r in rates):
+        if not self.training:
             return None
-        keep = 1.0 - torch.tensor([r for r in rates for _ in (0, 1)], dtype=torch.float32, device=device).unsqueeze(1)
-        u = torch.rand((2 * len(rates), B), dtype=torch.float32, device=device)
-        return (torch.floor(keep + u) / keep).contiguous()
+        rates = self._drop_rates()
+        if all(r == 0. for r in rates):
+            return None
+        key = (tuple(rates), str(device))
+        cached = getattr(self, "_keep_cache", None)
+        if cached is None or cached[0] != key:                  # one small H2D copy per (rates, device), not per step
+            keep = 1.0 - torch.tensor([r for r in rates for _ in (0, 1)], dtype=torch.float32, device=device).unsqueeze(1)
+            cached = self._keep_cache = (key, keep)
+        keep = cached[1]
+        u = torch.rand((keep.shape[0], B), dtype=torch.float32, device=device)
+        return u.add_(keep).floor_().div_(keep)
 
     def kernel_launches(self) -> int:
         return 0 if self._net is None else int(load_library().tulip_net_kernel_launches(self._net))
@@ -473,6 +572,7 @@ class TULIP(nn.Module):
         if drop is not None:
             drop = drop.to(device=x.device, dtype=torch.float32).contiguous()
         win_mode = self._window_modes()
+        self._grad_mode_hint = torch.is_grad_enabled()
         pred, loss, pixel = _TulipFunction.apply(self, x, tgt, drop, win_mode, *self._param_list)
         if mc_drop:
             return pred

@@ -28,14 +28,15 @@ def _f32(t):
     return None if t is None else t.to(torch.float32).contiguous()
 
 
-def linear(x, w, bias=None, epilogue=EPI_STORE, aux=None, row_scale=None, rows_per_sample=1, impl=GEMM_AUTO):
-    """x [M,K] bf16, w [N,K] bf16 -> [M,N] bf16; EPI_GELU returns (gelu(pre), pre)."""
+def linear(x, w, bias=None, epilogue=EPI_STORE, aux=None, row_scale=None, rows_per_sample=1, impl=GEMM_AUTO, save_pre=True):
+    """x [M,K] bf16, w [N,K] bf16 -> [M,N] bf16; EPI_GELU returns (gelu(pre), pre) -- pre is None with save_pre=False
+    (the configuration the network executor uses: the backward pass recomputes the pre-activation)."""
     _cuda(x, w)
     x, w = _bf16(x), _bf16(w)
     M, K = x.shape
     N = w.shape[0]
     out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
-    out2 = torch.empty_like(out) if epilogue == EPI_GELU else None
+    out2 = torch.empty_like(out) if (epilogue == EPI_GELU and save_pre) else None
     aux = None if aux is None else _bf16(aux)
     bias, row_scale = _f32(bias), _f32(row_scale)
     check(load_library().tulip_gemm_nt(ptr(x), ptr(w), ptr(bias), ptr(out), ptr(out2), ptr(aux), ptr(row_scale), rows_per_sample,
