@@ -206,38 +206,15 @@ class _TulipFunction(torch.autograd.Function):
     """One autograd node for the whole network: forward = tulip_net_forward, backward = tulip_net_backward."""
 
     @staticmethod
-    def forward(ctx, model, x, target, drop_scales, win_mode, *params):
-        lib = load_library()
-        B = x.shape[0]
-        dev = x.device
-        Ht, Wt = model.target_img_size
-        # Stable addresses let the executor replay the whole direction as one CUDA graph (tulip_net::run_graphed): the step
-        # runs on the module's persistent buffers (inputs copied in, pred / losses copied out: ~45 MB of device copies, ~15 us)
-        # unless an earlier forward on those buffers still waits for its backward -- then this call gets buffers of its own.
-        pers = model._step_buffers(B, dev) if model._persistent_free() else None
-        if pers is not None:
-            ws, xin, pred_w, losses_w = pers["ws"], pers["lo"], pers["pred"], pers["losses"]
-            xin.copy_(x)
-            tin = None
-            if target is not None:
-                tin = pers["hi"]
-                tin.copy_(target)
-            din = None
-            if drop_scales is not None:
-                din = pers["drop"]
-                din.copy_(drop_scales)
-        else:
-            ws = torch.empty(model._workspace_bytes(B), dtype=torch.uint8, device=dev)
-            xin, tin, din = x, target, drop_scales
-            pred_w = torch.empty((B, model.in_chans, Ht, Wt), dtype=torch.float32, device=dev)
-            losses_w = torch.zeros(2, dtype=torch.float32, device=dev)
-        check(lib.tulip_net_forward(model._net, B, ptr(model._flat), model._offsets_p, ptr(xin), ptr(tin), ptr(din),
-                                    win_mode.ctypes.data_as(C.c_void_p), ptr(ws), ptr(pred_w), ptr(losses_w), current_stream()),
-              "tulip_net_forward")
+    def forward(ctx, model, launched, target_given, win_mode, *params):
+        # the kernels were already launched by TULIP._launch_forward (before autograd spent ~0.2 ms wiring 212 parameter
+        # edges): this node only records what the backward needs
+        pers, ws, xin, tin, din, pred_w, losses_w, B = launched
+        dev = xin.device
         if pers is not None:
             pred = pred_w.clone()
-            losses = losses_w.clone() if target is not None else torch.zeros(2, dtype=torch.float32, device=dev)
-            if target is not None and model._grad_mode_hint:    # (grad mode is always off inside Function.forward)
+            losses = losses_w.clone() if target_given else torch.zeros(2, dtype=torch.float32, device=dev)
+            if target_given and model._grad_mode_hint:         # (grad mode is always off inside Function.forward)
                 model._persistent_owner = weakref.ref(ctx)      # released by backward (or when the autograd graph dies)
         else:
             pred, losses = pred_w, losses_w
@@ -256,7 +233,7 @@ class _TulipFunction(torch.autograd.Function):
             raise NotImplementedError("tulip_b200: gradients through `pred` are not implemented; back-propagate total_loss")
         if target is None:
             raise RuntimeError("tulip_b200: backward needs the forward to have been given a target")
-        n_fixed = 5
+        n_fixed = 4
         if g_loss is None:
             return (None,) * (n_fixed + len(model._param_list))
         lib = load_library()
@@ -466,6 +443,37 @@ class TULIP(nn.Module):
                 return g
         raise RuntimeError("tulip_b200: both gradient buffers are aliased by live .grad tensors")
 
+    def _launch_forward(self, x, target, drop_scales, win_mode):
+        """Stage the inputs and launch tulip_net_forward on the current stream.  Stable addresses let the executor replay the
+        whole direction as one CUDA graph (tulip_net::run_graphed): the step runs on the module's persistent buffers (inputs
+        copied in, pred / losses copied out: ~45 MB of device copies, ~15 us) unless an earlier forward on those buffers still
+        waits for its backward -- then this call gets buffers of its own."""
+        lib = load_library()
+        B = x.shape[0]
+        dev = x.device
+        Ht, Wt = self.target_img_size
+        pers = self._step_buffers(B, dev) if self._persistent_free() else None
+        if pers is not None:
+            ws, xin, pred_w, losses_w = pers["ws"], pers["lo"], pers["pred"], pers["losses"]
+            xin.copy_(x)
+            tin = None
+            if target is not None:
+                tin = pers["hi"]
+                tin.copy_(target)
+            din = None
+            if drop_scales is not None:
+                din = pers["drop"]
+                din.copy_(drop_scales)
+        else:
+            ws = torch.empty(self._workspace_bytes(B), dtype=torch.uint8, device=dev)
+            xin, tin, din = x, target, drop_scales
+            pred_w = torch.empty((B, self.in_chans, Ht, Wt), dtype=torch.float32, device=dev)
+            losses_w = torch.zeros(2, dtype=torch.float32, device=dev)
+        check(lib.tulip_net_forward(self._net, B, ptr(self._flat), self._offsets_p, ptr(xin), ptr(tin), ptr(din),
+                                    win_mode.ctypes.data_as(C.c_void_p), ptr(ws), ptr(pred_w), ptr(losses_w), current_stream()),
+              "tulip_net_forward")
+        return (pers, ws, xin, tin, din, pred_w, losses_w, B)
+
     def _persistent_free(self) -> bool:
         owner = getattr(self, "_persistent_owner", None)
         return owner is None or owner() is None
@@ -573,7 +581,8 @@ class TULIP(nn.Module):
             drop = drop.to(device=x.device, dtype=torch.float32).contiguous()
         win_mode = self._window_modes()
         self._grad_mode_hint = torch.is_grad_enabled()
-        pred, loss, pixel = _TulipFunction.apply(self, x, tgt, drop, win_mode, *self._param_list)
+        launched = self._launch_forward(x, tgt, drop, win_mode)
+        pred, loss, pixel = _TulipFunction.apply(self, launched, tgt is not None, win_mode, *self._param_list)
         if mc_drop:
             return pred
         return pred, loss, pixel
