@@ -171,6 +171,39 @@ def test_full_size_batch32_properties():
     assert all(torch.isfinite(v).all() for v in g32.values())
 
 
+@pytest.mark.parametrize("name,cfg,large,B", [("durlar_b16", Cfg(img_size=(32, 2048), target_img_size=(128, 2048)), False, 16),
+                                               ("large_kitti_b8", TULIP_LARGE, True, 8)])
+def test_full_size_other_configs_properties(name, cfg, large, B):
+    """BASELINE cfg3 (DurLAR 32x2048 -> 128x2048, batch 16) and the 5-stage tulip_large at batch 8, at full size: frames are
+    independent, so selected frames must equal their B=1 runs bit for bit (different tile schedules, same arithmetic), the
+    loss must equal the mean over pred, and a step must leave finite gradients on every parameter."""
+    pn = make_params(cfg, 41)
+    lo, hi = make_inputs(cfg, B, 42)
+    lo_t, hi_t = torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda()
+    model = build(cfg, large).eval()
+    load_params(model, pn)
+    model.cuda()
+    pred, loss, pixel = model(lo_t, hi_t)
+    assert tuple(pred.shape) == (B, 1, *cfg.target_img_size) and torch.isfinite(pred).all() and torch.isfinite(loss)
+    assert abs(loss.item() - (pred - hi_t).abs().mean().item()) <= 1e-5
+    loss.backward()
+    grads = {n: q.grad.clone() for n, q in model.named_parameters()}
+    assert all(torch.isfinite(g).all() and g.abs().sum() > 0 for g in grads.values())
+    model.zero_grad()
+    for b in (0, B - 1):
+        pb, _, _ = model(lo_t[b:b + 1], hi_t[b:b + 1])
+        assert torch.equal(pb, pred[b:b + 1])
+    # the same batch again, on CUDA-graph replay by now (third identical call): identical pred, gradients equal up to the
+    # ordering of the fp32 atomics in the weight-gradient reductions
+    for _ in range(2):
+        model.zero_grad()
+        pred2, loss2, _ = model(lo_t, hi_t)
+        loss2.backward()
+    assert torch.equal(pred2, pred)
+    errs = [rel_l2(q.grad, grads[n]) for n, q in model.named_parameters()]
+    assert max(errs) <= 1e-3, max(errs)
+
+
 def test_gradient_accumulation_and_buffer_aliasing():
     """.grad tensors are views of one flat buffer; a second backward without zero_grad must accumulate, not alias."""
     from tulip_b200.parallel import flat_grad_of
