@@ -396,6 +396,168 @@ __global__ void __launch_bounds__(256) patch_embed_bwd_kernel(const EmbedArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// PatchEmbedding, patch height 1, E = 12 * LPT (96 or 192): a group of LPT lanes owns a token and each lane 12 consecutive
+// channels with its 12 x 8 conv weights in registers, so a warp finishes 32 / LPT tokens per iteration with two short
+// group reductions.  The one-warp-per-token kernels above spend ~100 (forward) / ~190 (backward) instructions per token
+// and were issue-bound (60 / 74 us for 27 MB of traffic); this layout needs about half.
+template <int LPT>
+__global__ void __launch_bounds__(128) patch_embed_fwd12_kernel(const EmbedArgs a) {
+  pdl_sync();
+  constexpr int TPW = 32 / LPT;
+  const int lane = threadIdx.x & 31, sub = lane % LPT, slot = lane / LPT;
+  const int c0 = sub * 12;
+  float w[12][8], cb[12], lw[12], lb[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const float4 w0 = *reinterpret_cast<const float4*>(a.w + (c0 + i) * 8), w1 = *reinterpret_cast<const float4*>(a.w + (c0 + i) * 8 + 4);
+    w[i][0] = w0.x; w[i][1] = w0.y; w[i][2] = w0.z; w[i][3] = w0.w; w[i][4] = w1.x; w[i][5] = w1.y; w[i][6] = w1.z; w[i][7] = w1.w;
+    cb[i] = a.b[c0 + i]; lw[i] = a.ln_w[c0 + i]; lb[i] = a.ln_b[c0 + i];
+  }
+  const int Wo = a.Wimg / 4;
+  const int tokens = a.B * a.Himg * Wo;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float invE = 1.0f / (float)a.E;
+  auto load_x = [&](int t, float (&xv)[8]) {
+    const int tt = t < tokens ? t : tokens - 1;
+    const int wo = tt % Wo;
+    const float* row = a.x + (long)(tt / Wo) * a.Wimg;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int wi = 4 * wo + j - 2;
+      wi = wi < 0 ? wi + a.Wimg : (wi >= a.Wimg ? wi - a.Wimg : wi);
+      xv[j] = __ldg(row + wi);
+    }
+  };
+  float xn[8];
+  int t = warp * TPW + slot;
+  load_x(t, xn);
+  for (; t - slot < tokens; t += nwarps * TPW) {
+    float xv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xv[j] = xn[j];
+    load_x(t + nwarps * TPW, xn);                          // next iteration's pixels are in flight during this one's math
+    float u[12], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      float acc = cb[i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(w[i][j], xv[j], acc);
+      u[i] = acc; s += acc;
+    }
+    const float mean = group_sum<LPT>(s) * invE;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) sq += (u[i] - mean) * (u[i] - mean);
+    const float rstd = rsqrtf(group_sum<LPT>(sq) * invE + a.eps);
+    if (t < tokens) {
+      uint32_t o[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        o[i] = pack_bf16((u[2 * i] - mean) * rstd * lw[2 * i] + lb[2 * i], (u[2 * i + 1] - mean) * rstd * lw[2 * i + 1] + lb[2 * i + 1]);
+      uint2* dst = reinterpret_cast<uint2*>(a.y + (long)t * a.E + c0);
+      dst[0] = make_uint2(o[0], o[1]); dst[1] = make_uint2(o[2], o[3]); dst[2] = make_uint2(o[4], o[5]);
+    }
+  }
+}
+
+// Backward, E = 96: 16 lanes per token, 6 channels per lane (weights and the 6 x 8 weight-gradient accumulators in registers).
+__global__ void __launch_bounds__(128) patch_embed_bwd6_kernel(const EmbedArgs a) {
+  pdl_sync();
+  extern __shared__ float s_acc[];                        // [E][12] per-CTA accumulators: 8 dW taps, db, dgamma, dbeta
+  for (int i = threadIdx.x; i < a.E * 12; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  constexpr int LPT = 16, TPW = 2;
+  const int lane = threadIdx.x & 31, sub = lane % LPT, slot = lane / LPT;
+  const int c0 = sub * 6;
+  float w[6][8], cb[6], lw[6], gw[6][8], gb[6], glw[6], glb[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float4 w0 = *reinterpret_cast<const float4*>(a.w + (c0 + i) * 8), w1 = *reinterpret_cast<const float4*>(a.w + (c0 + i) * 8 + 4);
+    w[i][0] = w0.x; w[i][1] = w0.y; w[i][2] = w0.z; w[i][3] = w0.w; w[i][4] = w1.x; w[i][5] = w1.y; w[i][6] = w1.z; w[i][7] = w1.w;
+    cb[i] = a.b[c0 + i]; lw[i] = a.ln_w[c0 + i];
+    gb[i] = glw[i] = glb[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gw[i][j] = 0.f;
+  }
+  const int Wo = a.Wimg / 4;
+  const int tokens = a.B * a.Himg * Wo;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float invE = 1.0f / (float)a.E;
+  for (int t = warp * TPW + slot; t - slot < tokens; t += nwarps * TPW) {
+    const bool valid = t < tokens;
+    const int tt = valid ? t : tokens - 1;
+    const int wo = tt % Wo;
+    const float* row = a.x + (long)(tt / Wo) * a.Wimg;
+    float xv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int wi = 4 * wo + j - 2;
+      wi = wi < 0 ? wi + a.Wimg : (wi >= a.Wimg ? wi - a.Wimg : wi);
+      xv[j] = __ldg(row + wi);
+    }
+    const uint32_t* dyp = reinterpret_cast<const uint32_t*>(a.dy + (long)tt * a.E + c0);
+    const uint32_t d01 = dyp[0], d23 = dyp[1], d45 = dyp[2];
+    float dy[6];
+    { const float2 f0 = unpack_bf16(d01), f1 = unpack_bf16(d23), f2 = unpack_bf16(d45);
+      dy[0] = f0.x; dy[1] = f0.y; dy[2] = f1.x; dy[3] = f1.y; dy[4] = f2.x; dy[5] = f2.y; }
+    if (!valid) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) dy[i] = 0.f;             // a padded slot contributes nothing
+    }
+    float u[6], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      float acc = cb[i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(w[i][j], xv[j], acc);
+      u[i] = acc; s += acc;
+    }
+    const float mean = group_sum<LPT>(s) * invE;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sq += (u[i] - mean) * (u[i] - mean);
+    const float rstd = rsqrtf(group_sum<LPT>(sq) * invE + a.eps);
+    float s1 = 0.f, s2 = 0.f, h[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      h[i] = (u[i] - mean) * rstd;
+      const float g = dy[i] * lw[i];
+      s1 += g; s2 += g * h[i];
+      glw[i] += dy[i] * h[i]; glb[i] += dy[i];
+    }
+    const float m1 = group_sum<LPT>(s1) * invE, m2 = group_sum<LPT>(s2) * invE;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float du = valid ? rstd * (dy[i] * lw[i] - m1 - h[i] * m2) : 0.f;
+      gb[i] += du;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gw[i][j] = fmaf(du, xv[j], gw[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = c0 + i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[c * 12 + j], gw[i][j]);
+    atomicAdd(&s_acc[c * 12 + 8], gb[i]);
+    atomicAdd(&s_acc[c * 12 + 9], glw[i]);
+    atomicAdd(&s_acc[c * 12 + 10], glb[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.E * 12; i += blockDim.x) {
+    const int c = i / 12, k = i % 12;
+    const float v = s_acc[i];
+    const int co = a.dcopies > 1 ? (int)(blockIdx.x % a.dcopies) * a.dstride : 0;
+    if (k < 8) atomicAdd(a.dw + co + c * 8 + k, v);
+    else if (k == 8) atomicAdd(a.db + co + c, v);
+    else if (k == 9) atomicAdd(a.dln_w + co + c, v);
+    else if (k == 10) atomicAdd(a.dln_b + co + c, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp32 -> bf16 weight repack, 32x32 tiles, optional row permutation and transposed copy.
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ flat, bf16* __restrict__ arena,
                                                            const PackItem* __restrict__ items, int n_items) {
@@ -625,6 +787,14 @@ int patch_embed_fwd(const EmbedArgs& a, cudaStream_t st) {
   TULIP_REQUIRE(a.E % 32 == 0 && a.E <= 192, "patch_embed: embed_dim must be a multiple of 32, <= 192");
   TULIP_REQUIRE(a.Wimg % 4 == 0 && a.Himg % a.ph == 0 && a.Wimg >= 4, "patch_embed: image not divisible by the patch");
   const int tokens = a.B * (a.Himg / a.ph) * (a.Wimg / 4);
+  if (a.ph == 1 && (a.E == 96 || a.E == 192)) {
+    const int tpw = a.E == 96 ? 4 : 2;
+    const int want = ceil_div(tokens, 4 * tpw);
+    if (a.E == 96) { const int grid = wave_grid(patch_embed_fwd12_kernel<8>, 128, 0, want); tulip_launch(patch_embed_fwd12_kernel<8>, grid, 128, 0, st, a); }
+    else { const int grid = wave_grid(patch_embed_fwd12_kernel<16>, 128, 0, want); tulip_launch(patch_embed_fwd12_kernel<16>, grid, 128, 0, st, a); }
+    TULIP_CHECK_LAUNCH();
+    return TULIP_OK;
+  }
   const int smem = a.E * a.ph * 8 * (int)sizeof(float);
   const int grid = min(ceil_div(tokens, 8 * 4), tulip_num_sms() * 8);
   switch (a.E / 32) {
@@ -643,6 +813,13 @@ int patch_embed_bwd(const EmbedArgs& a, cudaStream_t st) {
   TULIP_REQUIRE(a.E % 32 == 0 && a.E <= 192, "patch_embed: embed_dim must be a multiple of 32, <= 192");
   TULIP_REQUIRE(a.ph == 1, "patch_embed backward: patch height must be 1");
   const int tokens = a.B * a.Himg * (a.Wimg / 4);
+  if (a.E == 96) {
+    const int smem6 = a.E * 12 * (int)sizeof(float);
+    const int grid6 = wave_grid(patch_embed_bwd6_kernel, 128, smem6, ceil_div(tokens, 8));
+    tulip_launch(patch_embed_bwd6_kernel, grid6, 128, smem6, st, a);
+    TULIP_CHECK_LAUNCH();
+    return TULIP_OK;
+  }
   const int grid = min(ceil_div(tokens, 8 * 8), tulip_num_sms() * 6);
   const int smem = a.E * 20 * (int)sizeof(float);
   switch (a.E / 32) {
