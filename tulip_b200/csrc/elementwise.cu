@@ -464,8 +464,8 @@ __global__ void __launch_bounds__(128) patch_embed_fwd12_kernel(const EmbedArgs 
 // Backward, E = 96: 16 lanes per token, 6 channels per lane (weights and the 6 x 8 weight-gradient accumulators in registers).
 __global__ void __launch_bounds__(128) patch_embed_bwd6_kernel(const EmbedArgs a) {
   pdl_sync();
-  extern __shared__ float s_acc[];                        // [E][12] per-CTA accumulators: 8 dW taps, db, dgamma, dbeta
-  for (int i = threadIdx.x; i < a.E * 12; i += blockDim.x) s_acc[i] = 0.f;
+  extern __shared__ float s_acc[];                        // [E][13] per-CTA accumulators: 8 dW taps, db, dgamma, dbeta (+2 pad)
+  for (int i = threadIdx.x; i < a.E * 13; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   constexpr int LPT = 16, TPW = 2;
   const int lane = threadIdx.x & 31, sub = lane % LPT, slot = lane / LPT;
@@ -485,12 +485,11 @@ __global__ void __launch_bounds__(128) patch_embed_bwd6_kernel(const EmbedArgs a
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const float invE = 1.0f / (float)a.E;
-  for (int t = warp * TPW + slot; t - slot < tokens; t += nwarps * TPW) {
-    const bool valid = t < tokens;
-    const int tt = valid ? t : tokens - 1;
+  // a warp's iterations are serialised on its own loads unless the next token's pixels and gradient row are already in flight
+  auto load_tok = [&](int t, float (&xv)[8], uint32_t (&dv)[3]) {
+    const int tt = t < tokens ? t : tokens - 1;
     const int wo = tt % Wo;
     const float* row = a.x + (long)(tt / Wo) * a.Wimg;
-    float xv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       int wi = 4 * wo + j - 2;
@@ -498,7 +497,17 @@ __global__ void __launch_bounds__(128) patch_embed_bwd6_kernel(const EmbedArgs a
       xv[j] = __ldg(row + wi);
     }
     const uint32_t* dyp = reinterpret_cast<const uint32_t*>(a.dy + (long)tt * a.E + c0);
-    const uint32_t d01 = dyp[0], d23 = dyp[1], d45 = dyp[2];
+    dv[0] = dyp[0]; dv[1] = dyp[1]; dv[2] = dyp[2];
+  };
+  float xn[8]; uint32_t dn[3];
+  load_tok(warp * TPW + slot, xn, dn);
+  for (int t = warp * TPW + slot; t - slot < tokens; t += nwarps * TPW) {
+    const bool valid = t < tokens;
+    float xv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xv[j] = xn[j];
+    const uint32_t d01 = dn[0], d23 = dn[1], d45 = dn[2];
+    load_tok(t + nwarps * TPW, xn, dn);
     float dy[6];
     { const float2 f0 = unpack_bf16(d01), f1 = unpack_bf16(d23), f2 = unpack_bf16(d45);
       dy[0] = f0.x; dy[1] = f0.y; dy[2] = f1.x; dy[3] = f1.y; dy[4] = f2.x; dy[5] = f2.y; }
@@ -537,18 +546,28 @@ __global__ void __launch_bounds__(128) patch_embed_bwd6_kernel(const EmbedArgs a
     }
   }
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    const int c = c0 + i;
+  for (int i = 0; i < 6; ++i) {                             // fold the warp's two token slots, then lanes 0..15 add to the CTA
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[c * 12 + j], gw[i][j]);
-    atomicAdd(&s_acc[c * 12 + 8], gb[i]);
-    atomicAdd(&s_acc[c * 12 + 9], glw[i]);
-    atomicAdd(&s_acc[c * 12 + 10], glb[i]);
+    for (int j = 0; j < 8; ++j) gw[i][j] += __shfl_xor_sync(0xffffffffu, gw[i][j], 16);
+    gb[i] += __shfl_xor_sync(0xffffffffu, gb[i], 16);
+    glw[i] += __shfl_xor_sync(0xffffffffu, glw[i], 16);
+    glb[i] += __shfl_xor_sync(0xffffffffu, glb[i], 16);
+  }
+  if (slot == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int c = c0 + i;                                 // rows of 13 floats: the 16 lanes hit 16 different banks
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[c * 13 + j], gw[i][j]);
+      atomicAdd(&s_acc[c * 13 + 8], gb[i]);
+      atomicAdd(&s_acc[c * 13 + 9], glw[i]);
+      atomicAdd(&s_acc[c * 13 + 10], glb[i]);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < a.E * 12; i += blockDim.x) {
-    const int c = i / 12, k = i % 12;
-    const float v = s_acc[i];
+  for (int i = threadIdx.x; i < a.E * 11; i += blockDim.x) {
+    const int c = i / 11, k = i % 11;
+    const float v = s_acc[c * 13 + k];
     const int co = a.dcopies > 1 ? (int)(blockIdx.x % a.dcopies) * a.dstride : 0;
     if (k < 8) atomicAdd(a.dw + co + c * 8 + k, v);
     else if (k == 8) atomicAdd(a.db + co + c, v);
@@ -814,7 +833,7 @@ int patch_embed_bwd(const EmbedArgs& a, cudaStream_t st) {
   TULIP_REQUIRE(a.ph == 1, "patch_embed backward: patch height must be 1");
   const int tokens = a.B * a.Himg * (a.Wimg / 4);
   if (a.E == 96) {
-    const int smem6 = a.E * 12 * (int)sizeof(float);
+    const int smem6 = a.E * 13 * (int)sizeof(float);
     const int grid6 = wave_grid(patch_embed_bwd6_kernel, 128, smem6, ceil_div(tokens, 8));
     tulip_launch(patch_embed_bwd6_kernel, grid6, 128, smem6, st, a);
     TULIP_CHECK_LAUNCH();
