@@ -410,10 +410,28 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
   Ctx c{this, B, params_, offs, nullptr, drop_scales, win_mode, reinterpret_cast<unsigned char*>(ws), st};
   const int E = cfg.embed_dim;
 
+  // The weight repack is only needed by the first GEMM: it runs on the side stream next to PatchEmbed and the first LayerNorm.
+  const bool use_side = !profiling && !side_stream_disabled();
+  if (use_side && !side) TULIP_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  sync_used = 0;
+  const cudaStream_t pst = use_side ? side : st;
+  if (use_side) {
+    cudaEvent_t e = next_sync_event();
+    cudaEventRecord(e, st);
+    cudaStreamWaitEvent(side, e, 0);
+  }
   tag(K_PACK, 0, 8.0 * warena_elems / 2);
-  RUN(pack_weights(params_, warena, items_dev, n_items, n_tiles, st));
+  RUN(pack_weights(params_, warena, items_dev, n_items, n_tiles, pst));
   for (const Linear& l : linears)
-    if (l.pbias_off >= 0) RUN(permute_bias(c.P(l.slot_b), faux + l.pbias_off, l.N, l.perm_R2, l.perm_Cc, st));
+    if (l.pbias_off >= 0) RUN(permute_bias(c.P(l.slot_b), faux + l.pbias_off, l.N, l.perm_R2, l.perm_Cc, pst));
+  bool pack_pending = use_side;
+  auto join_pack = [&]() {
+    if (!pack_pending) return;
+    cudaEvent_t e = next_sync_event();
+    cudaEventRecord(e, side);
+    cudaStreamWaitEvent(st, e, 0);
+    pack_pending = false;
+  };
 
   {
     EmbedArgs e;
@@ -440,6 +458,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     const float* ds1 = drop_scales ? drop_scales + (long)(2 * b.index) * B : nullptr;
     const float* ds2 = drop_scales ? drop_scales + (long)(2 * b.index + 1) * B : nullptr;
     RUN(ln(x_in, b.n1w, b.n1b, c.A(bb.xn1), c.F(bb.st1), T, C, 0, 0, 0));
+    join_pack();
     {
       const Linear& l = linears[b.qkv];
       GemmArgs g = nt_args(c.A(bb.xn1), C, c.W(l), C, T, 3 * C, C, c.bias(l), c.A(bb.qkv), 3 * C);
@@ -550,15 +569,6 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   const int T0 = B * H0 * W0;
   int rc;
 
-  // zero the whole flat gradient span covered by the parameters
-  {
-    long lo = offs[0], hi = offs[0] + params[0].numel;
-    for (size_t i = 0; i < params.size(); ++i) {
-      if (offs[i] < lo) lo = offs[i];
-      if (offs[i] + params[i].numel > hi) hi = offs[i] + params[i].numel;
-    }
-    TULIP_CUDA(cudaMemsetAsync(grads + lo, 0, (size_t)(hi - lo) * sizeof(float), st));
-  }
 
   // Weight-gradient GEMMs (gemm_tn) are leaves of the backward graph: nothing on the dX chain reads them.  They run on a
   // side stream, forked after the kernel that produced their dY operand and joined before that buffer is overwritten, so
@@ -567,6 +577,22 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   if (use_side && !side) TULIP_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
   sync_used = 0;
   bool side_pending = false;
+  // zero the whole flat gradient span covered by the parameters.  Only the side-stream GEMMs and the final sum_copies write
+  // into it (every other gradient goes to the scratch copies), so the 108 MB fill runs on the side stream under the head kernels.
+  {
+    long lo = offs[0], hi = offs[0] + params[0].numel;
+    for (size_t i = 0; i < params.size(); ++i) {
+      if (offs[i] < lo) lo = offs[i];
+      if (offs[i] + params[i].numel > hi) hi = offs[i] + params[i].numel;
+    }
+    if (use_side) {
+      cudaEvent_t e = next_sync_event();
+      cudaEventRecord(e, st);
+      cudaStreamWaitEvent(side, e, 0);
+      side_pending = true;
+    }
+    TULIP_CUDA(cudaMemsetAsync(grads + lo, 0, (size_t)(hi - lo) * sizeof(float), use_side ? side : st));
+  }
   auto fork = [&]() {                                     // side stream is ordered after everything issued on `st` so far
     cudaEvent_t e = next_sync_event();
     cudaEventRecord(e, st);
@@ -840,6 +866,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     RUN(patch_embed_bwd(e, st));
   }
   TULIP_REQUIRE(!gscr_overflow, "tulip_b200: gradient-copy scratch exhausted (too many blocks for GRAD_SCRATCH_BYTES / 128 items)");
+  join();                                                 // the gradient fill and every weight-gradient GEMM precede the fold
   tag(K_ELEMWISE, 0, 8.0 * gscr_used);
   RUN(sum_copies(sum_args, st));
   join();                                                 // every gradient is complete on `st` when backward returns
