@@ -90,6 +90,10 @@ int tulip_net_backward(tulip_net* net, int batch, const float* params, const int
  * TN: dW[N,K] += dY[M,N]^T . X[M,K]; db[N] += colsum(dY)   (autograd of the above) */
 int tulip_gemm_nt(const void* A, const void* W, const float* bias, void* out, void* out2, const void* aux,
                   const float* row_scale, int rows_per_sample, int M, int N, int K, int epilogue, int impl, void* stream);
+/* host-side tiling decision of tulip_gemm_nt for (M, N, K, epilogue) on the tcgen05 path -- no device work:
+ * out10 = {tile width BN, resident-weight schedule (0/1), n_chunks, tiles per chunk, workers, A ring stages, K blocks,
+ *          MMA steps in the last K block, grid size, operand ring stages} */
+int tulip_gemm_nt_plan(int M, int N, int K, int epilogue, int save_pre, int* out10);
 int tulip_gemm_tn(const void* dY, const void* X, float* dW, float* db, int M, int N, int K, int impl, void* stream);
 
 /* ---- window attention core: tulip.py:289-317 without the two Linears; shift/partition/mask/bias in-kernel ---- */

@@ -123,3 +123,34 @@ def test_init_matches_reference_rng_stream():
     ours = tulip_base(**KW).state_dict()
     for k in ref:
         assert torch.equal(ref[k], ours[k]), k
+
+
+def test_gemm_tiling_plan_host_logic():
+    """The tile-width / schedule decision of the tcgen05 GEMM launcher is pure host logic (tulip_gemm_nt_plan): check its
+    invariants for every Linear shape of the KITTI / DurLAR steps at the bench batch sizes, without a GPU."""
+    import ctypes as C
+    from tulip_b200._lib import load_library
+    lib = load_library()
+    keys = ("bn", "panel", "n_chunks", "npc", "nworkers", "nsa", "kb", "klast", "grid", "stages")
+    seen_panel = 0
+    for tokens0, in ((32 * 16 * 256,), (16 * 32 * 512,)):
+        for s in range(4):
+            T, Cc = tokens0 >> (2 * s), 96 << s
+            for (N, K, epi) in ((3 * Cc, Cc, 0), (Cc, Cc, 2), (4 * Cc, Cc, 1), (Cc, 4 * Cc, 2), (Cc, 3 * Cc, 0), (Cc, 4 * Cc, 0), (4 * Cc, Cc, 5)):
+                out = (C.c_int * 10)()
+                assert lib.tulip_gemm_nt_plan(T, N, K, epi, 0, out) == 0
+                p = dict(zip(keys, out))
+                assert p["bn"] in (96, 192) and N % p["bn"] == 0
+                assert p["kb"] == -(-K // 64) and 1 <= p["klast"] <= 4 and 16 * (p["klast"] - 1) < K - 64 * (p["kb"] - 1) <= 16 * p["klast"]
+                assert 1 <= p["grid"] <= 148 and 2 <= p["stages"] <= 8
+                if p["panel"]:
+                    seen_panel += 1
+                    assert p["n_chunks"] * p["npc"] * p["bn"] == N and p["grid"] == p["n_chunks"] * p["nworkers"]
+                    assert p["nsa"] >= (p["kb"] + 1 if p["npc"] > 1 else 3) and p["nsa"] <= 8
+                    area = p["stages"] * (128 * 64 * 2 + p["bn"] * 64 * 2)
+                    assert p["npc"] * p["kb"] * p["bn"] * 128 + p["nsa"] * 128 * 64 * 2 <= area      # resident B + A ring fit the ring area
+                    assert -(-T // 128) >= 4 * p["nworkers"]                                       # enough row panels per worker
+    assert seen_panel >= 8                                                                         # the wide stages do use it
+    out = (C.c_int * 10)()
+    assert lib.tulip_gemm_nt_plan(1000, 100, 96, 0, 0, out) != 0                                   # N % 96: not a tcgen05 shape
+    assert lib.tulip_gemm_nt_plan(131072, 384, 96, 1, 1, out) == 0 and out[0] == 96              # saved pre-activation: narrow tile

@@ -50,6 +50,7 @@ SIGNATURES = {
     "tulip_net_forward": (_i, [_vp, _i, _fp, _vp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _vp]),
     "tulip_net_backward": (_i, [_vp, _i, _fp, _vp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _vp, _vp]),
     "tulip_gemm_nt": (_i, [_vp, _vp, _fp, _vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
+    "tulip_gemm_nt_plan": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i)]),
     "tulip_gemm_tn": (_i, [_vp, _vp, _fp, _fp, _i, _i, _i, _i, _vp]),
     "tulip_window_attention_fwd": (_i, [_vp, _fp, _vp] + [_i] * 12 + [_vp]),
     "tulip_window_attention_bwd": (_i, [_vp, _fp, _vp, _vp, _fp] + [_i] * 12 + [_vp]),

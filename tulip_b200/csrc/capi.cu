@@ -261,6 +261,13 @@ int tulip_gemm_nt(const void* A, const void* W, const float* bias, void* out, vo
   return gemm_nt(g, epilogue, (cudaStream_t)stream);
 }
 
+int tulip_gemm_nt_plan(int M, int N, int K, int epilogue, int save_pre, int* out10) {
+  if (!out10) { tulip_set_error("tulip_gemm_nt_plan: null output"); return TULIP_ERR_ARG; }
+  const int rc = gemm_nt_tc05_plan(M, N, K, epilogue, save_pre, out10);
+  if (rc) tulip_set_error("tulip_gemm_nt_plan: shape not handled by the tcgen05 GEMM (N % 96, K % 8)");
+  return rc;
+}
+
 int tulip_gemm_tn(const void* dY, const void* X, float* dW, float* db, int M, int N, int K, int impl, void* stream) {
   GemmTNArgs g;
   memset(&g, 0, sizeof g);

@@ -62,6 +62,7 @@ int gemm_nt_mma(const GemmArgs& g, int epi, cudaStream_t st);
 int gemm_tn_mma(const GemmTNArgs& g, cudaStream_t st);
 int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st);   // returns TULIP_ERR_UNSUPPORTED for shapes it does not take
 int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st);
+int gemm_nt_tc05_plan(int M, int N, int K, int epi, int save_pre, int* out10);   // host-side tiling decision (tests, tooling)
 int gemm_nt(const GemmArgs& g, int epi, cudaStream_t st);        // dispatch (env TULIP_B200_GEMM=mma forces the legacy path)
 int gemm_tn(const GemmTNArgs& g, cudaStream_t st);
 bool gemm_forced_mma();                                          // env TULIP_B200_GEMM=mma

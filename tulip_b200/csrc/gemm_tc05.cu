@@ -1,13 +1,14 @@
 // tcgen05 / TMEM / TMA GEMMs for sm_100a.
 //
-// NT: out[M,N] = A[M,K] . B[N,K]^T with fused epilogues (gemm.cuh).  Persistent, warp-specialised CTA:
-//   warp 0      TMA producer: A (128 x 64) and B (BN x 64) bf16 tiles, 128B-swizzled, mbarrier ring; also prefetches
-//               the epilogue's auxiliary tile (residual / GELU pre-activation) into shared memory
-//   warp 1      MMA issuer: one elected lane, tcgen05.mma cta_group::1 M=128 N=BN K=16, fp32 accumulators in TMEM
-//   warps 2..13 epilogue (12 warps: the erf / exp math of the GELU epilogues needs the issue slots): tcgen05.ld (one
-//               accumulator row per thread, one 32-column box per warp) -> bias / GELU / residual -> bf16 tile in shared
-//               memory (64B-swizzled) -> TMA store.  Scatter epilogues (PixelShuffle, split, head) store directly.
-// Two TMEM accumulator buffers let the epilogue of tile i overlap the loads and MMAs of tile i+1.
+// NT: out[M,N] = A[M,K] . B[N,K]^T with fused epilogues (gemm.cuh).  Persistent, warp-specialised CTA of 14 warps:
+//   warp 0      TMA producer: A (128 x 64) and B (BN x 64) bf16 blocks, 128B-swizzled, through an mbarrier ring -- or, in
+//               the B-stationary schedule (struct Sched), the weight rows of the CTA's n-chunk once and then only A blocks
+//   warp 1      MMA issuer: tcgen05.mma cta_group::1 M=128 N=BN K=16, fp32 accumulators in TMEM (2 buffers, 3 for the head)
+//   warps 2..13 epilogue, each warp autonomous: tcgen05.ld (one accumulator row per thread, one 32-column box per warp) ->
+//               bias / GELU / residual / ... -> its own 2 KB slices of the bf16 staging tile (64B-swizzled) -> its own
+//               32 x 32 TMA stores.  The residual / saved pre-activation tile is TMA-loaded into those slices one tile ahead
+//               and transformed in place.  Scatter epilogues (PixelShuffle, split, head) store directly.
+// Producer and issuer run as whole warps and predicate only the issuing instruction on elect.sync (see tc05.cuh).
 // K is walked in 64-column blocks per *segment*; TMA's out-of-bounds zero fill pads K = 96 / 288 to the block size and
 // makes the two-source concat (skip Linear) and the PixelShuffle-backward gather (5-D tensor map) plain coordinates.
 #include "gemm.cuh"
@@ -619,6 +620,22 @@ Sched make_sched(int bn, int epi, const GemmArgs& g, const Segments& sg) {
   return sc;
 }
 
+// Tile width and schedule of one launch.  Wide tiles (BN = 192) where the problem has enough of them to fill the chip (deep
+// K: tensor / operand-traffic bound); narrow tiles if only they allow the resident-B schedule (not for GELU: its epilogue wants
+// the wide tile); GELU with a saved pre-activation needs both staging buffers, which only the narrow tile has.
+Sched choose_tiling(const GemmArgs& g, int epi, const Segments& sg, int* bn_out) {
+  const bool head = (epi == EPI_HEAD || epi == EPI_HEAD_BWD);
+  int bn = (!head && epi != EPI_DGELU2 && g.N % 192 == 0 && (long)ceil_div(g.M, BM) * (g.N / 192) >= tulip_num_sms()) ? 192 : 96;
+  if (epi == EPI_GELU && g.out2 != nullptr) bn = 96;
+  Sched sc = make_sched(bn, epi, g, sg);
+  if (bn == 192 && !sc.panel && epi != EPI_GELU) {
+    const Sched s96 = make_sched(96, epi, g, sg);
+    if (s96.panel) { bn = 96; sc = s96; }
+  }
+  *bn_out = bn;
+  return sc;
+}
+
 template <int BN, int EPI>
 int launch(const Maps& maps, const GemmArgs& g, const Segments& sg, const Sched& sc, cudaStream_t st) {
   using CF = Cfg<BN, EPI>;
@@ -688,8 +705,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     return TULIP_ERR_UNSUPPORTED;
   const bool head = (epi == EPI_HEAD || epi == EPI_HEAD_BWD);
   if (epi == EPI_HEAD_BWD && g.hd_E != 96) return TULIP_ERR_UNSUPPORTED;      // per-CTA dwd accumulation assumes one 96-channel group
-  // wide tiles only where the problem is tensor-bound (deep K) and there are enough tiles to fill the chip
-  int bn = (!head && epi != EPI_DGELU2 && g.N % 192 == 0 && (long)ceil_div(g.M, BM) * (g.N / 192) >= tulip_num_sms()) ? 192 : 96;
+  int bn = 96;                                            // chosen with the schedule once the K segments are known
 
   Segments sg;
   memset(&sg, 0, sizeof sg);
@@ -726,12 +742,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
       sg.n = 2; sg.len[1] = g.K - K1; sg.amap[1] = 1; sg.bcol[1] = K1;
     }
   }
-  if (epi == EPI_GELU && g.out2 != nullptr) bn = 96;                     // saving the pre-activation needs both staging buffers
-  Sched sc = make_sched(bn, epi, g, sg);
-  if (bn == 192 && !sc.panel && epi != EPI_GELU) {                       // narrow tiles if only they allow the resident-B schedule
-    const Sched s96 = make_sched(96, epi, g, sg);                        // (not for GELU: its epilogue wants the wide tile)
-    if (s96.panel) { bn = 96; sc = s96; }
-  }
+  const Sched sc = choose_tiling(g, epi, sg, &bn);
   {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
     const uint64_t str[1] = {(uint64_t)g.ldb * 2};
@@ -788,6 +799,25 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
 }
 
 
+int gemm_nt_tc05_plan(int M, int N, int K, int epi, int save_pre, int* out) {
+  // host-side tiling decision for a plain (single-segment) launch, for tests and tooling:
+  // out = {bn, panel, n_chunks, npc, nworkers, nsa, kb, klast, grid, stages}
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.M = M; g.N = N; g.K = K; g.K1 = K;
+  if (save_pre) g.out2 = reinterpret_cast<bf16*>(16);
+  if (N % 96 || K % 8 || M <= 0) return TULIP_ERR_UNSUPPORTED;
+  Segments sg;
+  memset(&sg, 0, sizeof sg);
+  sg.n = 1; sg.len[0] = K;
+  int bn = 96;
+  const Sched sc = choose_tiling(g, epi, sg, &bn);
+  out[0] = bn; out[1] = sc.panel; out[2] = sc.n_chunks; out[3] = sc.npc; out[4] = sc.nworkers; out[5] = sc.nsa; out[6] = sc.kb;
+  out[7] = sc.klast; out[8] = sc.panel ? sc.n_chunks * sc.nworkers : min(sc.tiles_m * sc.tiles_n, tulip_num_sms());
+  out[9] = cfg_stages(bn, epi);
+  return TULIP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // TN: dW[N,K] += dY[M,N]^T . X[M,K]  (+ db[N] += colsum(dY)) -- weight gradients.
 // Both operands are MN-major for the tensor core (the contraction runs over tokens, the strided dimension), which
@@ -798,7 +828,6 @@ namespace {
 
 constexpr int TN_TOK = 64;                  // tokens per pipeline stage (4 UMMA K-steps)
 constexpr int TN_STAGES = 4;
-constexpr int TN_MAXB = 4;                  // B boxes per stage: up to 3 data boxes (192 columns of X) + the ones box
 constexpr int TN_BOX = 64 * TN_TOK * 2;     // 8 KB
 constexpr int TN_STAGE_BYTES = (2 + 3) * TN_BOX;          // A: 2 boxes (128 dW rows), B: up to 3 boxes
 constexpr int TN_ONES_OFF = TN_STAGES * TN_STAGE_BYTES;

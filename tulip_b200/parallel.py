@@ -28,8 +28,11 @@ def allreduce_flat_(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
     world = dist.get_world_size(group)
     if world == 1:
         return flat_grad
-    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
-    flat_grad.mul_(1.0 / world)
+    if flat_grad.is_cuda and dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG, group=group)     # mean inside NCCL: no second pass over 108 MB
+    else:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+        flat_grad.mul_(1.0 / world)
     return flat_grad
 
 
