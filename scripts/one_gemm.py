@@ -9,7 +9,7 @@ x = torch.randn(M, K, device="cuda").bfloat16(); w = (torch.randn(N, K, device="
 aux = torch.randn(M, N, device="cuda").bfloat16()
 for _ in range(4):
     if epi == 0: ops.linear(x, w, b, impl=2)
-    elif epi == 1: ops.linear(x, w, b, epilogue=1, impl=2)
+    elif epi == 1: ops.linear(x, w, b, epilogue=1, impl=2, save_pre=False)   # the executor's configuration (pre-activation recomputed)
     elif epi == 2: ops.linear(x, w, b, epilogue=2, aux=aux, impl=2)
     elif epi == 5: ops.linear(x, w, None, epilogue=5, aux=aux, impl=2)
     elif epi == 9:
