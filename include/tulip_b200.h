@@ -117,6 +117,14 @@ int tulip_patch_embed_bwd(const float* x, const float* w, const float* b, const 
                           void* stream);
 
 /* ---- loss (tulip.py:690-700); scratch2 and out2 are 2 floats each ---- */
+/* ---- evaluation post-processing: engine_upsampling.py:174-244 of evaluate(), fused into one pass ----
+ * pred, target [B,1,H,W], x_lo [B,1,h_lo,W] fp32 as the model saw / produced them (log1p space when log_transform).
+ * out [B,1,H,W]: expm1 (:177-180), clipped to [clip_lo, 1] else 0 (:183-188; 2/80 kitti & carla, 0.3/120 durlar), and with every
+ * (H/h_lo)-th row overwritten by the sensor's own row when keep_low_res (:214-221, :236-244).
+ * losses [B][2]: per frame {mean |out_before_overwrite - target| (:192-193), mean over the sensor rows |pred_row - x_lo| (:216-219)}.
+ * scratch: 2*B floats. */
+int tulip_eval_postprocess(const float* pred, const float* x_lo, const float* target, float* out, float* losses, float* scratch,
+                           int B, int H, int W, int h_lo, int log_transform, float clip_lo, int keep_low_res, void* stream);
 int tulip_l1_loss(const float* pred, const float* target, int64_t n, int log_transform, float* scratch2, float* out2,
                   void* stream);
 

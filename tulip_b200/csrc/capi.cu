@@ -344,6 +344,12 @@ int tulip_patch_embed_bwd(const float* x, const float* w, const float* b, const 
   return patch_embed_bwd(e, (cudaStream_t)stream);
 }
 
+int tulip_eval_postprocess(const float* pred, const float* x_lo, const float* target, float* out, float* losses, float* scratch,
+                            int B, int H, int W, int h_lo, int log_transform, float clip_lo, int keep_low_res, void* stream) {
+  if (!pred || !x_lo || !target || !out || !losses || !scratch) { tulip_set_error("tulip_eval_postprocess: null argument"); return TULIP_ERR_ARG; }
+  return eval_postprocess(pred, x_lo, target, out, losses, scratch, B, H, W, h_lo, log_transform, clip_lo, keep_low_res, (cudaStream_t)stream);
+}
+
 int tulip_l1_loss(const float* pred, const float* target, int64_t n, int log_transform, float* scratch2, float* out2, void* stream) {
   return l1_loss(pred, target, (long)n, log_transform, scratch2, out2, (cudaStream_t)stream);
 }

@@ -909,6 +909,83 @@ int l1_loss(const float* pred, const float* target, long n, int log_transform, f
   return TULIP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Evaluation post-processing of one batch of predictions (reference engine_upsampling.py:174-244, evaluate()):
+//   expm1 of pred / target / input when the model was trained in log space (:177-180), range clip of the prediction to
+//   [clip_lo, 1] else 0 (:183-188), pixel loss = mean |pred - target| per frame (:192-193), and for the rows the sensor
+//   measured (every `factor`-th row, :214-221, :236-244) the loss against the input and the overwrite pred[row] = input.
+// One CTA-strided pass: each byte read once, pred written once; per-frame sums via block reduction + 2 atomics per CTA.
+__global__ void __launch_bounds__(256) eval_postprocess_kernel(const float* __restrict__ pred, const float* __restrict__ lo,
+                                                               const float* __restrict__ hi, float* __restrict__ out,
+                                                               float* __restrict__ sums, int H, int W, int factor, int log_transform,
+                                                               float clip_lo, int keep_low_res, int chunks_per_frame) {
+  pdl_sync();
+  const int b = blockIdx.x / chunks_per_frame, chunk = blockIdx.x % chunks_per_frame;
+  const long frame = (long)H * W;
+  const int h_lo = H / factor;
+  float s_pix = 0.f, s_low = 0.f;
+  for (long i = (long)chunk * blockDim.x + threadIdx.x; i < frame / 4; i += (long)chunks_per_frame * blockDim.x) {
+    const long px = 4 * i;
+    const int row = (int)(px / W), col = (int)(px % W);
+    const float4 p4 = *reinterpret_cast<const float4*>(pred + b * frame + px);
+    const float4 t4 = *reinterpret_cast<const float4*>(hi + b * frame + px);
+    const bool sensor_row = keep_low_res && (row % factor == 0);
+    float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sensor_row) l4 = *reinterpret_cast<const float4*>(lo + ((long)b * h_lo + row / factor) * W + col);
+    float p[4] = {p4.x, p4.y, p4.z, p4.w}, t[4] = {t4.x, t4.y, t4.z, t4.w}, l[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v = log_transform ? expm1f(p[k]) : p[k];
+      const float tv = log_transform ? expm1f(t[k]) : t[k];
+      v = (v >= clip_lo && v <= 1.0f) ? v : 0.f;
+      s_pix += fabsf(v - tv);
+      if (sensor_row) {
+        const float lv = log_transform ? expm1f(l[k]) : l[k];
+        s_low += fabsf(v - lv);
+        v = lv;
+      }
+      p[k] = v;
+    }
+    *reinterpret_cast<float4*>(out + b * frame + px) = make_float4(p[0], p[1], p[2], p[3]);
+  }
+  __shared__ float red[2][8];
+  s_pix = warp_sum(s_pix); s_low = warp_sum(s_low);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s_pix; red[1][threadIdx.x >> 5] = s_low; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[threadIdx.x][w];
+    atomicAdd(sums + 2 * b + threadIdx.x, a);
+  }
+}
+
+__global__ void eval_postprocess_finalize_kernel(const float* sums, float* losses, int B, float inv_pix, float inv_low) {
+  pdl_sync();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    losses[2 * b] = sums[2 * b] * inv_pix;
+    losses[2 * b + 1] = sums[2 * b + 1] * inv_low;
+  }
+}
+
+int eval_postprocess(const float* pred, const float* lo, const float* hi, float* out, float* losses, float* scratch, int B, int H, int W,
+                     int h_lo, int log_transform, float clip_lo, int keep_low_res, cudaStream_t st) {
+  TULIP_REQUIRE(B > 0 && H > 0 && W > 0 && h_lo > 0 && H % h_lo == 0, "eval_postprocess: H must be a multiple of the input height");
+  TULIP_REQUIRE(W % 4 == 0, "eval_postprocess: width must be a multiple of 4");
+  const int factor = H / h_lo;
+  const long quads = (long)H * W / 4;
+  int chunks = (int)((quads + 255) / 256);
+  const int want = max(1, 4 * tulip_num_sms() / B);
+  if (chunks > want) chunks = want;
+  TULIP_CUDA(cudaMemsetAsync(scratch, 0, 2 * B * sizeof(float), st));
+  tulip_launch(eval_postprocess_kernel, B * chunks, 256, 0, st, pred, lo, hi, out, scratch, H, W, factor, log_transform, clip_lo,
+               keep_low_res, chunks);
+  tulip_launch(eval_postprocess_finalize_kernel, 1, 128, 0, st, scratch, losses, B, 1.0f / ((float)H * W),
+               keep_low_res ? 1.0f / ((float)h_lo * W) : 0.f);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
 int window_gather(const bf16* x, bf16* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, cudaStream_t st) {
   TULIP_REQUIRE(C % 8 == 0 && H % Mh == 0 && W % Mw == 0, "H or W is not divisible by window_size");
   const long n = (long)B * H * W * (C / 8);

@@ -68,6 +68,9 @@ struct SumCopiesItem { float* dst; const float* src; int n; int stride; };   // 
 struct SumCopiesArgs { SumCopiesItem item[128]; int count; int copies; };
 int sum_copies(const SumCopiesArgs& a, cudaStream_t st);
 int scale_rows_bf16(bf16* dst, const bf16* src, const float* row_scale, int rows, int C, int rows_per_sample, cudaStream_t st);
+// evaluation post-processing (engine_upsampling.py:174-244): losses [B][2] = {pixel loss, low-res-row loss}, scratch [2B] floats
+int eval_postprocess(const float* pred, const float* lo, const float* hi, float* out, float* losses, float* scratch, int B, int H, int W,
+                     int h_lo, int log_transform, float clip_lo, int keep_low_res, cudaStream_t st);
 int l1_loss(const float* pred, const float* target, long n, int log_transform, float* acc2, float* out2, cudaStream_t st);
 
 // stand-alone index ops (bit-exact tests of the index arithmetic used inside the fused kernels)

@@ -147,6 +147,23 @@ def l1_loss(pred, target, log_transform=True):
     return out[0], out[1]
 
 
+def eval_postprocess(pred, x_lo, target, log_transform=True, clip_lo=2.0 / 80.0, keep_low_res=True):
+    """Fused evaluation post-processing (reference engine_upsampling.py:174-244): returns (range image [B,1,H,W] fp32 with the
+    sensor rows restored, losses [B,2] = per-frame {pixel loss, loss on the sensor rows})."""
+    _cuda(pred, x_lo, target)
+    pred, x_lo, target = _f32(pred), _f32(x_lo), _f32(target)
+    B, _, H, W = pred.shape
+    if keep_low_res and x_lo.shape[-1] != W:
+        raise ValueError("eval_postprocess: keep_low_res needs input and target of equal width")
+    out = torch.empty_like(pred)
+    losses = torch.empty((B, 2), dtype=torch.float32, device=pred.device)
+    scratch = torch.empty(2 * B, dtype=torch.float32, device=pred.device)
+    check(load_library().tulip_eval_postprocess(ptr(pred), ptr(x_lo), ptr(target), ptr(out), ptr(losses), ptr(scratch), B, H, W,
+                                                x_lo.shape[2], int(log_transform), float(clip_lo), int(keep_low_res),
+                                                current_stream()), "tulip_eval_postprocess")
+    return out, losses
+
+
 def window_partition(x, window=(2, 8), shift=(0, 0)):
     """(B,H,W,C) bf16 -> ((B Nh Nw), Mh, Mw, C): torch.roll(x, (-sh,-sw)) then the reference's window_partition."""
     _cuda(x)
