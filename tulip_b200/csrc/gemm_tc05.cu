@@ -827,7 +827,7 @@ int gemm_nt_tc05_plan(int M, int N, int K, int epi, int save_pre, int* out) {
 namespace {
 
 constexpr int TN_TOK = 64;                  // tokens per pipeline stage (4 UMMA K-steps)
-constexpr int TN_STAGES = 4;
+constexpr int TN_STAGES = 5;                  // 5 x 40 KB ring (4 -> 5: 3-6 % on the HBM-bound launches; two 2-stage CTAs per SM lost 5 %)
 constexpr int TN_BOX = 64 * TN_TOK * 2;     // 8 KB
 constexpr int TN_STAGE_BYTES = (2 + 3) * TN_BOX;          // A: 2 boxes (128 dW rows), B: up to 3 boxes
 constexpr int TN_ONES_OFF = TN_STAGES * TN_STAGE_BYTES;
