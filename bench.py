@@ -314,6 +314,18 @@ def run_ours(args, rank, world, local_rank):
         ms_e = e0.elapsed_time(e1) / 30
         eval_path[f"b{eb}"] = {"ms_per_call": round(ms_e, 4), "frames_per_s": round(eb / (ms_e * 1e-3), 1)}
     model.train()
+    # metric block of evaluate() for one frame: projection x2, Chamfer distance, voxel IoU / precision / recall
+    from tulip_b200 import metrics as tb_metrics
+    with torch.no_grad():
+        img_p, _ = upsample(model, lo_d[:1].contiguous(), hi_d[:1].contiguous(), "kitti")
+        img_g = torch.expm1(hi_d[:1]).contiguous()
+        for _ in range(2):
+            tb_metrics.evaluate_frame(img_p, img_g, "kitti", 0.1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            tb_metrics.evaluate_frame(img_p, img_g, "kitti", 0.1)
+        eval_path["frame_metrics_ms"] = round((time.perf_counter() - t0) * 100.0, 4)
     # optimizer cost, outside the metric (torch fused AdamW over the 212 parameter views)
     # (rank 0 only from here on: no collectives)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), fused=True)

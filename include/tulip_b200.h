@@ -125,6 +125,21 @@ int tulip_patch_embed_bwd(const float* x, const float* w, const float* b, const 
  * scratch: 2*B floats. */
 int tulip_eval_postprocess(const float* pred, const float* x_lo, const float* target, float* out, float* losses, float* scratch,
                            int B, int H, int W, int h_lo, int log_transform, float clip_lo, int keep_low_res, void* stream);
+/* ---- evaluation metrics on the device (reference tulip/util/evaluation.py, engine_upsampling.py:223-277) ----
+ * range image -> points (evaluation.py:52-116, img_to_pcd_kitti / img_to_pcd_carla): img [B,H,W] normalised range,
+ * points [B, H*W, 3]; x = (sin_h[w] cos_v[h]) r, y = (cos_h[w] cos_v[h]) r, z = sin_v[h] r, r = img * max_range.  The four
+ * float32 tables hold the sines / cosines of the sensor's column and row angles (host side: tulip_b200.metrics.angle_tables). */
+int tulip_range_to_points(const float* img, const float* sin_h, const float* cos_h, const float* sin_v, const float* cos_v,
+                          float max_range, float* points, int B, int H, int W, void* stream);
+/* voxel IoU / precision / recall / F1 of two clouds of n points (evaluation.py:148-175 + engine_upsampling.py:259-277): the voxel
+ * index of a point is int((p - min) / grid_size) with min over both clouds; occupied voxels are kept in hash sets (no dense grid).
+ * out4: doubles {iou, precision, recall, f1}. */
+int64_t tulip_voxel_metrics_workspace_bytes(int n_points);
+int tulip_voxel_metrics(const float* pts_pred, const float* pts_gt, int n_points, float grid_size, void* workspace, double* out4,
+                        void* stream);
+/* Chamfer distance as evaluation.py:125-134 uses it: dist_a[i] = min_j |a_i - b_j|^2, dist_b likewise (the un-vendored
+ * github.com/otaheri/chamfer_distance extension), out3 = {mean(dist_a) + mean(dist_b), mean(dist_a), mean(dist_b)}. */
+int tulip_chamfer_distance(const float* a, const float* b, int na, int nb, float* dist_a, float* dist_b, float* out3, void* stream);
 int tulip_l1_loss(const float* pred, const float* target, int64_t n, int log_transform, float* scratch2, float* out2,
                   void* stream);
 

@@ -59,6 +59,10 @@ SIGNATURES = {
     "tulip_patch_embed_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, C.c_float, _vp]),
     "tulip_patch_embed_bwd": (_i, [_fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, C.c_float, _vp]),
     "tulip_eval_postprocess": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, C.c_float, _i, _vp]),
+    "tulip_range_to_points": (_i, [_fp, _fp, _fp, _fp, _fp, C.c_float, _fp, _i, _i, _i, _vp]),
+    "tulip_voxel_metrics_workspace_bytes": (_i64, [_i]),
+    "tulip_voxel_metrics": (_i, [_fp, _fp, _i, C.c_float, _vp, _vp, _vp]),
+    "tulip_chamfer_distance": (_i, [_fp, _fp, _i, _i, _fp, _fp, _fp, _vp]),
     "tulip_l1_loss": (_i, [_fp, _fp, _i64, _i, _fp, _fp, _vp]),
     "tulip_window_partition": (_i, [_vp, _vp] + [_i] * 8 + [_vp]),
     "tulip_window_reverse": (_i, [_vp, _vp] + [_i] * 8 + [_vp]),

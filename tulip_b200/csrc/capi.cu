@@ -350,6 +350,25 @@ int tulip_eval_postprocess(const float* pred, const float* x_lo, const float* ta
   return eval_postprocess(pred, x_lo, target, out, losses, scratch, B, H, W, h_lo, log_transform, clip_lo, keep_low_res, (cudaStream_t)stream);
 }
 
+int tulip_range_to_points(const float* img, const float* sin_h, const float* cos_h, const float* sin_v, const float* cos_v,
+                          float max_range, float* points, int B, int H, int W, void* stream) {
+  if (!img || !sin_h || !cos_h || !sin_v || !cos_v || !points) { tulip_set_error("tulip_range_to_points: null argument"); return TULIP_ERR_ARG; }
+  return range_to_points(img, sin_h, cos_h, sin_v, cos_v, max_range, points, B, H, W, (cudaStream_t)stream);
+}
+
+int64_t tulip_voxel_metrics_workspace_bytes(int n_points) { return n_points > 0 ? (int64_t)voxel_metrics_workspace_bytes(n_points) : 0; }
+
+int tulip_voxel_metrics(const float* pts_pred, const float* pts_gt, int n_points, float grid_size, void* workspace, double* out4,
+                        void* stream) {
+  if (!pts_pred || !pts_gt || !workspace || !out4) { tulip_set_error("tulip_voxel_metrics: null argument"); return TULIP_ERR_ARG; }
+  return voxel_metrics(pts_pred, pts_gt, n_points, grid_size, workspace, out4, (cudaStream_t)stream);
+}
+
+int tulip_chamfer_distance(const float* a, const float* b, int na, int nb, float* dist_a, float* dist_b, float* out3, void* stream) {
+  if (!a || !b || !dist_a || !dist_b || !out3) { tulip_set_error("tulip_chamfer_distance: null argument"); return TULIP_ERR_ARG; }
+  return chamfer_distance(a, b, na, nb, dist_a, dist_b, out3, (cudaStream_t)stream);
+}
+
 int tulip_l1_loss(const float* pred, const float* target, int64_t n, int log_transform, float* scratch2, float* out2, void* stream) {
   return l1_loss(pred, target, (long)n, log_transform, scratch2, out2, (cudaStream_t)stream);
 }

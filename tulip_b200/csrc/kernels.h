@@ -80,3 +80,10 @@ int shift_mask(float* out, int H, int W, int Mh, int Mw, int sh, int sw, cudaStr
 int rel_bias_gather(const float* table, float* out, int heads, int Mh, int Mw, cudaStream_t st);
 int merge_gather(const bf16* x, bf16* out, int B, int H, int W, int C, cudaStream_t st);
 int pixel_shuffle_nhwc(const bf16* x, bf16* out, int B, int H, int W, int Cout, int r, cudaStream_t st);
+
+// evaluation metrics (metrics.cu; reference tulip/util/evaluation.py)
+int range_to_points(const float* img, const float* sin_h, const float* cos_h, const float* sin_v, const float* cos_v, float max_range,
+                    float* points, int B, int H, int W, cudaStream_t st);
+long voxel_metrics_workspace_bytes(int n);
+int voxel_metrics(const float* pts_pred, const float* pts_gt, int n, float grid_size, void* workspace, double* out4, cudaStream_t st);
+int chamfer_distance(const float* a, const float* b, int na, int nb, float* dist_a, float* dist_b, float* out3, cudaStream_t st);
