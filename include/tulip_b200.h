@@ -140,6 +140,14 @@ int tulip_voxel_metrics(const float* pts_pred, const float* pts_gt, int n_points
 /* Chamfer distance as evaluation.py:125-134 uses it: dist_a[i] = min_j |a_i - b_j|^2, dist_b likewise (the un-vendored
  * github.com/otaheri/chamfer_distance extension), out3 = {mean(dist_a) + mean(dist_b), mean(dist_a), mean(dist_b)}. */
 int tulip_chamfer_distance(const float* a, const float* b, int na, int nb, float* dist_a, float* dist_b, float* out3, void* stream);
+/* ---- input pipeline: the transform chains of tulip/util/datasets.py:244-369 in one pass ----
+ * raw [B,H,W,channels] fp32 range frames in metres as the loaders return them (channel 0 = range, npy_loader :187-191);
+ * v = raw * scale (ScaleTensor :140-144; 1/80 kitti & carla, 1/120 durlar); if filter: v outside [min_range, max_range] -> 0
+ * (FilterInvalidPixels :146-154; durlar 0.3/120, carla 2/80; kitti has none); if log_transform: log1p (:73-75).
+ * hi [B,1,H,W] gets every pixel, lo [B,1,H/row_factor,W/col_factor] rows 0, rf, 2rf, ... and columns 0, cf, ... of it
+ * (DownsampleTensor :120-128, DownsampleTensorWidth :130-138). */
+int tulip_preprocess_range(const float* raw, int channels, float scale, int filter, float min_range, float max_range, int row_factor,
+                           int col_factor, int log_transform, float* hi, float* lo, int B, int H, int W, void* stream);
 int tulip_l1_loss(const float* pred, const float* target, int64_t n, int log_transform, float* scratch2, float* out2,
                   void* stream);
 

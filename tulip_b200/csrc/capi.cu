@@ -369,6 +369,13 @@ int tulip_chamfer_distance(const float* a, const float* b, int na, int nb, float
   return chamfer_distance(a, b, na, nb, dist_a, dist_b, out3, (cudaStream_t)stream);
 }
 
+int tulip_preprocess_range(const float* raw, int channels, float scale, int filter, float min_range, float max_range, int row_factor,
+                           int col_factor, int log_transform, float* hi, float* lo, int B, int H, int W, void* stream) {
+  if (!raw || !hi || !lo) { tulip_set_error("tulip_preprocess_range: null argument"); return TULIP_ERR_ARG; }
+  return preprocess_range(raw, channels, scale, filter, min_range, max_range, row_factor, col_factor, log_transform, hi, lo, B, H, W,
+                          (cudaStream_t)stream);
+}
+
 int tulip_l1_loss(const float* pred, const float* target, int64_t n, int log_transform, float* scratch2, float* out2, void* stream) {
   return l1_loss(pred, target, (long)n, log_transform, scratch2, out2, (cudaStream_t)stream);
 }

@@ -986,6 +986,40 @@ int eval_postprocess(const float* pred, const float* lo, const float* hi, float*
   return TULIP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Input pipeline of one batch of raw range frames (reference tulip/util/datasets.py): npy_loader's channel pick (:187-191),
+// ScaleTensor (:140-144), FilterInvalidPixels (:146-154, durlar / carla only), DownsampleTensor rows (:120-128) and
+// DownsampleTensorWidth (:130-138) for the low-resolution input, LogTransform (:73-75) -- the transform chains of
+// build_{kitti,durlar,carla}_upsampling_dataset (:244-369) -- as one pass that writes both model inputs.
+__global__ void __launch_bounds__(256) preprocess_range_kernel(const float* __restrict__ raw, int channels, float scale, int filter,
+                                                               float min_range, float max_range, int row_factor, int col_factor,
+                                                               int log_transform, float* __restrict__ hi, float* __restrict__ lo, long n,
+                                                               int H, int W) {
+  pdl_sync();
+  const int h_lo = H / row_factor, w_lo = W / col_factor;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W), h = (int)((i / W) % H);
+    const long b = i / ((long)W * H);
+    float v = __fmul_rn(raw[i * channels], scale);
+    if (filter) v = (v >= min_range && v <= max_range) ? v : 0.f;
+    if (log_transform) v = log1pf(v);
+    hi[i] = v;
+    if (h % row_factor == 0 && w % col_factor == 0) lo[(b * h_lo + h / row_factor) * w_lo + w / col_factor] = v;
+  }
+}
+
+int preprocess_range(const float* raw, int channels, float scale, int filter, float min_range, float max_range, int row_factor,
+                     int col_factor, int log_transform, float* hi, float* lo, int B, int H, int W, cudaStream_t st) {
+  TULIP_REQUIRE(B > 0 && H > 0 && W > 0 && channels >= 1, "preprocess_range: empty input");
+  TULIP_REQUIRE(row_factor >= 1 && col_factor >= 1 && H % row_factor == 0 && W % col_factor == 0,
+                "preprocess_range: image size is not a multiple of the downsampling factors");
+  const long n = (long)B * H * W;
+  tulip_launch(preprocess_range_kernel, ew_grid(n, 256), 256, 0, st, raw, channels, scale, filter, min_range, max_range, row_factor,
+               col_factor, log_transform, hi, lo, n, H, W);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
 int window_gather(const bf16* x, bf16* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, cudaStream_t st) {
   TULIP_REQUIRE(C % 8 == 0 && H % Mh == 0 && W % Mw == 0, "H or W is not divisible by window_size");
   const long n = (long)B * H * W * (C / 8);

@@ -87,3 +87,7 @@ int range_to_points(const float* img, const float* sin_h, const float* cos_h, co
 long voxel_metrics_workspace_bytes(int n);
 int voxel_metrics(const float* pts_pred, const float* pts_gt, int n, float grid_size, void* workspace, double* out4, cudaStream_t st);
 int chamfer_distance(const float* a, const float* b, int na, int nb, float* dist_a, float* dist_b, float* out3, cudaStream_t st);
+
+// input pipeline (reference tulip/util/datasets.py transform chains): raw [B,H,W,channels] -> hi [B,1,H,W], lo [B,1,H/rf,W/cf]
+int preprocess_range(const float* raw, int channels, float scale, int filter, float min_range, float max_range, int row_factor,
+                     int col_factor, int log_transform, float* hi, float* lo, int B, int H, int W, cudaStream_t st);
