@@ -340,6 +340,18 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     torch.cuda.synchronize()
     adamw_ms = e0.elapsed_time(e1) / 5
+    # the same update as ONE launch over the flat buffers (tulip_b200.optim.FlatAdamW)
+    from tulip_b200.optim import FlatAdamW
+    fopt = FlatAdamW(model, lr=1e-4, betas=(0.9, 0.95))
+    for _ in range(2):
+        fopt.step()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        fopt.step()
+    e1.record()
+    torch.cuda.synchronize()
+    flat_adamw_ms = e0.elapsed_time(e1) / 5
 
     # per-kernel profile (extra steps, CUDA events around every launch on the launching stream)
     prof_steps = 3
@@ -406,7 +418,7 @@ def run_ours(args, rank, world, local_rank):
         "eval_path": eval_path,
         "model_tflops": round(model_tflops, 2),
         "model_frac_of_tensor_roofline": round(model_tflops / pk["tflops_sustained"], 4),
-        "adamw_ms": round(adamw_ms, 4),
+        "adamw_ms": round(adamw_ms, 4), "flat_adamw_ms": round(flat_adamw_ms, 4),
         "cpu_baseline": cpu,
     }
     print(json.dumps(out), flush=True)

@@ -148,6 +148,23 @@ int tulip_chamfer_distance(const float* a, const float* b, int na, int nb, float
  * (DownsampleTensor :120-128, DownsampleTensorWidth :130-138). */
 int tulip_preprocess_range(const float* raw, int channels, float scale, int filter, float min_range, float max_range, int row_factor,
                            int col_factor, int log_transform, float* hi, float* lo, int B, int H, int W, void* stream);
+/* ---- optimizer step over the flat buffers: torch.optim.AdamW(param_groups_layer_decay(...), betas=(0.9, 0.95))
+ * (main_lidar_upsampling.py:281-283) and get_grad_norm_ (util/misc.py:317-329) as one launch each ----
+ * segments (device array, sorted by offset): parameter i occupies [offset, offset + numel) of the flat fp32 buffers and belongs to
+ * optimizer group `group`; hyper (host struct, passed by value to the kernel): per-group lr and weight decay for this step (the
+ * reference's scheduler rewrites lr every iteration, util/lr_sched.py), betas, eps, the two bias corrections of the step and a factor
+ * applied to the gradients on the fly (1 / loss scale; 1 if the gradients were unscaled already).  Update = torch's
+ * _single_tensor_adamw (decoupled weight decay, no amsgrad).  span = extent of the flat buffers in floats (multiple of 4). */
+typedef struct { int64_t offset; int64_t numel; int group; int pad; } tulip_adamw_segment;
+typedef struct {
+  float lr[64]; float weight_decay[64];
+  float beta1, beta2, eps, bias_correction1, bias_correction2_sqrt, grad_scale;
+} tulip_adamw_hyper;
+int tulip_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const tulip_adamw_segment* segments_dev,
+                     int n_segments, int64_t span, const tulip_adamw_hyper* hyper_host, void* stream);
+/* global L2 norm of the gradients of all segments -> out[0] (device float); scratch: one double */
+int tulip_grad_norm(const float* grads, const tulip_adamw_segment* segments_dev, int n_segments, int64_t span, double* scratch, float* out,
+                    void* stream);
 int tulip_l1_loss(const float* pred, const float* target, int64_t n, int log_transform, float* scratch2, float* out2,
                   void* stream);
 

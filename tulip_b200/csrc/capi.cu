@@ -376,6 +376,22 @@ int tulip_preprocess_range(const float* raw, int channels, float scale, int filt
                           (cudaStream_t)stream);
 }
 
+int tulip_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const tulip_adamw_segment* segments_dev,
+                     int n_segments, int64_t span, const tulip_adamw_hyper* hyper_host, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !segments_dev || !hyper_host) { tulip_set_error("tulip_adamw_step: null argument"); return TULIP_ERR_ARG; }
+  static_assert(sizeof(tulip_adamw_segment) == sizeof(AdamwSegment) && sizeof(tulip_adamw_hyper) == sizeof(AdamwHyper), "ABI structs");
+  AdamwHyper hp;
+  memcpy(&hp, hyper_host, sizeof hp);
+  return adamw_step(params, grads, exp_avg, exp_avg_sq, reinterpret_cast<const AdamwSegment*>(segments_dev), n_segments, (long)span, hp,
+                    (cudaStream_t)stream);
+}
+
+int tulip_grad_norm(const float* grads, const tulip_adamw_segment* segments_dev, int n_segments, int64_t span, double* scratch, float* out,
+                    void* stream) {
+  if (!grads || !segments_dev || !scratch || !out) { tulip_set_error("tulip_grad_norm: null argument"); return TULIP_ERR_ARG; }
+  return grad_norm(grads, reinterpret_cast<const AdamwSegment*>(segments_dev), n_segments, (long)span, scratch, out, (cudaStream_t)stream);
+}
+
 int tulip_l1_loss(const float* pred, const float* target, int64_t n, int log_transform, float* scratch2, float* out2, void* stream) {
   return l1_loss(pred, target, (long)n, log_transform, scratch2, out2, (cudaStream_t)stream);
 }

@@ -1020,6 +1020,92 @@ int preprocess_range(const float* raw, int channels, float scale, int filter, fl
   return TULIP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// AdamW over the flat parameter / gradient buffers (reference: torch.optim.AdamW over param_groups_layer_decay groups,
+// main_lidar_upsampling.py:281-283; the update is torch's _single_tensor_adamw, decoupled weight decay, no amsgrad) and the global
+// gradient L2 norm (util/misc.py:317-329 get_grad_norm_).  The 212 parameters are segments of one buffer, so the step is ONE
+// launch (p, g, m, v read once, p, m, v written once) instead of a multi-tensor apply over 212 tensors.
+__device__ __forceinline__ int adamw_find_segment(const AdamwSegment* __restrict__ segs, int n, long i) {
+  int lo = 0, hi = n - 1;                                  // last segment with offset <= i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].offset <= i) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) adamw_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, const AdamwSegment* __restrict__ segs, int n_segs,
+                                                         long span4, const __grid_constant__ AdamwHyper hp) {
+  pdl_sync();
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < span4; q += (long)gridDim.x * blockDim.x) {
+    const long i = 4 * q;
+    const AdamwSegment sg = segs[adamw_find_segment(segs, n_segs, i)];
+    if (i < sg.offset || i >= sg.offset + sg.numel) continue;             // alignment padding between parameters
+    const float lr = hp.lr[sg.group], wd = hp.weight_decay[sg.group];
+    const float step_size = lr / hp.bias_correction1;
+    float4 p4 = *reinterpret_cast<float4*>(p + i), m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
+    const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+    float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    const float gg[4] = {g4.x * hp.grad_scale, g4.y * hp.grad_scale, g4.z * hp.grad_scale, g4.w * hp.grad_scale};
+    const int valid = (int)min(4l, sg.offset + sg.numel - i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k >= valid) break;
+      pp[k] = pp[k] * (1.0f - lr * wd);                                    // param.mul_(1 - lr * weight_decay)
+      mm[k] = mm[k] + (gg[k] - mm[k]) * (1.0f - hp.beta1);                 // exp_avg.lerp_(grad, 1 - beta1)
+      vv[k] = vv[k] * hp.beta2 + (1.0f - hp.beta2) * gg[k] * gg[k];        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+      const float denom = sqrtf(vv[k]) / hp.bias_correction2_sqrt + hp.eps;
+      pp[k] = pp[k] - step_size * (mm[k] / denom);                         // param.addcdiv_(exp_avg, denom, value=-step_size)
+    }
+    *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict__ g, const AdamwSegment* __restrict__ segs, int n_segs,
+                                                         long span4, double* __restrict__ acc) {
+  pdl_sync();
+  double s = 0.0;
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < span4; q += (long)gridDim.x * blockDim.x) {
+    const long i = 4 * q;
+    const AdamwSegment sg = segs[adamw_find_segment(segs, n_segs, i)];
+    if (i < sg.offset || i >= sg.offset + sg.numel) continue;
+    const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    const int valid = (int)min(4l, sg.offset + sg.numel - i);
+    for (int k = 0; k < valid; ++k) s += (double)gg[k] * gg[k];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(acc, t);
+  }
+}
+__global__ void grad_norm_finalize_kernel(const double* acc, float* out) { pdl_sync(); out[0] = (float)sqrt(acc[0]); }
+
+int adamw_step(float* p, const float* g, float* m, float* v, const AdamwSegment* segs_dev, int n_segs, long span, const AdamwHyper& hp,
+               cudaStream_t st) {
+  TULIP_REQUIRE(n_segs > 0 && span > 0 && span % 4 == 0, "adamw_step: empty or unaligned parameter span");
+  tulip_launch(adamw_step_kernel, ew_grid(span / 4, 256), 256, 0, st, p, g, m, v, segs_dev, n_segs, span / 4, hp);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int grad_norm(const float* g, const AdamwSegment* segs_dev, int n_segs, long span, double* scratch, float* out, cudaStream_t st) {
+  TULIP_REQUIRE(n_segs > 0 && span > 0 && span % 4 == 0, "grad_norm: empty or unaligned parameter span");
+  TULIP_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), st));
+  tulip_launch(grad_sumsq_kernel, ew_grid(span / 4, 256), 256, 0, st, g, segs_dev, n_segs, span / 4, scratch);
+  tulip_launch(grad_norm_finalize_kernel, 1, 1, 0, st, (const double*)scratch, out);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
 int window_gather(const bf16* x, bf16* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, cudaStream_t st) {
   TULIP_REQUIRE(C % 8 == 0 && H % Mh == 0 && W % Mw == 0, "H or W is not divisible by window_size");
   const long n = (long)B * H * W * (C / 8);

@@ -91,3 +91,13 @@ int chamfer_distance(const float* a, const float* b, int na, int nb, float* dist
 // input pipeline (reference tulip/util/datasets.py transform chains): raw [B,H,W,channels] -> hi [B,1,H,W], lo [B,1,H/rf,W/cf]
 int preprocess_range(const float* raw, int channels, float scale, int filter, float min_range, float max_range, int row_factor,
                      int col_factor, int log_transform, float* hi, float* lo, int B, int H, int W, cudaStream_t st);
+
+// fused AdamW / gradient norm over the flat buffers (layout mirrored by tulip_adamw_segment / tulip_adamw_hyper in the C header)
+struct AdamwSegment { long offset; long numel; int group; int pad; };
+struct AdamwHyper {
+  float lr[64]; float weight_decay[64];          // per parameter group (param_groups_layer_decay makes ~2 * (layers + 2) of them)
+  float beta1, beta2, eps, bias_correction1, bias_correction2_sqrt, grad_scale;
+};
+int adamw_step(float* p, const float* g, float* m, float* v, const AdamwSegment* segs_dev, int n_segs, long span, const AdamwHyper& hp,
+               cudaStream_t st);
+int grad_norm(const float* g, const AdamwSegment* segs_dev, int n_segs, long span, double* scratch, float* out, cudaStream_t st);
