@@ -137,6 +137,15 @@ int tulip_range_to_points(const float* img, const float* sin_h, const float* cos
 int64_t tulip_voxel_metrics_workspace_bytes(int n_points);
 int tulip_voxel_metrics(const float* pts_pred, const float* pts_gt, int n_points, float grid_size, void* workspace, double* out4,
                         void* stream);
+/* DurLAR (Ouster OS1-128) projection, evaluation.py:19-50 (img_to_pcd_durlar): float64 points [B, H*W, 3]; per-column tables
+ * cos / sin(encoder + azimuth), cos / sin(encoder), per-row cos / sin(elevation) and the per-row column offset LUT come from the host
+ * (tulip_b200.metrics); the point of pixel (row, col) is stored at row * W + (col + W - offset_lut[row]) % W. */
+int tulip_range_to_points_durlar(const float* img, const double* cos_ea, const double* sin_ea, const double* cos_e, const double* sin_e,
+                                 const double* cos_el, const double* sin_el, const int* offset_lut, float max_range, double origin_offset,
+                                 double z_offset, double* points, int B, int H, int W, void* stream);
+/* tulip_voxel_metrics for float64 clouds (the DurLAR projection is float64 in the reference) */
+int tulip_voxel_metrics_f64(const double* pts_pred, const double* pts_gt, int n_points, double grid_size, void* workspace, double* out4,
+                            void* stream);
 /* Chamfer distance as evaluation.py:125-134 uses it: dist_a[i] = min_j |a_i - b_j|^2, dist_b likewise (the un-vendored
  * github.com/otaheri/chamfer_distance extension), out3 = {mean(dist_a) + mean(dist_b), mean(dist_a), mean(dist_b)}. */
 int tulip_chamfer_distance(const float* a, const float* b, int na, int nb, float* dist_a, float* dist_b, float* out3, void* stream);

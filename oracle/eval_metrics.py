@@ -34,6 +34,50 @@ def angle_tables_carla(rows, cols):
     return np.sin(h), np.cos(h), np.sin(v), np.cos(v)
 
 
+# Ouster OS1-128 calibration constants of the DurLAR sensor as listed in evaluation.py:7-17 (beam elevation per row in degrees, the
+# per-row column stagger, and the beam-origin offsets)
+DURLAR_OFFSET_LUT = np.tile(np.array([48, 32, 16, 0]), 32)
+DURLAR_ELEVATION_LUT = np.array([
+    21.42, 21.12, 20.81, 20.5, 20.2, 19.9, 19.58, 19.26, 18.95, 18.65, 18.33, 18.02, 17.68, 17.37, 17.05, 16.73, 16.4, 16.08, 15.76, 15.43,
+    15.1, 14.77, 14.45, 14.11, 13.78, 13.45, 13.13, 12.79, 12.44, 12.12, 11.77, 11.45, 11.1, 10.77, 10.43, 10.1, 9.74, 9.4, 9.06, 8.72,
+    8.36, 8.02, 7.68, 7.34, 6.98, 6.63, 6.29, 5.95, 5.6, 5.25, 4.9, 4.55, 4.19, 3.85, 3.49, 3.15, 2.79, 2.44, 2.1, 1.75, 1.38, 1.03, 0.68,
+    0.33, -0.03, -0.38, -0.73, -1.07, -1.45, -1.8, -2.14, -2.49, -2.85, -3.19, -3.54, -3.88, -4.26, -4.6, -4.95, -5.29, -5.66, -6.01,
+    -6.34, -6.69, -7.05, -7.39, -7.73, -8.08, -8.44, -8.78, -9.12, -9.45, -9.82, -10.16, -10.5, -10.82, -11.19, -11.52, -11.85, -12.18,
+    -12.54, -12.87, -13.2, -13.52, -13.88, -14.21, -14.53, -14.85, -15.2, -15.53, -15.84, -16.16, -16.5, -16.83, -17.14, -17.45, -17.8,
+    -18.11, -18.42, -18.72, -19.06, -19.37, -19.68, -19.97, -20.31, -20.61, -20.92, -21.22])
+DURLAR_ORIGIN_OFFSET = 0.015806
+DURLAR_Z_OFFSET = 0.03618
+DURLAR_ANGLE_OFF = np.pi * 4.2285 / 180.
+
+
+def durlar_tables(rows, cols):
+    """float64 tables of px_to_xyz (evaluation.py:27-45): cos / sin(encoder + azimuth), cos / sin(encoder) per column, cos / sin(elevation)
+    per row, and the per-row column offsets of idx_from_px (:19-23)."""
+    col = np.arange(cols)
+    u = (cols + col) % cols
+    encoder = 2.0 * np.pi - (u * (np.pi * 2.0 / cols))
+    elevation = np.pi * DURLAR_ELEVATION_LUT[np.arange(rows)] / 180.
+    return (np.cos(encoder + DURLAR_ANGLE_OFF), np.sin(encoder + DURLAR_ANGLE_OFF), np.cos(encoder), np.sin(encoder),
+            np.cos(elevation), np.sin(elevation), DURLAR_OFFSET_LUT[:rows].astype(np.int32))
+
+
+def range_to_points_durlar(img, maximum_range=120):
+    """img (H, W) float32 -> (H*W, 3) float64 exactly as img_to_pcd_durlar (evaluation.py:47-58)."""
+    img = np.asarray(img, np.float32)
+    rows, cols = img.shape
+    ca, sa, ce, se, cel, sel, off = durlar_tables(rows, cols)
+    rr = (img * maximum_range) - np.float32(DURLAR_ORIGIN_OFFSET)          # float32, as numpy promotes `array - python float`
+    x = rr * ca[None, :] * cel[:, None] + DURLAR_ORIGIN_OFFSET * ce[None, :]
+    y = rr * sa[None, :] * cel[:, None] + DURLAR_ORIGIN_OFFSET * se[None, :]
+    z = rr * sel[:, None]
+    pts = np.stack((-x, -y, z + DURLAR_Z_OFFSET), axis=-1)
+    col, row = np.arange(cols), np.arange(rows)
+    idx = row[:, None] * cols + (col[None, :] + cols - off[:, None]) % cols
+    out = np.zeros((rows * cols, 3))
+    out[idx.reshape(-1)] = pts.reshape(-1, 3)
+    return out
+
+
 def range_to_points(img, tables, maximum_range):
     """img (H,W) float32 normalised range -> (H*W, 3) float32, row-major over (row, col): evaluation.py:75-84 / :106-114."""
     sin_h, cos_h, sin_v, cos_v = tables

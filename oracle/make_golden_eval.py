@@ -47,6 +47,20 @@ def main():
     ref_m = np.array([iou, prec, rec, 2 * prec * rec / (prec + rec)])
     ora_m = M.voxel_metrics(pk, gk, 0.1)
     assert np.allclose(ref_m, ora_m, rtol=0, atol=1e-15), (ref_m, ora_m)
+    # DurLAR (Ouster LUT projection, float64) and the float64 voxel metrics on it
+    gd = (rng.random((128, 2048), dtype=np.float32) * 0.5 + 0.01).astype(np.float32)
+    pd_ = np.clip(gd + rng.normal(0, 0.003, gd.shape).astype(np.float32), 0, 1).astype(np.float32)
+    ref_d = E.img_to_pcd_durlar(pd_, maximum_range=120)
+    assert ref_d.dtype == np.float64 and np.array_equal(ref_d, M.range_to_points_durlar(pd_, 120)), "durlar projection differs"
+    assert np.array_equal(E.offset_lut, M.DURLAR_OFFSET_LUT) and np.array_equal(E.elevation_lut, M.DURLAR_ELEVATION_LUT)
+    pdd, gdd = E.img_to_pcd_durlar(pd_, 12), E.img_to_pcd_durlar(gd, 12)
+    alld = np.vstack((pdd, gdd))
+    mnd, mxd = np.min(alld, axis=0), np.max(alld, axis=0)
+    ioud, precd, recd = E.calculate_metrics(E.voxelize_point_cloud(pdd, 0.1, mnd, mxd), E.voxelize_point_cloud(gdd, 0.1, mnd, mxd))
+    ref_md = np.array([ioud, precd, recd, 2 * precd * recd / (precd + recd)])
+    assert np.allclose(ref_md, M.voxel_metrics(pdd, gdd, 0.1), rtol=0, atol=1e-15)
+    out.update({"durlar_points_head": ref_d[:4096].copy(), "durlar_voxel_metrics_range12_grid01": ref_md,
+                "durlar_points_sha": np.frombuffer(__import__("hashlib").sha256(ref_d.tobytes()).digest()[:8], np.uint8)})
     sub = slice(0, 65536, 16)
     cd, d1, d2 = M.chamfer_distance(gk[sub], pk[sub])
     out.update({"kitti_points_sha": np.frombuffer(__import__("hashlib").sha256(ref_k.tobytes()).digest()[:8], np.uint8),

@@ -73,3 +73,27 @@ def test_evaluate_frame_full_size():
     m2 = metrics.evaluate_frame(torch.from_numpy(gt).cuda(), torch.from_numpy(pred).cuda(), "kitti", 0.1)
     assert abs(m["chamfer_dist"] - m2["chamfer_dist"]) <= 1e-6 and m["chamfer_dist"] > 0
     assert abs(m["precision"] - m2["recall"]) <= 1e-15
+
+
+def images_durlar():
+    rng = np.random.Generator(np.random.PCG64(123))                 # continue the stream of make_golden_eval.py past the kitti images
+    gt = rng.random((64, 1024), dtype=np.float32); rng.normal(0, 0.004, gt.shape); rng.random(gt.shape)
+    gd = (rng.random((128, 2048), dtype=np.float32) * 0.5 + 0.01).astype(np.float32)
+    pd_ = np.clip(gd + rng.normal(0, 0.003, gd.shape).astype(np.float32), 0, 1).astype(np.float32)
+    return gd, pd_
+
+
+def test_durlar_projection_and_float64_voxel_metrics():
+    from tulip_b200 import metrics
+    gd, pd_ = images_durlar()
+    g = np.load(GOLDEN)
+    want = M.range_to_points_durlar(pd_, 120)
+    got = metrics.range_to_points(torch.from_numpy(pd_).cuda(), "durlar")[0].cpu().numpy()
+    assert got.dtype == np.float64 and np.array_equal(got, want)
+    assert np.array_equal(got[:4096], g["durlar_points_head"])                              # the reference's own output
+    pp = metrics.range_to_points(torch.from_numpy(pd_).cuda(), "durlar", 12)[0]
+    pg = metrics.range_to_points(torch.from_numpy(gd).cuda(), "durlar", 12)[0]
+    vm = metrics.voxel_metrics(pp, pg, 0.1).cpu().numpy()
+    np.testing.assert_allclose(vm, g["durlar_voxel_metrics_range12_grid01"], rtol=0, atol=1e-15)   # reference dense grids, float64
+    m = metrics.evaluate_frame(torch.from_numpy(pd_).cuda(), torch.from_numpy(gd).cuda(), "durlar", 0.1)
+    assert m["chamfer_dist"] > 0 and 0 < m["iou"] < 1

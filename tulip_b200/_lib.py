@@ -62,6 +62,8 @@ SIGNATURES = {
     "tulip_range_to_points": (_i, [_fp, _fp, _fp, _fp, _fp, C.c_float, _fp, _i, _i, _i, _vp]),
     "tulip_voxel_metrics_workspace_bytes": (_i64, [_i]),
     "tulip_voxel_metrics": (_i, [_fp, _fp, _i, C.c_float, _vp, _vp, _vp]),
+    "tulip_range_to_points_durlar": (_i, [_fp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_double, C.c_double, _vp, _i, _i, _i, _vp]),
+    "tulip_voxel_metrics_f64": (_i, [_vp, _vp, _i, C.c_double, _vp, _vp, _vp]),
     "tulip_chamfer_distance": (_i, [_fp, _fp, _i, _i, _fp, _fp, _fp, _vp]),
     "tulip_preprocess_range": (_i, [_fp, _i, C.c_float, _i, C.c_float, C.c_float, _i, _i, _i, _fp, _fp, _i, _i, _i, _vp]),
     "tulip_adamw_step": (_i, [_fp, _fp, _fp, _fp, _vp, _i, _i64, _vp, _vp]),

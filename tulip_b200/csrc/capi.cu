@@ -364,6 +364,23 @@ int tulip_voxel_metrics(const float* pts_pred, const float* pts_gt, int n_points
   return voxel_metrics(pts_pred, pts_gt, n_points, grid_size, workspace, out4, (cudaStream_t)stream);
 }
 
+int tulip_range_to_points_durlar(const float* img, const double* cos_ea, const double* sin_ea, const double* cos_e, const double* sin_e,
+                                 const double* cos_el, const double* sin_el, const int* offset_lut, float max_range, double origin_offset,
+                                 double z_offset, double* points, int B, int H, int W, void* stream) {
+  if (!img || !cos_ea || !sin_ea || !cos_e || !sin_e || !cos_el || !sin_el || !offset_lut || !points) {
+    tulip_set_error("tulip_range_to_points_durlar: null argument");
+    return TULIP_ERR_ARG;
+  }
+  return range_to_points_durlar(img, cos_ea, sin_ea, cos_e, sin_e, cos_el, sin_el, offset_lut, max_range, origin_offset, z_offset, points, B,
+                                H, W, (cudaStream_t)stream);
+}
+
+int tulip_voxel_metrics_f64(const double* pts_pred, const double* pts_gt, int n_points, double grid_size, void* workspace, double* out4,
+                            void* stream) {
+  if (!pts_pred || !pts_gt || !workspace || !out4) { tulip_set_error("tulip_voxel_metrics_f64: null argument"); return TULIP_ERR_ARG; }
+  return voxel_metrics_f64(pts_pred, pts_gt, n_points, grid_size, workspace, out4, (cudaStream_t)stream);
+}
+
 int tulip_chamfer_distance(const float* a, const float* b, int na, int nb, float* dist_a, float* dist_b, float* out3, void* stream) {
   if (!a || !b || !dist_a || !dist_b || !out3) { tulip_set_error("tulip_chamfer_distance: null argument"); return TULIP_ERR_ARG; }
   return chamfer_distance(a, b, na, nb, dist_a, dist_b, out3, (cudaStream_t)stream);

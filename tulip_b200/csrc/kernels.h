@@ -101,3 +101,7 @@ struct AdamwHyper {
 int adamw_step(float* p, const float* g, float* m, float* v, const AdamwSegment* segs_dev, int n_segs, long span, const AdamwHyper& hp,
                cudaStream_t st);
 int grad_norm(const float* g, const AdamwSegment* segs_dev, int n_segs, long span, double* scratch, float* out, cudaStream_t st);
+int voxel_metrics_f64(const double* pts_pred, const double* pts_gt, int n, double grid_size, void* workspace, double* out4, cudaStream_t st);
+int range_to_points_durlar(const float* img, const double* ca, const double* sa, const double* ce, const double* se, const double* cel,
+                           const double* sel, const int* offset_lut, float max_range, double origin_offset, double z_offset,
+                           double* points, int B, int H, int W, cudaStream_t st);

@@ -25,6 +25,30 @@ __global__ void __launch_bounds__(256) range_to_points_kernel(const float* __res
   }
 }
 
+// DurLAR (Ouster OS1-128) projection, evaluation.py:19-50: r = img * max_range and r - origin_offset in float32, everything after in
+// float64 on host tables of cos / sin(encoder + azimuth), cos / sin(encoder) per column and cos / sin(elevation) per row, in the
+// reference's multiplication order, no contraction; the point of pixel (row, col) lands at row * W + (col + W - offset_lut[row]) % W.
+__global__ void __launch_bounds__(256) range_to_points_durlar_kernel(const float* __restrict__ img, const double* __restrict__ ca,
+                                                                     const double* __restrict__ sa, const double* __restrict__ ce,
+                                                                     const double* __restrict__ se, const double* __restrict__ cel,
+                                                                     const double* __restrict__ sel, const int* __restrict__ offset_lut,
+                                                                     float max_range, float origin_offset_f, double origin_offset,
+                                                                     double z_offset, double* __restrict__ pts, long n, int H, int W) {
+  pdl_sync();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W), h = (int)((i / W) % H);
+    const long b = i / ((long)W * H);
+    const double rr = (double)__fsub_rn(__fmul_rn(img[i], max_range), origin_offset_f);
+    const double x = __dadd_rn(__dmul_rn(__dmul_rn(rr, ca[w]), cel[h]), __dmul_rn(origin_offset, ce[w]));
+    const double y = __dadd_rn(__dmul_rn(__dmul_rn(rr, sa[w]), cel[h]), __dmul_rn(origin_offset, se[w]));
+    const double z = __dmul_rn(rr, sel[h]);
+    const long o = (b * H + h) * W + (w + W - offset_lut[h]) % W;
+    pts[3 * o] = -x;
+    pts[3 * o + 1] = -y;
+    pts[3 * o + 2] = __dadd_rn(z, z_offset);
+  }
+}
+
 // ---- voxel metrics ---------------------------------------------------------------------------------------------------------------
 // workspace layout (8-byte words): [0..5] min xyz, max xyz as floats (two per word is avoided: one float per word, low half),
 // [8..10] counters |A|, |B|, |A & B|, then two open-addressing key tables of `cap` words each.
@@ -36,46 +60,62 @@ struct VoxelWs {
   int cap;
 };
 
-__device__ __forceinline__ unsigned int float_ordered(float f) {           // monotone map float -> uint for atomicMin / atomicMax
+// monotone maps of the coordinates to unsigned integers for atomicMin / atomicMax (float: 32-bit image in a 64-bit slot)
+__device__ __forceinline__ unsigned long long to_ordered(float f) {
   const unsigned int u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-__device__ __forceinline__ float ordered_float(unsigned int u) {
-  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+__device__ __forceinline__ unsigned long long to_ordered(double f) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(f);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ void from_ordered(unsigned long long u, float* f) {
+  const unsigned int w = (unsigned int)u;
+  *f = __uint_as_float((w & 0x80000000u) ? (w & 0x7fffffffu) : ~w);
+}
+__device__ __forceinline__ void from_ordered(unsigned long long u, double* f) {
+  *f = __longlong_as_double((long long)((u >> 63) ? (u & 0x7fffffffffffffffull) : ~u));
 }
 
-__global__ void voxel_init_kernel(unsigned int* mm_ord, unsigned long long* cnt, long long* tables, long words) {
+__global__ void voxel_init_kernel(unsigned long long* mm_ord, unsigned long long* cnt, long long* tables, long words, int is_f32) {
   pdl_sync();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 3) { mm_ord[i] = 0xffffffffu; mm_ord[3 + i] = 0u; cnt[i] = 0ull; }
+  if (i < 3) { mm_ord[i] = is_f32 ? 0xffffffffull : ~0ull; mm_ord[3 + i] = 0ull; cnt[i] = 0ull; }
   for (long k = i; k < words; k += (long)gridDim.x * blockDim.x) tables[k] = -1ll;
 }
 
-__global__ void __launch_bounds__(256) voxel_minmax_kernel(const float* __restrict__ a, const float* __restrict__ b, int n,
-                                                           unsigned int* mm_ord) {
+template <class T>
+__global__ void __launch_bounds__(256) voxel_minmax_kernel(const T* __restrict__ a, const T* __restrict__ b, int n,
+                                                           unsigned long long* mm_ord) {
   pdl_sync();
-  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  T mn[3] = {(T)INFINITY, (T)INFINITY, (T)INFINITY}, mx[3] = {(T)-INFINITY, (T)-INFINITY, (T)-INFINITY};
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < 2l * n; i += (long)gridDim.x * blockDim.x) {
-    const float* p = (i < n) ? a + 3 * i : b + 3 * (i - n);
+    const T* p = (i < n) ? a + 3 * i : b + 3 * (i - n);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], p[k]); mx[k] = fmaxf(mx[k], p[k]); }
+    for (int k = 0; k < 3; ++k) { mn[k] = p[k] < mn[k] ? p[k] : mn[k]; mx[k] = p[k] > mx[k] ? p[k] : mx[k]; }
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     for (int o = 16; o > 0; o >>= 1) {
-      mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-      mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+      const T omn = __shfl_xor_sync(0xffffffffu, mn[k], o), omx = __shfl_xor_sync(0xffffffffu, mx[k], o);
+      mn[k] = omn < mn[k] ? omn : mn[k];
+      mx[k] = omx > mx[k] ? omx : mx[k];
     }
-    if ((threadIdx.x & 31) == 0) { atomicMin(mm_ord + k, float_ordered(mn[k])); atomicMax(mm_ord + 3 + k, float_ordered(mx[k])); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(mm_ord + k, to_ordered(mn[k])); atomicMax(mm_ord + 3 + k, to_ordered(mx[k])); }
   }
 }
 
-// voxel key exactly as voxelize_point_cloud (evaluation.py:148-159): dims = int((max - min) / g) + 1, idx = int((p - min) / g),
-// float32 arithmetic with IEEE division; the dense-grid position becomes a linear int64 key
-__device__ __forceinline__ long long voxel_key(const float* p, const float* mn, const float* mx, float g) {
-  const int dy = (int)__fdiv_rn(__fsub_rn(mx[1], mn[1]), g) + 1, dz = (int)__fdiv_rn(__fsub_rn(mx[2], mn[2]), g) + 1;
-  const int ix = (int)__fdiv_rn(__fsub_rn(p[0], mn[0]), g), iy = (int)__fdiv_rn(__fsub_rn(p[1], mn[1]), g),
-            iz = (int)__fdiv_rn(__fsub_rn(p[2], mn[2]), g);
+// voxel key exactly as voxelize_point_cloud (evaluation.py:148-159): dims = int((max - min) / g) + 1, idx = int((p - min) / g), in
+// the precision of the clouds (float32 for kitti / carla, float64 for durlar) with IEEE division; the dense-grid position becomes a
+// linear int64 key
+__device__ __forceinline__ float vsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double vsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float vdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double vdiv(double a, double b) { return __ddiv_rn(a, b); }
+template <class T>
+__device__ __forceinline__ long long voxel_key(const T* p, const T* mn, const T* mx, T g) {
+  const int dy = (int)vdiv(vsub(mx[1], mn[1]), g) + 1, dz = (int)vdiv(vsub(mx[2], mn[2]), g) + 1;
+  const int ix = (int)vdiv(vsub(p[0], mn[0]), g), iy = (int)vdiv(vsub(p[1], mn[1]), g), iz = (int)vdiv(vsub(p[2], mn[2]), g);
   return ((long long)ix * dy + iy) * dz + iz;
 }
 __device__ __forceinline__ unsigned int hash64(unsigned long long k) {
@@ -83,16 +123,17 @@ __device__ __forceinline__ unsigned int hash64(unsigned long long k) {
   return (unsigned int)k;
 }
 
-__global__ void __launch_bounds__(256) voxel_insert_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float g,
-                                                           const unsigned int* mm_ord, long long* ta, long long* tb, int cap,
+template <class T>
+__global__ void __launch_bounds__(256) voxel_insert_kernel(const T* __restrict__ a, const T* __restrict__ b, int n, T g,
+                                                           const unsigned long long* mm_ord, long long* ta, long long* tb, int cap,
                                                            unsigned long long* cnt) {
   pdl_sync();
-  float mn[3], mx[3];
+  T mn[3], mx[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { mn[k] = ordered_float(mm_ord[k]); mx[k] = ordered_float(mm_ord[3 + k]); }
+  for (int k = 0; k < 3; ++k) { from_ordered(mm_ord[k], &mn[k]); from_ordered(mm_ord[3 + k], &mx[k]); }
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < 2l * n; i += (long)gridDim.x * blockDim.x) {
     const bool first = i < n;
-    const float* p = first ? a + 3 * i : b + 3 * (i - n);
+    const T* p = first ? a + 3 * i : b + 3 * (i - n);
     long long* tab = first ? ta : tb;
     const long long key = voxel_key(p, mn, mx, g);
     unsigned int slot = hash64((unsigned long long)key) & (cap - 1);
@@ -190,20 +231,40 @@ int range_to_points(const float* img, const float* sin_h, const float* cos_h, co
 
 long voxel_metrics_workspace_bytes(int n) { return 128 + 2l * pow2_at_least(4l * n) * 8; }
 
-int voxel_metrics(const float* pts_pred, const float* pts_gt, int n, float grid_size, void* workspace, double* out4, cudaStream_t st) {
-  TULIP_REQUIRE(n > 0 && grid_size > 0.f, "voxel_metrics: empty cloud or non-positive grid size");
+template <class T>
+int voxel_metrics_t(const T* pts_pred, const T* pts_gt, int n, T grid_size, void* workspace, double* out4, cudaStream_t st) {
+  TULIP_REQUIRE(n > 0 && grid_size > (T)0, "voxel_metrics: empty cloud or non-positive grid size");
   const int cap = pow2_at_least(4l * n);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
-  unsigned int* mm_ord = reinterpret_cast<unsigned int*>(ws);
+  unsigned long long* mm_ord = reinterpret_cast<unsigned long long*>(ws);
   unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ws + 64);
   long long* ta = reinterpret_cast<long long*>(ws + 128);
   long long* tb = ta + cap;
   const int grid = 2 * tulip_num_sms();
-  tulip_launch(voxel_init_kernel, grid, 256, 0, st, mm_ord, cnt, ta, 2l * cap);
-  tulip_launch(voxel_minmax_kernel, grid, 256, 0, st, pts_pred, pts_gt, n, mm_ord);
-  tulip_launch(voxel_insert_kernel, grid, 256, 0, st, pts_pred, pts_gt, n, grid_size, (const unsigned int*)mm_ord, ta, tb, cap, cnt);
+  tulip_launch(voxel_init_kernel, grid, 256, 0, st, mm_ord, cnt, ta, 2l * cap, (int)(sizeof(T) == 4));
+  tulip_launch(voxel_minmax_kernel<T>, grid, 256, 0, st, pts_pred, pts_gt, n, mm_ord);
+  tulip_launch(voxel_insert_kernel<T>, grid, 256, 0, st, pts_pred, pts_gt, n, grid_size, (const unsigned long long*)mm_ord, ta, tb, cap, cnt);
   tulip_launch(voxel_intersect_kernel, grid, 256, 0, st, (const long long*)ta, (const long long*)tb, cap, cnt);
   tulip_launch(voxel_finalize_kernel, 1, 1, 0, st, (const unsigned long long*)cnt, out4);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+int voxel_metrics(const float* pts_pred, const float* pts_gt, int n, float grid_size, void* workspace, double* out4, cudaStream_t st) {
+  return voxel_metrics_t<float>(pts_pred, pts_gt, n, grid_size, workspace, out4, st);
+}
+int voxel_metrics_f64(const double* pts_pred, const double* pts_gt, int n, double grid_size, void* workspace, double* out4, cudaStream_t st) {
+  return voxel_metrics_t<double>(pts_pred, pts_gt, n, grid_size, workspace, out4, st);
+}
+
+int range_to_points_durlar(const float* img, const double* ca, const double* sa, const double* ce, const double* se, const double* cel,
+                           const double* sel, const int* offset_lut, float max_range, double origin_offset, double z_offset,
+                           double* points, int B, int H, int W, cudaStream_t st) {
+  TULIP_REQUIRE(B > 0 && H > 0 && W > 0, "range_to_points_durlar: empty image");
+  const long n = (long)B * H * W;
+  const int grid = (int)((n + 255) / 256 < 4l * tulip_num_sms() ? (n + 255) / 256 : 4l * tulip_num_sms());
+  tulip_launch(range_to_points_durlar_kernel, grid, 256, 0, st, img, ca, sa, ce, se, cel, sel, offset_lut, max_range, (float)origin_offset,
+               origin_offset, z_offset, points, n, H, W);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
