@@ -218,6 +218,7 @@ def run_ours(args, rank, world, local_rank):
     B = args.batch
     torch.manual_seed(0)                                   # identical replicas on every rank (reference: DDP broadcast)
     model = tulip_base(**MODEL_KW).to(dev).train()         # train mode: DropPath masks are drawn every step, as in the reference
+    torch.manual_seed(0 + rank)                            # per-rank RNG stream for the DropPath masks (reference: seed + rank, main:155)
     lo_h, hi_h = synth_inputs(B, 1 + rank)
     lo_pin, hi_pin = lo_h.pin_memory(), hi_h.pin_memory()
     lo_d, hi_d = lo_pin.to(dev), hi_pin.to(dev)

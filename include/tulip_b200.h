@@ -96,6 +96,45 @@ int tulip_gemm_nt(const void* A, const void* W, const float* bias, void* out, vo
 int tulip_gemm_nt_plan(int M, int N, int K, int epilogue, int save_pre, int* out10);
 int tulip_gemm_tn(const void* dY, const void* X, float* dW, float* db, int M, int N, int K, int impl, void* stream);
 
+/* The same two contractions with every operand mode and fused epilogue of the path spelled out (per-kernel parity tests of
+ * PatchUnmerging, the skip Linear and the head bind these).  bf16 operands, fp32 parameters; 0 / NULL = unused.
+ * epilogue: 0 store | 1 bias+GELU | 2 residual | 3 NHWC PixelShuffle(2) scatter (PatchUnmerging, tulip.py:117-123; W rows in
+ *   the order n' = (2i+j)*Cc + c) | 4 split columns at split_col into out / out2 (skip Linear backward, tulip.py:715-716) |
+ *   5 acc * gelu'(aux) | 6 head: pred[pixel] = sum_c wd[c] * leaky(acc + bias) (tulip.py:174-178, 731) |
+ *   7 head backward: recomputes the pre-activation, out = dh, dwd += ... with dpred = sign(pred - target) * gscale / npix |
+ *   8 row scale | 9 (A.B^T) * gelu'(A2.B2^T + bias)
+ * a_mode 1: A[m=(b,h,w), k=(2i+j)*Cc+c] = src[b, 2h+i, 2w+j, c] (PixelShuffle(2) backward gather), geometry g_H, g_W, g_Cc */
+typedef struct tulip_gemm_desc {
+  const void* A; int64_t lda;
+  const void* A2; int64_t lda2; int K1;        /* columns k >= K1 of the virtual A come from A2 (concat); K1 = K when unused */
+  const void* B; int64_t ldb;
+  const void* B2; int64_t ldb2; int K2;        /* epilogue 9 */
+  int M, N, K;
+  int a_mode, g_H, g_W, g_Cc;
+  const float* bias;
+  void* out; int64_t ldo;
+  void* out2; int64_t ldo2;
+  const void* aux; int64_t ldaux;
+  const float* row_scale; int rows_per_sample;
+  int split_col;
+  const float* wd; const float* target; float* pred; const float* gscale; float* dwd;
+  int hd_H, hd_W, hd_r, hd_E;
+} tulip_gemm_desc;
+int tulip_gemm_nt_ex(const tulip_gemm_desc* d, int epilogue, void* stream);
+/* dW[N,K] += dY^T . [X | X2]; rows written un-permuted when perm_R2 > 1 (row n' = ij*Cc + c -> c*R2 + ij); y_mode 1 gathers
+ * dY through the PixelShuffle(2) backward view */
+typedef struct tulip_gemm_tn_desc {
+  const void* dY; int64_t ldy;
+  const void* X; int64_t ldx;
+  const void* X2; int64_t ldx2; int K1;
+  int M, N, K;
+  int y_mode, g_H, g_W, g_Cc;
+  float* dW; int64_t lddw;
+  float* db;
+  int perm_R2, perm_Cc;
+} tulip_gemm_tn_desc;
+int tulip_gemm_tn_ex(const tulip_gemm_tn_desc* d, void* stream);
+
 /* ---- window attention core: tulip.py:289-317 without the two Linears; shift/partition/mask/bias in-kernel ---- */
 int tulip_window_attention_fwd(const void* qkv, const float* bias_table, void* out, int B, int H, int W, int C, int heads,
                                int Mh, int Mw, int sh, int sw, int masked, int bias_Mh, int bias_Mw, void* stream);

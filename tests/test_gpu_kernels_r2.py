@@ -1,0 +1,131 @@
+"""Per-kernel GPU parity of the scatter / gather / split / head epilogues against fixtures computed by the reference's own
+modules (tests/golden/modules_r2.npz, oracle/make_golden_r2.py): PatchUnmerging (tulip.py:109-123), the skip Linear on
+cat([x, skip]) (:715-716) and norm_up + PixelShuffleHead + decoder_pred + L1 (:720-731, 690-693), forward and backward.
+
+Tolerances.  A kernel that rounds once (fp32 accumulate -> one bf16 store) is held to rel-L2 <= 1e-3 against the bf16-rounded
+reference output.  fp32 outputs (pred, weight gradients accumulated in fp32 from exact bf16 operands) to 1e-3 against the
+reference directly.  Chains of two rounded stages (dh is stored as bf16 before it feeds the next GEMM; LayerNorm output is stored
+as bf16 before the head GEMM) are held to 4e-3: two independent bf16 roundings of 2^-9 relative each, measured ~2e-3."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import bf16r, dec, rel_l2
+from oracle.params import bf16_bits_to_f32
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods(golden_dir):
+    return np.load(os.path.join(golden_dir, "modules_r2.npz"))
+
+
+def P(mods, key):
+    v = mods[key]
+    return torch.from_numpy(bf16_bits_to_f32(v) if v.dtype == np.uint16 else v).cuda()
+
+
+def bf(t):
+    return t.to(torch.bfloat16).contiguous()
+
+
+def test_patch_unmerging_fwd_bwd(mods):
+    from tulip_b200 import ops
+    x = P(mods, "unmerge.x")                                   # [B, H, W, C]
+    B, H, W, C = x.shape
+    Cc, T = C // 2, B * H * W
+    w = P(mods, "unmerge.p.expand.weight").reshape(2 * C, C)
+    b = P(mods, "unmerge.p.expand.bias")
+    wp, bp = ops.permute_rows_for_shuffle(w, 4, Cc), ops.permute_rows_for_shuffle(b, 4, Cc)
+    xb, wb = bf(x.reshape(T, C)), bf(wp)
+    out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_nt_ex(ops.EPI_PIXSHUF, A=xb, lda=C, K1=C, B=wb, ldb=C, M=T, N=2 * C, K=C, bias=bp.contiguous(), out=out, ldo=Cc,
+                   g_H=H, g_W=W, g_Cc=Cc)
+    y = P(mods, "unmerge.y")
+    assert rel_l2(out.float(), bf16r(y)) <= 1e-3
+    # backward: dX = gather(gy) . W' (A_UNSHUFFLE), dW = gather(gy)^T . x written back in the reference's row order
+    gy = bf(P(mods, "unmerge.gy"))
+    wtb = bf(wp.t())                                           # [C, 2C]
+    gx = torch.empty((T, C), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_nt_ex(ops.EPI_STORE, A=gy, lda=Cc, K1=2 * C, B=wtb, ldb=2 * C, M=T, N=C, K=2 * C, out=gx, ldo=C, a_mode=ops.A_UNSHUFFLE,
+                   g_H=H, g_W=W, g_Cc=Cc)
+    assert rel_l2(gx.float().reshape(B, H, W, C), bf16r(P(mods, "unmerge.gx"))) <= 1e-3
+    dW = torch.zeros((2 * C, C), dtype=torch.float32, device="cuda")
+    db = torch.zeros(2 * C, dtype=torch.float32, device="cuda")
+    ops.gemm_tn_ex(dY=gy, ldy=Cc, X=xb, ldx=C, K1=C, M=T, N=2 * C, K=C, y_mode=ops.A_UNSHUFFLE, g_H=H, g_W=W, g_Cc=Cc, dW=dW, lddw=C,
+                   db=db, perm_R2=4, perm_Cc=Cc)
+    assert rel_l2(dW, P(mods, "unmerge.g_w").reshape(2 * C, C)) <= 1e-3
+    assert rel_l2(db, P(mods, "unmerge.g_b")) <= 1e-3
+
+
+def test_skip_linear_fwd_bwd(mods):
+    from tulip_b200 import ops
+    x, skip = P(mods, "skip.x"), P(mods, "skip.skip")
+    B, H, W, C = x.shape
+    T = B * H * W
+    w, b = P(mods, "skip.p.weight"), P(mods, "skip.p.bias")    # [C, 2C]
+    xb, sb, wb = bf(x.reshape(T, C)), bf(skip.reshape(T, C)), bf(w)
+    out = torch.empty((T, C), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_nt_ex(ops.EPI_STORE, A=xb, lda=C, A2=sb, lda2=C, K1=C, B=wb, ldb=2 * C, M=T, N=C, K=2 * C, bias=b.contiguous(), out=out, ldo=C)
+    assert rel_l2(out.float().reshape(B, H, W, C), bf16r(P(mods, "skip.y"))) <= 1e-3
+    gy = bf(P(mods, "skip.gy").reshape(T, C))
+    wtb = bf(w.t())                                            # [2C, C]
+    gx = torch.empty((T, C), dtype=torch.bfloat16, device="cuda")
+    gs = torch.empty((T, C), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_nt_ex(ops.EPI_SPLIT2, A=gy, lda=C, K1=C, B=wtb, ldb=C, M=T, N=2 * C, K=C, out=gx, ldo=C, out2=gs, ldo2=C, split_col=C)
+    assert rel_l2(gx.float().reshape(B, H, W, C), bf16r(P(mods, "skip.gx"))) <= 1e-3
+    assert rel_l2(gs.float().reshape(B, H, W, C), bf16r(P(mods, "skip.gskip"))) <= 1e-3
+    dW = torch.zeros((C, 2 * C), dtype=torch.float32, device="cuda")
+    db = torch.zeros(C, dtype=torch.float32, device="cuda")
+    ops.gemm_tn_ex(dY=gy, ldy=C, X=xb, ldx=C, X2=sb, ldx2=C, K1=C, M=T, N=C, K=2 * C, dW=dW, lddw=2 * C, db=db)
+    assert rel_l2(dW, P(mods, "skip.g_w")) <= 1e-3
+    assert rel_l2(db, P(mods, "skip.g_b")) <= 1e-3
+
+
+@pytest.mark.parametrize("E", [96, 192])
+def test_head_fwd_bwd(mods, E):
+    """norm_up -> conv_expand -> LeakyReLU -> PixelShuffle(4) -> decoder_pred -> L1, and its backward."""
+    from tulip_b200 import ops
+    tag, r = f"head{E}", 4
+    x = P(mods, f"{tag}.x")                                    # [B, H, W, E] NHWC tokens
+    B, H, W, _ = x.shape
+    T, N = B * H * W, E * r * r
+    nw, nb = P(mods, f"{tag}.norm.weight"), P(mods, f"{tag}.norm.bias")
+    we = P(mods, f"{tag}.ps.conv_expand.0.weight").reshape(N, E)
+    be = P(mods, f"{tag}.ps.conv_expand.0.bias")
+    wd = P(mods, f"{tag}.dec.weight").reshape(E).contiguous()
+    target = P(mods, f"{tag}.target").contiguous()
+    wep, bep = ops.permute_rows_for_shuffle(we, r * r, E), ops.permute_rows_for_shuffle(be, r * r, E).contiguous()
+    xb = bf(x.reshape(T, E))
+    xn, stats = ops.layernorm(xb, nw, nb)
+    pred = torch.zeros((B, 1, H * r, W * r), dtype=torch.float32, device="cuda")
+    wb = bf(wep)
+    ops.gemm_nt_ex(ops.EPI_HEAD, A=xn, lda=E, K1=E, B=wb, ldb=E, M=T, N=N, K=E, bias=bep, wd=wd, pred=pred, hd_H=H, hd_W=W, hd_r=r, hd_E=E)
+    want = P(mods, f"{tag}.pred")
+    assert rel_l2(pred, want) <= 4e-3                          # LayerNorm output is a bf16 tensor: two rounded stages
+    loss, _ = ops.l1_loss(pred, target, log_transform=False)
+    assert abs(loss.item() - float(mods[f"{tag}.loss"])) <= 2e-3 * float(mods[f"{tag}.loss"])
+    # backward.  dpred = sign(pred - target) / numel is formed inside the kernel from pred / target.
+    dh = torch.empty((T, N), dtype=torch.bfloat16, device="cuda")
+    dwd = torch.zeros(E, dtype=torch.float32, device="cuda")
+    gscale = torch.ones(1, dtype=torch.float32, device="cuda")
+    ops.gemm_nt_ex(ops.EPI_HEAD_BWD, A=xn, lda=E, K1=E, B=wb, ldb=E, M=T, N=N, K=E, bias=bep, wd=wd, pred=pred, target=target,
+                   gscale=gscale, dwd=dwd, out=dh, ldo=N, hd_H=H, hd_W=W, hd_r=r, hd_E=E)
+    # sign(pred - target) flips where the two paths' pred straddle the target: a handful of pixels, each worth 1/numel
+    assert rel_l2(dwd, P(mods, f"{tag}.g_wd").reshape(E)) <= 1e-2
+    dWe = torch.zeros((N, E), dtype=torch.float32, device="cuda")
+    dbe = torch.zeros(N, dtype=torch.float32, device="cuda")
+    ops.gemm_tn_ex(dY=dh, ldy=N, X=xn, ldx=E, K1=E, M=T, N=N, K=E, dW=dWe, lddw=E, db=dbe, perm_R2=r * r, perm_Cc=E)
+    g_we = P(mods, f"{tag}.g_we").reshape(-1, E)
+    stride = N // g_we.shape[0]
+    assert rel_l2(dWe[::stride], g_we) <= 1e-2
+    assert rel_l2(dbe, P(mods, f"{tag}.g_be")) <= 1e-2
+    dxn = torch.empty((T, E), dtype=torch.bfloat16, device="cuda")
+    wtb = bf(wep.t())
+    ops.gemm_nt_ex(ops.EPI_STORE, A=dh, lda=N, K1=N, B=wtb, ldb=N, M=T, N=E, K=N, out=dxn, ldo=E)
+    gx, gnw, gnb = ops.layernorm_bwd(xb, nw, stats, dxn)
+    assert rel_l2(gx.float().reshape(B, H, W, E), P(mods, f"{tag}.gx")) <= 1e-2
+    assert rel_l2(gnw, P(mods, f"{tag}.g_norm_w")) <= 1e-2 and rel_l2(gnb, P(mods, f"{tag}.g_norm_b")) <= 1e-2

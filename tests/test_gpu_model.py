@@ -25,7 +25,13 @@ KW = dict(patch_size=(1, 4), in_chans=1, window_size=[2, 8], swin_v2=False, pixe
 
 
 def build(cfg, large=False):
-    from tulip_b200.model.tulip import tulip_base, tulip_large
+    from functools import partial
+    from tulip_b200.model.tulip import TULIP, tulip_base, tulip_large
+    if cfg.embed_dim != 96 or (tuple(cfg.depths) not in ((2, 2, 2, 2), (2, 2, 2, 2, 2))):
+        # the TULIP constructor itself (tulip.py:531-584), as the BASELINE cfg5 surrogate needs it (SURVEY 8d option i)
+        return TULIP(img_size=cfg.img_size, target_img_size=cfg.target_img_size, embed_dim=cfg.embed_dim, depths=cfg.depths,
+                     num_heads=cfg.num_heads, mlp_ratio=4, qkv_bias=True, drop_rate=0, attn_drop_rate=0, drop_path_rate=0.1,
+                     norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), **KW)
     fn = tulip_large if large else tulip_base
     return fn(img_size=cfg.img_size, target_img_size=cfg.target_img_size, **KW)
 
@@ -35,8 +41,10 @@ def load_params(model, pn):
     model.load_state_dict(sd, strict=True)                 # same strict load as misc.load_model (misc.py:382)
 
 
+TULIP_WIDE = Cfg(embed_dim=192, depths=(2, 2, 18, 2), num_heads=(6, 12, 24, 48))      # BASELINE cfg5 surrogate (SURVEY 8d option i)
 CASES = [("model_base_kitti_b2", TULIP_BASE, False), ("model_large_kitti_b1", TULIP_LARGE, True),
-         ("model_base_durlar_b1", Cfg(img_size=(32, 2048), target_img_size=(128, 2048)), False)]
+         ("model_base_durlar_b1", Cfg(img_size=(32, 2048), target_img_size=(128, 2048)), False),
+         ("model_wide_kitti_b1", TULIP_WIDE, False)]
 
 
 @pytest.mark.parametrize("name,cfg,large", CASES)
@@ -204,6 +212,45 @@ def test_full_size_other_configs_properties(name, cfg, large, B):
     assert max(errs) <= 1e-3, max(errs)
 
 
+def oracle_chunked(cfg, pn, lo, hi, chunk):
+    """Oracle forward + backward of the mean-L1 loss over the whole batch, run `chunk` frames at a time on the host (the fp32
+    autograd tape of a full BASELINE batch would take 8-17 GB): losses and gradients of the chunks are averaged."""
+    B = lo.shape[0]
+    p = O.to_torch(pn, requires_grad=True)
+    preds, loss = [], 0.0
+    for b0 in range(0, B, chunk):
+        pr, l, _ = O.forward(p, cfg, torch.from_numpy(lo[b0:b0 + chunk]), torch.from_numpy(hi[b0:b0 + chunk]), state={})
+        (l * (pr.shape[0] / B)).backward()
+        preds.append(pr.detach())
+        loss += l.item() * pr.shape[0] / B
+    return torch.cat(preds), loss, {k: v.grad for k, v in p.items() if v.grad is not None}
+
+
+@pytest.mark.parametrize("name,cfg,B,chunk", [("kitti_b32", TULIP_BASE, 32, 8),
+                                               ("durlar_b16", Cfg(img_size=(32, 2048), target_img_size=(128, 2048)), 16, 4),
+                                               ("wide_b8", TULIP_WIDE, 8, 2)])
+def test_full_size_vs_oracle(name, cfg, B, chunk):
+    """BASELINE cfg2 / cfg3 / cfg5-surrogate at their FULL batch sizes against the oracle on the same seeded inputs: pred, loss
+    and every gradient tensor (these sizes were only covered by self-consistency properties)."""
+    torch.set_num_threads(max(1, (os.cpu_count() or 1)))
+    pn = make_params(cfg, 61)
+    lo, hi = make_inputs(cfg, B, 62)
+    pred_o, loss_o, grads_o = oracle_chunked(cfg, pn, lo, hi, chunk)
+    model = build(cfg).eval()
+    load_params(model, pn)
+    model.cuda()
+    pred, loss, _ = model(torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda())
+    loss.backward()
+    e_pred = rel_l2(pred, pred_o)
+    errs = {n: rel_l2(q.grad, grads_o[n]) for n, q in model.named_parameters()}
+    worst = max(errs, key=errs.get)
+    med = float(np.median(list(errs.values())))
+    print(f"\n[{name}] pred rel-L2 {e_pred:.3e}  loss {loss.item():.6f} vs {loss_o:.6f}  grad rel-L2 median {med:.3e} "
+          f"worst {errs[worst]:.3e} ({worst})")
+    assert e_pred <= 1e-2 and abs(loss.item() - loss_o) <= 1e-3 * loss_o
+    assert med <= 2e-2 and errs[worst] <= 0.3
+
+
 def test_gradient_accumulation_and_buffer_aliasing():
     """.grad tensors are views of one flat buffer; a second backward without zero_grad must accumulate, not alias."""
     from tulip_b200.parallel import flat_grad_of
@@ -247,6 +294,7 @@ def test_reference_engine_call_pattern_trains():
             _, total_loss, pixel_loss = model(lo_t, hi_t, eval=False)
         losses.append(total_loss.item())
         assert np.isfinite(losses[-1]) and np.isfinite(pixel_loss.item())
+        total_loss /= 1                                       # engine_upsampling.py:92 (`total_loss /= accum_iter`, in place)
         scaler.scale(total_loss).backward()
         scaler.unscale_(opt)
         norm = torch.norm(torch.stack([torch.norm(p.grad.detach(), 2.0) for p in model.parameters()]), 2.0)
@@ -257,3 +305,43 @@ def test_reference_engine_call_pattern_trains():
         torch.cuda.synchronize()
     assert scaler.get_scale() == 65536.0, "a step was skipped: inf/nan gradients"
     assert losses[-1] < 0.8 * losses[0], losses
+
+
+def test_deepcopy_and_pickle_after_forward():
+    """EMA wrappers deep-copy the model (the reference's train_one_epoch has an `ema` hook); after the first forward
+    the module holds a C handle and raw pointers, which must not travel with the copy."""
+    import copy
+    import io
+    cfg = TULIP_BASE
+    model = build(cfg).cuda().eval()
+    lo, hi = make_inputs(cfg, 1, 7)
+    lo_t, hi_t = torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda()
+    pred, _, _ = model(lo_t, hi_t)
+    twin = copy.deepcopy(model)
+    assert twin._net is None
+    pred2, _, _ = twin(lo_t, hi_t)
+    assert twin._net is not None and twin._net.value != model._net.value
+    assert torch.equal(pred, pred2)
+    buf = io.BytesIO()
+    torch.save(model, buf)
+    buf.seek(0)
+    again = torch.load(buf, weights_only=False)
+    assert torch.equal(again(lo_t, hi_t)[0], pred)
+
+
+def test_parameter_storage_swap_is_noticed():
+    """replacing a parameter's storage (EMA swap, load_state_dict(assign=True)) must reach the next forward."""
+    cfg = TULIP_BASE
+    model = build(cfg).cuda().eval()
+    lo, hi = make_inputs(cfg, 1, 7)
+    lo_t, hi_t = torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda()
+    pred, _, _ = model(lo_t, hi_t)
+    p = model.layers[1].blocks[0].mlp.fc1.weight                # not one of the spot-checked parameters of round 1
+    p.data = p.data.clone() * 1.5
+    pred2, _, _ = model(lo_t, hi_t)
+    assert not torch.equal(pred, pred2)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["norm_up.weight"] = sd["norm_up.weight"] * 2.0
+    model.load_state_dict(sd, assign=True)
+    pred3, _, _ = model(lo_t, hi_t)
+    assert not torch.equal(pred2, pred3)

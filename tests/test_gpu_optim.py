@@ -86,3 +86,36 @@ def test_flat_adamw_grad_scale_and_state_dict():
     opt3 = FlatAdamW(model, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.01)
     opt3.load_state_dict(sd)
     assert opt3.steps == 1 and torch.equal(opt3.exp_avg, opt1.exp_avg) and torch.equal(opt3.exp_avg_sq, opt2.exp_avg_sq)
+
+
+def test_flat_adamw_state_dict_interchanges_with_torch_adamw():
+    """a checkpoint written by torch.optim.AdamW (what misc.save_model stores, util/misc.py:338-344) must resume
+    under FlatAdamW with its moments and step count, and the other way round."""
+    from tulip_b200.optim import FlatAdamW
+    cfg = TULIP_BASE
+    lo, hi = make_inputs(cfg, 2, 52)
+    lo_t, hi_t = torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda()
+    model = build(cfg).train()
+    load_params(model, make_params(cfg, 51))
+    model.cuda()
+    ref = torch.optim.AdamW(groups_of(model, 5e-4, 0.05), lr=5e-4, betas=(0.9, 0.95))
+    for _ in range(2):
+        model.zero_grad()
+        _, loss, _ = model(lo_t, hi_t)
+        loss.backward()
+        ref.step()
+    sd = ref.state_dict()
+    opt = FlatAdamW(model, groups_of(model, 5e-4, 0.05), lr=5e-4, betas=(0.9, 0.95))
+    opt.load_state_dict(sd)
+    assert opt.steps == 2
+    k0 = next(iter(sd["state"]))
+    p0 = ref.param_groups[0]["params"][0]
+    o, n, shape = model._views[[id(p) for p in model._param_list].index(id(p0))]
+    assert torch.equal(opt.exp_avg[o:o + n].view(shape), sd["state"][k0]["exp_avg"])
+    # ... and back: torch.optim.AdamW resumes from FlatAdamW's state_dict and both take the same third step
+    back = torch.optim.AdamW(groups_of(model, 5e-4, 0.05), lr=5e-4, betas=(0.9, 0.95))
+    back.load_state_dict(opt.state_dict())
+    assert int(float(back.state[p0]["step"])) == 2 and torch.equal(back.state[p0]["exp_avg_sq"], sd["state"][k0]["exp_avg_sq"])
+    with pytest.raises(ValueError):
+        bad = {"state": {0: {"foo": 1}}, "param_groups": sd["param_groups"]}
+        FlatAdamW(model, groups_of(model, 5e-4, 0.05), lr=5e-4, betas=(0.9, 0.95)).load_state_dict(bad)

@@ -24,6 +24,26 @@ class TulipConfig(C.Structure):
     ]
 
 
+class GemmDesc(C.Structure):                     # tulip_gemm_desc (include/tulip_b200.h)
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("A2", C.c_void_p), ("lda2", C.c_int64), ("K1", C.c_int),
+                ("B", C.c_void_p), ("ldb", C.c_int64), ("B2", C.c_void_p), ("ldb2", C.c_int64), ("K2", C.c_int),
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("a_mode", C.c_int), ("g_H", C.c_int), ("g_W", C.c_int), ("g_Cc", C.c_int),
+                ("bias", C.c_void_p),
+                ("out", C.c_void_p), ("ldo", C.c_int64), ("out2", C.c_void_p), ("ldo2", C.c_int64),
+                ("aux", C.c_void_p), ("ldaux", C.c_int64),
+                ("row_scale", C.c_void_p), ("rows_per_sample", C.c_int), ("split_col", C.c_int),
+                ("wd", C.c_void_p), ("target", C.c_void_p), ("pred", C.c_void_p), ("gscale", C.c_void_p), ("dwd", C.c_void_p),
+                ("hd_H", C.c_int), ("hd_W", C.c_int), ("hd_r", C.c_int), ("hd_E", C.c_int)]
+
+
+class GemmTNDesc(C.Structure):                   # tulip_gemm_tn_desc
+    _fields_ = [("dY", C.c_void_p), ("ldy", C.c_int64), ("X", C.c_void_p), ("ldx", C.c_int64), ("X2", C.c_void_p), ("ldx2", C.c_int64),
+                ("K1", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("y_mode", C.c_int), ("g_H", C.c_int), ("g_W", C.c_int), ("g_Cc", C.c_int),
+                ("dW", C.c_void_p), ("lddw", C.c_int64), ("db", C.c_void_p), ("perm_R2", C.c_int), ("perm_Cc", C.c_int)]
+
+
 def lib_path() -> str:
     return os.environ.get("TULIP_B200_LIB", os.path.join(_HERE, "lib", "libtulip_b200.so"))
 
@@ -52,6 +72,8 @@ SIGNATURES = {
     "tulip_gemm_nt": (_i, [_vp, _vp, _fp, _vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
     "tulip_gemm_nt_plan": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i)]),
     "tulip_gemm_tn": (_i, [_vp, _vp, _fp, _fp, _i, _i, _i, _i, _vp]),
+    "tulip_gemm_nt_ex": (_i, [C.POINTER(GemmDesc), _i, _vp]),
+    "tulip_gemm_tn_ex": (_i, [C.POINTER(GemmTNDesc), _vp]),
     "tulip_window_attention_fwd": (_i, [_vp, _fp, _vp] + [_i] * 12 + [_vp]),
     "tulip_window_attention_bwd": (_i, [_vp, _fp, _vp, _vp, _fp] + [_i] * 12 + [_vp]),
     "tulip_layernorm_fwd": (_i, [_vp, _fp, _fp, _vp, _fp, _i, _i, C.c_float, _i, _i, _i, _vp]),

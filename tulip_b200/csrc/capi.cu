@@ -282,6 +282,42 @@ int tulip_gemm_tn(const void* dY, const void* X, float* dW, float* db, int M, in
   return gemm_tn(g, (cudaStream_t)stream);
 }
 
+int tulip_gemm_nt_ex(const tulip_gemm_desc* d, int epilogue, void* stream) {
+  if (!d) { tulip_set_error("tulip_gemm_nt_ex: null descriptor"); return TULIP_ERR_ARG; }
+  if (epilogue < EPI_STORE || epilogue > EPI_DGELU2) { tulip_set_error("tulip_gemm_nt_ex: unknown epilogue"); return TULIP_ERR_ARG; }
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.A = (const bf16*)d->A; g.lda = d->lda; g.A2 = (const bf16*)d->A2; g.lda2 = d->lda2; g.K1 = d->K1 > 0 ? d->K1 : d->K;
+  g.B = (const bf16*)d->B; g.ldb = d->ldb; g.B2 = (const bf16*)d->B2; g.ldb2 = d->ldb2; g.K2 = d->K2;
+  g.M = d->M; g.N = d->N; g.K = d->K;
+  g.a_mode = d->a_mode; g.g_H = d->g_H; g.g_W = d->g_W; g.g_Cc = d->g_Cc;
+  g.bias = d->bias;
+  g.out = (bf16*)d->out; g.ldo = d->ldo; g.out2 = (bf16*)d->out2; g.ldo2 = d->ldo2; g.aux = (const bf16*)d->aux; g.ldaux = d->ldaux;
+  g.row_scale = d->row_scale; g.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
+  g.split_col = d->split_col;
+  g.wd = d->wd; g.target = d->target; g.pred = d->pred; g.gscale = d->gscale; g.dwd = d->dwd; g.dwd_copies = 1;
+  g.hd_H = d->hd_H; g.hd_W = d->hd_W; g.hd_r = d->hd_r; g.hd_E = d->hd_E;
+  if (d->hd_r > 0) g.hd_inv_npix = 1.0f / ((float)d->M * d->hd_r * d->hd_r);
+  return gemm_nt(g, epilogue, (cudaStream_t)stream);
+}
+
+int tulip_gemm_tn_ex(const tulip_gemm_tn_desc* d, void* stream) {
+  if (!d) { tulip_set_error("tulip_gemm_tn_ex: null descriptor"); return TULIP_ERR_ARG; }
+  GemmTNArgs g;
+  memset(&g, 0, sizeof g);
+  g.dY = (const bf16*)d->dY; g.ldy = d->ldy; g.X = (const bf16*)d->X; g.ldx = d->ldx; g.X2 = (const bf16*)d->X2; g.ldx2 = d->ldx2;
+  g.K1 = d->K1 > 0 ? d->K1 : d->K;
+  g.M = d->M; g.N = d->N; g.K = d->K;
+  g.y_mode = d->y_mode; g.g_H = d->g_H; g.g_W = d->g_W; g.g_Cc = d->g_Cc;
+  g.dW = d->dW; g.lddw = d->lddw; g.db = d->db;
+  g.perm_R2 = d->perm_R2 > 1 ? d->perm_R2 : 1; g.perm_Cc = d->perm_R2 > 1 ? d->perm_Cc : 1;
+  const int tiles = (g.N / 96) * (g.K / 96);
+  int splits = tiles > 0 ? (2 * tulip_num_sms() + tiles - 1) / tiles : 1;
+  const int max_splits = (g.M + 255) / 256;
+  g.splits = splits > max_splits ? max_splits : (splits < 1 ? 1 : splits);
+  return gemm_tn(g, (cudaStream_t)stream);
+}
+
 static AttnArgs make_attn(const void* qkv, const float* table, int B, int H, int W, int C, int heads, int Mh, int Mw, int sh, int sw,
                           int masked, int bMh, int bMw) {
   AttnArgs a;

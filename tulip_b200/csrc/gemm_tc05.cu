@@ -163,7 +163,8 @@ __device__ __forceinline__ void epi_direct16(const GemmArgs& g, int m, int n, fl
   p[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
 }
 
-template <int BN, int EPI>
+// VAR = 1: head backward with two 96-channel groups (hd_E = 192): a second set of d(decoder_pred.weight) accumulators
+template <int BN, int EPI, int VAR = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmArgs g, const __grid_constant__ Segments sg,
                     const __grid_constant__ Sched sc) {
@@ -343,12 +344,16 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
     const int q = warp & 3;                                   // TMEM lane quarter this warp may access
     const int jgrp = (warp - 2) >> 2;                         // which column boxes of the tile this warp handles
     const int r = q * 32 + lane;                              // row inside the tile
-    float cwacc[(CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS][32];   // HEAD_BWD: per-thread column sums for d(decoder_pred.weight)
+    // HEAD_BWD: per-thread column sums for d(decoder_pred.weight), one set per 96-channel group of the head (hd_E = 96 or 192)
+    float cwacc[(CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS][32], cwacc_hi[VAR == 1 ? (CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS : 1][32];
     if (EPI == EPI_HEAD_BWD) {
 #pragma unroll
       for (int a = 0; a < (CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS; ++a)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) cwacc[a][i] = 0.f;
+        for (int i = 0; i < 32; ++i) {
+          cwacc[a][i] = 0.f;
+          if (VAR == 1) cwacc_hi[a][i] = 0.f;
+        }
     }
     // Every epilogue warp is autonomous: it owns rows [32q, 32q+32) of its column boxes, stages them in its own 2 KB
     // slices of the output buffers and issues its own 32 x 32 TMA stores.  No CTA-wide barrier sits on the per-tile path;
@@ -483,12 +488,15 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
 #pragma unroll
             for (int i = 0; i < 32; ++i) wdv[i] = 0.f;
             add_bias32(g.wd, c0 + j * BOXC, wdv);                          // vector loads of decoder_pred.weight
+            if (VAR != 1 || c0 == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float pre = v[i];
-              cwacc[jj][i] += dp * leaky(pre);
-              v[i] = dp * wdv[i] * (pre > 0.f ? 1.f : 0.01f);
+              for (int i = 0; i < 32; ++i) cwacc[jj][i] += dp * leaky(v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) cwacc_hi[jj][i] += dp * leaky(v[i]);
             }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = dp * wdv[i] * (v[i] > 0.f ? 1.f : 0.01f);
           }
           store_box_row((two_out ? ob2 : ob) + j * BOX_BYTES, r, v);
         }
@@ -553,7 +561,8 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       if (++buf == NBUF) { buf = 0; tphase ^= 1; }
     }
     if (EPI == EPI_HEAD_BWD) {
-      // hd_E == BN on this path (checked by the launcher), so every tile of this CTA covers channels c = 0..95
+      // hd_E is BN or 2 BN on this path (checked by the launcher): a tile covers channels c0 .. c0 + 95 with c0 = 0 or 96
+      float* dwd = g.dwd + (g.dwd_copies > 1 ? (int)(blockIdx.x % g.dwd_copies) * g.hd_E : 0);
 #pragma unroll
       for (int jj = 0; jj < (CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS; ++jj) {
         const int j = jgrp + jj * EPI_GROUPS;
@@ -561,7 +570,14 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float cw = warp_sum(cwacc[jj][i]);
-            if (lane == i) atomicAdd(g.dwd + (g.dwd_copies > 1 ? (int)(blockIdx.x % g.dwd_copies) * g.hd_E : 0) + j * BOXC + i, cw);
+            if (lane == i) atomicAdd(dwd + j * BOXC + i, cw);
+          }
+          if (VAR == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float cw = warp_sum(cwacc_hi[jj][i]);
+              if (lane == i) atomicAdd(dwd + BN + j * BOXC + i, cw);
+            }
           }
         }
       }
@@ -636,16 +652,16 @@ Sched choose_tiling(const GemmArgs& g, int epi, const Segments& sg, int* bn_out)
   return sc;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int VAR = 0>
 int launch(const Maps& maps, const GemmArgs& g, const Segments& sg, const Sched& sc, cudaStream_t st) {
   using CF = Cfg<BN, EPI>;
   static bool configured = false;
   if (!configured) {
-    TULIP_CUDA(cudaFuncSetAttribute(gemm_nt_tc05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::TOTAL));
+    TULIP_CUDA(cudaFuncSetAttribute(gemm_nt_tc05_kernel<BN, EPI, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::TOTAL));
     configured = true;
   }
   const int grid = sc.panel ? sc.n_chunks * sc.nworkers : min(sc.tiles_m * sc.tiles_n, tulip_num_sms());
-  tulip_launch(gemm_nt_tc05_kernel<BN, EPI>, grid, THREADS, CF::TOTAL, st, maps, g, sg, sc);
+  tulip_launch(gemm_nt_tc05_kernel<BN, EPI, VAR>, grid, THREADS, CF::TOTAL, st, maps, g, sg, sc);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
@@ -704,7 +720,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15) || (g.lda % 8) || (g.ldb % 8))
     return TULIP_ERR_UNSUPPORTED;
   const bool head = (epi == EPI_HEAD || epi == EPI_HEAD_BWD);
-  if (epi == EPI_HEAD_BWD && g.hd_E != 96) return TULIP_ERR_UNSUPPORTED;      // per-CTA dwd accumulation assumes one 96-channel group
+  if (epi == EPI_HEAD_BWD && g.hd_E != 96 && g.hd_E != 192) return TULIP_ERR_UNSUPPORTED;   // dwd accumulators: one or two 96-channel groups
   int bn = 96;                                            // chosen with the schedule once the K segments are known
 
   Segments sg;
@@ -793,7 +809,8 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     case EPI_DGELU2: return launch<96, EPI_DGELU2>(maps, g, sg, sc, st);     // two accumulators x two buffers: BN = 96 only
     case EPI_ROWSCALE: return launch_bn<EPI_ROWSCALE>(bn, maps, g, sg, sc, st);
     case EPI_HEAD: return launch<96, EPI_HEAD>(maps, g, sg, sc, st);
-    case EPI_HEAD_BWD: return launch<96, EPI_HEAD_BWD>(maps, g, sg, sc, st);
+    case EPI_HEAD_BWD:
+      return g.hd_E == 96 ? launch<96, EPI_HEAD_BWD>(maps, g, sg, sc, st) : launch<96, EPI_HEAD_BWD, 1>(maps, g, sg, sc, st);
   }
   return TULIP_ERR_UNSUPPORTED;
 }

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <utility>
 
 namespace {
@@ -276,9 +277,25 @@ Plan tulip_net::plan(int B) const {
   p.g_save.assign(L, -1);
   for (int s = 0; s < L - 1; ++s) p.g_save[s] = act((long)B * (H0 >> s) * (W0 >> s), E << s);
   p.loss_acc = bump.take(256);
-  p.gscr = bump.take(GRAD_SCRATCH_BYTES);
+  p.gscr_bytes = grad_scratch_bytes();
+  p.gscr = bump.take(p.gscr_bytes);
   p.total = bump.off;
   return p;
+}
+
+// bytes of gradient-copy scratch the backward pass hands out (GRAD_COPIES copies of every small gradient, 64-float granules):
+// mirrors the grad_scratch() calls of backward()
+long tulip_net::grad_scratch_bytes() const {
+  const long E = cfg.embed_dim;
+  const int nbias = (2 * cfg.win_h - 1) * (2 * cfg.win_w - 1);
+  auto take = [](long n) { return align_up(n * GRAD_COPIES, 64); };
+  long fl = take(E) + take(2 * E) + take(11 * E);                  // decoder_pred.weight, norm_up, PatchEmbed
+  for (const BlockDef& b : blocks) {
+    const long C = E << b.stage;
+    fl += 2 * take(2 * C) + take((long)nbias * cfg.num_heads[b.stage]);
+  }
+  for (int s = 0; s + 1 < L; ++s) fl += take(2 * 4 * (E << s));    // PatchMerging norms
+  return fl * 4 + 1024;
 }
 
 int tulip_net::upload_pack_table(const int64_t* offs, cudaStream_t st) {
@@ -622,21 +639,18 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
 
   // gradient copies (net.h GRAD_COPIES): grad_scratch(n) hands out GRAD_COPIES x n zeroed floats; sum_to() registers where
   // elements [off, off + n) of every copy are finally added
-  TULIP_CUDA(cudaMemsetAsync(c.F(p.gscr), 0, (size_t)GRAD_SCRATCH_BYTES, st));
+  TULIP_CUDA(cudaMemsetAsync(c.F(p.gscr), 0, (size_t)p.gscr_bytes, st));
   long gscr_used = 0;
-  SumCopiesArgs sum_args;
-  memset(&sum_args, 0, sizeof sum_args);
-  sum_args.copies = GRAD_COPIES;
+  std::vector<SumCopiesItem> sum_items;
   bool gscr_overflow = false;
   auto grad_scratch = [&](int n) -> float* {
     float* ptr = c.F(p.gscr) + gscr_used;
     gscr_used += align_up((long)n * GRAD_COPIES, 64);
-    if (gscr_used * 4 > GRAD_SCRATCH_BYTES) { gscr_overflow = true; return c.F(p.gscr); }
+    if (gscr_used * 4 > p.gscr_bytes) { gscr_overflow = true; return c.F(p.gscr); }
     return ptr;
   };
   auto sum_to = [&](float* dst, const float* scr, int off, int n, int stride) {
-    if (sum_args.count >= 128) { gscr_overflow = true; return; }
-    sum_args.item[sum_args.count++] = SumCopiesItem{dst, scr + off, n, stride};
+    sum_items.push_back(SumCopiesItem{dst, scr + off, n, stride});
   };
 
   // optional fused DropPath scale for the consumer of dx: set before calling ln_bwd, consumed (reset) by it
@@ -865,10 +879,17 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     tag(K_EMBED_BWD, 0, 4.0 * B * cfg.img_h * cfg.img_w + 2.0 * B * H0 * W0 * E);
     RUN(patch_embed_bwd(e, st));
   }
-  TULIP_REQUIRE(!gscr_overflow, "tulip_b200: gradient-copy scratch exhausted (too many blocks for GRAD_SCRATCH_BYTES / 128 items)");
+  TULIP_REQUIRE(!gscr_overflow, "tulip_b200: gradient-copy scratch exhausted (grad_scratch_bytes() out of step with backward())");
   join();                                                 // the gradient fill and every weight-gradient GEMM precede the fold
-  tag(K_ELEMWISE, 0, 8.0 * gscr_used);
-  RUN(sum_copies(sum_args, st));
+  for (size_t first = 0; first < sum_items.size(); first += 128) {     // 128 (dst, src) pairs per launch (kernel-parameter space)
+    SumCopiesArgs sum_args;
+    memset(&sum_args, 0, sizeof sum_args);
+    sum_args.copies = GRAD_COPIES;
+    sum_args.count = (int)std::min<size_t>(128, sum_items.size() - first);
+    for (int i = 0; i < sum_args.count; ++i) sum_args.item[i] = sum_items[first + i];
+    tag(K_ELEMWISE, 0, 8.0 * gscr_used * sum_args.count / (double)sum_items.size());
+    RUN(sum_copies(sum_args, st));
+  }
   join();                                                 // every gradient is complete on `st` when backward returns
 #undef TN_SIDE
   return TULIP_OK;

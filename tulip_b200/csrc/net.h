@@ -61,7 +61,7 @@ struct Plan {
   long gA, gB, scr_gs, scr_gsm, scr_big, scr_dxn, scr_do, scr_dqkv;
   std::vector<long> g_save;
   long loss_acc;
-  long gscr;                                       // fp32 scratch for gradient copies (see GRAD_COPIES)
+  long gscr, gscr_bytes;                           // fp32 scratch for gradient copies (see GRAD_COPIES)
   long total;
 };
 
@@ -69,7 +69,6 @@ struct Plan {
 // to GRAD_COPIES scratch copies (CTA b -> copy b % GRAD_COPIES) and are summed by one kernel at the end of the backward
 // pass: same-address global atomics from a whole grid serialise in L2 (7-11 us per launch, measured).
 constexpr int GRAD_COPIES = 32;
-constexpr long GRAD_SCRATCH_BYTES = 12l << 20;
 
 struct tulip_net {
   tulip_config cfg;
@@ -119,6 +118,7 @@ struct tulip_net {
   int build();
   int ensure_device();
   Plan plan(int B) const;
+  long grad_scratch_bytes() const;
   int upload_pack_table(const int64_t* offs, cudaStream_t st);
   int forward(int B, const float* params, const int64_t* offs, const float* x_lo, const float* target, const float* drop_scales,
               const int* win_mode, void* ws, float* pred, float* losses, cudaStream_t st);

@@ -213,15 +213,20 @@ class _TulipFunction(torch.autograd.Function):
         dev = xin.device
         if pers is not None:
             pred = pred_w.clone()
-            losses = losses_w.clone() if target_given else torch.zeros(2, dtype=torch.float32, device=dev)
             if target_given and model._grad_mode_hint:         # (grad mode is always off inside Function.forward)
                 model._persistent_owner = weakref.ref(ctx)      # released by backward (or when the autograd graph dies)
         else:
-            pred, losses = pred_w, losses_w
+            pred = pred_w
         ctx.model, ctx.B, ctx.win_mode, ctx.pers = model, B, win_mode, pers
         ctx.save_for_backward(xin, tin, din, ws, pred_w)
         ctx.set_materialize_grads(False)
-        loss, pixel = losses[0], losses[1]
+        # the two losses leave this node as tensors of their own, never as views of the 2-element buffer: the reference engine
+        # divides total_loss in place (`total_loss /= accum_iter`, engine_upsampling.py:92) and autograd forbids in-place
+        # edits of a view returned by a custom Function
+        if target_given:
+            loss, pixel = losses_w[0].clone(), losses_w[1].clone()
+        else:
+            loss, pixel = torch.zeros((), dtype=torch.float32, device=dev), torch.zeros((), dtype=torch.float32, device=dev)
         ctx.mark_non_differentiable(pixel)
         return pred, loss, pixel
 
@@ -405,11 +410,9 @@ class TULIP(nn.Module):
         if self._net is None:
             self._create_net()
         if self._param_list is not None and self._flat is not None and self._flat.device == device:
-            # hot path: spot-check three parameters every call, all 212 only now and then (a full scan costs ~60 us of host time)
-            self._flat_checks = getattr(self, "_flat_checks", 0) + 1
-            base, pl, vw = self._flat.data_ptr(), self._param_list, self._views
-            quick = all(pl[i].data_ptr() == base + 4 * vw[i][0] for i in (0, len(pl) // 2, len(pl) - 1))
-            if quick and (self._flat_checks % 64 or self._is_flat(device)):
+            # every parameter must still alias the flat buffer (load_state_dict(assign=True), an EMA swap through `p.data = ...`
+            # or `.to()` replace storages); the scan costs ~60 us of host time per call and hides under the previous step's kernels
+            if self._is_flat(device):
                 return
         named = dict(self.named_parameters())
         plist = [named[k] for k in self._schema]
@@ -431,6 +434,30 @@ class TULIP(nn.Module):
         out = super()._apply(fn, *a, **k)
         self._flat = None           # parameters were re-created by .to()/.cuda()/.float(); re-pack lazily
         return out
+
+    def load_state_dict(self, state_dict, *a, **k):
+        out = super().load_state_dict(state_dict, *a, **k)
+        self._flat = None           # assign=True replaces the Parameter objects themselves; re-pack lazily
+        return out
+
+    # runtime state that must not travel with copy.deepcopy / pickle / torch.save(model): the C handle and raw ctypes pointers
+    # (not picklable), buffers tied to that handle, and weak references.  A copy re-creates all of it lazily on its first forward.
+    _RUNTIME_STATE = ("_net", "_flat", "_grad_bufs", "_views", "_param_list", "_offsets", "_offsets_p", "_ws_bytes", "_step_bufs",
+                      "_persistent_owner", "_win_modes_cache", "_keep_cache", "_schema", "_grad_mode_hint")
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in self._RUNTIME_STATE:
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._net = None
+        self._flat = None
+        self._grad_bufs = [None, None]
+        self._views = self._param_list = self._offsets = None
+        self._ws_bytes = {}
 
     def _grad_buffer(self):
         """Flat fp32 gradient buffer that no live `.grad` aliases (so autograd's accumulation stays correct)."""

@@ -8,10 +8,34 @@ from __future__ import annotations
 
 import torch
 
-from ._lib import check, current_stream, load_library, ptr
+import ctypes as _C
+
+from ._lib import GemmDesc, GemmTNDesc, check, current_stream, load_library, ptr
 
 GEMM_AUTO, GEMM_MMA, GEMM_TC05 = 0, 1, 2
-EPI_STORE, EPI_GELU, EPI_RESID, EPI_DGELU = 0, 1, 2, 5
+EPI_STORE, EPI_GELU, EPI_RESID, EPI_PIXSHUF, EPI_SPLIT2, EPI_DGELU, EPI_HEAD, EPI_HEAD_BWD, EPI_ROWSCALE, EPI_DGELU2 = range(10)
+A_PLAIN, A_UNSHUFFLE = 0, 1
+
+
+def gemm_nt_ex(epilogue, **fields):
+    """tulip_gemm_nt_ex: every operand mode / fused epilogue of the NT contraction.  Tensor-valued fields are passed as tensors
+    (the caller keeps them alive and supplies the leading dimensions)."""
+    d = GemmDesc()
+    for k, v in fields.items():
+        setattr(d, k, ptr(v) if isinstance(v, torch.Tensor) else v)
+    check(load_library().tulip_gemm_nt_ex(_C.byref(d), epilogue, current_stream()), "tulip_gemm_nt_ex")
+
+
+def gemm_tn_ex(**fields):
+    d = GemmTNDesc()
+    for k, v in fields.items():
+        setattr(d, k, ptr(v) if isinstance(v, torch.Tensor) else v)
+    check(load_library().tulip_gemm_tn_ex(_C.byref(d), current_stream()), "tulip_gemm_tn_ex")
+
+
+def permute_rows_for_shuffle(w, R2, Cc):
+    """Row order the PixelShuffle-feeding GEMMs use: destination row n' = ij*Cc + c holds source row c*R2 + ij."""
+    return w.reshape(Cc, R2, *w.shape[1:]).transpose(0, 1).reshape(w.shape).contiguous()
 
 
 def _cuda(*ts):

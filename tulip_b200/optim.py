@@ -99,16 +99,57 @@ class FlatAdamW(torch.optim.Optimizer):
                                              ptr(out), current_stream()), "tulip_grad_norm")
         return out[0]
 
+    def _packed_params(self):
+        """(packed index, parameter) pairs in the order torch.optim.Optimizer.state_dict numbers them."""
+        out, idx = [], 0
+        for group in self.param_groups:
+            for p in group["params"]:
+                out.append((idx, p))
+                idx += 1
+        return out
+
     def state_dict(self):
+        """The standard torch.optim.AdamW layout: state[i] = {step, exp_avg, exp_avg_sq} per parameter (the moments are views of
+        the flat buffers), so a checkpoint written by `misc.save_model` (util/misc.py:332-349) resumes under either optimizer."""
         sd = super().state_dict()
-        sd["flat"] = {"steps": self.steps, "exp_avg": getattr(self, "exp_avg", None), "exp_avg_sq": getattr(self, "exp_avg_sq", None)}
+        if self.steps > 0 and getattr(self, "exp_avg", None) is not None:
+            index = {id(p): i for i, p in enumerate(self.model._param_list)}
+            state = {}
+            for k, p in self._packed_params():
+                o, n, shape = self.model._views[index[id(p)]]
+                state[k] = {"step": torch.tensor(float(self.steps)), "exp_avg": self.exp_avg[o:o + n].view(shape),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(shape)}
+            sd["state"] = state
         return sd
 
     def load_state_dict(self, state_dict):
+        """Accepts the standard per-parameter AdamW state (a reference / torch.optim.AdamW checkpoint) and the round-1 private
+        `flat` entry.  A state that holds neither for a non-empty optimizer raises instead of silently restarting the moments."""
         flat = state_dict.get("flat")
-        super().load_state_dict({k: v for k, v in state_dict.items() if k != "flat"})
+        state = state_dict.get("state", {})
+        super().load_state_dict({"state": {}, "param_groups": state_dict["param_groups"]})
         if flat is not None:
             self.steps = int(flat["steps"])
             if flat["exp_avg"] is not None:
                 self._prepare()
                 self.exp_avg.copy_(flat["exp_avg"]); self.exp_avg_sq.copy_(flat["exp_avg_sq"])
+            return
+        if not state:
+            self.steps = 0
+            if getattr(self, "exp_avg", None) is not None:
+                self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+            return
+        self._prepare()
+        index = {id(p): i for i, p in enumerate(self.model._param_list)}
+        steps = set()
+        for k, p in self._packed_params():
+            st = state.get(k, state.get(str(k)))
+            if st is None or "exp_avg" not in st or "exp_avg_sq" not in st or "step" not in st:
+                raise ValueError(f"FlatAdamW.load_state_dict: no AdamW state (step / exp_avg / exp_avg_sq) for parameter {k}")
+            o, n, shape = self.model._views[index[id(p)]]
+            self.exp_avg[o:o + n].view(shape).copy_(st["exp_avg"])
+            self.exp_avg_sq[o:o + n].view(shape).copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) != 1:
+            raise ValueError(f"FlatAdamW.load_state_dict: parameters disagree on the step count ({sorted(steps)})")
+        self.steps = steps.pop()
