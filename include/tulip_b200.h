@@ -67,6 +67,9 @@ int tulip_net_profile_read(tulip_net* net, int tag, char* name, int name_cap, do
 /* the same records one launch at a time, in launch order: returns the number of records; if i is in range also fills
  * tag, device time (ms), algorithmic FLOPs and bytes of launch i */
 int tulip_net_profile_record(tulip_net* net, int i, int* tag, double* ms, double* flops, double* bytes);
+/* where launch i of the recording belongs: stage (0 = widest), part (0 glue: merge / unmerge / skip / embed, 1 attention
+ * half-block, 2 MLP half-block, 3 head + loss), backward (0 / 1).  Returns the number of records. */
+int tulip_net_profile_where(tulip_net* net, int i, int* stage, int* part, int* backward);
 
 /* forward: x_lo [B,1,h,w] fp32, target [B,1,H,W] fp32 or NULL (mc_drop=True, tulip.py:733-734)
  * params: flat fp32 buffer; param_offsets_host[i] = element offset of parameter i (schema order)
@@ -76,6 +79,9 @@ int tulip_net_profile_record(tulip_net* net, int i, int* tag, double* ms, double
 int tulip_net_forward(tulip_net* net, int batch, const float* params, const int64_t* param_offsets_host,
                       const float* x_lo, const float* target, const float* drop_scales, const int* win_mode_host,
                       void* workspace, float* pred, float* losses, void* stream);
+/* forward_only = 1: the following tulip_net_forward calls will not be followed by tulip_net_backward (evaluate(), MCdrop(),
+ * torch.no_grad()): the fused half-block kernels run and no intermediate is saved.  0 (default) restores training mode. */
+int tulip_net_set_inference(tulip_net* net, int forward_only);
 /* backward of total_loss * grad_loss[0] (device scalar; GradScaler's 65536 arrives here, misc.py:294-295).
  * grads: flat fp32 buffer laid out like params; it is OVERWRITTEN (zeroed, then accumulated).
  * workspace must be the buffer the matching forward ran on, untouched since. */
@@ -134,6 +140,19 @@ typedef struct tulip_gemm_tn_desc {
   int perm_R2, perm_Cc;
 } tulip_gemm_tn_desc;
 int tulip_gemm_tn_ex(const tulip_gemm_tn_desc* d, void* stream);
+
+/* ---- fused W-MSA / SW-MSA half-block (SURVEY 8b tulip_wmsa_block_fwd): ONE launch for
+ *   y = x + row_scale[b] * proj(attn(qkv(LayerNorm(x))))          tulip.py:338-346 with WindowAttention.forward :282-324
+ * LayerNorm, cyclic shift, window partition / reverse, rel-pos bias, shift mask, softmax, both Linears and the residual; the
+ * two weight matrices stay resident in shared memory, q/k/v/S/P/O never reach HBM.  x, y: bf16 [B*H*W, C]; wqkv [3C, C] and
+ * wproj [C, C] bf16 row-major (nn.Linear layout); everything else fp32.  row_scale: per-sample DropPath scale or NULL.
+ * Built for C = 96 (3 heads of 32, stage 0 of both factories); other shapes return
+ * an error (tulip_wmsa_block_supported says which) and the caller runs the unfused chain. */
+int tulip_wmsa_block_supported(int B, int H, int W, int C, int heads, int Mh, int Mw);
+int tulip_wmsa_block_fwd(const void* x, void* y, const float* ln_w, const float* ln_b, const void* wqkv, const float* bqkv,
+                         const void* wproj, const float* bproj, const float* bias_table, const float* row_scale,
+                         int B, int H, int W, int C, int heads, int Mh, int Mw, int sh, int sw, int masked,
+                         int bias_Mh, int bias_Mw, float eps, void* stream);
 
 /* ---- window attention core: tulip.py:289-317 without the two Linears; shift/partition/mask/bias in-kernel ---- */
 int tulip_window_attention_fwd(const void* qkv, const float* bias_table, void* out, int B, int H, int W, int C, int heads,

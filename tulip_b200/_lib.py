@@ -67,6 +67,8 @@ SIGNATURES = {
     "tulip_net_profile_read": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(_i64)]),
     "tulip_net_profile_record": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "tulip_net_set_inference": (_i, [_vp, _i]),
+    "tulip_net_profile_where": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "tulip_net_forward": (_i, [_vp, _i, _fp, _vp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _vp]),
     "tulip_net_backward": (_i, [_vp, _i, _fp, _vp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _vp, _vp]),
     "tulip_gemm_nt": (_i, [_vp, _vp, _fp, _vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
@@ -74,6 +76,8 @@ SIGNATURES = {
     "tulip_gemm_tn": (_i, [_vp, _vp, _fp, _fp, _i, _i, _i, _i, _vp]),
     "tulip_gemm_nt_ex": (_i, [C.POINTER(GemmDesc), _i, _vp]),
     "tulip_gemm_tn_ex": (_i, [C.POINTER(GemmTNDesc), _vp]),
+    "tulip_wmsa_block_supported": (_i, [_i] * 7),
+    "tulip_wmsa_block_fwd": (_i, [_vp, _vp, _fp, _fp, _vp, _fp, _vp, _fp, _fp, _fp] + [_i] * 12 + [C.c_float, _vp]),
     "tulip_window_attention_fwd": (_i, [_vp, _fp, _vp] + [_i] * 12 + [_vp]),
     "tulip_window_attention_bwd": (_i, [_vp, _fp, _vp, _vp, _fp] + [_i] * 12 + [_vp]),
     "tulip_layernorm_fwd": (_i, [_vp, _fp, _fp, _vp, _fp, _i, _i, C.c_float, _i, _i, _i, _vp]),

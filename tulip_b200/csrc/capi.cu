@@ -211,6 +211,17 @@ int tulip_net_profile_record(tulip_net* n, int i, int* tag, double* ms, double* 
   return cnt;
 }
 
+int tulip_net_profile_where(tulip_net* n, int i, int* stage, int* part, int* backward) {
+  if (!n) { tulip_set_error("tulip_net_profile_where: null net"); return -1; }
+  const int cnt = (int)n->recs.size();
+  if (i < 0 || i >= cnt) return cnt;
+  const int w = n->recs[i].where;
+  if (stage) *stage = w & 0xff;
+  if (part) *part = (w >> 8) & 0xff;
+  if (backward) *backward = (w >> 16) & 1;
+  return cnt;
+}
+
 int tulip_net_forward(tulip_net* n, int batch, const float* params, const int64_t* offs, const float* x_lo, const float* target,
                       const float* drop_scales, const int* win_mode, void* ws, float* pred, float* losses, void* stream) {
   if (!n || !params || !offs || !x_lo || !ws || !pred) { tulip_set_error("tulip_net_forward: null argument"); return TULIP_ERR_ARG; }
@@ -224,16 +235,24 @@ int tulip_net_forward(tulip_net* n, int batch, const float* params, const int64_
   const std::vector<uint64_t> key = {
       (uint64_t)batch, (uint64_t)(uintptr_t)params, hash_words(offs, n->params.size() * sizeof(int64_t)), (uint64_t)(uintptr_t)x_lo,
       (uint64_t)(uintptr_t)target, (uint64_t)(uintptr_t)drop_scales, win_mode ? hash_words(win_mode, n->blocks.size() * sizeof(int)) : 0,
-      (uint64_t)(uintptr_t)ws, (uint64_t)(uintptr_t)pred, (uint64_t)(uintptr_t)losses, (uint64_t)(uintptr_t)stream};
+      (uint64_t)(uintptr_t)ws, (uint64_t)(uintptr_t)pred, (uint64_t)(uintptr_t)losses, (uint64_t)(uintptr_t)stream,
+      (uint64_t)n->inference};
   return n->run_graphed(n->graph_fwd, key, st, [&]() {
     return n->forward(batch, params, offs, x_lo, target, drop_scales, win_mode, ws, pred, losses, st);
   });
+}
+
+int tulip_net_set_inference(tulip_net* n, int forward_only) {
+  if (!n) { tulip_set_error("tulip_net_set_inference: null net"); return TULIP_ERR_ARG; }
+  n->inference = forward_only != 0;
+  return TULIP_OK;
 }
 
 int tulip_net_backward(tulip_net* n, int batch, const float* params, const int64_t* offs, float* grads, const float* x_lo,
                        const float* target, const float* pred, const float* grad_loss, const float* drop_scales,
                        const int* win_mode, void* ws, void* stream) {
   if (!n || !params || !offs || !grads || !x_lo || !ws) { tulip_set_error("tulip_net_backward: null argument"); return TULIP_ERR_ARG; }
+  if (n->inference) { tulip_set_error("tulip_net_backward: the last forward ran in forward-only mode (tulip_net_set_inference)"); return TULIP_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   const std::vector<uint64_t> key = {
       (uint64_t)batch, (uint64_t)(uintptr_t)params, hash_words(offs, n->params.size() * sizeof(int64_t)), (uint64_t)(uintptr_t)grads,
@@ -316,6 +335,23 @@ int tulip_gemm_tn_ex(const tulip_gemm_tn_desc* d, void* stream) {
   const int max_splits = (g.M + 255) / 256;
   g.splits = splits > max_splits ? max_splits : (splits < 1 ? 1 : splits);
   return gemm_tn(g, (cudaStream_t)stream);
+}
+
+int tulip_wmsa_block_supported(int B, int H, int W, int C, int heads, int Mh, int Mw) {
+  return wmsa_block_supported(B, H, W, C, heads, Mh, Mw) ? 1 : 0;
+}
+
+int tulip_wmsa_block_fwd(const void* x, void* y, const float* ln_w, const float* ln_b, const void* wqkv, const float* bqkv,
+                         const void* wproj, const float* bproj, const float* bias_table, const float* row_scale, int B, int H, int W,
+                         int C, int heads, int Mh, int Mw, int sh, int sw, int masked, int bias_Mh, int bias_Mw, float eps,
+                         void* stream) {
+  WmsaBlockArgs a;
+  memset(&a, 0, sizeof a);
+  a.x = (const bf16*)x; a.y = (bf16*)y; a.ln_w = ln_w; a.ln_b = ln_b; a.wqkv = (const bf16*)wqkv; a.bqkv = bqkv;
+  a.wproj = (const bf16*)wproj; a.bproj = bproj; a.bias_table = bias_table; a.row_scale = row_scale;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.Mh = Mh; a.Mw = Mw; a.sh = sh; a.sw = sw; a.masked = masked;
+  a.bMh = bias_Mh; a.bMw = bias_Mw; a.eps = eps;
+  return wmsa_block_fwd(a, (cudaStream_t)stream);
 }
 
 static AttnArgs make_attn(const void* qkv, const float* table, int B, int H, int W, int C, int heads, int Mh, int Mw, int sh, int sw,

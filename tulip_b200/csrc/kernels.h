@@ -20,6 +20,21 @@ struct AttnArgs {
 int win_attn_fwd(const AttnArgs& a, cudaStream_t st);
 int win_attn_bwd(const AttnArgs& a, cudaStream_t st);
 
+// fused W-MSA / SW-MSA half-block (wmsa.cu): y = x + row_scale[b] * proj(attn(qkv(LN1(x))))   (tulip.py:338-346, 282-324)
+struct WmsaBlockArgs {
+  const bf16* x; bf16* y;                 // [B*H*W, C] natural NHWC token order
+  const float* ln_w; const float* ln_b;   // norm1
+  const bf16* wqkv; const float* bqkv;    // [3C, C] bf16 (feature f = t*C + head*32 + d), [3C]
+  const bf16* wproj; const float* bproj;  // [C, C] bf16, [C]
+  const float* bias_table;                // [nbias, heads] fp32
+  const float* row_scale;                 // [B] DropPath scales or null
+  int B, H, W, C, heads;
+  int Mh, Mw, sh, sw, masked, bMh, bMw;   // as AttnArgs
+  float eps;
+};
+bool wmsa_block_supported(int B, int H, int W, int C, int heads, int Mh, int Mw);
+int wmsa_block_fwd(const WmsaBlockArgs& a, cudaStream_t st);
+
 struct LnArgs {
   const bf16* x;              // LN input rows [rows, C]; with gather: source tensor [B, 2*H2, 2*W2, C/4]
   const float* w; const float* b;

@@ -29,7 +29,7 @@ const char* ktag_name(int t) {
       "misc", "gemm_nt<store>", "gemm_nt<gelu>", "gemm_nt<resid>", "gemm_nt<pixshuf>", "gemm_nt<split2>", "gemm_nt<dgelu>",
       "gemm_nt<head>", "gemm_nt<head_bwd>", "gemm_nt<rowscale>", "gemm_nt<unshuffle>", "gemm_tn", "gemm_tn<unshuffle>",
       "win_attn_fwd", "win_attn_bwd", "layernorm_fwd", "layernorm_bwd", "patch_embed_fwd", "patch_embed_bwd", "pack_weights",
-      "elementwise", "l1_loss"};
+      "elementwise", "l1_loss", "wmsa_block_fwd"};
   return (t >= 0 && t < K_COUNT) ? names[t] : "?";
 }
 
@@ -46,7 +46,7 @@ void tulip_net::prof_begin(cudaStream_t st) {
 void tulip_net::prof_end(cudaStream_t st) {
   if (profiling) {
     cudaEventRecord(ev_pool[ev_used + 1], st);
-    recs.push_back(ProfRec{cur_tag, cur_flops, cur_bytes, ev_pool[ev_used], ev_pool[ev_used + 1]});
+    recs.push_back(ProfRec{cur_tag, cur_flops, cur_bytes, ev_pool[ev_used], ev_pool[ev_used + 1], cur_stage | (cur_part << 8) | (cur_dir << 16)});
     ev_used += 2;
   }
   cur_tag = K_MISC; cur_flops = 0; cur_bytes = 0;
@@ -426,6 +426,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
   const Plan p = plan(B);
   Ctx c{this, B, params_, offs, nullptr, drop_scales, win_mode, reinterpret_cast<unsigned char*>(ws), st};
   const int E = cfg.embed_dim;
+  cur_dir = 0; at(0, 0);
 
   // The weight repack is only needed by the first GEMM: it runs on the side stream next to PatchEmbed and the first LayerNorm.
   const bool use_side = !profiling && !side_stream_disabled();
@@ -474,6 +475,24 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     const int Hs = H0 >> b.stage, Ws = W0 >> b.stage, C = E << b.stage, T = B * Hs * Ws;
     const float* ds1 = drop_scales ? drop_scales + (long)(2 * b.index) * B : nullptr;
     const float* ds2 = drop_scales ? drop_scales + (long)(2 * b.index + 1) * B : nullptr;
+    at(b.stage, 1);
+    {
+      // attention half as ONE kernel where the shape qualifies and no backward pass needs the intermediates (wmsa.cu)
+      AttnArgs a0 = attn_args(c, b, nullptr);
+      if (inference && wmsa_block_supported(B, Hs, Ws, C, a0.heads, a0.Mh, a0.Mw)) {
+        join_pack();
+        WmsaBlockArgs w;
+        memset(&w, 0, sizeof w);
+        w.x = x_in; w.y = c.A(bb.xmid); w.ln_w = c.P(b.n1w); w.ln_b = c.P(b.n1b);
+        w.wqkv = c.W(linears[b.qkv]); w.bqkv = c.bias(linears[b.qkv]); w.wproj = c.W(linears[b.proj]); w.bproj = c.bias(linears[b.proj]);
+        w.bias_table = a0.bias_table; w.row_scale = ds1;
+        w.B = B; w.H = Hs; w.W = Ws; w.C = C; w.heads = a0.heads; w.Mh = a0.Mh; w.Mw = a0.Mw; w.sh = a0.sh; w.sw = a0.sw;
+        w.masked = a0.masked; w.bMh = a0.bMh; w.bMw = a0.bMw; w.eps = cfg.ln_eps;
+        tag(K_WMSA_FWD, 8.0 * T * C * C + 64.0 * T * C, 4.0 * T * C);
+        RUN(wmsa_block_fwd(w, st));
+        goto mlp_half;
+      }
+    }
     RUN(ln(x_in, b.n1w, b.n1b, c.A(bb.xn1), c.F(bb.st1), T, C, 0, 0, 0));
     join_pack();
     {
@@ -493,6 +512,8 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
       g.aux = x_in; g.ldaux = C; g.row_scale = ds1; g.rows_per_sample = Hs * Ws;
       RUN_NT(g, EPI_RESID);
     }
+  mlp_half:
+    at(b.stage, 2);
     RUN(ln(c.A(bb.xmid), b.n2w, b.n2b, c.A(bb.xn2), c.F(bb.st2), T, C, 0, 0, 0));
     {
       const Linear& l = linears[b.fc1];
@@ -526,6 +547,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
       if (rc) return rc;
       x = c.A(p.blocks[bi].xout);
     }
+    at(s, 0);
     if (s < L - 1) {
       const int Hs = H0 >> s, Ws = W0 >> s, C = E << s, T4 = B * Hs * Ws / 4;
       RUN(ln(x, merge_nw[s], merge_nb[s], c.A(p.xn_m[s]), c.F(p.st_m[s]), T4, 4 * C, 1, Hs / 2, Ws / 2));
@@ -535,12 +557,14 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
       x = c.A(p.x_merged[s]);
     }
   }
+  at(L - 1, 0);
   rc = unmerge_fwd(linears[fpe_lin], x, c.A(p.x_fpe), H0 >> (L - 1), W0 >> (L - 1), E << (L - 1));
   if (rc) return rc;
   x = c.A(p.x_fpe);
   for (int u = 0; u < L - 1; ++u) {
     const int s = L - u - 2;
     const int Hs = H0 >> s, Ws = W0 >> s, C = E << s, T = B * Hs * Ws;
+    at(s, 0);
     {
       // Linear(2C -> C) on cat([x, x_save[s]], -1) without materialising the concat (tulip.py:715-716)
       const Linear& l = linears[skip_lin[u]];
@@ -554,6 +578,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
       if (rc) return rc;
       x = c.A(p.blocks[bi].xout);
     }
+    at(s, 0);
     if (u < L - 2) {
       rc = unmerge_fwd(linears[up_lin[u]], x, c.A(p.x_up[u]), Hs, Ws, C);
       if (rc) return rc;
@@ -562,6 +587,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
   }
   // norm_up -> ps_head -> decoder_pred, fused: the E*r^2-channel tensor never exists (tulip.py:720-731)
   const int T0 = B * H0 * W0;
+  at(0, 3);                                               // part 3 = head + loss
   RUN(ln(x, slot_normup_w, slot_normup_b, c.A(p.xn_up), c.F(p.st_up), T0, E, 0, 0, 0));
   {
     const Linear& l = linears[head_lin];
@@ -585,7 +611,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   const int E = cfg.embed_dim;
   const int T0 = B * H0 * W0;
   int rc;
-
+  cur_dir = 1; at(0, 3);
 
   // Weight-gradient GEMMs (gemm_tn) are leaves of the backward graph: nothing on the dX chain reads them.  They run on a
   // side stream, forked after the kernel that produced their dY operand and joined before that buffer is overwritten, so
@@ -726,6 +752,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     const float* ds1 = drop_scales ? drop_scales + (long)(2 * b.index) * B : nullptr;
     const float* ds2 = drop_scales ? drop_scales + (long)(2 * b.index + 1) * B : nullptr;
     // ---- MLP half: x_out = x_mid + s2 * fc2(gelu(fc1(LN2(x_mid)))) ----
+    at(b.stage, 2);
     join();                                               // side work issued outside blocks still reads the g buffers
     const bf16* gy = g_io;
     if (ds2) {
@@ -758,6 +785,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     if (ds1) { ln_dxs = c.A(p.scr_gs); ln_scale = ds1; ln_rps = Hs * Ws; }       // scaled copy for the attention branch
     RUN(ln_bwd(c.A(bb.xmid), b.n2w, b.n2b, c.F(bb.st2), c.A(p.scr_dxn), g_io, g_tmp, T, C, 0, 0, 0));   // g_tmp = dL/dx_mid
     // ---- attention half: x_mid = x_in + s1 * proj(attn(qkv(LN1(x_in)))) ----
+    at(b.stage, 1);
     gy = ds1 ? c.A(p.scr_gs) : g_tmp;
     {
       const Linear& lp = linears[b.proj];
@@ -802,6 +830,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   for (int u = L - 2; u >= 0; --u) {
     const int s = L - u - 2;
     const int Hs = H0 >> s, Ws = W0 >> s, C = E << s, T = B * Hs * Ws;
+    at(s, 0);
     if (u < L - 2) {
       const bf16* x_before = c.A(p.blocks[dec_blocks[u].back()].xout);
       rc = unmerge_bwd(linears[up_lin[u]], x_before, g_cur, g_alt, Hs, Ws, C);
@@ -814,6 +843,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       rc = block_bwd(bi, x_in, g_cur, g_alt, k > 0 ? dec_blocks[u][k - 1] : -1);
       if (rc) return rc;
     }
+    at(s, 0);
     {
       // skip Linear backward: d[x | skip] = g . Wskip ; the skip half is parked until the encoder stage is reached
       const Linear& l = linears[skip_lin[u]];
@@ -832,6 +862,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   // ---- first_patch_expanding ----
   {
     const int s = L - 1;
+    at(s, 0);
     const bf16* x_top = c.A(p.blocks[enc_blocks[s].back()].xout);
     rc = unmerge_bwd(linears[fpe_lin], x_top, g_cur, g_alt, H0 >> s, W0 >> s, E << s);
     if (rc) return rc;
@@ -840,6 +871,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   // ---- encoder, top stage first ----
   for (int s = L - 1; s >= 0; --s) {
     const int Hs = H0 >> s, Ws = W0 >> s, C = E << s, T = B * Hs * Ws;
+    at(s, 0);
     if (s < L - 1) {
       // PatchMerging backward: g_cur is dL/d(x_merged[s]) [T/4, 2C]
       const Linear& l = linears[merge_lin[s]];
@@ -859,6 +891,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       rc = block_bwd(bi, x_in, g_cur, g_alt, k > 0 ? enc_blocks[s][k - 1] : -1);
       if (rc) return rc;
     }
+    at(s, 0);
     tag(K_ELEMWISE, 0, 6.0 * T * C);
     if (s < L - 1) RUN(add_inplace_bf16(g_cur, c.A(p.g_save[s]), (long)T * C, st));     // skip-connection gradient (tulip.py:708,715)
   }

@@ -13,7 +13,7 @@
 enum KTag : int {
   K_MISC = 0, K_NT_STORE, K_NT_GELU, K_NT_RESID, K_NT_PIXSHUF, K_NT_SPLIT2, K_NT_DGELU, K_NT_HEAD, K_NT_HEAD_BWD, K_NT_ROWSCALE,
   K_NT_UNSHUFFLE, K_TN, K_TN_UNSHUFFLE, K_ATTN_FWD, K_ATTN_BWD, K_LN_FWD, K_LN_BWD, K_EMBED_FWD, K_EMBED_BWD, K_PACK,
-  K_ELEMWISE, K_LOSS, K_COUNT
+  K_ELEMWISE, K_LOSS, K_WMSA_FWD, K_COUNT
 };
 const char* ktag_name(int tag);
 inline int nt_tag(int epi) {
@@ -26,7 +26,7 @@ inline int nt_tag(int epi) {
   return K_MISC;
 }
 
-struct ProfRec { int tag; double flops, bytes; cudaEvent_t e0, e1; };
+struct ProfRec { int tag; double flops, bytes; cudaEvent_t e0, e1; int where; };   // where = stage | part << 8 | backward << 16
 
 struct ParamInfo {
   std::string name;
@@ -89,9 +89,13 @@ struct tulip_net {
   PackItem* items_dev = nullptr; int n_items = 0, n_tiles = 0;
   std::vector<long> items_offsets_cache;           // parameter offsets the uploaded pack table was built for
   long kernel_launches = 0;
+  // forward-only mode (no backward will follow): the fused half-block kernels run and nothing is saved for autograd
+  bool inference = false;
   // per-launch profiler (off by default; adds two cudaEventRecord per launch when on)
   bool profiling = false;
   int cur_tag = K_MISC; double cur_flops = 0, cur_bytes = 0;
+  int cur_stage = 0, cur_part = 0, cur_dir = 0;     // where the next launches belong: stage, 0 other / 1 attention half / 2 MLP half, 0 fwd / 1 bwd
+  void at(int stage, int part) { cur_stage = stage; cur_part = part; }
   std::vector<ProfRec> recs;
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   // CUDA-graph replay of a whole direction (forward or backward): once the same call (same batch, same pointers) has been

@@ -22,7 +22,8 @@ def upsample(model, x_lo: torch.Tensor, target: torch.Tensor, dataset: str = "ki
     if was_training:                                                               # (walking the module tree costs ~0.2 ms: call
         model.eval()                                                               #  model.eval() once yourself in a loop) :137
     try:
-        pred, _, _ = model(x_lo, target, eval=True)                                # :169-171
+        with torch.no_grad():                                                      # evaluate() is @torch.no_grad() (:126): forward-only kernels
+            pred, _, _ = model(x_lo, target, eval=True)                            # :169-171
     finally:
         if was_training:
             model.train(True)

@@ -496,6 +496,8 @@ class TULIP(nn.Module):
             xin, tin, din = x, target, drop_scales
             pred_w = torch.empty((B, self.in_chans, Ht, Wt), dtype=torch.float32, device=dev)
             losses_w = torch.zeros(2, dtype=torch.float32, device=dev)
+        # forward-only calls (torch.no_grad(): evaluate(), MCdrop(), inference) take the fused half-block kernels
+        check(lib.tulip_net_set_inference(self._net, 0 if (self._grad_mode_hint and target is not None) else 1))
         check(lib.tulip_net_forward(self._net, B, ptr(self._flat), self._offsets_p, ptr(xin), ptr(tin), ptr(din),
                                     win_mode.ctypes.data_as(C.c_void_p), ptr(ws), ptr(pred_w), ptr(losses_w), current_stream()),
               "tulip_net_forward")

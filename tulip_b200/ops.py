@@ -80,6 +80,21 @@ def linear_wgrad(dy, x, want_bias=True, impl=GEMM_AUTO):
     return dW, db
 
 
+def wmsa_block(x, ln_w, ln_b, wqkv, bqkv, wproj, bproj, bias_table, B, H, W, heads, window=(2, 8), shift=(0, 0), masked=False,
+               bias_window=(2, 8), row_scale=None, eps=1e-6):
+    """Fused attention half-block: x [B*H*W, C] bf16 -> x + row_scale[b] * proj(attn(qkv(LayerNorm(x)))) (tulip.py:338-346)."""
+    _cuda(x, wqkv, wproj)
+    x, wqkv, wproj = _bf16(x), _bf16(wqkv), _bf16(wproj)
+    ln_w, ln_b, bqkv, bproj, bias_table, row_scale = (_f32(t) for t in (ln_w, ln_b, bqkv, bproj, bias_table, row_scale))
+    C = x.shape[1]
+    y = torch.empty_like(x)
+    check(load_library().tulip_wmsa_block_fwd(ptr(x), ptr(y), ptr(ln_w), ptr(ln_b), ptr(wqkv), ptr(bqkv), ptr(wproj), ptr(bproj),
+                                              ptr(bias_table), ptr(row_scale), B, H, W, C, heads, window[0], window[1], shift[0],
+                                              shift[1], int(masked), bias_window[0], bias_window[1], float(eps), current_stream()),
+          "tulip_wmsa_block_fwd")
+    return y
+
+
 def window_attention(qkv, bias_table, B, H, W, heads, window=(2, 8), shift=(0, 0), masked=False, bias_window=(2, 8)):
     """qkv [B*H*W, 3C] bf16 (natural token order) -> [B*H*W, C] bf16."""
     _cuda(qkv, bias_table)
