@@ -44,18 +44,19 @@ for shift in (False, True):
 import ctypes as C
 from tulip_b200._lib import load_library
 lib = load_library()
-tr = torch.zeros(3 * 8 * 8, dtype=torch.int64, device="cuda")
+tr = torch.zeros(4 * 8 * 8, dtype=torch.int64, device="cuda")
 lib.tulip_debug_wmsa_trace.argtypes = [C.c_void_p]
 lib.tulip_debug_wmsa_trace(tr.data_ptr())
 fused(True); torch.cuda.synchronize()
 lib.tulip_debug_wmsa_trace(None)
-t = tr.cpu().view(3, 8, 8)
+t = tr.cpu().view(4, 8, 8)
 t0 = int(t[t > 0].min())
 names = {0: ["mma: loop top", "a_full ok", "qkv_empty ok", "o_full ok", "proj issued"],
          1: ["ln: -", "-", "-", "norm start", "raw landed", "a_empty ok", "norm end"],
+         3: ["epi(it): start", "p_full ok", "tmem loaded", "chunks done", "fenced+arrived", "S done (compute)", "softmax done"],
          2: ["at: top", "qkv_full ok", "frags loaded", "computed", "o_empty ok", "O stored", "epi(it-1) done"]}
 print('entry -> setup done -> t0 -> exit (cycles rel. t0):', [int(v) - t0 for v in t[0, 7][:3]])
-for role in range(3):
+for role in range(4):
     for it in range(7):
         row = [(int(v) - t0) if v > 0 else -1 for v in t[role, it][:len(names[role])]]
         print(f"role {role} tile {it}: " + "  ".join(f"{n}={v}" for n, v in zip(names[role], row)))

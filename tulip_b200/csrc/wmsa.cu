@@ -67,10 +67,14 @@ struct WmsaArgs {
   int ntiles, nwin;                         // 128-row tiles (the last one may hold fewer than 8 windows) and windows
   long long* trace;                         // bring-up: clock64() stamps of CTA 0 (tulip_debug_wmsa_trace), null in production
 };
+#ifdef TULIP_WMSA_TRACE
 #define WM_TRACE(role, it, k)                                                                      \
   do {                                                                                             \
     if (a.trace && blockIdx.x == 0 && (it) < 8 && lane == 0) a.trace[(((role) * 8 + (it)) * 8) + (k)] = clock64(); \
   } while (0)
+#else
+#define WM_TRACE(role, it, k) do { } while (0)
+#endif
 
 // n / d for n * d < 2^32 with mul = ceil(2^32 / d) (d == 1: mul = 0 and the quotient is n)
 __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t mul) { return mul ? __umulhi(n, mul) : n; }
@@ -108,6 +112,14 @@ __device__ __forceinline__ void tmem_ld_use(float (&v)[16]) {
   asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
                "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]));
 }
+// branch-free pick of one of four values by a per-lane index (selp; a ternary chain compiled to divergent branches)
+__device__ __forceinline__ float sel4(int k, float a, float b, float c, float d) {
+  float lo, hi, r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %2, %1, p;\n\t}" : "=f"(lo) : "f"(a), "f"(b), "r"(k & 1));
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %2, %1, p;\n\t}" : "=f"(hi) : "f"(c), "f"(d), "r"(k & 1));
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %2, %1, p;\n\t}" : "=f"(r) : "f"(lo), "f"(hi), "r"(k & 2));
+  return r;
+}
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ uint32_t movm_trans(uint32_t x) {
@@ -131,7 +143,9 @@ wmsa_block_fwd_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_co
                       const __grid_constant__ WmsaArgs a) {
   extern __shared__ unsigned char smem_raw[];
   pdl_trigger();
+#ifdef TULIP_WMSA_TRACE
   if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[7 * 8 + 0] = clock64();      // kernel entry
+#endif
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* spar = reinterpret_cast<float*>(smem + OFF_PAR);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -164,7 +178,9 @@ wmsa_block_fwd_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_co
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef TULIP_WMSA_TRACE
   if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[7 * 8 + 1] = clock64();      // barriers + TMEM ready
+#endif
   const int my_tiles = (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp < IO_WARP0) {
@@ -393,13 +409,14 @@ wmsa_block_fwd_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_co
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int i = g + (e >> 1) * 8, j = nt * 8 + 2 * t + (e & 1);
-        bias[nt][e] = a.bias_table[rel_bias_index(a.bMh, a.bMw, i, j) * WH + head];
+        bias[nt][e] = a.bias_table[rel_bias_index(a.bMh, a.bMw, i, j) * WH + head] * 1.4426950408889634f;
         if (((i / a.Mw) >= a.Mh - a.sh) != ((j / a.Mw) >= a.Mh - a.sh)) diffH |= 1u << (nt * 4 + e);
         if (((i % a.Mw) >= a.Mw - a.sw) != ((j % a.Mw) >= a.Mw - a.sw)) diffW |= 1u << (nt * 4 + e);
       }
     // q|k|v bias at this thread's fragment columns (8 per tensor: cols 8j + 2t, +1 of the head's 32): re-read from shared
     // memory every tile instead of living in 24 registers
     const float* s_qb = spar + head * 32 + 2 * t;
+    const float scale_l2e = a.scale * 1.4426950408889634f;
     unsigned char* sO = smem + OFF_O + head * A_BLK;           // K block `head` of the O tile: this head's 32 columns
     // Epilogue of a finished tile, spread over the 12 attention warps (one accumulator row per lane, this head's 32 columns):
     // projection accumulator + bias, DropPath scale and the residual, written IN PLACE over the raw tile; the storer warp sends
@@ -415,8 +432,10 @@ wmsa_block_fwd_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_co
         rs = a.row_scale[b];
       }
       unsigned char* xr = smem + OFF_RAW + slot * RAW_TILE + (q * 32 + lane) * ROWB + head * 64;   // residual in, y out (in place)
+      if (warp == AT_WARP0) WM_TRACE(3, it, 0);
       tc::mbar_wait(p_full + pb, (it >> 1) & 1);
       tc::fence_after_sync();
+      if (warp == AT_WARP0) WM_TRACE(3, it, 1);
       // four 16-byte chunks per lane, visited in an order rotated by (lane >> 1): 8 consecutive rows (192 B apart) then touch
       // 8 different bank groups (as in the LayerNorm passes).  TMEM addresses must be warp-uniform, so all 32 columns are
       // loaded and the chunk of each step is picked with selects.
@@ -429,12 +448,13 @@ wmsa_block_fwd_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_co
       tmem_ld_row8(taddr + 24, v3);
       tmem_ld_wait();
       tmem_ld_use8(v0); tmem_ld_use8(v1); tmem_ld_use8(v2); tmem_ld_use8(v3);
+      if (warp == AT_WARP0) WM_TRACE(3, it, 2);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int k = (c + rot) & 3;
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (k == 0) ? v0[e] : ((k == 1) ? v1[e] : ((k == 2) ? v2[e] : v3[e]));
+        for (int e = 0; e < 8; ++e) v[e] = sel4(k, v0[e], v1[e], v2[e], v3[e]);
         const uint4 xx = *reinterpret_cast<const uint4*>(xr + k * 16);
         const uint32_t w4[4] = {xx.x, xx.y, xx.z, xx.w};
         const float4 p0 = *reinterpret_cast<const float4*>(s_bp + k * 8), p1 = *reinterpret_cast<const float4*>(s_bp + k * 8 + 4);
@@ -447,10 +467,12 @@ wmsa_block_fwd_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_co
         }
         *reinterpret_cast<uint4*>(xr + k * 16) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
       }
+      if (warp == AT_WARP0) WM_TRACE(3, it, 3);
       tc::fence_before_sync();
       tc::fence_proxy_async();                                // the y tile is read by TMA stores
       __syncwarp();
       if (lane == 0) { tc::mbar_arrive(p_empty + pb); tc::mbar_arrive(y_full + slot); }
+      if (warp == AT_WARP0) WM_TRACE(3, it, 4);
     };
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
@@ -540,10 +562,11 @@ wmsa_block_fwd_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_co
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float v = fmaf(s[u][nt][e], a.scale, bias[nt][e]);
-            if ((maskbits[u] >> (nt * 4 + e)) & 1u) v += -100.0f;
+            float v = fmaf(s[u][nt][e], scale_l2e, bias[nt][e]);          // scores in log2 units: exp(x) = 2^(x log2 e)
+            if ((maskbits[u] >> (nt * 4 + e)) & 1u) v += -100.0f * 1.4426950408889634f;
             s[u][nt][e] = v;
           }
+      if (warp == AT_WARP0) WM_TRACE(3, it, 5);
       // softmax over the 16 keys of each row (rows g and g + 8; a row lives in the 4 lanes of a quad): 4 rows in flight
       float mx[2][2], sm[2][2];
 #pragma unroll
@@ -564,7 +587,7 @@ wmsa_block_fwd_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_co
           sm[u][hf] = 0.f;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float e = __expf(s[u][k >> 1][hf * 2 + (k & 1)] - mx[u][hf]);
+            const float e = fast_ex2(s[u][k >> 1][hf * 2 + (k & 1)] - mx[u][hf]);
             s[u][k >> 1][hf * 2 + (k & 1)] = e;
             sm[u][hf] += e;
           }
@@ -584,6 +607,7 @@ wmsa_block_fwd_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_co
         pf[u][2] = pack_bf16(s[u][1][0] * i0, s[u][1][1] * i0);
         pf[u][3] = pack_bf16(s[u][1][2] * i1, s[u][1][3] * i1);
       }
+      if (warp == AT_WARP0) WM_TRACE(3, it, 6);
       float o[2][4][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -614,7 +638,9 @@ wmsa_block_fwd_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_co
   }
   tc::fence_before_sync();
   __syncthreads();
+#ifdef TULIP_WMSA_TRACE
   if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[7 * 8 + 2] = clock64();      // all roles done
+#endif
   if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
 }
 
