@@ -154,6 +154,17 @@ int tulip_wmsa_block_fwd(const void* x, void* y, const float* ln_w, const float*
                          int B, int H, int W, int C, int heads, int Mh, int Mw, int sh, int sw, int masked,
                          int bias_Mh, int bias_Mw, float eps, void* stream);
 
+/* ---- fused MLP half-block (SURVEY 8b tulip_mlp_block_fwd): ONE launch for
+ *   y = x + row_scale[sample] * fc2(gelu(fc1(LayerNorm(x))))      tulip.py:347-352 with Mlp.forward :194-200 (exact-erf GELU)
+ * x, y: bf16 [T, C]; w1 [4C, C], w2 [C, 4C] bf16 row-major (nn.Linear layout); everything else fp32.  The hidden tensor lives
+ * in TMEM / shared memory only.  Training: pass xn [T, C] bf16, stats [T, 2] fp32 and hact [T, 4C] bf16 (all three or none) and
+ * the same launch also stores the LayerNorm output, its (mean, rstd) and the activated hidden tensor for the backward pass.
+ * Built for C = 96 (stage 0 of both factories); tulip_mlp_block_supported says whether a shape qualifies. */
+int tulip_mlp_block_supported(int T, int C);
+int tulip_mlp_block_fwd(const void* x, void* y, const float* ln_w, const float* ln_b, const void* w1, const float* b1,
+                        const void* w2, const float* b2, const float* row_scale, int rows_per_sample,
+                        void* xn, float* stats, void* hact, int T, int C, float eps, void* stream);
+
 /* ---- window attention core: tulip.py:289-317 without the two Linears; shift/partition/mask/bias in-kernel ---- */
 int tulip_window_attention_fwd(const void* qkv, const float* bias_table, void* out, int B, int H, int W, int C, int heads,
                                int Mh, int Mw, int sh, int sw, int masked, int bias_Mh, int bias_Mw, void* stream);

@@ -78,6 +78,8 @@ SIGNATURES = {
     "tulip_gemm_tn_ex": (_i, [C.POINTER(GemmTNDesc), _vp]),
     "tulip_wmsa_block_supported": (_i, [_i] * 7),
     "tulip_wmsa_block_fwd": (_i, [_vp, _vp, _fp, _fp, _vp, _fp, _vp, _fp, _fp, _fp] + [_i] * 12 + [C.c_float, _vp]),
+    "tulip_mlp_block_supported": (_i, [_i, _i]),
+    "tulip_mlp_block_fwd": (_i, [_vp, _vp, _fp, _fp, _vp, _fp, _vp, _fp, _fp, _i, _vp, _fp, _vp, _i, _i, C.c_float, _vp]),
     "tulip_window_attention_fwd": (_i, [_vp, _fp, _vp] + [_i] * 12 + [_vp]),
     "tulip_window_attention_bwd": (_i, [_vp, _fp, _vp, _vp, _fp] + [_i] * 12 + [_vp]),
     "tulip_layernorm_fwd": (_i, [_vp, _fp, _fp, _vp, _fp, _i, _i, C.c_float, _i, _i, _i, _vp]),

@@ -354,6 +354,19 @@ int tulip_wmsa_block_fwd(const void* x, void* y, const float* ln_w, const float*
   return wmsa_block_fwd(a, (cudaStream_t)stream);
 }
 
+int tulip_mlp_block_supported(int T, int C) { return mlp_block_supported(T, C) ? 1 : 0; }
+
+int tulip_mlp_block_fwd(const void* x, void* y, const float* ln_w, const float* ln_b, const void* w1, const float* b1, const void* w2,
+                        const float* b2, const float* row_scale, int rows_per_sample, void* xn, float* stats, void* hact, int T, int C,
+                        float eps, void* stream) {
+  MlpBlockArgs a;
+  memset(&a, 0, sizeof a);
+  a.x = (const bf16*)x; a.y = (bf16*)y; a.ln_w = ln_w; a.ln_b = ln_b; a.w1 = (const bf16*)w1; a.b1 = b1; a.w2 = (const bf16*)w2; a.b2 = b2;
+  a.row_scale = row_scale; a.rows_per_sample = rows_per_sample; a.xn = (bf16*)xn; a.stats = stats; a.hact = (bf16*)hact;
+  a.T = T; a.C = C; a.eps = eps;
+  return mlp_block_fwd(a, (cudaStream_t)stream);
+}
+
 static AttnArgs make_attn(const void* qkv, const float* table, int B, int H, int W, int C, int heads, int Mh, int Mw, int sh, int sw,
                           int masked, int bMh, int bMw) {
   AttnArgs a;

@@ -35,6 +35,21 @@ struct WmsaBlockArgs {
 bool wmsa_block_supported(int B, int H, int W, int C, int heads, int Mh, int Mw);
 int wmsa_block_fwd(const WmsaBlockArgs& a, cudaStream_t st);
 
+// fused MLP half-block (mlp.cu): y = x + row_scale[b] * fc2(gelu(fc1(LN2(x))))   (tulip.py:347-352, 194-200)
+struct MlpBlockArgs {
+  const bf16* x; bf16* y;                 // [T, C]
+  const float* ln_w; const float* ln_b;   // norm2
+  const bf16* w1; const float* b1;        // [4C, C] bf16, [4C]
+  const bf16* w2; const float* b2;        // [C, 4C] bf16, [C]
+  const float* row_scale; int rows_per_sample;   // per-sample DropPath scale or null
+  // training by-products (all three or none): LayerNorm output [T, C], its (mean, rstd) [T, 2], activated hidden tensor [T, 4C]
+  bf16* xn; float* stats; bf16* hact;
+  int T, C;
+  float eps;
+};
+bool mlp_block_supported(int T, int C);
+int mlp_block_fwd(const MlpBlockArgs& a, cudaStream_t st);
+
 struct LnArgs {
   const bf16* x;              // LN input rows [rows, C]; with gather: source tensor [B, 2*H2, 2*W2, C/4]
   const float* w; const float* b;

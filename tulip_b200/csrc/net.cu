@@ -29,7 +29,7 @@ const char* ktag_name(int t) {
       "misc", "gemm_nt<store>", "gemm_nt<gelu>", "gemm_nt<resid>", "gemm_nt<pixshuf>", "gemm_nt<split2>", "gemm_nt<dgelu>",
       "gemm_nt<head>", "gemm_nt<head_bwd>", "gemm_nt<rowscale>", "gemm_nt<unshuffle>", "gemm_tn", "gemm_tn<unshuffle>",
       "win_attn_fwd", "win_attn_bwd", "layernorm_fwd", "layernorm_bwd", "patch_embed_fwd", "patch_embed_bwd", "pack_weights",
-      "elementwise", "l1_loss", "wmsa_block_fwd"};
+      "elementwise", "l1_loss", "wmsa_block_fwd", "mlp_block_fwd"};
   return (t >= 0 && t < K_COUNT) ? names[t] : "?";
 }
 
@@ -514,6 +514,21 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     }
   mlp_half:
     at(b.stage, 2);
+    if (bb.hpre < 0 && mlp_block_supported(T, C)) {
+      // MLP half as ONE kernel (mlp.cu); in training it also stores the LayerNorm output, its statistics and the activated
+      // hidden tensor, which is everything the backward pass reads
+      join_pack();
+      MlpBlockArgs m;
+      memset(&m, 0, sizeof m);
+      m.x = c.A(bb.xmid); m.y = c.A(bb.xout); m.ln_w = c.P(b.n2w); m.ln_b = c.P(b.n2b);
+      m.w1 = c.W(linears[b.fc1]); m.b1 = c.bias(linears[b.fc1]); m.w2 = c.W(linears[b.fc2]); m.b2 = c.bias(linears[b.fc2]);
+      m.row_scale = ds2; m.rows_per_sample = Hs * Ws;
+      if (!inference) { m.xn = c.A(bb.xn2); m.stats = c.F(bb.st2); m.hact = c.A(bb.hact); }
+      m.T = T; m.C = C; m.eps = cfg.ln_eps;
+      tag(K_MLP_FWD, 16.0 * T * C * C, (inference ? 4.0 : 14.0) * T * C);
+      RUN(mlp_block_fwd(m, st));
+      return TULIP_OK;
+    }
     RUN(ln(c.A(bb.xmid), b.n2w, b.n2b, c.A(bb.xn2), c.F(bb.st2), T, C, 0, 0, 0));
     {
       const Linear& l = linears[b.fc1];

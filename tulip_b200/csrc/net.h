@@ -13,7 +13,7 @@
 enum KTag : int {
   K_MISC = 0, K_NT_STORE, K_NT_GELU, K_NT_RESID, K_NT_PIXSHUF, K_NT_SPLIT2, K_NT_DGELU, K_NT_HEAD, K_NT_HEAD_BWD, K_NT_ROWSCALE,
   K_NT_UNSHUFFLE, K_TN, K_TN_UNSHUFFLE, K_ATTN_FWD, K_ATTN_BWD, K_LN_FWD, K_LN_BWD, K_EMBED_FWD, K_EMBED_BWD, K_PACK,
-  K_ELEMWISE, K_LOSS, K_WMSA_FWD, K_COUNT
+  K_ELEMWISE, K_LOSS, K_WMSA_FWD, K_MLP_FWD, K_COUNT
 };
 const char* ktag_name(int tag);
 inline int nt_tag(int epi) {

@@ -95,6 +95,23 @@ def wmsa_block(x, ln_w, ln_b, wqkv, bqkv, wproj, bproj, bias_table, B, H, W, hea
     return y
 
 
+def mlp_block(x, ln_w, ln_b, w1, b1, w2, b2, row_scale=None, rows_per_sample=1, save=False, eps=1e-6):
+    """Fused MLP half-block: x [T, C] bf16 -> x + row_scale[sample] * fc2(gelu(fc1(LayerNorm(x)))) (tulip.py:347-352).
+    save=True also returns (xn, stats, hact), what the backward pass consumes."""
+    _cuda(x, w1, w2)
+    x, w1, w2 = _bf16(x), _bf16(w1), _bf16(w2)
+    ln_w, ln_b, b1, b2, row_scale = (_f32(t) for t in (ln_w, ln_b, b1, b2, row_scale))
+    T, C = x.shape
+    y = torch.empty_like(x)
+    xn = torch.empty_like(x) if save else None
+    stats = torch.empty((T, 2), dtype=torch.float32, device=x.device) if save else None
+    hact = torch.empty((T, 4 * C), dtype=torch.bfloat16, device=x.device) if save else None
+    check(load_library().tulip_mlp_block_fwd(ptr(x), ptr(y), ptr(ln_w), ptr(ln_b), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(row_scale),
+                                             rows_per_sample, ptr(xn), ptr(stats), ptr(hact), T, C, float(eps), current_stream()),
+          "tulip_mlp_block_fwd")
+    return (y, xn, stats, hact) if save else y
+
+
 def window_attention(qkv, bias_table, B, H, W, heads, window=(2, 8), shift=(0, 0), masked=False, bias_window=(2, 8)):
     """qkv [B*H*W, 3C] bf16 (natural token order) -> [B*H*W, C] bf16."""
     _cuda(qkv, bias_table)
