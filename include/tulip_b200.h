@@ -79,6 +79,10 @@ int tulip_net_profile_where(tulip_net* net, int i, int* stage, int* part, int* b
 int tulip_net_forward(tulip_net* net, int batch, const float* params, const int64_t* param_offsets_host,
                       const float* x_lo, const float* target, const float* drop_scales, const int* win_mode_host,
                       void* workspace, float* pred, float* losses, void* stream);
+/* Parameter version: any number that changes whenever the fp32 parameters change (e.g. the sum of the tensors' version
+ * counters).  While it stays the same (and `params` is the same buffer) tulip_net_forward skips the fp32 -> bf16 weight re-pack
+ * (216 MB of traffic per call for tulip_base).  A negative version (the default) means "unknown": re-pack on every forward. */
+int tulip_net_set_params_version(tulip_net* net, long long version);
 /* forward_only = 1: the following tulip_net_forward calls will not be followed by tulip_net_backward (evaluate(), MCdrop(),
  * torch.no_grad()): the fused half-block kernels run and no intermediate is saved.  0 (default) restores training mode. */
 int tulip_net_set_inference(tulip_net* net, int forward_only);
@@ -194,6 +198,11 @@ int tulip_patch_embed_bwd(const float* x, const float* w, const float* b, const 
  * scratch: 2*B floats. */
 int tulip_eval_postprocess(const float* pred, const float* x_lo, const float* target, float* out, float* losses, float* scratch,
                            int B, int H, int W, int h_lo, int log_transform, float clip_lo, int keep_low_res, void* stream);
+/* Monte-Carlo-dropout aggregation of MCdrop() (engine_upsampling.py:423-427): preds [n_passes, npix] fp32 (the stacked mc_drop
+ * forward passes of ONE frame) -> out [npix] = mean over the passes, zeroed where std (unbiased) > threshold * mean; std_out
+ * [npix] or NULL. */
+int tulip_mc_dropout_aggregate(const float* preds, float* out, float* std_out, int n_passes, int64_t npix, float threshold,
+                               void* stream);
 /* ---- evaluation metrics on the device (reference tulip/util/evaluation.py, engine_upsampling.py:223-277) ----
  * range image -> points (evaluation.py:52-116, img_to_pcd_kitti / img_to_pcd_carla): img [B,H,W] normalised range,
  * points [B, H*W, 3]; x = (sin_h[w] cos_v[h]) r, y = (cos_h[w] cos_v[h]) r, z = sin_v[h] r, r = img * max_range.  The four

@@ -32,3 +32,13 @@ def eval_postprocess(pred, lo, hi, log_transform=True, dataset="kitti"):
         losses[:, 1] = np.abs(part - lo).reshape(B, -1).mean(axis=1)                                    # :216-219
         pred[:, :, rows, :] = lo                                                                        # :221, :244
     return pred, losses
+
+
+def mc_dropout_aggregate(preds, noise_threshold=0.03):
+    """preds (N,1,H,W) float32 -> (1,1,H,W): engine_upsampling.py:423-427 (mean, unbiased std, zero where std > thr * mean)."""
+    preds = np.asarray(preds, np.float32)
+    mean = preds.mean(axis=0, keepdims=True, dtype=np.float32)
+    std = preds.std(axis=0, keepdims=True, ddof=1, dtype=np.float32)
+    out = mean.copy()
+    out[std > np.float32(noise_threshold) * mean] = 0
+    return out, std

@@ -63,3 +63,30 @@ def test_upsample_entry_matches_model_plus_oracle():
         np.testing.assert_allclose(out.cpu().numpy(), want, rtol=2e-6, atol=1e-7)
         np.testing.assert_allclose(losses.cpu().numpy(), want_l, rtol=1e-5, atol=1e-7)
     assert (outs[0][0][0, 0, ::4] == torch.expm1(lo_t[0, 0])).all()
+
+
+def test_mc_dropout_aggregate_and_entry():
+    """MCdrop()'s aggregation (engine_upsampling.py:423-427) as one kernel against the oracle, and the per-frame entry point."""
+    import numpy as np
+    import torch
+    from oracle.eval_post import mc_dropout_aggregate
+    from oracle.params import TULIP_BASE, make_inputs
+    from tests.test_gpu_model import build
+    from tulip_b200 import ops
+    from tulip_b200.inference import mc_dropout_upsample
+    g = torch.Generator().manual_seed(3)
+    base = torch.rand(1, 1, 64, 1024, generator=g)
+    preds = base + 0.02 * torch.randn(50, 1, 64, 1024, generator=g) * (torch.rand(1, 1, 64, 1024, generator=g) > 0.5)
+    want, want_std = mc_dropout_aggregate(preds.numpy(), 0.03)
+    got, got_std = ops.mc_dropout_aggregate(preds.cuda(), 0.03, return_std=True)
+    np.testing.assert_allclose(got_std.cpu().numpy(), want_std, rtol=2e-5, atol=2e-6)
+    keep = np.abs(want_std - 0.03 * preds.numpy().mean(0, keepdims=True)) > 1e-6
+    np.testing.assert_allclose(got.cpu().numpy()[keep], want[keep], rtol=1e-6, atol=1e-7)
+    model = build(TULIP_BASE).cuda().eval()
+    lo, hi = make_inputs(TULIP_BASE, 1, 9)
+    lo_t, hi_t = torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda()
+    out = mc_dropout_upsample(model, lo_t, hi_t, iterations=18, iteration_batch=8)
+    with torch.no_grad():
+        single = model(lo_t, hi_t, mc_drop=True)
+    # deterministic model (all dropout p = 0): every pass equals the single pass, std = 0, nothing is removed where mean > 0
+    assert torch.allclose(out[single > 0], single[single > 0], rtol=1e-6, atol=1e-7)

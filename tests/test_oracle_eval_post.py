@@ -49,3 +49,21 @@ def test_eval_postprocess_carla_width_mismatch_keeps_prediction_rows():
     lo = torch.rand(2, 1, 16, 512, generator=g)
     out, losses = eval_postprocess(hi.numpy(), lo.numpy(), hi.numpy(), False, "carla")   # engine_upsampling.py:207-208
     assert (losses[:, 1] == 0).all() and losses.shape == (2, 2)
+
+
+def test_mc_dropout_aggregate_oracle_matches_reference_statements():
+    """engine_upsampling.py:423-427 executed as written, against the numpy restatement."""
+    from oracle.eval_post import mc_dropout_aggregate
+    g = torch.Generator().manual_seed(3)
+    base = torch.rand(1, 1, 16, 64, generator=g)
+    pred_img_iteration = base + 0.02 * torch.randn(50, 1, 16, 64, generator=g) * (torch.rand(1, 1, 16, 64, generator=g) > 0.5)
+    noise_threshold = 0.03
+    pred_img = torch.mean(pred_img_iteration, dim=0, keepdim=True)                 # :423
+    pred_img_var = torch.std(pred_img_iteration, dim=0, keepdim=True)              # :424
+    noise_removal = pred_img_var > noise_threshold * pred_img                      # :425
+    pred_img[noise_removal] = 0                                                    # :427
+    out, std = mc_dropout_aggregate(pred_img_iteration.numpy(), noise_threshold)
+    np.testing.assert_allclose(std, pred_img_var.numpy(), rtol=2e-5, atol=2e-6)   # identical passes: two-pass std is an ulp of the mean, Welford gives 0
+    keep = np.abs(pred_img_var.numpy() - noise_threshold * torch.mean(pred_img_iteration, 0, keepdim=True).numpy()) > 1e-6
+    np.testing.assert_allclose(out[keep], pred_img.numpy()[keep], rtol=1e-6, atol=1e-7)
+    assert (out == 0).any() and (out != 0).any()

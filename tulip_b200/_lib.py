@@ -68,6 +68,7 @@ SIGNATURES = {
                                     C.POINTER(_i64)]),
     "tulip_net_profile_record": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "tulip_net_set_inference": (_i, [_vp, _i]),
+    "tulip_net_set_params_version": (_i, [_vp, C.c_longlong]),
     "tulip_net_profile_where": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "tulip_net_forward": (_i, [_vp, _i, _fp, _vp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _vp]),
     "tulip_net_backward": (_i, [_vp, _i, _fp, _vp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _vp, _vp]),
@@ -87,6 +88,7 @@ SIGNATURES = {
     "tulip_patch_embed_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, C.c_float, _vp]),
     "tulip_patch_embed_bwd": (_i, [_fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, C.c_float, _vp]),
     "tulip_eval_postprocess": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, C.c_float, _i, _vp]),
+    "tulip_mc_dropout_aggregate": (_i, [_fp, _fp, _fp, _i, _i64, C.c_float, _vp]),
     "tulip_range_to_points": (_i, [_fp, _fp, _fp, _fp, _fp, C.c_float, _fp, _i, _i, _i, _vp]),
     "tulip_voxel_metrics_workspace_bytes": (_i64, [_i]),
     "tulip_voxel_metrics": (_i, [_fp, _fp, _i, C.c_float, _vp, _vp, _vp]),

@@ -236,10 +236,17 @@ int tulip_net_forward(tulip_net* n, int batch, const float* params, const int64_
       (uint64_t)batch, (uint64_t)(uintptr_t)params, hash_words(offs, n->params.size() * sizeof(int64_t)), (uint64_t)(uintptr_t)x_lo,
       (uint64_t)(uintptr_t)target, (uint64_t)(uintptr_t)drop_scales, win_mode ? hash_words(win_mode, n->blocks.size() * sizeof(int)) : 0,
       (uint64_t)(uintptr_t)ws, (uint64_t)(uintptr_t)pred, (uint64_t)(uintptr_t)losses, (uint64_t)(uintptr_t)stream,
-      (uint64_t)n->inference};
+      (uint64_t)n->inference,
+      (uint64_t)((n->params_version < 0 || n->params_version != n->packed_version || n->packed_from != params) ? 1 : 0)};
   return n->run_graphed(n->graph_fwd, key, st, [&]() {
     return n->forward(batch, params, offs, x_lo, target, drop_scales, win_mode, ws, pred, losses, st);
   });
+}
+
+int tulip_net_set_params_version(tulip_net* n, long long version) {
+  if (!n) { tulip_set_error("tulip_net_set_params_version: null net"); return TULIP_ERR_ARG; }
+  n->params_version = version;
+  return TULIP_OK;
 }
 
 int tulip_net_set_inference(tulip_net* n, int forward_only) {
@@ -433,6 +440,11 @@ int tulip_eval_postprocess(const float* pred, const float* x_lo, const float* ta
                             int B, int H, int W, int h_lo, int log_transform, float clip_lo, int keep_low_res, void* stream) {
   if (!pred || !x_lo || !target || !out || !losses || !scratch) { tulip_set_error("tulip_eval_postprocess: null argument"); return TULIP_ERR_ARG; }
   return eval_postprocess(pred, x_lo, target, out, losses, scratch, B, H, W, h_lo, log_transform, clip_lo, keep_low_res, (cudaStream_t)stream);
+}
+
+int tulip_mc_dropout_aggregate(const float* preds, float* out, float* std_out, int n_passes, int64_t npix, float threshold, void* stream) {
+  if (!preds || !out) { tulip_set_error("tulip_mc_dropout_aggregate: null argument"); return TULIP_ERR_ARG; }
+  return mc_aggregate(preds, out, std_out, n_passes, (long)npix, threshold, (cudaStream_t)stream);
 }
 
 int tulip_range_to_points(const float* img, const float* sin_h, const float* cos_h, const float* sin_v, const float* cos_v,

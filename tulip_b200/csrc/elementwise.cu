@@ -968,6 +968,34 @@ __global__ void eval_postprocess_finalize_kernel(const float* sums, float* losse
   }
 }
 
+// Monte-Carlo-dropout aggregation (engine_upsampling.py:423-427): mean and unbiased std over the N stochastic passes of a pixel,
+// pixels whose std exceeds threshold * mean are zeroed.  One thread per pixel, two passes over its N values (N <= a few dozen).
+__global__ void __launch_bounds__(256) mc_aggregate_kernel(const float* __restrict__ preds, float* __restrict__ out, float* __restrict__ std_out,
+                                                           int n, long npix, float threshold) {
+  pdl_sync();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
+    float sum = 0.f;
+    for (int k = 0; k < n; ++k) sum += preds[(long)k * npix + i];
+    const float mean = sum / (float)n;
+    float sq = 0.f;
+    for (int k = 0; k < n; ++k) {
+      const float d = preds[(long)k * npix + i] - mean;
+      sq = fmaf(d, d, sq);
+    }
+    const float sd = sqrtf(sq / (float)(n - 1));              // torch.std: Bessel's correction
+    if (std_out) std_out[i] = sd;
+    out[i] = (sd > threshold * mean) ? 0.f : mean;
+  }
+}
+
+int mc_aggregate(const float* preds, float* out, float* std_out, int n, long npix, float threshold, cudaStream_t st) {
+  TULIP_REQUIRE(n >= 2 && npix > 0, "mc_aggregate: needs at least two passes");
+  const int grid = (int)min((npix + 255) / 256, (long)tulip_num_sms() * 8);
+  tulip_launch(mc_aggregate_kernel, grid, 256, 0, st, preds, out, std_out, n, npix, threshold);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
 int eval_postprocess(const float* pred, const float* lo, const float* hi, float* out, float* losses, float* scratch, int B, int H, int W,
                      int h_lo, int log_transform, float clip_lo, int keep_low_res, cudaStream_t st) {
   TULIP_REQUIRE(B > 0 && H > 0 && W > 0 && h_lo > 0 && H % h_lo == 0, "eval_postprocess: H must be a multiple of the input height");

@@ -1049,9 +1049,21 @@ int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st) {
   const int row_tiles_per_seg = ceil_div(row_seg_len, 128);
   const int n_tiles = nseg * row_tiles_per_seg, k_tiles = ceil_div(g.K, kcols);
   const int tb_total = ceil_div(g.M, TN_TOK);
-  int splits = tulip_num_sms() / (n_tiles * k_tiles);
-  if (splits < 1) splits = 1;
-  if (splits > tb_total) splits = tb_total;
+  // Token splits: every CTA streams its [tokens, 128 + kcols] operand slice over its own SM<->L2 link, so the launch takes
+  // waves(s) / s of the one-split time.  Pick the s that minimises that (ties: fewer splits = fewer atomics); a split keeps at
+  // least four token blocks so the ring fills.
+  const int tiles = n_tiles * k_tiles, sms = tulip_num_sms();
+  int splits = 1;
+  {
+    double best = 1e30;
+    const int smax = max(1, min(tb_total / 4, 4 * sms / tiles + 1));
+    for (int sp = 1; sp <= smax; ++sp) {
+      const int per_ = ceil_div(tb_total, sp);
+      const int real = ceil_div(tb_total, per_);
+      const double cost = (double)ceil_div(tiles * real, sms) * per_ + 2.0 * ceil_div(tiles * real, sms);   // + a fixed cost per wave
+      if (cost < best - 1e-9) { best = cost; splits = real; }
+    }
+  }
   const int per = ceil_div(tb_total, splits);
   splits = ceil_div(tb_total, per);
   dim3 grid(n_tiles, k_tiles, splits);

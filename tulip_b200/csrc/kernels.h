@@ -101,6 +101,8 @@ int scale_rows_bf16(bf16* dst, const bf16* src, const float* row_scale, int rows
 // evaluation post-processing (engine_upsampling.py:174-244): losses [B][2] = {pixel loss, low-res-row loss}, scratch [2B] floats
 int eval_postprocess(const float* pred, const float* lo, const float* hi, float* out, float* losses, float* scratch, int B, int H, int W,
                      int h_lo, int log_transform, float clip_lo, int keep_low_res, cudaStream_t st);
+// Monte-Carlo-dropout aggregation (engine_upsampling.py:423-427): preds [n, npix] -> out [npix] (mean, zeroed where std > threshold * mean)
+int mc_aggregate(const float* preds, float* out, float* std_out, int n, long npix, float threshold, cudaStream_t st);
 int l1_loss(const float* pred, const float* target, long n, int log_transform, float* acc2, float* out2, cudaStream_t st);
 
 // stand-alone index ops (bit-exact tests of the index arithmetic used inside the fused kernels)

@@ -438,10 +438,14 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     cudaEventRecord(e, st);
     cudaStreamWaitEvent(side, e, 0);
   }
-  tag(K_PACK, 0, 8.0 * warena_elems / 2);
-  RUN(pack_weights(params_, warena, items_dev, n_items, n_tiles, pst));
-  for (const Linear& l : linears)
-    if (l.pbias_off >= 0) RUN(permute_bias(c.P(l.slot_b), faux + l.pbias_off, l.N, l.perm_R2, l.perm_Cc, pst));
+  const bool repack = params_version < 0 || params_version != packed_version || packed_from != params_;
+  if (repack) {
+    tag(K_PACK, 0, 8.0 * warena_elems / 2);
+    RUN(pack_weights(params_, warena, items_dev, n_items, n_tiles, pst));
+    for (const Linear& l : linears)
+      if (l.pbias_off >= 0) RUN(permute_bias(c.P(l.slot_b), faux + l.pbias_off, l.N, l.perm_R2, l.perm_Cc, pst));
+    packed_version = params_version; packed_from = params_;
+  }
   bool pack_pending = use_side;
   auto join_pack = [&]() {
     if (!pack_pending) return;

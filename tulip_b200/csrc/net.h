@@ -91,6 +91,9 @@ struct tulip_net {
   long kernel_launches = 0;
   // forward-only mode (no backward will follow): the fused half-block kernels run and nothing is saved for autograd
   bool inference = false;
+  // parameter version announced by the caller (tulip_net_set_params_version): the bf16 weight arena is re-packed only when it
+  // differs from the version (and buffer) the arena was packed from; -1 = unknown, always re-pack
+  long long params_version = -1, packed_version = -1; const float* packed_from = nullptr;
   // per-launch profiler (off by default; adds two cudaEventRecord per launch when on)
   bool profiling = false;
   int cur_tag = K_MISC; double cur_flops = 0, cur_bytes = 0;

@@ -29,3 +29,23 @@ def upsample(model, x_lo: torch.Tensor, target: torch.Tensor, dataset: str = "ki
             model.train(True)
     keep = not (dataset == "carla" and x_lo.shape[-1] != target.shape[-1])         # :207-208
     return ops.eval_postprocess(pred, x_lo, target, log_transform, CLIP_LO[dataset], keep)
+
+
+@torch.no_grad()
+def mc_dropout_upsample(model, x_lo: torch.Tensor, target: torch.Tensor, iterations: int = 50, iteration_batch: int = 8,
+                        noise_threshold: float = 0.03):
+    """MCdrop()'s prediction for ONE frame (engine_upsampling.py:365-427): `iterations` stochastic passes in batches of
+    `iteration_batch` tiles of the input through `model(tile, target, mc_drop=True)`, then mean / std / noise removal as one
+    kernel.  (Every Dropout of both factories has p = 0 and DropPath is not re-enabled by enable_dropout, so with the shipped
+    models the passes are identical and std = 0 -- SURVEY 3.4; the path is the reference's nevertheless.)"""
+    if x_lo.shape[0] != 1:
+        raise ValueError("mc_dropout_upsample: one frame at a time (the reference's evaluation loader has batch_size 1)")
+    if iterations <= iteration_batch:
+        raise ValueError("iterations must exceed iteration_batch")                 # engine_upsampling.py:369
+    preds = torch.empty((iterations, *target.shape[1:]), dtype=torch.float32, device=x_lo.device)
+    done = 0
+    while done < iterations:
+        nb = min(iteration_batch, iterations - done)                               # :413
+        preds[done:done + nb] = model(x_lo.expand(nb, -1, -1, -1).contiguous(), target, mc_drop=True)      # :414-421
+        done += nb
+    return ops.mc_dropout_aggregate(preds, noise_threshold)                        # :423-427

@@ -399,9 +399,12 @@ class TULIP(nn.Module):
         if self._flat is None or self._flat.device != device:
             return False
         base = self._flat.data_ptr()
+        version = self._flat._version + getattr(self, "_param_epoch", 0)
         for p, (o, n, _s) in zip(self._param_list, self._views):
             if p.data_ptr() != base + 4 * o or p.dtype != torch.float32 or not p.is_contiguous():
                 return False
+            version += p._version                       # in-place updates (optimizers, copy_, load_state_dict) bump these
+        self._params_version = version
         return True
 
     def _ensure_flat(self, device):
@@ -426,6 +429,8 @@ class TULIP(nn.Module):
                 flat[o:o + n].view(s).copy_(p.detach().to(device=device, dtype=torch.float32))
                 p.data = flat[o:o + n].view(s)
         self._flat, self._views, self._param_list = flat, views, plist
+        self._param_epoch = getattr(self, "_param_epoch", 0) + 1      # a re-packed flat buffer is a new parameter version
+        self._params_version = -1
         self._grad_bufs = [None, None]
         self._offsets = np.ascontiguousarray([o for o, _, _ in views], dtype=np.int64)
         self._offsets_p = self._offsets.ctypes.data_as(C.c_void_p)
@@ -498,6 +503,8 @@ class TULIP(nn.Module):
             losses_w = torch.zeros(2, dtype=torch.float32, device=dev)
         # forward-only calls (torch.no_grad(): evaluate(), MCdrop(), inference) take the fused half-block kernels
         check(lib.tulip_net_set_inference(self._net, 0 if (self._grad_mode_hint and target is not None) else 1))
+        # unchanged parameters (evaluation loops): the executor keeps its bf16 weight arena instead of re-packing it
+        check(lib.tulip_net_set_params_version(self._net, int(getattr(self, "_params_version", -1))))
         check(lib.tulip_net_forward(self._net, B, ptr(self._flat), self._offsets_p, ptr(xin), ptr(tin), ptr(din),
                                     win_mode.ctypes.data_as(C.c_void_p), ptr(ws), ptr(pred_w), ptr(losses_w), current_stream()),
               "tulip_net_forward")

@@ -220,6 +220,19 @@ def eval_postprocess(pred, x_lo, target, log_transform=True, clip_lo=2.0 / 80.0,
     return out, losses
 
 
+def mc_dropout_aggregate(preds, noise_threshold=0.03, return_std=False):
+    """preds [N, 1, H, W] fp32 (stacked mc_drop passes of one frame) -> [1, 1, H, W]: mean over the passes with the pixels whose
+    unbiased std exceeds noise_threshold * mean zeroed (engine_upsampling.py:423-427)."""
+    _cuda(preds)
+    preds = _f32(preds)
+    n = preds.shape[0]
+    out = torch.empty((1, *preds.shape[1:]), dtype=torch.float32, device=preds.device)
+    std = torch.empty_like(out) if return_std else None
+    check(load_library().tulip_mc_dropout_aggregate(ptr(preds), ptr(out), ptr(std), n, out.numel(), float(noise_threshold),
+                                                    current_stream()), "tulip_mc_dropout_aggregate")
+    return (out, std) if return_std else out
+
+
 def window_partition(x, window=(2, 8), shift=(0, 0)):
     """(B,H,W,C) bf16 -> ((B Nh Nw), Mh, Mw, C): torch.roll(x, (-sh,-sw)) then the reference's window_partition."""
     _cuda(x)

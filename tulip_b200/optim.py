@@ -88,6 +88,7 @@ class FlatAdamW(torch.optim.Optimizer):
         hp.grad_scale = grad_scale
         check(load_library().tulip_adamw_step(ptr(self.model._flat), ptr(gbuf), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self._segs),
                                               self._n_segs, self._span, C.byref(hp), current_stream()), "tulip_adamw_step")
+        self.model._param_epoch = getattr(self.model, "_param_epoch", 0) + 1     # the kernel wrote the parameters behind autograd's back
         return loss
 
     @torch.no_grad()
