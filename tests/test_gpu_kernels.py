@@ -4,8 +4,8 @@ same bf16-exact inputs.
 Tolerances (SURVEY.md 8c -- the north star's 1e-3 is attainable per kernel, not end-to-end in bf16):
   * kernels whose only rounding is the final bf16 store: rel-L2 <= 1e-3 against the bf16-rounded fp32 oracle and
     >= 99 % of elements within 1 bf16 ulp;
-  * kernels with bf16 intermediates inside (attention: P and dS are rounded before their MMAs): rel-L2 <= 4e-3
-    against the fp32 oracle; the qkv-GEMM -> attention -> proj-GEMM chain checked against the reference
+  * the attention core keeps P and dS as two-term bf16 splits (hi + lo) for their MMAs: rel-L2 <= 1e-3 against the bf16-rounded
+    fp32 oracle, like a single-rounding kernel; the qkv-GEMM -> attention -> proj-GEMM chain checked against the reference
     WindowAttention fixtures stores bf16 three times on inputs of std ~2: rel-L2 <= 8e-3 (measured 4.8-5.0e-3);
   * fp32 outputs (weight / bias / LayerNorm / table gradients, loss): rel-L2 <= 1e-3 (2e-3 where bf16 operands feed them).
 """
@@ -195,7 +195,9 @@ def test_window_attention_core_vs_oracle(ops, B, H, W, C, heads):
     o = (attn @ t[2]).permute(0, 2, 1, 3).reshape(Bn, 16, C)
     want = torch.roll(O.window_reverse(o, (2, 8), B, H, W), (1, 4), (1, 2)).reshape(-1, C)
     got = ops.window_attention(qkv.cuda(), table.cuda(), B, H, W, heads, (2, 8), (1, 4), True).float().cpu()
-    assert rel_l2(got, want) <= 4e-3
+    # P enters its MMA as a two-term bf16 split, so the only rounding left is the bf16 store of the output
+    assert rel_l2(got, bf16r(want)) <= 1e-3
+    assert rel_l2(got, want) <= 2.5e-3
 
 
 def test_patch_embed_fwd_bwd(ops, mods):

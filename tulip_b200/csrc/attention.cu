@@ -190,8 +190,11 @@ __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
     float s[2][4];
     scores(a, sq, warp, win_maskbits(a, wt, wh, ww), bias, s, lane);
     softmax_rows(s);
-    uint32_t pf[4] = {pack_bf16(s[0][0], s[0][1]), pack_bf16(s[0][2], s[0][3]), pack_bf16(s[1][0], s[1][1]),
-                      pack_bf16(s[1][2], s[1][3])};
+    // P enters the tensor core as a two-term bf16 split (hi + lo, 16 significand bits): its rounding would otherwise be the
+    // largest error of the kernel (2^-9 per element); the kernel is HBM-bound, the four extra MMAs are free
+    uint32_t pf[4], pl[4];
+    split_bf16(s[0][0], s[0][1], pf[0], pl[0]); split_bf16(s[0][2], s[0][3], pf[1], pl[1]);
+    split_bf16(s[1][0], s[1][1], pf[2], pl[2]); split_bf16(s[1][2], s[1][3], pf[3], pl[3]);
     float o[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
@@ -204,6 +207,8 @@ __global__ void __launch_bounds__(96) win_attn_fwd_kernel(const AttnArgs a) {
       ldmatrix_x4_trans(bfr, sq + ((mat & 1) * 8 + (lane & 7)) * QLD + 2 * HG * HD + warp * HD + np * 16 + (mat >> 1) * 8);
       mma_bf16_16816(o[2 * np], pf, bfr[0], bfr[1]);
       mma_bf16_16816(o[2 * np + 1], pf, bfr[2], bfr[3]);
+      mma_bf16_16816(o[2 * np], pl, bfr[0], bfr[1]);
+      mma_bf16_16816(o[2 * np + 1], pl, bfr[2], bfr[3]);
     }
     const int tq = lane & 3;
 #pragma unroll
@@ -226,8 +231,8 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* sbuf = reinterpret_cast<bf16*>(smem_raw);             // NB x { [16][QLD] q|k|v, [16][OLD] dO }: two windows in flight
   constexpr int BUF = L * QLD + L * OLD;
-  bf16* sp = sbuf + BWD_NB * BUF;                             // [3 warps][2][16][PLD]  P and dS scratch
-  float* s_dtab = reinterpret_cast<float*>(sp + 3 * 2 * L * PLD);   // [HG][nbias]
+  bf16* sp = sbuf + BWD_NB * BUF;                             // [3 warps][4][16][PLD]  P and dS scratch (hi and lo parts)
+  float* s_dtab = reinterpret_cast<float*>(sp + 3 * 4 * L * PLD);   // [HG][nbias]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int li = tid / 12, lc8 = (tid % 12) * 8;
   const WinThread wt = win_thread(a, li, lane);
@@ -323,16 +328,24 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
       for (int q = 0; q < 4; ++q) dsacc[nt][q] += ds[nt][q];
-    // stash P and dS (bf16, [i][j]) for the transposed operands
-    bf16* wp = sp + warp * 2 * L * PLD;
+    // P and dS as two-term bf16 splits (hi + lo): stash both parts ([i][j]) for the transposed operands
+    bf16* wp = sp + warp * 4 * L * PLD;
     bf16* wds = wp + L * PLD;
+    bf16* wpl = wds + L * PLD;
+    bf16* wdsl = wpl + L * PLD;
+    uint32_t dsf[4], dsl[4];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int i = gq + hf * 8, j = nt * 8 + 2 * tq;
-        *reinterpret_cast<uint32_t*>(wp + i * PLD + j) = pack_bf16(p[nt][hf * 2], p[nt][hf * 2 + 1]);
-        *reinterpret_cast<uint32_t*>(wds + i * PLD + j) = pack_bf16(ds[nt][hf * 2], ds[nt][hf * 2 + 1]);
+        uint32_t ph, pl_;
+        split_bf16(p[nt][hf * 2], p[nt][hf * 2 + 1], ph, pl_);
+        split_bf16(ds[nt][hf * 2], ds[nt][hf * 2 + 1], dsf[nt * 2 + hf], dsl[nt * 2 + hf]);
+        *reinterpret_cast<uint32_t*>(wp + i * PLD + j) = ph;
+        *reinterpret_cast<uint32_t*>(wpl + i * PLD + j) = pl_;
+        *reinterpret_cast<uint32_t*>(wds + i * PLD + j) = dsf[nt * 2 + hf];
+        *reinterpret_cast<uint32_t*>(wdsl + i * PLD + j) = dsl[nt * 2 + hf];
       }
     __syncwarp();
 
@@ -341,11 +354,11 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int q = 0; q < 4; ++q) dq[nt][q] = dk[nt][q] = dv[nt][q] = 0.f;
-    uint32_t dsf[4] = {pack_bf16(ds[0][0], ds[0][1]), pack_bf16(ds[0][2], ds[0][3]), pack_bf16(ds[1][0], ds[1][1]),
-                       pack_bf16(ds[1][2], ds[1][3])};
-    uint32_t ptf[4], dstf[4];                                  // P^T and dS^T as A operands (rows j, contraction i)
+    uint32_t ptf[4], dstf[4], ptl[4], dstl[4];                  // P^T and dS^T (hi, lo) as A operands (rows j, contraction i)
     ldmatrix_x4_trans(ptf, wp + ((mat >> 1) * 8 + (lane & 7)) * PLD + (mat & 1) * 8);
     ldmatrix_x4_trans(dstf, wds + ((mat >> 1) * 8 + (lane & 7)) * PLD + (mat & 1) * 8);
+    ldmatrix_x4_trans(ptl, wpl + ((mat >> 1) * 8 + (lane & 7)) * PLD + (mat & 1) * 8);
+    ldmatrix_x4_trans(dstl, wdsl + ((mat >> 1) * 8 + (lane & 7)) * PLD + (mat & 1) * 8);
 #pragma unroll
     for (int np = 0; np < 2; ++np) {
       uint32_t bdo[4], bk[4], bq[4];
@@ -360,6 +373,12 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
       mma_bf16_16816(dq[2 * np + 1], dsf, bk[2], bk[3]);
       mma_bf16_16816(dk[2 * np], dstf, bq[0], bq[1]);
       mma_bf16_16816(dk[2 * np + 1], dstf, bq[2], bq[3]);
+      mma_bf16_16816(dv[2 * np], ptl, bdo[0], bdo[1]);
+      mma_bf16_16816(dv[2 * np + 1], ptl, bdo[2], bdo[3]);
+      mma_bf16_16816(dq[2 * np], dsl, bk[0], bk[1]);
+      mma_bf16_16816(dq[2 * np + 1], dsl, bk[2], bk[3]);
+      mma_bf16_16816(dk[2 * np], dstl, bq[0], bq[1]);
+      mma_bf16_16816(dk[2 * np + 1], dstl, bq[2], bq[3]);
     }
     // dq|dk|dv replace this head's q|k|v columns in the staging buffer (only this warp reads or writes them), then the CTA
     // writes the window back with the same coalesced 16-byte pattern it was loaded with: 6 stores per thread instead of 24
@@ -442,7 +461,7 @@ int win_attn_bwd(const AttnArgs& a_in, cudaStream_t st) {
   int rc = check_attn(a);
   if (rc) return rc;
   const int hgn = a.heads / HG, nwin = a.B * (a.H / a.Mh) * (a.W / a.Mw);
-  const int smem = (BWD_NB * (L * QLD + L * OLD) + 3 * 2 * L * PLD) * 2 + HG * a.nbias * 4;
+  const int smem = (BWD_NB * (L * QLD + L * OLD) + 3 * 4 * L * PLD) * 2 + HG * a.nbias * 4;
   static int per_sm = 0;
   if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, win_attn_bwd_kernel, 96, smem) != cudaSuccess || per_sm < 1)) per_sm = 4;
   const int slots = max(1, min(nwin, per_sm * tulip_num_sms() / hgn));

@@ -547,14 +547,15 @@ wmsa_block_fwd_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_co
         for (int u = 0; u < 2; ++u)
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) sm[u][hf] += __shfl_xor_sync(0xffffffffu, sm[u][hf], o);
-      uint32_t pf[2][4];
+      // P as a two-term bf16 split (hi + lo): its rounding would otherwise be the largest error of the attention core
+      uint32_t pf[2][4], pl[2][4];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const float i0 = 1.0f / sm[u][0], i1 = 1.0f / sm[u][1];
-        pf[u][0] = pack_bf16(s[u][0][0] * i0, s[u][0][1] * i0);
-        pf[u][1] = pack_bf16(s[u][0][2] * i1, s[u][0][3] * i1);
-        pf[u][2] = pack_bf16(s[u][1][0] * i0, s[u][1][1] * i0);
-        pf[u][3] = pack_bf16(s[u][1][2] * i1, s[u][1][3] * i1);
+        split_bf16(s[u][0][0] * i0, s[u][0][1] * i0, pf[u][0], pl[u][0]);
+        split_bf16(s[u][0][2] * i1, s[u][0][3] * i1, pf[u][1], pl[u][1]);
+        split_bf16(s[u][1][0] * i0, s[u][1][1] * i0, pf[u][2], pl[u][2]);
+        split_bf16(s[u][1][2] * i1, s[u][1][3] * i1, pf[u][3], pl[u][3]);
       }
       if (warp == AT_WARP0) WM_TRACE(3, it, 6);
       float o[2][4][4];
@@ -565,6 +566,7 @@ wmsa_block_fwd_kernel(const __grid_constant__ CUtensorMap mapWq, const __grid_co
 #pragma unroll
           for (int e = 0; e < 4; ++e) o[u][j][e] = 0.f;
           mma_bf16_16816(o[u][j], pf[u], vf[u][2 * j], vf[u][2 * j + 1]);
+          mma_bf16_16816(o[u][j], pl[u], vf[u][2 * j], vf[u][2 * j + 1]);
         }
       // O tile: rows 32q + 16u + g (+8), this head's K block, 16-byte chunk j, bytes 4t..4t+3
       if (warp == AT_WARP0) WM_TRACE(2, it, 3);
