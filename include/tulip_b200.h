@@ -92,6 +92,17 @@ int tulip_net_set_inference(tulip_net* net, int forward_only);
 int tulip_net_backward(tulip_net* net, int batch, const float* params, const int64_t* param_offsets_host,
                        float* grads, const float* x_lo, const float* target, const float* pred, const float* grad_loss,
                        const float* drop_scales, const int* win_mode_host, void* workspace, void* stream);
+/* The same pass in up to three calls, so that a data-parallel host can start the all-reduce of finished gradient slices under
+ * the rest of the pass (reference: DDP's bucketed reduce during backward, main_lidar_upsampling.py:277).  Phases, in order:
+ *   0  head, decoder (layers_up.*), first_patch_expanding, skip_connection_layers, norm_up   (also zero-fills `grads`)
+ *   1  top encoder stage (layers.{L-1}.*)
+ *   2  remaining encoder stages (layers.{0..L-2}.*) and patch_embed
+ * Call with [phase_lo, phase_hi] = [0,0], [1,1], [2,2] (or [0,2] = tulip_net_backward); when a call returns, the gradients of its
+ * phases are complete on `stream`. */
+int tulip_net_backward_phases(tulip_net* net, int batch, const float* params, const int64_t* param_offsets_host,
+                              float* grads, const float* x_lo, const float* target, const float* pred, const float* grad_loss,
+                              const float* drop_scales, const int* win_mode_host, void* workspace, void* stream,
+                              int phase_lo, int phase_hi);
 
 /* ---- dense contractions ----
  * NT: out[M,N] = A[M,K] . W[N,K]^T (+bias) -- every nn.Linear / 1x1 Conv2d on the path

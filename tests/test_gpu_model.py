@@ -345,3 +345,26 @@ def test_parameter_storage_swap_is_noticed():
     model.load_state_dict(sd, assign=True)
     pred3, _, _ = model(lo_t, hi_t)
     assert not torch.equal(pred2, pred3)
+
+
+@pytest.mark.parametrize("cfg,large", [(TULIP_BASE, False), (TULIP_LARGE, True)])
+def test_backward_in_three_phases_equals_one_pass(cfg, large):
+    """tulip_net_backward_phases (the host of the overlapped gradient all-reduce): phases 0, 1, 2 issued as three calls give the
+    gradients of the single call -- bit for bit where no atomics are involved, to fp32 atomic-order noise elsewhere."""
+    pn = make_params(cfg, 71)
+    lo, hi = make_inputs(cfg, 2, 72)
+    lo_t, hi_t = torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda()
+    model = build(cfg, large).eval()
+    load_params(model, pn)
+    model.cuda()
+    _, loss, _ = model(lo_t, hi_t)
+    loss.backward()
+    want = {n: q.grad.clone() for n, q in model.named_parameters()}
+    model._force_phases = True
+    for _ in range(3):                                        # third call replays the three per-phase CUDA graphs
+        model.zero_grad()
+        _, loss, _ = model(lo_t, hi_t)
+        loss.backward()
+    errs = {n: rel_l2(q.grad, want[n]) for n, q in model.named_parameters()}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] <= 1e-4, (worst, errs[worst])

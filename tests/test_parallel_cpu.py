@@ -56,3 +56,31 @@ def test_shard_range_rejects_ragged():
     assert list(shard_range(8, 1, 4)) == [2, 3]
     t = torch.ones(4)
     assert allreduce_flat_(t) is t          # no process group: identity
+
+
+def test_phase_slices_partition_the_flat_buffer():
+    """tulip_b200.parallel.phase_slices: the three backward phases' gradient ranges are disjoint, cover every parameter and follow
+    the order in which tulip_net_backward_phases completes them (head + decoder, top encoder stage, rest + PatchEmbed)."""
+    import numpy as np
+    from oracle.params import TULIP_BASE, TULIP_LARGE, param_shapes
+    from tulip_b200.parallel import phase_slices
+    for cfg in (TULIP_BASE, TULIP_LARGE):
+        shapes = param_shapes(cfg)
+        names = [k for k in shapes if not k.endswith("relative_position_index")]
+        views, off = [], 0
+        for n in names:
+            k = int(np.prod(shapes[n]))
+            views.append((off, k, shapes[n]))
+            off += (k + 63) // 64 * 64
+        sl = phase_slices(names, views, cfg.num_layers)
+        covered = np.zeros(off, dtype=np.int8)
+        for ph in range(3):
+            for lo, hi in sl[ph]:
+                assert 0 <= lo < hi <= off
+                covered[lo:hi] += 1
+        assert covered.max() == 1 and covered.min() == 1
+        top = f"layers.{cfg.num_layers - 1}."
+        for n, (o, k, _) in zip(names, views):
+            ph = [i for i in range(3) if any(lo <= o and o + k <= hi for lo, hi in sl[i])]
+            want = 2 if n.startswith("patch_embed.") else (1 if n.startswith(top) else (2 if n.startswith("layers.") else 0))
+            assert ph == [want], n

@@ -72,6 +72,7 @@ SIGNATURES = {
     "tulip_net_profile_where": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "tulip_net_forward": (_i, [_vp, _i, _fp, _vp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _vp]),
     "tulip_net_backward": (_i, [_vp, _i, _fp, _vp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _vp, _vp]),
+    "tulip_net_backward_phases": (_i, [_vp, _i, _fp, _vp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _vp, _vp, _i, _i]),
     "tulip_gemm_nt": (_i, [_vp, _vp, _fp, _vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
     "tulip_gemm_nt_plan": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i)]),
     "tulip_gemm_tn": (_i, [_vp, _vp, _fp, _fp, _i, _i, _i, _i, _vp]),

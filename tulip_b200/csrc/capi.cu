@@ -255,20 +255,34 @@ int tulip_net_set_inference(tulip_net* n, int forward_only) {
   return TULIP_OK;
 }
 
-int tulip_net_backward(tulip_net* n, int batch, const float* params, const int64_t* offs, float* grads, const float* x_lo,
-                       const float* target, const float* pred, const float* grad_loss, const float* drop_scales,
-                       const int* win_mode, void* ws, void* stream) {
+static int net_backward(tulip_net* n, int batch, const float* params, const int64_t* offs, float* grads, const float* x_lo,
+                        const float* target, const float* pred, const float* grad_loss, const float* drop_scales,
+                        const int* win_mode, void* ws, void* stream, int phase_lo, int phase_hi) {
   if (!n || !params || !offs || !grads || !x_lo || !ws) { tulip_set_error("tulip_net_backward: null argument"); return TULIP_ERR_ARG; }
   if (n->inference) { tulip_set_error("tulip_net_backward: the last forward ran in forward-only mode (tulip_net_set_inference)"); return TULIP_ERR_ARG; }
+  if (phase_lo < 0 || phase_hi > 2 || phase_lo > phase_hi) { tulip_set_error("tulip_net_backward_phases: phases are 0..2"); return TULIP_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   const std::vector<uint64_t> key = {
       (uint64_t)batch, (uint64_t)(uintptr_t)params, hash_words(offs, n->params.size() * sizeof(int64_t)), (uint64_t)(uintptr_t)grads,
       (uint64_t)(uintptr_t)x_lo, (uint64_t)(uintptr_t)target, (uint64_t)(uintptr_t)pred, (uint64_t)(uintptr_t)grad_loss,
       (uint64_t)(uintptr_t)drop_scales, win_mode ? hash_words(win_mode, n->blocks.size() * sizeof(int)) : 0, (uint64_t)(uintptr_t)ws,
-      (uint64_t)(uintptr_t)stream};
-  return n->run_graphed(n->graph_bwd, key, st, [&]() {
-    return n->backward(batch, params, offs, grads, x_lo, target, pred, grad_loss, drop_scales, win_mode, ws, st);
+      (uint64_t)(uintptr_t)stream, (uint64_t)(phase_lo * 4 + phase_hi)};
+  tulip_net::GraphSlot& slot = (phase_lo == 0 && phase_hi == 2) ? n->graph_bwd : n->graph_bwd_phase[phase_lo];
+  return n->run_graphed(slot, key, st, [&]() {
+    return n->backward(batch, params, offs, grads, x_lo, target, pred, grad_loss, drop_scales, win_mode, ws, st, phase_lo, phase_hi);
   });
+}
+
+int tulip_net_backward(tulip_net* n, int batch, const float* params, const int64_t* offs, float* grads, const float* x_lo,
+                       const float* target, const float* pred, const float* grad_loss, const float* drop_scales,
+                       const int* win_mode, void* ws, void* stream) {
+  return net_backward(n, batch, params, offs, grads, x_lo, target, pred, grad_loss, drop_scales, win_mode, ws, stream, 0, 2);
+}
+
+int tulip_net_backward_phases(tulip_net* n, int batch, const float* params, const int64_t* offs, float* grads, const float* x_lo,
+                              const float* target, const float* pred, const float* grad_loss, const float* drop_scales,
+                              const int* win_mode, void* ws, void* stream, int phase_lo, int phase_hi) {
+  return net_backward(n, batch, params, offs, grads, x_lo, target, pred, grad_loss, drop_scales, win_mode, ws, stream, phase_lo, phase_hi);
 }
 
 int tulip_gemm_nt(const void* A, const void* W, const float* bias, void* out, void* out2, const void* aux, const float* row_scale,

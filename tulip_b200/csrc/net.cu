@@ -328,11 +328,13 @@ int tulip_net::upload_pack_table(const int64_t* offs, cudaStream_t st) {
 
 #define RUN(call)                   \
   do {                              \
-    prof_begin(st);                 \
-    int rc__ = (call);              \
-    if (rc__ != TULIP_OK) return rc__; \
-    prof_end(st);                   \
-    ++kernel_launches;              \
+    if (live) {                     \
+      prof_begin(st);               \
+      int rc__ = (call);            \
+      if (rc__ != TULIP_OK) return rc__; \
+      prof_end(st);                 \
+      ++kernel_launches;            \
+    }                               \
   } while (0)
 
 // tagged GEMM launches: the tag names the kernel function (template instantiation) that runs
@@ -622,7 +624,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
 
 int tulip_net::backward(int B, const float* params_, const int64_t* offs, float* grads, const float* x_lo, const float* target,
                         const float* pred, const float* grad_loss, const float* drop_scales, const int* win_mode, void* ws,
-                        cudaStream_t st) {
+                        cudaStream_t st, int phase_lo, int phase_hi) {
   TULIP_REQUIRE(B > 0 && target && pred && grad_loss, "tulip backward: needs target, pred and grad_loss");
   TULIP_REQUIRE(warena != nullptr, "tulip backward: no forward has run on this net");
   const Plan p = plan(B);
@@ -631,6 +633,9 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   const int T0 = B * H0 * W0;
   int rc;
   cur_dir = 1; at(0, 3);
+  // The host walk below always covers the whole pass (buffer rotation and scratch offsets are the same in every call); `live`
+  // says whether the launches of the part being walked are issued (backward phases, net.h).
+  live = phase_lo <= 0;
 
   // Weight-gradient GEMMs (gemm_tn) are leaves of the backward graph: nothing on the dX chain reads them.  They run on a
   // side stream, forked after the kernel that produced their dY operand and joined before that buffer is overwritten, so
@@ -647,15 +652,18 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       if (offs[i] < lo) lo = offs[i];
       if (offs[i] + params[i].numel > hi) hi = offs[i] + params[i].numel;
     }
-    if (use_side) {
-      cudaEvent_t e = next_sync_event();
-      cudaEventRecord(e, st);
-      cudaStreamWaitEvent(side, e, 0);
-      side_pending = true;
+    if (live) {
+      if (use_side) {
+        cudaEvent_t e = next_sync_event();
+        cudaEventRecord(e, st);
+        cudaStreamWaitEvent(side, e, 0);
+        side_pending = true;
+      }
+      TULIP_CUDA(cudaMemsetAsync(grads + lo, 0, (size_t)(hi - lo) * sizeof(float), use_side ? side : st));
     }
-    TULIP_CUDA(cudaMemsetAsync(grads + lo, 0, (size_t)(hi - lo) * sizeof(float), use_side ? side : st));
   }
   auto fork = [&]() {                                     // side stream is ordered after everything issued on `st` so far
+    if (!live) return;
     cudaEvent_t e = next_sync_event();
     cudaEventRecord(e, st);
     cudaStreamWaitEvent(side, e, 0);
@@ -668,6 +676,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     side_pending = false;
   };
   auto run_tn = [&](const GemmTNArgs& gw) -> int {        // one weight-gradient GEMM, on the side stream when enabled
+    if (!live) return TULIP_OK;
     if (!use_side) { RUN_TN(gw); return TULIP_OK; }
     fork();
     const int rc_ = gemm_tn(gw, side);
@@ -684,7 +693,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
 
   // gradient copies (net.h GRAD_COPIES): grad_scratch(n) hands out GRAD_COPIES x n zeroed floats; sum_to() registers where
   // elements [off, off + n) of every copy are finally added
-  TULIP_CUDA(cudaMemsetAsync(c.F(p.gscr), 0, (size_t)p.gscr_bytes, st));
+  if (live) TULIP_CUDA(cudaMemsetAsync(c.F(p.gscr), 0, (size_t)p.gscr_bytes, st));
   long gscr_used = 0;
   std::vector<SumCopiesItem> sum_items;
   bool gscr_overflow = false;
@@ -695,7 +704,31 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     return ptr;
   };
   auto sum_to = [&](float* dst, const float* scr, int off, int n, int stride) {
-    sum_items.push_back(SumCopiesItem{dst, scr + off, n, stride});
+    if (live) sum_items.push_back(SumCopiesItem{dst, scr + off, n, stride});
+  };
+  // fold the gradient copies registered so far into the flat gradient (end of a phase / end of the pass)
+  auto flush_sums = [&]() -> int {
+    for (size_t first = 0; first < sum_items.size(); first += 128) {   // 128 (dst, src) pairs per launch (kernel-parameter space)
+      SumCopiesArgs sum_args;
+      memset(&sum_args, 0, sizeof sum_args);
+      sum_args.copies = GRAD_COPIES;
+      sum_args.count = (int)std::min<size_t>(128, sum_items.size() - first);
+      for (int i = 0; i < sum_args.count; ++i) sum_args.item[i] = sum_items[first + i];
+      tag(K_ELEMWISE, 0, 8.0 * GRAD_COPIES * 64.0 * sum_args.count);
+      RUN(sum_copies(sum_args, st));
+    }
+    sum_items.clear();
+    return TULIP_OK;
+  };
+  // phase boundary: what the finished phase produced is complete on `st` (side stream joined, copies folded)
+  auto enter_phase = [&](int ph) -> int {
+    if (live) {
+      if (side_pending) { cudaEvent_t e = next_sync_event(); cudaEventRecord(e, side); cudaStreamWaitEvent(st, e, 0); side_pending = false; }
+      const int rc_ = flush_sums();
+      if (rc_) return rc_;
+    }
+    live = ph >= phase_lo && ph <= phase_hi;
+    return TULIP_OK;
   };
 
   // optional fused DropPath scale for the consumer of dx: set before calling ln_bwd, consumed (reset) by it
@@ -890,6 +923,8 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   // ---- encoder, top stage first ----
   for (int s = L - 1; s >= 0; --s) {
     const int Hs = H0 >> s, Ws = W0 >> s, C = E << s, T = B * Hs * Ws;
+    if (s == L - 1) { rc = enter_phase(1); if (rc) return rc; }
+    if (s == L - 2) { rc = enter_phase(2); if (rc) return rc; }
     at(s, 0);
     if (s < L - 1) {
       // PatchMerging backward: g_cur is dL/d(x_merged[s]) [T/4, 2C]
@@ -933,16 +968,12 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   }
   TULIP_REQUIRE(!gscr_overflow, "tulip_b200: gradient-copy scratch exhausted (grad_scratch_bytes() out of step with backward())");
   join();                                                 // the gradient fill and every weight-gradient GEMM precede the fold
-  for (size_t first = 0; first < sum_items.size(); first += 128) {     // 128 (dst, src) pairs per launch (kernel-parameter space)
-    SumCopiesArgs sum_args;
-    memset(&sum_args, 0, sizeof sum_args);
-    sum_args.copies = GRAD_COPIES;
-    sum_args.count = (int)std::min<size_t>(128, sum_items.size() - first);
-    for (int i = 0; i < sum_args.count; ++i) sum_args.item[i] = sum_items[first + i];
-    tag(K_ELEMWISE, 0, 8.0 * gscr_used * sum_args.count / (double)sum_items.size());
-    RUN(sum_copies(sum_args, st));
+  if (live) {
+    rc = flush_sums();
+    if (rc) return rc;
   }
   join();                                                 // every gradient is complete on `st` when backward returns
+  live = true;
 #undef TN_SIDE
   return TULIP_OK;
 }

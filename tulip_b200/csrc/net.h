@@ -110,7 +110,10 @@ struct tulip_net {
     std::vector<uint64_t> last;         // key of the previous call
     long launches = 0;                  // kernels per replay
   };
-  GraphSlot graph_fwd, graph_bwd;
+  GraphSlot graph_fwd, graph_bwd, graph_bwd_phase[3];
+  // backward phases (gradient slices finish in this order, so their all-reduce can start under the rest of the pass):
+  // 0 head + decoder + first_patch_expanding, 1 top encoder stage, 2 remaining encoder stages + PatchEmbed
+  bool live = true;                                 // launches are issued only while the walk is inside the requested phases
   template <class F>
   int run_graphed(GraphSlot& slot, const std::vector<uint64_t>& key, cudaStream_t st, F&& body);
   // side stream for the weight-gradient GEMMs of the backward pass (they are off the dX critical path)
@@ -131,5 +134,5 @@ struct tulip_net {
               const int* win_mode, void* ws, float* pred, float* losses, cudaStream_t st);
   int backward(int B, const float* params, const int64_t* offs, float* grads, const float* x_lo, const float* target,
                const float* pred, const float* grad_loss, const float* drop_scales, const int* win_mode, void* ws,
-               cudaStream_t st);
+               cudaStream_t st, int phase_lo = 0, int phase_hi = 2);
 };

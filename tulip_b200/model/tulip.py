@@ -249,9 +249,27 @@ class _TulipFunction(torch.autograd.Function):
         else:
             g_loss = g_loss.to(torch.float32).reshape(1).contiguous()
         gbuf = model._grad_buffer()
-        check(lib.tulip_net_backward(model._net, ctx.B, ptr(model._flat), model._offsets_p, ptr(gbuf), ptr(x), ptr(target),
-                                     ptr(pred), ptr(g_loss), ptr(drop_scales), ctx.win_mode.ctypes.data_as(C.c_void_p), ptr(ws),
-                                     current_stream()), "tulip_net_backward")
+        sync = getattr(model, "_grad_sync", None)
+        dist_on = sync is not None and torch.distributed.is_available() and torch.distributed.is_initialized() \
+            and torch.distributed.get_world_size(None if sync is True else sync) > 1
+        if dist_on or getattr(model, "_force_phases", False):
+            # data-parallel exchange under the pass (tulip_b200.parallel.overlap_gradient_allreduce): three phases, the all-reduce of
+            # each finished slice of the flat buffer runs on NCCL's stream while the next phase computes
+            from ..parallel import launch_slice_allreduce, phase_slices
+            group = None if sync is True else sync
+            slices = phase_slices(model._schema, model._views, model.num_layers)
+            works = []
+            for ph in range(3):
+                check(lib.tulip_net_backward_phases(model._net, ctx.B, ptr(model._flat), model._offsets_p, ptr(gbuf), ptr(x), ptr(target),
+                                                    ptr(pred), ptr(g_loss), ptr(drop_scales), ctx.win_mode.ctypes.data_as(C.c_void_p),
+                                                    ptr(ws), current_stream(), ph, ph), "tulip_net_backward_phases")
+                if dist_on:
+                    works += launch_slice_allreduce(gbuf, slices[ph], group)
+            model._grad_sync_pending = works if dist_on else None
+        else:
+            check(lib.tulip_net_backward(model._net, ctx.B, ptr(model._flat), model._offsets_p, ptr(gbuf), ptr(x), ptr(target),
+                                         ptr(pred), ptr(g_loss), ptr(drop_scales), ctx.win_mode.ctypes.data_as(C.c_void_p), ptr(ws),
+                                         current_stream()), "tulip_net_backward")
         if ctx.pers is not None:
             model._persistent_owner = None
         # fresh views every time: autograd only adopts an incoming gradient as `.grad` (no copy) if nothing else references it

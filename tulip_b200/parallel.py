@@ -51,5 +51,63 @@ def flat_grad_of(model) -> torch.Tensor:
 
 
 def allreduce_gradients(model, group=None) -> torch.Tensor:
-    """The data-parallel exchange step: one all-reduce of all 27.1 M (tulip_base) gradients."""
+    """The data-parallel exchange step: one all-reduce of all 27.1 M (tulip_base) gradients.  A model with
+    `overlap_gradient_allreduce` enabled has already exchanged them inside backward(): then this only waits for that."""
+    pending = getattr(model, "_grad_sync_pending", None)
+    if pending is not None:
+        for w in pending:
+            w.wait()                                   # stream-level wait on the NCCL stream, not a host sync
+        model._grad_sync_pending = None
+        return flat_grad_of(model)
     return allreduce_flat_(flat_grad_of(model), group)
+
+
+def phase_slices(names, views, num_layers: int):
+    """Element ranges of the flat gradient buffer that are complete after backward phase 0, 1 and 2 (tulip_net_backward_phases):
+    -> ([(lo, hi), ...] per phase).  `names` / `views` are the module's parameter names and (offset, numel, shape) triples in
+    flat-buffer order (state_dict order: layers.*, layers_up.*, first_patch_expanding, skip_connection_layers, norm_up,
+    patch_embed, decoder_pred, ps_head)."""
+    top = f"layers.{num_layers - 1}."
+
+    def phase_of(n):
+        if n.startswith("patch_embed."):
+            return 2
+        if n.startswith("layers."):
+            return 1 if n.startswith(top) else 2
+        return 0
+    end = max(o + k for o, k, _ in views)
+    bounds = [o for o, _, _ in views] + [end]
+    out = ([], [], [])
+    for i, n in enumerate(names):
+        ph, lo, hi = phase_of(n), bounds[i], bounds[i + 1]
+        if out[ph] and out[ph][-1][1] == lo:
+            out[ph][-1] = (out[ph][-1][0], hi)         # contiguous with the previous range of the same phase (padding included)
+        else:
+            out[ph].append((lo, hi))
+    return out
+
+
+def overlap_gradient_allreduce(model, group=None, enabled: bool = True):
+    """Exchange the gradients INSIDE backward(): the pass runs as three phases (head + decoder, top encoder stage, the rest) and
+    the all-reduce of each finished slice of the flat buffer is launched on NCCL's stream under the remaining phases -- what the
+    reference gets from DDP's bucketed reduce (main_lidar_upsampling.py:277).  Same arithmetic as one flat all-reduce (mean over
+    ranks of every element), 4 collectives instead of 1.  Call `allreduce_gradients(model)` after backward() as before: it then
+    only joins the NCCL stream.  Do not combine with DistributedDataParallel or with gradient accumulation across backward() calls."""
+    model._grad_sync = (group if group is not None else True) if enabled else None
+    model._grad_sync_pending = None
+    return model
+
+
+def launch_slice_allreduce(gbuf: torch.Tensor, slices, group) -> list:
+    """async mean all-reduce of element ranges of the flat gradient buffer; returns the work handles"""
+    works = []
+    nccl = gbuf.is_cuda and dist.get_backend(group) == "nccl"
+    for lo, hi in slices:
+        t = gbuf[lo:hi]
+        if nccl:
+            works.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=True))
+        else:
+            w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True)
+            w.wait()
+            t.mul_(1.0 / dist.get_world_size(group))
+    return works
