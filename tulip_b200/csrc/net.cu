@@ -733,8 +733,9 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
 
   // optional fused DropPath scale for the consumer of dx: set before calling ln_bwd, consumed (reset) by it
   bf16* ln_dxs = nullptr; const float* ln_scale = nullptr; int ln_rps = 1;
-  auto ln_bwd = [&](const bf16* x, int wslot, int bslot, const float* stats, const bf16* dy, const bf16* dres, bf16* dx, int rows,
-                    int C, int gather, int H2, int W2) {
+  // Builds the arguments on every walk (live or not): the scratch offsets must not depend on the requested phases.
+  auto ln_bwd_args = [&](const bf16* x, int wslot, int bslot, const float* stats, const bf16* dy, const bf16* dres, bf16* dx,
+                         int rows, int C, int gather, int H2, int W2) -> LnArgs {
     LnArgs a;
     memset(&a, 0, sizeof a);
     a.dxs = ln_dxs; a.row_scale = ln_scale; a.rows_per_sample = ln_rps;
@@ -748,8 +749,13 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       sum_to(c.G(bslot), scr, C, C, 2 * C);
     }
     tag(K_LN_BWD, 0, (dres ? 8.0 : 6.0) * rows * C + 8.0 * rows + (a.dxs ? 2.0 * rows * C : 0.0));
-    return layernorm_bwd(a, st);
+    return a;
   };
+#define LN_BWD(...)                               \
+  do {                                            \
+    const LnArgs la__ = ln_bwd_args(__VA_ARGS__); \
+    RUN(layernorm_bwd(la__, st));                 \
+  } while (0)
   auto dw = [&](const Linear& l, const bf16* dY, const bf16* X, int M) {
     GemmTNArgs g = tn_args(dY, l.N, X, l.K, M, l.N, l.K, c.G(l.slot_w), l.slot_b >= 0 ? c.G(l.slot_b) : nullptr);
     g.perm_R2 = l.perm_R2; g.perm_Cc = l.perm_R2 > 1 ? l.perm_Cc : 1;
@@ -793,7 +799,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     GemmArgs gx = nt_args(dh, (long)E * r * r, c.Wt(l), (long)E * r * r, T0, E, E * r * r, nullptr, c.A(p.scr_dxn), E);
     RUN_NT(gx, EPI_STORE);
     want_scaled_for(dec_blocks[L - 2].back(), H0 * W0);
-    RUN(ln_bwd(x_last, slot_normup_w, slot_normup_b, c.F(p.st_up), c.A(p.scr_dxn), nullptr, g_cur, T0, E, 0, 0, 0));
+    LN_BWD(x_last, slot_normup_w, slot_normup_b, c.F(p.st_up), c.A(p.scr_dxn), nullptr, g_cur, T0, E, 0, 0, 0);
   }
 
   auto block_bwd = [&](int bi, const bf16* x_in, bf16* g_io, bf16* g_tmp, int bi_next) -> int {
@@ -835,7 +841,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       RUN_NT(g1, EPI_STORE);
     }
     if (ds1) { ln_dxs = c.A(p.scr_gs); ln_scale = ds1; ln_rps = Hs * Ws; }       // scaled copy for the attention branch
-    RUN(ln_bwd(c.A(bb.xmid), b.n2w, b.n2b, c.F(bb.st2), c.A(p.scr_dxn), g_io, g_tmp, T, C, 0, 0, 0));   // g_tmp = dL/dx_mid
+    LN_BWD(c.A(bb.xmid), b.n2w, b.n2b, c.F(bb.st2), c.A(p.scr_dxn), g_io, g_tmp, T, C, 0, 0, 0);   // g_tmp = dL/dx_mid
     // ---- attention half: x_mid = x_in + s1 * proj(attn(qkv(LN1(x_in)))) ----
     at(b.stage, 1);
     gy = ds1 ? c.A(p.scr_gs) : g_tmp;
@@ -861,7 +867,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     }
     join();                                               // the LayerNorm backward below overwrites g_io / the scaled copies
     want_scaled_for(bi_next, Hs * Ws);                    // next block in backward order lives on the same grid
-    RUN(ln_bwd(x_in, b.n1w, b.n1b, c.F(bb.st1), c.A(p.scr_dxn), g_tmp, g_io, T, C, 0, 0, 0));            // g_io = dL/dx_in
+    LN_BWD(x_in, b.n1w, b.n1b, c.F(bb.st1), c.A(p.scr_dxn), g_tmp, g_io, T, C, 0, 0, 0);            // g_io = dL/dx_in
     return TULIP_OK;
   };
 
@@ -935,8 +941,8 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       GemmArgs g = nt_args(g_cur, 2 * C, c.Wt(l), 2 * C, T / 4, 4 * C, 2 * C, nullptr, c.A(p.scr_big), 4 * C);
       RUN_NT(g, EPI_STORE);
       want_scaled_for(enc_blocks[s].back(), (Hs / 2) * (Ws / 2));       // rows here are merged (2x2) tokens
-      RUN(ln_bwd(x_stage_out, merge_nw[s], merge_nb[s], c.F(p.st_m[s]), c.A(p.scr_big), nullptr, g_alt, T / 4, 4 * C, 1, Hs / 2,
-                 Ws / 2));
+      LN_BWD(x_stage_out, merge_nw[s], merge_nb[s], c.F(p.st_m[s]), c.A(p.scr_big), nullptr, g_alt, T / 4, 4 * C, 1, Hs / 2,
+                 Ws / 2);
       std::swap(g_cur, g_alt);
     }
     for (int k = (int)enc_blocks[s].size() - 1; k >= 0; --k) {
@@ -975,5 +981,6 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   join();                                                 // every gradient is complete on `st` when backward returns
   live = true;
 #undef TN_SIDE
+#undef LN_BWD
   return TULIP_OK;
 }
