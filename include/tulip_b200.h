@@ -140,6 +140,11 @@ typedef struct tulip_gemm_desc {
   int split_col;
   const float* wd; const float* target; float* pred; const float* gscale; float* dwd;
   int hd_H, hd_W, hd_r, hd_E;
+  /* epilogue 10 (LayerNorm backward on the output rows, N = 96 or 192): aux = LN input rows, aux2 = gradient added to dx or
+   * NULL, ln_w = gamma [N], ln_stats = (mean, rstd) per row, ln_dw / ln_db += d(gamma) / d(beta); out2 (optional) =
+   * row_scale[sample] * out */
+  const void* aux2; int64_t ldaux2;
+  const float* ln_w; const float* ln_stats; float* ln_dw; float* ln_db;
 } tulip_gemm_desc;
 int tulip_gemm_nt_ex(const tulip_gemm_desc* d, int epilogue, void* stream);
 /* dW[N,K] += dY^T . [X | X2]; rows written un-permuted when perm_R2 > 1 (row n' = ij*Cc + c -> c*R2 + ij); y_mode 1 gathers

@@ -143,3 +143,55 @@ def test_head_fwd_bwd(mods, E):
     assert rel_l2(dWe[::stride], g_we) <= 0.15 and rel_l2(dbe, P(mods, f"{tag}.g_be")) <= 0.15
     assert rel_l2(gx.float().reshape(B, H, W, E), P(mods, f"{tag}.gx")) <= 0.15
     assert rel_l2(gnw, P(mods, f"{tag}.g_norm_w")) <= 0.15 and rel_l2(gnb, P(mods, f"{tag}.g_norm_b")) <= 0.15
+
+
+@pytest.mark.parametrize("M,C,K,res,scaled", [
+    (1000, 96, 288, True, False),          # ragged last tile, qkv-backward shape of stage 0
+    (128 * 300 + 37, 96, 384, True, True),  # several tiles per CTA, fc1-backward shape, DropPath-scaled second output
+    (777, 192, 576, False, True),          # two boxes per warp, no residual-path gradient
+    (4096, 192, 768, True, False),
+])
+def test_gemm_layernorm_backward_epilogue(M, C, K, res, scaled):
+    """EPI_LNBWD (gemm.cuh): dX GEMM whose epilogue is the LayerNorm backward of tulip.py:338,348 (norm1 / norm2) -- against the
+    same formulas in fp32 torch on the same bf16 operands.  dx is rounded once (1e-3 against the bf16-rounded fp32 result, the
+    cancellation in g - mean(g) - xhat mean(g xhat) included); d(gamma), d(beta) are fp32 sums of fp32 accumulators (1e-4)."""
+    from tulip_b200 import ops
+    gen = torch.Generator(device="cpu").manual_seed(M + C + K)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=gen) * scale)
+    A, W = bf(rnd(M, K).cuda()), bf(rnd(C, K, scale=K ** -0.5).cuda())
+    x = bf((rnd(M, C, scale=1.5) + 0.3).cuda())
+    dres = bf(rnd(M, C).cuda()) if res else None
+    gamma = (1.0 + 0.2 * rnd(C)).cuda().contiguous()
+    eps = 1e-5
+    xf = x.float()
+    mean = xf.mean(-1)
+    rstd = torch.rsqrt(xf.var(-1, unbiased=False) + eps)
+    stats = torch.stack([mean, rstd], dim=-1).contiguous()
+    rps = 64
+    scale = (torch.rand((M + rps - 1) // rps, generator=gen) + 0.5).cuda().contiguous() if scaled else None
+
+    dy = A.float() @ W.float().t()
+    xh = (xf - mean[:, None]) * rstd[:, None]
+    g = dy * gamma
+    want = rstd[:, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+    if res:
+        want = want + dres.float()
+    want_dw, want_db = (dy * xh).sum(0), dy.sum(0)
+
+    dx = torch.full((M, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    dxs = torch.full((M, C), float("nan"), dtype=torch.bfloat16, device="cuda") if scaled else None
+    dw = torch.zeros(C, dtype=torch.float32, device="cuda")
+    db = torch.zeros(C, dtype=torch.float32, device="cuda")
+    kw = dict(A=A, lda=K, K1=K, B=W, ldb=K, M=M, N=C, K=K, out=dx, ldo=C, aux=x, ldaux=C, ln_w=gamma, ln_stats=stats, ln_dw=dw, ln_db=db)
+    if res:
+        kw.update(aux2=dres, ldaux2=C)
+    if scaled:
+        kw.update(out2=dxs, ldo2=C, row_scale=scale, rows_per_sample=rps)
+    ops.gemm_nt_ex(ops.EPI_LNBWD, **kw)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dx.float()).all()
+    assert rel_l2(dx.float(), bf16r(want)) <= 1e-3
+    assert rel_l2(dw, want_dw) <= 1e-4 and rel_l2(db, want_db) <= 1e-4
+    if scaled:
+        rows = torch.arange(M, device="cuda") // rps
+        assert torch.equal(dxs, bf(scale[rows][:, None] * dx.float()))

@@ -18,6 +18,9 @@ enum GemmEpi : int {
   EPI_ROWSCALE = 8,   // out = row_scale[sample] * acc                      (DropPath backward on a branch dX)
   EPI_DGELU2 = 9,     // out = (A . B^T) * gelu'(A2 . B2^T + bias): the GELU pre-activation is RECOMPUTED by a second
                       // accumulator instead of being saved by the forward pass (tcgen05 path only)
+  EPI_LNBWD = 10,     // the output rows (N = 96 or 192: one tile holds whole rows) are dL/dy of a LayerNorm whose input rows are
+                      // `aux`:  out = [aux2 +] rstd * (g - mean(g) - xhat * mean(g * xhat)), g = acc * ln_w;  out2 = row_scale * out;
+                      // ln_dw += colsum(acc * xhat), ln_db += colsum(acc)   (tcgen05 path only; replaces GEMM + layernorm_bwd)
 };
 
 enum GemmAMode : int {
@@ -44,6 +47,10 @@ struct GemmArgs {
   const float* wd; const float* target; float* pred; const float* gscale;
   float* dwd; int dwd_copies;              // EPI_HEAD_BWD: CTA b adds into copy b % dwd_copies (stride hd_E); 0/1 = in place
   int hd_H, hd_W, hd_r, hd_E; float hd_inv_npix;
+  // EPI_LNBWD
+  const bf16* aux2; long ldaux2;           // residual-path gradient added to dx, or null
+  const float* ln_w; const float* ln_stats;    // gamma [N], (mean, rstd) per row [M, 2]
+  float* ln_dw; float* ln_db; int ln_copies, ln_stride;   // CTA b adds into copy b % ln_copies (ln_stride floats apart)
 };
 
 struct GemmTNArgs {
@@ -66,6 +73,7 @@ int gemm_nt_tc05_plan(int M, int N, int K, int epi, int save_pre, int* out10);  
 int gemm_nt(const GemmArgs& g, int epi, cudaStream_t st);        // dispatch (env TULIP_B200_GEMM=mma forces the legacy path)
 int gemm_tn(const GemmTNArgs& g, cudaStream_t st);
 bool gemm_forced_mma();                                          // env TULIP_B200_GEMM=mma
+bool gemm_nt_lnbwd_supported(int M, int N, int K);               // EPI_LNBWD takes this shape (else: EPI_STORE + layernorm_bwd)
 
 // ---- epilogue math on a run of NV consecutive columns of one output row (shared by both GEMMs) ----
 

@@ -322,7 +322,10 @@ int gemm_nt_mma(const GemmArgs& g, int epi, cudaStream_t st) {
     case EPI_HEAD_BWD: return launch_nt<EPI_HEAD_BWD, A_PLAIN>(g, st);
     case EPI_ROWSCALE: return launch_nt<EPI_ROWSCALE, A_PLAIN>(g, st);
   }
-  if (epi == EPI_DGELU2) { tulip_set_error("gemm_nt: EPI_DGELU2 exists on the tcgen05 path only"); return TULIP_ERR_UNSUPPORTED; }
+  if (epi == EPI_DGELU2 || epi == EPI_LNBWD) {
+    tulip_set_error("gemm_nt: EPI_DGELU2 / EPI_LNBWD exist on the tcgen05 path only (and EPI_LNBWD for N = 96 or 192)");
+    return TULIP_ERR_UNSUPPORTED;
+  }
   tulip_set_error("gemm_nt: unknown epilogue");
   return TULIP_ERR_ARG;
 }

@@ -37,7 +37,7 @@ struct Segments {
 };
 
 struct Maps {
-  CUtensorMap A, A2, B, B2, out, out2, aux;
+  CUtensorMap A, A2, B, B2, out, out2, aux, aux2;
 };
 
 // How the 128 x BN output tiles are dealt to the persistent CTAs.
@@ -72,9 +72,12 @@ __device__ __forceinline__ bool tile_at(const Sched& sc, int it, int& mt, int& n
 constexpr int NSA_MAX = 8;
 
 __host__ __device__ constexpr bool epi_tma_out(int epi) {
-  return epi == EPI_STORE || epi == EPI_GELU || epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_HEAD_BWD || epi == EPI_DGELU2;
+  return epi == EPI_STORE || epi == EPI_GELU || epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_HEAD_BWD || epi == EPI_DGELU2 ||
+         epi == EPI_LNBWD;
 }
-__host__ __device__ constexpr bool epi_has_aux(int epi) { return epi == EPI_RESID || epi == EPI_DGELU; }
+__host__ __device__ constexpr bool epi_has_aux(int epi) { return epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_LNBWD; }
+// EPI_LNBWD: per-row partial sums exchanged by the three warps of a TMEM lane quarter, [2 parities][4][3][32] float2
+__host__ __device__ constexpr int cfg_red_bytes(int epi) { return epi == EPI_LNBWD ? 2 * 4 * EPI_GROUPS * 32 * 8 : 0; }
 // Output staging buffers (each one [128, BN] bf16 tile).  Two let the stores of tile i overlap the epilogue of tile i+1 and,
 // for the aux epilogues, hold the in-place aux tile of the next tile.  The wide tile keeps one where it can: its GEMMs are
 // the deep-K ones, paced by the depth of the operand ring, and a CTA only sees a handful of tiles.
@@ -84,7 +87,7 @@ __host__ __device__ constexpr int cfg_out_bufs(int bn, int epi) {
 // operand ring stages: whatever fits next to the staging buffers (227 KB - barriers - alignment slack), at most 8
 __host__ __device__ constexpr int cfg_stages(int bn, int epi) {
   const int stage = (128 + bn) * 64 * 2;
-  const int n = (227 * 1024 - 512 - 1024 - cfg_out_bufs(bn, epi) * 128 * bn * 2) / stage;
+  const int n = (227 * 1024 - 512 - 1024 - cfg_out_bufs(bn, epi) * 128 * bn * 2 - cfg_red_bytes(epi)) / stage;
   return n > 8 ? 8 : n;
 }
 
@@ -103,7 +106,8 @@ struct Cfg {
   // epilogue warps and transformed in place, so it costs no shared memory of its own
   static constexpr int STAGES = cfg_stages(BN, EPI);
   static constexpr int OUT_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = OUT_OFF + OUT_BUFS * TILE_BYTES;
+  static constexpr int RED_OFF = OUT_OFF + OUT_BUFS * TILE_BYTES;
+  static constexpr int BAR_OFF = RED_OFF + cfg_red_bytes(EPI);
   static constexpr int TOTAL = BAR_OFF + 512 + 1024;                        // barriers + tmem slot, +1024 manual alignment
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
@@ -137,6 +141,22 @@ __device__ __forceinline__ void add_bias32(const float* __restrict__ bias, int n
     const float4 b = *reinterpret_cast<const float4*>(bias + n + 4 * q);
     v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
   }
+}
+
+// Column sums over the 32 lanes of a warp for 32 per-lane values: recursive halving (31 shuffles), lane i returns the sum of
+// v[i] over all lanes.  Fixed tree, so the result does not depend on timing.  Destroys v.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
 }
 
 // direct-store epilogues (scatter destinations): 16 consecutive columns of one row
@@ -381,6 +401,150 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       }
     };
     int mt, nt;
+    if (EPI == EPI_LNBWD) {
+      // ---- LayerNorm backward on whole output rows (tiles_n == 1).  Staging buffer 0: LN input rows x (-> scaled dx when a
+      // second output is asked for), buffer 1: residual-path gradient (-> dx), both transformed in place.  Per row the three
+      // warps of a lane quarter own one (BN 96) or two (BN 192) 32-column boxes each; their partial row sums meet in shared
+      // memory behind a 96-thread named barrier.  The column sums d(gamma), d(beta) are reduced over the 32 rows of a warp by
+      // recursive halving and accumulated in one register per box, so a CTA issues 2 N atomics in its whole life.
+      constexpr int MYBOX = CF::NBOX / EPI_GROUPS;
+      static_assert(EPI != EPI_LNBWD || CF::NBOX % EPI_GROUPS == 0, "whole boxes per warp");
+      unsigned char* const bx = smem + CF::OUT_OFF;
+      unsigned char* const br = smem + CF::OUT_OFF + CF::TILE_BYTES;
+      float2* const red = reinterpret_cast<float2*>(smem + CF::RED_OFF);
+      const bool has_res = g.aux2 != nullptr, has_dxs = g.out2 != nullptr;
+      const float invC = 1.0f / (float)BN;
+      float cg[MYBOX], cb[MYBOX];
+#pragma unroll
+      for (int jj = 0; jj < MYBOX; ++jj) cg[jj] = cb[jj] = 0.f;
+      auto issue_in = [&](int mt_a) {
+        const int m0a = mt_a * BM + q * 32;
+        if (m0a >= g.M) return;
+        tc::mbar_expect_tx(mybar, MYBOX * 2048 * (has_res ? 2 : 1));
+#pragma unroll
+        for (int jj = 0; jj < MYBOX; ++jj) {
+          const int j = jgrp + jj * EPI_GROUPS;
+          tc::tma_load_2d(bx + j * BOX_BYTES + q * 2048, &maps.aux, mybar, j * BOXC, m0a);
+          if (has_res) tc::tma_load_2d(br + j * BOX_BYTES + q * 2048, &maps.aux2, mybar, j * BOXC, m0a);
+        }
+      };
+      if (tile_at(sc, 0, mt, nt)) {
+        if (tc::elect_one_sync()) issue_in(mt);
+        __syncwarp();
+      }
+      uint32_t inphase = 0;
+      for (int it = 0; tile_at(sc, it, mt, nt); ++it) {
+        const int m0 = mt * BM, m = m0 + r;
+        const bool valid = m < g.M;
+        float mean = 0.f, rstd = 0.f, rsc = 1.f;
+        if (valid) {
+          const float2 st = *reinterpret_cast<const float2*>(g.ln_stats + 2 * (long)m);
+          mean = st.x; rstd = st.y;
+          if (has_dxs) rsc = g.row_scale[m / g.rows_per_sample];
+        }
+        tc::mbar_wait(tfull + buf, tphase);
+        tc::fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+        if (m0 + q * 32 < g.M) {
+          tc::mbar_wait(mybar, inphase);
+          inphase ^= 1u;
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < MYBOX; ++jj) {
+          const int j = jgrp + jj * EPI_GROUPS;
+          float v[32], h[32];
+          tc::tmem_ld32(taddr + j * BOXC, v);
+          load_box_row(bx + j * BOX_BYTES, r, h);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 w = *reinterpret_cast<const float4*>(g.ln_w + j * BOXC + 4 * q4);
+            const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * q4 + e;
+              const float xh = valid ? (h[i] - mean) * rstd : 0.f;
+              const float t = v[i] * ww[e];
+              s1 += t;
+              s2 = fmaf(t, xh, s2);
+              h[i] = v[i] * xh;
+            }
+          }
+          cg[jj] += warp_colsum32(h, lane);
+          cb[jj] += warp_colsum32(v, lane);
+        }
+        float2* const myred = red + ((it & 1) * 4 + q) * (EPI_GROUPS * 32);
+        myred[jgrp * 32 + lane] = make_float2(s1, s2);
+        tc::named_bar_sync(1 + q, 32 * EPI_GROUPS);
+        {
+          const float2 p0 = myred[lane], p1 = myred[32 + lane], p2 = myred[64 + lane];
+          s1 = (p0.x + p1.x) + p2.x;
+          s2 = (p0.y + p1.y) + p2.y;
+        }
+        const float m1 = s1 * invC, m2 = s2 * invC;
+#pragma unroll
+        for (int jj = 0; jj < MYBOX; ++jj) {
+          const int j = jgrp + jj * EPI_GROUPS;
+          float v[32], h[32];
+          tc::tmem_ld32(taddr + j * BOXC, v);
+          load_box_row(bx + j * BOX_BYTES, r, h);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 w = *reinterpret_cast<const float4*>(g.ln_w + j * BOXC + 4 * q4);
+            const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * q4 + e;
+              const float xh = valid ? (h[i] - mean) * rstd : 0.f;
+              v[i] = rstd * (v[i] * ww[e] - m1 - xh * m2);
+            }
+          }
+          if (has_res) {
+            load_box_row(br + j * BOX_BYTES, r, h);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += h[i];
+          }
+          store_box_row(br + j * BOX_BYTES, r, v);
+          if (has_dxs) {                                     // the scaled copy is formed from the rounded dx (as layernorm_bwd does)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = rsc * bf16_round(v[i]);
+            store_box_row(bx + j * BOX_BYTES, r, v);
+          }
+        }
+        tc::fence_before_sync();
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty + buf);
+        if (tc::elect_one_sync()) {
+          if (m0 + q * 32 < g.M) {
+#pragma unroll
+            for (int jj = 0; jj < MYBOX; ++jj) {
+              const int j = jgrp + jj * EPI_GROUPS;
+              tc::tma_store_2d(&maps.out, br + j * BOX_BYTES + q * 2048, j * BOXC, m0 + q * 32);
+              if (has_dxs) tc::tma_store_2d(&maps.out2, bx + j * BOX_BYTES + q * 2048, j * BOXC, m0 + q * 32);
+            }
+          }
+          tc::tma_store_commit();
+          int mt2, nt2;
+          if (tile_at(sc, it + 1, mt2, nt2)) {               // the slices are free once the stores have read them
+            tc::tma_store_wait_read<0>();
+            issue_in(mt2);
+          }
+        }
+        __syncwarp();
+        if (++buf == NBUF) { buf = 0; tphase ^= 1; }
+      }
+      {
+        const int copy_off = g.ln_copies > 1 ? (int)(blockIdx.x % g.ln_copies) * g.ln_stride : 0;
+#pragma unroll
+        for (int jj = 0; jj < MYBOX; ++jj) {
+          const int n = (jgrp + jj * EPI_GROUPS) * BOXC + lane;
+          atomicAdd(g.ln_dw + copy_off + n, cg[jj]);
+          atomicAdd(g.ln_db + copy_off + n, cb[jj]);
+        }
+      }
+      if (tc::elect_one_sync()) tc::tma_store_wait<0>();
+    } else {
     if (CF::HAS_AUX && tile_at(sc, 0, mt, nt)) {
       if (tc::elect_one_sync()) issue_aux(mt, nt, 0);
       __syncwarp();
@@ -583,6 +747,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       }
     }
     if (CF::TMA_OUT && tc::elect_one_sync()) tc::tma_store_wait<0>();   // global writes complete before the CTA retires
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -643,8 +808,9 @@ Sched choose_tiling(const GemmArgs& g, int epi, const Segments& sg, int* bn_out)
   const bool head = (epi == EPI_HEAD || epi == EPI_HEAD_BWD);
   int bn = (!head && epi != EPI_DGELU2 && g.N % 192 == 0 && (long)ceil_div(g.M, BM) * (g.N / 192) >= tulip_num_sms()) ? 192 : 96;
   if (epi == EPI_GELU && g.out2 != nullptr) bn = 96;
+  if (epi == EPI_LNBWD) bn = g.N;                         // one tile holds whole rows
   Sched sc = make_sched(bn, epi, g, sg);
-  if (bn == 192 && !sc.panel && epi != EPI_GELU) {
+  if (bn == 192 && !sc.panel && epi != EPI_GELU && epi != EPI_LNBWD) {
     const Sched s96 = make_sched(96, epi, g, sg);
     if (s96.panel) { bn = 96; sc = s96; }
   }
@@ -682,6 +848,15 @@ int make_io_map(CUtensorMap* map, const void* base, long ld, int M, int N, int b
 }
 
 }  // namespace
+
+bool gemm_nt_lnbwd_supported(int M, int N, int K) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("TULIP_B200_NO_FUSED_LNBWD");
+    off = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !off && !tc05_disabled() && !gemm_forced_mma() && M > 0 && (N == 96 || N == 192) && K % 8 == 0;
+}
 
 tulip_tmap_encode_fn tulip_tmap_encoder() {
   static tulip_tmap_encode_fn fn = nullptr;
@@ -722,6 +897,11 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     return TULIP_ERR_UNSUPPORTED;
   const bool head = (epi == EPI_HEAD || epi == EPI_HEAD_BWD);
   if (epi == EPI_HEAD_BWD && g.hd_E != 96 && g.hd_E != 192) return TULIP_ERR_UNSUPPORTED;   // dwd accumulators: one or two 96-channel groups
+  if (epi == EPI_LNBWD) {
+    if (!gemm_nt_lnbwd_supported(g.M, g.N, g.K) || g.a_mode != A_PLAIN || g.K1 < g.K) return TULIP_ERR_UNSUPPORTED;
+    TULIP_REQUIRE(g.aux && g.ln_w && g.ln_stats && g.ln_dw && g.ln_db && (!g.out2 || g.row_scale),
+                  "gemm_nt EPI_LNBWD: needs the LayerNorm input rows, gamma, row statistics and the two gradient accumulators");
+  }
   int bn = 96;                                            // chosen with the schedule once the K segments are known
 
   Segments sg;
@@ -767,7 +947,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     rc = tulip_make_tmap(&maps.B, g.B, 2, dims, str, box);
     if (rc) return rc;
   }
-  maps.B2 = maps.out = maps.out2 = maps.aux = maps.B;
+  maps.B2 = maps.out = maps.out2 = maps.aux = maps.aux2 = maps.B;
   if (epi == EPI_DGELU2) {
     // second product: pre = A2[M,K2] . B2[N,K2]^T feeds accumulator 1
     if (g.a_mode != A_PLAIN || g.K1 < g.K || !g.A2 || !g.B2 || (g.lda2 % 8) || (g.ldb2 % 8) || (g.K2 % 8) ||
@@ -789,7 +969,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(g.out) & 15) || (g.ldo % 8)) return TULIP_ERR_UNSUPPORTED;
     rc = make_io_map(&maps.out, g.out, g.ldo, g.M, g.N, 32);
     if (rc) return rc;
-    if (epi == EPI_GELU && g.out2) {
+    if ((epi == EPI_GELU || epi == EPI_LNBWD) && g.out2) {
       if ((reinterpret_cast<uintptr_t>(g.out2) & 15) || (g.ldo2 % 8)) return TULIP_ERR_UNSUPPORTED;
       rc = make_io_map(&maps.out2, g.out2, g.ldo2, g.M, g.N, 32);
       if (rc) return rc;
@@ -797,6 +977,12 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     if (epi_has_aux(epi)) {
       if (!g.aux || (reinterpret_cast<uintptr_t>(g.aux) & 15) || (g.ldaux % 8)) return TULIP_ERR_UNSUPPORTED;
       rc = make_io_map(&maps.aux, g.aux, g.ldaux, g.M, g.N, 32);
+      if (rc) return rc;
+    }
+    maps.aux2 = maps.aux;
+    if (epi == EPI_LNBWD && g.aux2) {
+      if ((reinterpret_cast<uintptr_t>(g.aux2) & 15) || (g.ldaux2 % 8)) return TULIP_ERR_UNSUPPORTED;
+      rc = make_io_map(&maps.aux2, g.aux2, g.ldaux2, g.M, g.N, 32);
       if (rc) return rc;
     }
   }
@@ -809,6 +995,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     case EPI_DGELU: return launch_bn<EPI_DGELU>(bn, maps, g, sg, sc, st);
     case EPI_DGELU2: return launch<96, EPI_DGELU2>(maps, g, sg, sc, st);     // two accumulators x two buffers: BN = 96 only
     case EPI_ROWSCALE: return launch_bn<EPI_ROWSCALE>(bn, maps, g, sg, sc, st);
+    case EPI_LNBWD: return launch_bn<EPI_LNBWD>(bn, maps, g, sg, sc, st);
     case EPI_HEAD: return launch<96, EPI_HEAD>(maps, g, sg, sc, st);
     case EPI_HEAD_BWD:
       return g.hd_E == 96 ? launch<96, EPI_HEAD_BWD>(maps, g, sg, sc, st) : launch<96, EPI_HEAD_BWD, 1>(maps, g, sg, sc, st);

@@ -29,7 +29,7 @@ const char* ktag_name(int t) {
       "misc", "gemm_nt<store>", "gemm_nt<gelu>", "gemm_nt<resid>", "gemm_nt<pixshuf>", "gemm_nt<split2>", "gemm_nt<dgelu>",
       "gemm_nt<head>", "gemm_nt<head_bwd>", "gemm_nt<rowscale>", "gemm_nt<unshuffle>", "gemm_tn", "gemm_tn<unshuffle>",
       "win_attn_fwd", "win_attn_bwd", "layernorm_fwd", "layernorm_bwd", "patch_embed_fwd", "patch_embed_bwd", "pack_weights",
-      "elementwise", "l1_loss", "wmsa_block_fwd", "mlp_block_fwd"};
+      "elementwise", "l1_loss", "wmsa_block_fwd", "mlp_block_fwd", "gemm_nt<ln_bwd>"};
   return (t >= 0 && t < K_COUNT) ? names[t] : "?";
 }
 
@@ -756,6 +756,24 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     const LnArgs la__ = ln_bwd_args(__VA_ARGS__); \
     RUN(layernorm_bwd(la__, st));                 \
   } while (0)
+  // dX GEMM whose output rows are dL/dy of a LayerNorm: where a tile holds whole rows (C = 96 / 192) the LayerNorm backward
+  // runs in the GEMM epilogue (EPI_LNBWD) and dy never reaches HBM; elsewhere the GEMM stores dy and layernorm_bwd follows.
+  auto lnbwd_fused = [&](GemmArgs& g, const LnArgs& a) {
+    g.aux = a.x; g.ldaux = a.C; g.aux2 = a.dres; g.ldaux2 = a.C;
+    g.out = a.dx; g.ldo = a.C; g.out2 = a.dxs; g.ldo2 = a.C; g.row_scale = a.row_scale; g.rows_per_sample = a.rows_per_sample;
+    g.ln_w = a.w; g.ln_stats = a.stats; g.ln_dw = a.dw; g.ln_db = a.db; g.ln_copies = a.dcopies; g.ln_stride = a.dstride;
+  };
+#define GEMM_LN_BWD(g, ...)                                                       \
+  do {                                                                            \
+    const LnArgs la__ = ln_bwd_args(__VA_ARGS__);                                 \
+    if (la__.gather == 0 && gemm_nt_lnbwd_supported((g).M, (g).N, (g).K)) {       \
+      lnbwd_fused((g), la__);                                                     \
+      RUN_NT((g), EPI_LNBWD);                                                     \
+    } else {                                                                      \
+      RUN_NT((g), EPI_STORE);                                                     \
+      RUN(layernorm_bwd(la__, st));                                               \
+    }                                                                             \
+  } while (0)
   auto dw = [&](const Linear& l, const bf16* dY, const bf16* X, int M) {
     GemmTNArgs g = tn_args(dY, l.N, X, l.K, M, l.N, l.K, c.G(l.slot_w), l.slot_b >= 0 ? c.G(l.slot_b) : nullptr);
     g.perm_R2 = l.perm_R2; g.perm_Cc = l.perm_R2 > 1 ? l.perm_Cc : 1;
@@ -797,9 +815,8 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     TN_SIDE(gw);
     // dxn_up = dh . We'          (A = dh [T0, E r^2], B = We'^T stored as Wt' [E, E r^2])
     GemmArgs gx = nt_args(dh, (long)E * r * r, c.Wt(l), (long)E * r * r, T0, E, E * r * r, nullptr, c.A(p.scr_dxn), E);
-    RUN_NT(gx, EPI_STORE);
     want_scaled_for(dec_blocks[L - 2].back(), H0 * W0);
-    LN_BWD(x_last, slot_normup_w, slot_normup_b, c.F(p.st_up), c.A(p.scr_dxn), nullptr, g_cur, T0, E, 0, 0, 0);
+    GEMM_LN_BWD(gx, x_last, slot_normup_w, slot_normup_b, c.F(p.st_up), c.A(p.scr_dxn), nullptr, g_cur, T0, E, 0, 0, 0);
   }
 
   auto block_bwd = [&](int bi, const bf16* x_in, bf16* g_io, bf16* g_tmp, int bi_next) -> int {
@@ -838,10 +855,9 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       const Linear& l1 = linears[b.fc1];
       TN_SIDE(dw(l1, c.A(p.scr_big), c.A(bb.xn2), T));
       GemmArgs g1 = nt_args(c.A(p.scr_big), 4 * C, c.Wt(l1), 4 * C, T, C, 4 * C, nullptr, c.A(p.scr_dxn), C);
-      RUN_NT(g1, EPI_STORE);
+      if (ds1) { ln_dxs = c.A(p.scr_gs); ln_scale = ds1; ln_rps = Hs * Ws; }     // scaled copy for the attention branch
+      GEMM_LN_BWD(g1, c.A(bb.xmid), b.n2w, b.n2b, c.F(bb.st2), c.A(p.scr_dxn), g_io, g_tmp, T, C, 0, 0, 0);   // g_tmp = dL/dx_mid
     }
-    if (ds1) { ln_dxs = c.A(p.scr_gs); ln_scale = ds1; ln_rps = Hs * Ws; }       // scaled copy for the attention branch
-    LN_BWD(c.A(bb.xmid), b.n2w, b.n2b, c.F(bb.st2), c.A(p.scr_dxn), g_io, g_tmp, T, C, 0, 0, 0);   // g_tmp = dL/dx_mid
     // ---- attention half: x_mid = x_in + s1 * proj(attn(qkv(LN1(x_in)))) ----
     at(b.stage, 1);
     gy = ds1 ? c.A(p.scr_gs) : g_tmp;
@@ -861,13 +877,12 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       tag(K_ATTN_BWD, 160.0 * T * C, 16.0 * T * C);
       RUN(win_attn_bwd(a, st));
       const Linear& lq = linears[b.qkv];
-      TN_SIDE(dw(lq, c.A(p.scr_dqkv), c.A(bb.xn1), T));
+      join();                                             // the LayerNorm backward below overwrites g_io / the scaled copies
+      TN_SIDE(dw(lq, c.A(p.scr_dqkv), c.A(bb.xn1), T));   // reads neither: runs beside it
       GemmArgs gq = nt_args(c.A(p.scr_dqkv), 3 * C, c.Wt(lq), 3 * C, T, C, 3 * C, nullptr, c.A(p.scr_dxn), C);
-      RUN_NT(gq, EPI_STORE);
+      want_scaled_for(bi_next, Hs * Ws);                  // next block in backward order lives on the same grid
+      GEMM_LN_BWD(gq, x_in, b.n1w, b.n1b, c.F(bb.st1), c.A(p.scr_dxn), g_tmp, g_io, T, C, 0, 0, 0);            // g_io = dL/dx_in
     }
-    join();                                               // the LayerNorm backward below overwrites g_io / the scaled copies
-    want_scaled_for(bi_next, Hs * Ws);                    // next block in backward order lives on the same grid
-    LN_BWD(x_in, b.n1w, b.n1b, c.F(bb.st1), c.A(p.scr_dxn), g_tmp, g_io, T, C, 0, 0, 0);            // g_io = dL/dx_in
     return TULIP_OK;
   };
 
@@ -982,5 +997,6 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   live = true;
 #undef TN_SIDE
 #undef LN_BWD
+#undef GEMM_LN_BWD
   return TULIP_OK;
 }
