@@ -867,20 +867,39 @@ int permute_bias(const float* src, float* dst, int n, int R2, int Cc, cudaStream
 }
 
 namespace {
+// block (item, y): 8 warps each sum every 8th copy of 32 consecutive elements (independent loads, all in flight together),
+// then warp 0 folds the 8 partial sums in a fixed order.  blockIdx.y strides over the element chunks of long items.
 __global__ void __launch_bounds__(256) sum_copies_kernel(const __grid_constant__ SumCopiesArgs a) {
   pdl_sync();
+  __shared__ float part[8][32];
   const SumCopiesItem it = a.item[blockIdx.x];
-  for (int i = threadIdx.x; i < it.n; i += blockDim.x) {
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  for (int base = blockIdx.y * 32; base < it.n; base += gridDim.y * 32) {
+    const int i = base + lane;
     float s = 0.f;
-    for (int c = 0; c < a.copies; ++c) s += it.src[(long)c * it.stride + i];
-    it.dst[i] += s;
+    if (i < it.n) {
+#pragma unroll 4
+      for (int c = grp; c < a.copies; c += 8) s += it.src[(long)c * it.stride + i];
+    }
+    part[grp][lane] = s;
+    __syncthreads();
+    if (grp == 0 && i < it.n) {
+      float t = part[0][lane];
+#pragma unroll
+      for (int g2 = 1; g2 < 8; ++g2) t += part[g2][lane];
+      it.dst[i] += t;
+    }
+    __syncthreads();
   }
 }
 }  // namespace
 
 int sum_copies(const SumCopiesArgs& a, cudaStream_t st) {
   if (a.count <= 0) return TULIP_OK;
-  tulip_launch(sum_copies_kernel, a.count, 256, 0, st, a);
+  int nmax = 0;
+  for (int i = 0; i < a.count; ++i) nmax = a.item[i].n > nmax ? a.item[i].n : nmax;
+  const int chunks = nmax > 256 ? 8 : (nmax + 31) / 32;
+  tulip_launch(sum_copies_kernel, dim3(a.count, chunks > 0 ? chunks : 1), 256, 0, st, a);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }

@@ -21,6 +21,8 @@ enum GemmEpi : int {
   EPI_LNBWD = 10,     // the output rows (N = 96 or 192: one tile holds whole rows) are dL/dy of a LayerNorm whose input rows are
                       // `aux`:  out = [aux2 +] rstd * (g - mean(g) - xhat * mean(g * xhat)), g = acc * ln_w;  out2 = row_scale * out;
                       // ln_dw += colsum(acc * xhat), ln_db += colsum(acc)   (tcgen05 path only; replaces GEMM + layernorm_bwd)
+  EPI_STORE_LN = 11,  // EPI_STORE / EPI_RESID whose output rows (N = 96 or 192) feed a LayerNorm next: also writes
+  EPI_RESID_LN = 12,  // ln_y = LayerNorm(out) (from the rounded rows, as layernorm_fwd reads them) and its (mean, rstd) rows
 };
 
 enum GemmAMode : int {
@@ -51,6 +53,8 @@ struct GemmArgs {
   const bf16* aux2; long ldaux2;           // residual-path gradient added to dx, or null
   const float* ln_w; const float* ln_stats;    // gamma [N], (mean, rstd) per row [M, 2]
   float* ln_dw; float* ln_db; int ln_copies, ln_stride;   // CTA b adds into copy b % ln_copies (ln_stride floats apart)
+  // EPI_STORE_LN / EPI_RESID_LN: ln_w = gamma, ln_b = beta, ln_y [M, N] bf16, ln_ystats [M, 2]
+  const float* ln_b; bf16* ln_y; float* ln_ystats; float ln_eps;
 };
 
 struct GemmTNArgs {
@@ -74,6 +78,7 @@ int gemm_nt(const GemmArgs& g, int epi, cudaStream_t st);        // dispatch (en
 int gemm_tn(const GemmTNArgs& g, cudaStream_t st);
 bool gemm_forced_mma();                                          // env TULIP_B200_GEMM=mma
 bool gemm_nt_lnbwd_supported(int M, int N, int K);               // EPI_LNBWD takes this shape (else: EPI_STORE + layernorm_bwd)
+bool gemm_nt_lnfwd_supported(int M, int N, int K);               // EPI_STORE_LN / EPI_RESID_LN take this shape
 
 // ---- epilogue math on a run of NV consecutive columns of one output row (shared by both GEMMs) ----
 

@@ -73,11 +73,15 @@ constexpr int NSA_MAX = 8;
 
 __host__ __device__ constexpr bool epi_tma_out(int epi) {
   return epi == EPI_STORE || epi == EPI_GELU || epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_HEAD_BWD || epi == EPI_DGELU2 ||
-         epi == EPI_LNBWD;
+         epi == EPI_LNBWD || epi == EPI_STORE_LN || epi == EPI_RESID_LN;
 }
-__host__ __device__ constexpr bool epi_has_aux(int epi) { return epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_LNBWD; }
+__host__ __device__ constexpr bool epi_ln_fwd(int epi) { return epi == EPI_STORE_LN || epi == EPI_RESID_LN; }
+// (for the staging-buffer count: the fused-LayerNorm epilogues always use two tiles, input/output and second output)
+__host__ __device__ constexpr bool epi_has_aux(int epi) {
+  return epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_LNBWD || epi_ln_fwd(epi);
+}
 // EPI_LNBWD: per-row partial sums exchanged by the three warps of a TMEM lane quarter, [2 parities][4][3][32] float2
-__host__ __device__ constexpr int cfg_red_bytes(int epi) { return epi == EPI_LNBWD ? 2 * 4 * EPI_GROUPS * 32 * 8 : 0; }
+__host__ __device__ constexpr int cfg_red_bytes(int epi) { return (epi == EPI_LNBWD || epi_ln_fwd(epi)) ? 2 * 4 * EPI_GROUPS * 32 * 8 : 0; }
 // Output staging buffers (each one [128, BN] bf16 tile).  Two let the stores of tile i overlap the epilogue of tile i+1 and,
 // for the aux epilogues, hold the in-place aux tile of the next tile.  The wide tile keeps one where it can: its GEMMs are
 // the deep-K ones, paced by the depth of the operand ring, and a CTA only sees a handful of tiles.
@@ -544,6 +548,117 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         }
       }
       if (tc::elect_one_sync()) tc::tma_store_wait<0>();
+    } else if (epi_ln_fwd(EPI)) {
+      // ---- EPI_STORE / EPI_RESID on whole rows followed by the LayerNorm that reads them next.  Staging buffer 0: residual
+      // tile -> out (in place), buffer 1: LayerNorm(out).  The statistics are taken from the bf16-rounded rows, in two passes
+      // (mean, then centred squares) as layernorm_fwd does; the three warps of a lane quarter exchange their partial sums
+      // through shared memory twice per tile.
+      constexpr bool RES = (EPI == EPI_RESID_LN);
+      constexpr int MYBOX = CF::NBOX / EPI_GROUPS;
+      unsigned char* const b0 = smem + CF::OUT_OFF;
+      unsigned char* const b1 = smem + CF::OUT_OFF + CF::TILE_BYTES;
+      float2* const red = reinterpret_cast<float2*>(smem + CF::RED_OFF);
+      const float invC = 1.0f / (float)BN;
+      auto issue_in = [&](int mt_a) {
+        const int m0a = mt_a * BM + q * 32;
+        if (!RES || m0a >= g.M) return;
+        tc::mbar_expect_tx(mybar, MYBOX * 2048);
+#pragma unroll
+        for (int jj = 0; jj < MYBOX; ++jj) {
+          const int j = jgrp + jj * EPI_GROUPS;
+          tc::tma_load_2d(b0 + j * BOX_BYTES + q * 2048, &maps.aux, mybar, j * BOXC, m0a);
+        }
+      };
+      if (RES && tile_at(sc, 0, mt, nt)) {
+        if (tc::elect_one_sync()) issue_in(mt);
+        __syncwarp();
+      }
+      uint32_t inphase = 0;
+      for (int it = 0; tile_at(sc, it, mt, nt); ++it) {
+        const int m0 = mt * BM, m = m0 + r;
+        const float rs = (RES && g.row_scale) ? g.row_scale[(m < g.M ? m : g.M - 1) / g.rows_per_sample] : 1.0f;
+        tc::mbar_wait(tfull + buf, tphase);
+        tc::fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+        if (RES && m0 + q * 32 < g.M) {
+          tc::mbar_wait(mybar, inphase);
+          inphase ^= 1u;
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < MYBOX; ++jj) {
+          const int j = jgrp + jj * EPI_GROUPS;
+          float v[32];
+          tc::tmem_ld32(taddr + j * BOXC, v);
+          if (g.bias) add_bias32(g.bias, j * BOXC, v);
+          if (RES) {
+            float a[32];
+            load_box_row(b0 + j * BOX_BYTES, r, a);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = a[i] + rs * v[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[i] = bf16_round(v[i]); s += v[i]; }
+          store_box_row(b0 + j * BOX_BYTES, r, v);
+        }
+        tc::fence_before_sync();                             // accumulator consumed
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty + buf);
+        float2* const red0 = red + (0 * 4 + q) * (EPI_GROUPS * 32);
+        float2* const red1 = red + (1 * 4 + q) * (EPI_GROUPS * 32);
+        red0[jgrp * 32 + lane].x = s;
+        tc::named_bar_sync(1 + q, 32 * EPI_GROUPS);
+        const float mean = ((red0[lane].x + red0[32 + lane].x) + red0[64 + lane].x) * invC;
+        float sq = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < MYBOX; ++jj) {
+          float v[32];
+          load_box_row(b0 + (jgrp + jj * EPI_GROUPS) * BOX_BYTES, r, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sq = fmaf(v[i] - mean, v[i] - mean, sq);
+        }
+        red1[jgrp * 32 + lane].x = sq;
+        tc::named_bar_sync(1 + q, 32 * EPI_GROUPS);
+        const float rstd = rsqrtf(((red1[lane].x + red1[32 + lane].x) + red1[64 + lane].x) * invC + g.ln_eps);
+#pragma unroll
+        for (int jj = 0; jj < MYBOX; ++jj) {
+          const int j = jgrp + jj * EPI_GROUPS;
+          float v[32];
+          load_box_row(b0 + j * BOX_BYTES, r, v);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 w = *reinterpret_cast<const float4*>(g.ln_w + j * BOXC + 4 * q4);
+            const float4 b = *reinterpret_cast<const float4*>(g.ln_b + j * BOXC + 4 * q4);
+            v[4 * q4] = (v[4 * q4] - mean) * rstd * w.x + b.x;
+            v[4 * q4 + 1] = (v[4 * q4 + 1] - mean) * rstd * w.y + b.y;
+            v[4 * q4 + 2] = (v[4 * q4 + 2] - mean) * rstd * w.z + b.z;
+            v[4 * q4 + 3] = (v[4 * q4 + 3] - mean) * rstd * w.w + b.w;
+          }
+          store_box_row(b1 + j * BOX_BYTES, r, v);
+        }
+        if (jgrp == 0 && m < g.M) *reinterpret_cast<float2*>(g.ln_ystats + 2 * (long)m) = make_float2(mean, rstd);
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (tc::elect_one_sync()) {
+          if (m0 + q * 32 < g.M) {
+#pragma unroll
+            for (int jj = 0; jj < MYBOX; ++jj) {
+              const int j = jgrp + jj * EPI_GROUPS;
+              tc::tma_store_2d(&maps.out, b0 + j * BOX_BYTES + q * 2048, j * BOXC, m0 + q * 32);
+              tc::tma_store_2d(&maps.out2, b1 + j * BOX_BYTES + q * 2048, j * BOXC, m0 + q * 32);
+            }
+          }
+          tc::tma_store_commit();
+          int mt2, nt2;
+          if (tile_at(sc, it + 1, mt2, nt2)) {               // the slices are free once the stores have read them
+            tc::tma_store_wait_read<0>();
+            issue_in(mt2);
+          }
+        }
+        __syncwarp();
+        if (++buf == NBUF) { buf = 0; tphase ^= 1; }
+      }
+      if (tc::elect_one_sync()) tc::tma_store_wait<0>();
     } else {
     if (CF::HAS_AUX && tile_at(sc, 0, mt, nt)) {
       if (tc::elect_one_sync()) issue_aux(mt, nt, 0);
@@ -808,9 +923,9 @@ Sched choose_tiling(const GemmArgs& g, int epi, const Segments& sg, int* bn_out)
   const bool head = (epi == EPI_HEAD || epi == EPI_HEAD_BWD);
   int bn = (!head && epi != EPI_DGELU2 && g.N % 192 == 0 && (long)ceil_div(g.M, BM) * (g.N / 192) >= tulip_num_sms()) ? 192 : 96;
   if (epi == EPI_GELU && g.out2 != nullptr) bn = 96;
-  if (epi == EPI_LNBWD) bn = g.N;                         // one tile holds whole rows
+  if (epi == EPI_LNBWD || epi_ln_fwd(epi)) bn = g.N;      // one tile holds whole rows
   Sched sc = make_sched(bn, epi, g, sg);
-  if (bn == 192 && !sc.panel && epi != EPI_GELU && epi != EPI_LNBWD) {
+  if (bn == 192 && !sc.panel && epi != EPI_GELU && epi != EPI_LNBWD && !epi_ln_fwd(epi)) {
     const Sched s96 = make_sched(96, epi, g, sg);
     if (s96.panel) { bn = 96; sc = s96; }
   }
@@ -853,6 +968,15 @@ bool gemm_nt_lnbwd_supported(int M, int N, int K) {
   static int off = -1;
   if (off < 0) {
     const char* e = getenv("TULIP_B200_NO_FUSED_LNBWD");
+    off = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !off && !tc05_disabled() && !gemm_forced_mma() && M > 0 && (N == 96 || N == 192) && K % 8 == 0;
+}
+
+bool gemm_nt_lnfwd_supported(int M, int N, int K) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("TULIP_B200_NO_FUSED_LNFWD");
     off = (e && e[0] == '1') ? 1 : 0;
   }
   return !off && !tc05_disabled() && !gemm_forced_mma() && M > 0 && (N == 96 || N == 192) && K % 8 == 0;
@@ -901,6 +1025,11 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     if (!gemm_nt_lnbwd_supported(g.M, g.N, g.K) || g.a_mode != A_PLAIN || g.K1 < g.K) return TULIP_ERR_UNSUPPORTED;
     TULIP_REQUIRE(g.aux && g.ln_w && g.ln_stats && g.ln_dw && g.ln_db && (!g.out2 || g.row_scale),
                   "gemm_nt EPI_LNBWD: needs the LayerNorm input rows, gamma, row statistics and the two gradient accumulators");
+  }
+  if (epi_ln_fwd(epi)) {
+    if (!gemm_nt_lnfwd_supported(g.M, g.N, g.K) || g.a_mode != A_PLAIN) return TULIP_ERR_UNSUPPORTED;
+    TULIP_REQUIRE(g.ln_w && g.ln_b && g.ln_y && g.ln_ystats && (epi == EPI_STORE_LN || g.aux),
+                  "gemm_nt EPI_STORE_LN / EPI_RESID_LN: needs gamma, beta, the LayerNorm output and its statistics rows");
   }
   int bn = 96;                                            // chosen with the schedule once the K segments are known
 
@@ -974,7 +1103,12 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
       rc = make_io_map(&maps.out2, g.out2, g.ldo2, g.M, g.N, 32);
       if (rc) return rc;
     }
-    if (epi_has_aux(epi)) {
+    if (epi_ln_fwd(epi)) {
+      if (reinterpret_cast<uintptr_t>(g.ln_y) & 15) return TULIP_ERR_UNSUPPORTED;
+      rc = make_io_map(&maps.out2, g.ln_y, g.N, g.M, g.N, 32);
+      if (rc) return rc;
+    }
+    if (epi_has_aux(epi) && epi != EPI_STORE_LN) {
       if (!g.aux || (reinterpret_cast<uintptr_t>(g.aux) & 15) || (g.ldaux % 8)) return TULIP_ERR_UNSUPPORTED;
       rc = make_io_map(&maps.aux, g.aux, g.ldaux, g.M, g.N, 32);
       if (rc) return rc;
@@ -996,6 +1130,8 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     case EPI_DGELU2: return launch<96, EPI_DGELU2>(maps, g, sg, sc, st);     // two accumulators x two buffers: BN = 96 only
     case EPI_ROWSCALE: return launch_bn<EPI_ROWSCALE>(bn, maps, g, sg, sc, st);
     case EPI_LNBWD: return launch_bn<EPI_LNBWD>(bn, maps, g, sg, sc, st);
+    case EPI_STORE_LN: return launch_bn<EPI_STORE_LN>(bn, maps, g, sg, sc, st);
+    case EPI_RESID_LN: return launch_bn<EPI_RESID_LN>(bn, maps, g, sg, sc, st);
     case EPI_HEAD: return launch<96, EPI_HEAD>(maps, g, sg, sc, st);
     case EPI_HEAD_BWD:
       return g.hd_E == 96 ? launch<96, EPI_HEAD_BWD>(maps, g, sg, sc, st) : launch<96, EPI_HEAD_BWD, 1>(maps, g, sg, sc, st);

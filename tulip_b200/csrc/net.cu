@@ -748,12 +748,15 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       sum_to(c.G(wslot), scr, 0, C, 2 * C);
       sum_to(c.G(bslot), scr, C, C, 2 * C);
     }
-    tag(K_LN_BWD, 0, (dres ? 8.0 : 6.0) * rows * C + 8.0 * rows + (a.dxs ? 2.0 * rows * C : 0.0));
     return a;
+  };
+  auto tag_ln_bwd = [&](const LnArgs& a) {
+    tag(K_LN_BWD, 0, (a.dres ? 8.0 : 6.0) * a.rows * a.C + 8.0 * a.rows + (a.dxs ? 2.0 * a.rows * a.C : 0.0));
   };
 #define LN_BWD(...)                               \
   do {                                            \
     const LnArgs la__ = ln_bwd_args(__VA_ARGS__); \
+    tag_ln_bwd(la__);                             \
     RUN(layernorm_bwd(la__, st));                 \
   } while (0)
   // dX GEMM whose output rows are dL/dy of a LayerNorm: where a tile holds whole rows (C = 96 / 192) the LayerNorm backward
@@ -771,6 +774,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       RUN_NT((g), EPI_LNBWD);                                                     \
     } else {                                                                      \
       RUN_NT((g), EPI_STORE);                                                     \
+      tag_ln_bwd(la__);                                                           \
       RUN(layernorm_bwd(la__, st));                                               \
     }                                                                             \
   } while (0)
