@@ -339,7 +339,6 @@ def run_ours(args, rank, world, local_rank):
     lo_d, hi_d = lo_pin.to(dev), hi_pin.to(dev)
 
     def local_step(lo, hi):
-        model.zero_grad(set_to_none=True)
         _, loss, _ = model(lo, hi)
         loss.backward()
         return loss
@@ -348,6 +347,9 @@ def run_ours(args, rank, world, local_rank):
         loss = local_step(lo, hi)
         if world > 1:
             allreduce_gradients(model)       # the one exchange step of the path: a single flat NCCL all-reduce
+        # gradients are dropped where the reference loop calls optimizer.zero_grad(): at the end of the iteration
+        # (engine_upsampling.py:97-98), i.e. while the GPU still runs this step, not between the loss read and the next forward
+        model.zero_grad(set_to_none=True)
         return loss
 
     def barrier():

@@ -145,6 +145,9 @@ typedef struct tulip_gemm_desc {
    * row_scale[sample] * out */
   const void* aux2; int64_t ldaux2;
   const float* ln_w; const float* ln_stats; float* ln_dw; float* ln_db;
+  /* epilogues 11 / 12 (= 0 / 2 on whole rows, N = 96 or 192, plus the LayerNorm that reads the output next): ln_w = gamma,
+   * ln_b = beta, ln_y [M, N] bf16 = LayerNorm(out), ln_ystats [M, 2] = (mean, rstd) */
+  const float* ln_b; void* ln_y; float* ln_ystats; float ln_eps;
 } tulip_gemm_desc;
 int tulip_gemm_nt_ex(const tulip_gemm_desc* d, int epilogue, void* stream);
 /* dW[N,K] += dY^T . [X | X2]; rows written un-permuted when perm_R2 > 1 (row n' = ij*Cc + c -> c*R2 + ij); y_mode 1 gathers

@@ -195,3 +195,43 @@ def test_gemm_layernorm_backward_epilogue(M, C, K, res, scaled):
     if scaled:
         rows = torch.arange(M, device="cuda") // rps
         assert torch.equal(dxs, bf(scale[rows][:, None] * dx.float()))
+
+
+@pytest.mark.parametrize("M,C,K,resid", [
+    (1000, 96, 192, False),                 # skip-Linear shape of stage 0 (ragged last tile)
+    (128 * 200 + 5, 96, 96, True),          # proj + residual, several tiles per CTA
+    (777, 192, 768, True),                  # fc2 + residual of stage 1: two boxes per warp
+    (4096, 192, 384, False),                # PatchMerging reduction feeding stage 1
+])
+def test_gemm_layernorm_forward_epilogue(M, C, K, resid):
+    """EPI_STORE_LN / EPI_RESID_LN (gemm.cuh): the Linear (+ residual + DropPath scale) and the LayerNorm that reads its output
+    (tulip.py:338,348: norm1 / norm2 of the next half-block) in one launch.  out must equal the plain epilogue's result bit for
+    bit; ln_y / statistics are checked against fp32 torch LayerNorm of that (bf16) output: one rounding, 1e-3."""
+    from tulip_b200 import ops
+    gen = torch.Generator(device="cpu").manual_seed(M + C + K)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=gen) * scale)
+    A, W = bf(rnd(M, K).cuda()), bf(rnd(C, K, scale=K ** -0.5).cuda())
+    bias = rnd(C, scale=0.1).cuda().contiguous()
+    gamma, beta = (1.0 + 0.2 * rnd(C)).cuda().contiguous(), (0.1 * rnd(C)).cuda().contiguous()
+    aux = bf((rnd(M, C, scale=2.0) + 0.5).cuda()) if resid else None
+    rps = 50
+    scale = (torch.rand((M + rps - 1) // rps, generator=gen) + 0.5).cuda().contiguous() if resid else None
+    eps = 1e-5
+    base = dict(A=A, lda=K, K1=K, B=W, ldb=K, M=M, N=C, K=K, bias=bias, ldo=C)
+    if resid:
+        base.update(aux=aux, ldaux=C, row_scale=scale, rows_per_sample=rps)
+    ref = torch.empty((M, C), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_nt_ex(ops.EPI_RESID if resid else ops.EPI_STORE, out=ref, **base)
+    out = torch.full((M, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    y = torch.full((M, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    stats = torch.full((M, 2), float("nan"), dtype=torch.float32, device="cuda")
+    ops.gemm_nt_ex(ops.EPI_RESID_LN if resid else ops.EPI_STORE_LN, out=out, ln_w=gamma, ln_b=beta, ln_y=y, ln_ystats=stats, ln_eps=eps,
+                   **base)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    xf = out.float()
+    want = torch.nn.functional.layer_norm(xf, (C,), gamma, beta, eps)
+    assert rel_l2(y.float(), bf16r(want)) <= 1e-3
+    mean, var = xf.mean(-1), xf.var(-1, unbiased=False)
+    assert torch.allclose(stats[:, 0], mean, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(stats[:, 1], torch.rsqrt(var + eps), rtol=1e-4, atol=0)

@@ -36,7 +36,8 @@ class GemmDesc(C.Structure):                     # tulip_gemm_desc (include/tuli
                 ("wd", C.c_void_p), ("target", C.c_void_p), ("pred", C.c_void_p), ("gscale", C.c_void_p), ("dwd", C.c_void_p),
                 ("hd_H", C.c_int), ("hd_W", C.c_int), ("hd_r", C.c_int), ("hd_E", C.c_int),
                 ("aux2", C.c_void_p), ("ldaux2", C.c_int64),
-                ("ln_w", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_dw", C.c_void_p), ("ln_db", C.c_void_p)]
+                ("ln_w", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_dw", C.c_void_p), ("ln_db", C.c_void_p),
+                ("ln_b", C.c_void_p), ("ln_y", C.c_void_p), ("ln_ystats", C.c_void_p), ("ln_eps", C.c_float)]
 
 
 class GemmTNDesc(C.Structure):                   # tulip_gemm_tn_desc

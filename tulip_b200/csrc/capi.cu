@@ -324,7 +324,7 @@ int tulip_gemm_tn(const void* dY, const void* X, float* dW, float* db, int M, in
 
 int tulip_gemm_nt_ex(const tulip_gemm_desc* d, int epilogue, void* stream) {
   if (!d) { tulip_set_error("tulip_gemm_nt_ex: null descriptor"); return TULIP_ERR_ARG; }
-  if (epilogue < EPI_STORE || epilogue > EPI_LNBWD) { tulip_set_error("tulip_gemm_nt_ex: unknown epilogue"); return TULIP_ERR_ARG; }
+  if (epilogue < EPI_STORE || epilogue > EPI_RESID_LN) { tulip_set_error("tulip_gemm_nt_ex: unknown epilogue"); return TULIP_ERR_ARG; }
   GemmArgs g;
   memset(&g, 0, sizeof g);
   g.A = (const bf16*)d->A; g.lda = d->lda; g.A2 = (const bf16*)d->A2; g.lda2 = d->lda2; g.K1 = d->K1 > 0 ? d->K1 : d->K;
@@ -340,6 +340,7 @@ int tulip_gemm_nt_ex(const tulip_gemm_desc* d, int epilogue, void* stream) {
   if (d->hd_r > 0) g.hd_inv_npix = 1.0f / ((float)d->M * d->hd_r * d->hd_r);
   g.aux2 = (const bf16*)d->aux2; g.ldaux2 = d->ldaux2;
   g.ln_w = d->ln_w; g.ln_stats = d->ln_stats; g.ln_dw = d->ln_dw; g.ln_db = d->ln_db; g.ln_copies = 1;
+  g.ln_b = d->ln_b; g.ln_y = (bf16*)d->ln_y; g.ln_ystats = d->ln_ystats; g.ln_eps = d->ln_eps;
   return gemm_nt(g, epilogue, (cudaStream_t)stream);
 }
 

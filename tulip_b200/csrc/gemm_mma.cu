@@ -322,8 +322,8 @@ int gemm_nt_mma(const GemmArgs& g, int epi, cudaStream_t st) {
     case EPI_HEAD_BWD: return launch_nt<EPI_HEAD_BWD, A_PLAIN>(g, st);
     case EPI_ROWSCALE: return launch_nt<EPI_ROWSCALE, A_PLAIN>(g, st);
   }
-  if (epi == EPI_DGELU2 || epi == EPI_LNBWD) {
-    tulip_set_error("gemm_nt: EPI_DGELU2 / EPI_LNBWD exist on the tcgen05 path only (and EPI_LNBWD for N = 96 or 192)");
+  if (epi == EPI_DGELU2 || epi == EPI_LNBWD || epi == EPI_STORE_LN || epi == EPI_RESID_LN) {
+    tulip_set_error("gemm_nt: EPI_DGELU2 and the fused-LayerNorm epilogues exist on the tcgen05 path only (the latter for N = 96 or 192)");
     return TULIP_ERR_UNSUPPORTED;
   }
   tulip_set_error("gemm_nt: unknown epilogue");

@@ -13,7 +13,7 @@
 enum KTag : int {
   K_MISC = 0, K_NT_STORE, K_NT_GELU, K_NT_RESID, K_NT_PIXSHUF, K_NT_SPLIT2, K_NT_DGELU, K_NT_HEAD, K_NT_HEAD_BWD, K_NT_ROWSCALE,
   K_NT_UNSHUFFLE, K_TN, K_TN_UNSHUFFLE, K_ATTN_FWD, K_ATTN_BWD, K_LN_FWD, K_LN_BWD, K_EMBED_FWD, K_EMBED_BWD, K_PACK,
-  K_ELEMWISE, K_LOSS, K_WMSA_FWD, K_MLP_FWD, K_NT_LNBWD, K_COUNT
+  K_ELEMWISE, K_LOSS, K_WMSA_FWD, K_MLP_FWD, K_NT_LNBWD, K_NT_STORE_LN, K_NT_RESID_LN, K_COUNT
 };
 const char* ktag_name(int tag);
 inline int nt_tag(int epi) {
@@ -22,6 +22,7 @@ inline int nt_tag(int epi) {
     case EPI_PIXSHUF: return K_NT_PIXSHUF; case EPI_SPLIT2: return K_NT_SPLIT2; case EPI_DGELU: return K_NT_DGELU;
     case EPI_HEAD: return K_NT_HEAD; case EPI_HEAD_BWD: return K_NT_HEAD_BWD; case EPI_ROWSCALE: return K_NT_ROWSCALE;
     case EPI_DGELU2: return K_NT_DGELU; case EPI_LNBWD: return K_NT_LNBWD;
+    case EPI_STORE_LN: return K_NT_STORE_LN; case EPI_RESID_LN: return K_NT_RESID_LN;
   }
   return K_MISC;
 }

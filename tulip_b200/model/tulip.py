@@ -622,7 +622,17 @@ class TULIP(nn.Module):
             raise RuntimeError("tulip_b200 runs on CUDA (sm_100a) only: no CPU or PyTorch fallback exists")
         if x.dim() != 4 or tuple(x.shape[1:]) != (self.in_chans, *self.img_size):
             raise ValueError(f"expected input (B, {self.in_chans}, {self.img_size[0]}, {self.img_size[1]}), got {tuple(x.shape)}")
-        self._ensure_flat(x.device)
+        # Training calls launch first and verify after: the scan that proves every nn.Parameter still aliases the flat buffer
+        # (~0.1 ms of host time for 212 parameters) then runs while the GPU already works -- it matters when the loop reads the
+        # loss every step and the GPU idles during host work.  A failed scan (storage swapped by an EMA / assign=True load)
+        # re-packs and launches again; the first launch only wrote scratch buffers.  Forward-only calls keep the scan first:
+        # it also yields the parameter version that lets the executor skip the weight repack.
+        optimistic = (torch.is_grad_enabled() and not mc_drop and self._flat is not None and self._param_list is not None
+                      and self._flat.device == x.device and self._net is not None)
+        if optimistic:
+            self._params_version = -1                            # a training step repacks: its weights have just been updated
+        else:
+            self._ensure_flat(x.device)
         B = x.shape[0]
         x = x.detach().to(torch.float32).contiguous()
         tgt = None
@@ -636,6 +646,10 @@ class TULIP(nn.Module):
         win_mode = self._window_modes()
         self._grad_mode_hint = torch.is_grad_enabled()
         launched = self._launch_forward(x, tgt, drop, win_mode)
+        if optimistic and not self._is_flat(x.device):
+            self._ensure_flat(x.device)
+            self._params_version = -1
+            launched = self._launch_forward(x, tgt, drop, self._window_modes())
         pred, loss, pixel = _TulipFunction.apply(self, launched, tgt is not None, win_mode, *self._param_list)
         if mc_drop:
             return pred
