@@ -163,6 +163,13 @@ typedef struct tulip_gemm_tn_desc {
   int perm_R2, perm_Cc;
 } tulip_gemm_tn_desc;
 int tulip_gemm_tn_ex(const tulip_gemm_tn_desc* d, void* stream);
+/* Up to 4 independent weight gradients (plain operands: no X2, y_mode 0) in ONE persistent launch: the way the executor
+ * issues the weight-gradient GEMMs of a Swin half-block (fc2 + fc1, proj + qkv; autograd of tulip.py:194-200, 282-324).
+ * CTAs walk (problem, dW tile, token range) work items with double-buffered TMEM accumulators.
+ * tulip_gemm_tn_group_plan: host-side cut of the token ranges for `sms` SMs: per4[p] = 64-token blocks per work item of
+ * problem p, *items = work items of the launch (tests, tooling; no GPU needed). */
+int tulip_gemm_tn_group(const tulip_gemm_tn_desc* d, int n, void* stream);
+int tulip_gemm_tn_group_plan(const int* M, const int* N, const int* K, int n, int sms, int* per4, int* items);
 
 /* ---- fused W-MSA / SW-MSA half-block (SURVEY 8b tulip_wmsa_block_fwd): ONE launch for
  *   y = x + row_scale[b] * proj(attn(qkv(LayerNorm(x))))          tulip.py:338-346 with WindowAttention.forward :282-324

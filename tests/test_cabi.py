@@ -154,3 +154,32 @@ def test_gemm_tiling_plan_host_logic():
     out = (C.c_int * 10)()
     assert lib.tulip_gemm_nt_plan(1000, 100, 96, 0, 0, out) != 0                                   # N % 96: not a tcgen05 shape
     assert lib.tulip_gemm_nt_plan(131072, 384, 96, 1, 1, out) == 0 and out[0] == 96              # saved pre-activation: narrow tile
+
+
+def test_tn_group_plan_host_logic():
+    """Work-item cut of the grouped weight-gradient launch (tulip_gemm_tn_group_plan, pure host logic): every token block of
+    every problem is covered exactly once, ranges keep >= 4 blocks where the problem has them, and the round-robin deal over
+    148 SMs is balanced for the half-block groups of BASELINE cfg2 (B = 32)."""
+    from tulip_b200 import ops
+    for T, C in [(131072, 96), (32768, 192), (8192, 384), (2048, 768)]:
+        for shapes in ([(T, C, 4 * C), (T, 4 * C, C)], [(T, C, C), (T, 3 * C, C)]):
+            per, items = ops.gemm_tn_group_plan(shapes, sms=148)
+            loads = [0.0] * 148
+            idx = 0
+            for (M, N, K), pp in zip(shapes, per):
+                tb = -(-M // 64)
+                assert 1 <= pp <= tb and (pp >= 4 or pp == tb)
+                splits = -(-tb // pp)
+                assert (splits - 1) * pp < tb
+                for s_ in range(splits):
+                    ntb = min(tb, (s_ + 1) * pp) - s_ * pp
+                    for nt in range(-(-N // 128)):
+                        for kt in range(-(-K // 192)):
+                            loads[idx % min(items, 148)] += ntb * (2 + -(-min(192, K - kt * 192) // 64))
+                            idx += 1
+            assert idx == items
+            used = [v for v in loads if v > 0]
+            assert len(used) >= 140                                   # no launch of these leaves SMs without work
+            assert max(used) <= 1.25 * (sum(used) / len(used))         # and the longest SM is within 25 % of the mean
+    with pytest.raises(RuntimeError):
+        ops.gemm_tn_group_plan([(0, 96, 96)])

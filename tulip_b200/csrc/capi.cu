@@ -361,6 +361,33 @@ int tulip_gemm_tn_ex(const tulip_gemm_tn_desc* d, void* stream) {
   return gemm_tn(g, (cudaStream_t)stream);
 }
 
+int tulip_gemm_tn_group(const tulip_gemm_tn_desc* d, int n, void* stream) {
+  if (!d || n < 1 || n > TN_GROUP_MAX) { tulip_set_error("tulip_gemm_tn_group: 1..4 descriptors"); return TULIP_ERR_ARG; }
+  GemmTNArgs gs[TN_GROUP_MAX];
+  for (int i = 0; i < n; ++i) {
+    GemmTNArgs& g = gs[i];
+    memset(&g, 0, sizeof g);
+    g.dY = (const bf16*)d[i].dY; g.ldy = d[i].ldy; g.X = (const bf16*)d[i].X; g.ldx = d[i].ldx;
+    g.K1 = d[i].K; g.M = d[i].M; g.N = d[i].N; g.K = d[i].K;
+    g.y_mode = d[i].y_mode;
+    g.dW = d[i].dW; g.lddw = d[i].lddw; g.db = d[i].db;
+    g.perm_R2 = d[i].perm_R2 > 1 ? d[i].perm_R2 : 1; g.perm_Cc = d[i].perm_R2 > 1 ? d[i].perm_Cc : 1;
+    g.splits = 1;
+    if (d[i].X2 || (d[i].K1 > 0 && d[i].K1 < d[i].K) || !gemm_tn_groupable(g)) {
+      tulip_set_error("tulip_gemm_tn_group: plain operands only (no X2, y_mode 0, 16-byte aligned, N % 8 == K % 8 == 0)");
+      return TULIP_ERR_UNSUPPORTED;
+    }
+  }
+  return gemm_tn_group(gs, n, (cudaStream_t)stream);
+}
+
+int tulip_gemm_tn_group_plan(const int* M, const int* N, const int* K, int n, int sms, int* per4, int* items) {
+  if (!M || !N || !K || !per4 || sms < 1) { tulip_set_error("tulip_gemm_tn_group_plan: null argument"); return TULIP_ERR_ARG; }
+  const int rc = gemm_tn_group_plan(M, N, K, n, sms, per4, items);
+  if (rc) tulip_set_error("tulip_gemm_tn_group_plan: 1..4 problems with positive sizes");
+  return rc;
+}
+
 int tulip_wmsa_block_supported(int B, int H, int W, int C, int heads, int Mh, int Mw) {
   return wmsa_block_supported(B, H, W, C, heads, Mh, Mw) ? 1 : 0;
 }

@@ -1176,9 +1176,15 @@ constexpr int TN_BAR_OFF = TN_ONES_OFF + TN_BOX;
 constexpr int TN_SMEM = TN_BAR_OFF + 256 + 1024;
 constexpr int TN_THREADS = 256;
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// dst[0 .. bytes/4) += src[0 .. bytes/4) as ONE bulk reduction (shared -> global, fp32 add performed at L2): a 32-column run
+// of an accumulator row costs one of these instead of eight 16-byte red.global.add (6144 per CTA: the reduction, not the
+// mainloop, was the larger part of a deep-stage launch)
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, int bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+               ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
+constexpr int TN_STG_PITCH = 144;             // per-thread staging run: 32 floats, pitch keeps 16-byte stores conflict-free
+static_assert(TN_THREADS * TN_STG_PITCH <= TN_STAGE_BYTES, "reduction staging aliases ring stage 0");
 
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX,
@@ -1296,15 +1302,21 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
     const int row = (g.perm_R2 > 1) ? (n % g.perm_Cc) * g.perm_R2 + n / g.perm_Cc : n;
     float* drow = g.dW + (long)row * g.lddw + k0;
     const int nchunks = (kvalid + 31) / 32;
+    // every MMA has completed (done barrier): the operand ring is free and stage 0 serves as the reduction staging area
+    unsigned char* const stg = smem + threadIdx.x * TN_STG_PITCH;
     for (int ch = half; ch < nchunks; ch += 2) {
       float v[32];
       tc::tmem_ld32(taddr + ch * 32, v);
       if (row_ok) {
+        tc::tma_store_wait_read<0>();                         // this thread's previous run has left its staging slot
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          if (ch * 32 + i < kvalid) red_add_v4(drow + ch * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(stg + 4 * i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        tc::fence_proxy_async();
+        bulk_reduce_add_f32(drow + ch * 32, stg, 4 * min(32, kvalid - ch * 32));
+        tc::tma_store_commit();
       }
     }
+    tc::tma_store_wait<0>();
     if (with_db && half == 1) {
       float v[16];
       tc::tmem_ld16(taddr + 64 * nbx, v);

@@ -66,6 +66,27 @@ cudaEvent_t tulip_net::next_sync_event() {
   return sync_pool[sync_used++];
 }
 
+// problems per grouped weight-gradient launch (TULIP_B200_TN_GROUP_MAX = 1: every problem goes out where it is registered)
+static int tn_group_limit() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TULIP_B200_TN_GROUP_MAX");
+    v = (e && atoi(e) >= 1 && atoi(e) <= TN_GROUP_MAX) ? atoi(e) : TN_GROUP_MAX;
+  }
+  return v;
+}
+
+// MEASUREMENT ONLY (TULIP_B200_DEBUG_SKIP_TN=1): the weight-gradient GEMMs are not launched, so the step that remains is the
+// dX chain alone -- the difference to the real step is what the weight gradients cost after overlap.  Gradients are wrong.
+static bool debug_skip_tn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TULIP_B200_DEBUG_SKIP_TN");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static bool side_stream_disabled() {
   static int v = -1;
   if (v < 0) {
@@ -724,15 +745,65 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     cudaEventRecord(e, st);
     cudaStreamWaitEvent(side, e, 0);
   };
+  // Weight-gradient GEMMs with plain operands are collected and issued together (gemm_tn_group: one persistent launch for
+  // the two of a half-block); flush_tn() sends what has been collected, ordered after everything issued on `st` so far.
+  // A deferred launch reads its operands later than the point it was registered at: callers flush before any kernel that
+  // overwrites them is issued.
+  std::vector<GemmTNArgs> tn_pending;
+  int tn_rc = TULIP_OK;                                   // first error of a deferred launch (checked by TN_FLUSH / at the end)
+  auto flush_tn_impl = [&]() -> int {
+    if (tn_pending.empty()) return TULIP_OK;
+    std::vector<GemmTNArgs> batch;
+    batch.swap(tn_pending);
+    if (!live) return TULIP_OK;
+    const int nb = (int)batch.size();
+    if (!use_side) {
+      double fl = 0.0, by = 0.0;
+      for (const GemmTNArgs& g_ : batch) {
+        fl += 2.0 * g_.M * g_.N * g_.K;
+        by += 2.0 * ((double)g_.M * g_.N + (double)g_.M * g_.K) + 4.0 * g_.N * g_.K;
+      }
+      tag(K_TN, fl, by);
+      RUN(gemm_tn_group(batch.data(), nb, st));
+      return TULIP_OK;
+    }
+    fork();
+    const int rc_ = gemm_tn_group(batch.data(), nb, side);
+    if (rc_ != TULIP_OK) return rc_;
+    ++kernel_launches;
+    side_pending = true;
+    return TULIP_OK;
+  };
+  auto flush_tn = [&]() {
+    const int rc_ = flush_tn_impl();
+    if (rc_ != TULIP_OK && tn_rc == TULIP_OK) tn_rc = rc_;
+  };
   auto join = [&]() {                                     // `st` waits for everything issued on the side stream so far
+    flush_tn();
     if (!side_pending) return;
     cudaEvent_t e = next_sync_event();
     cudaEventRecord(e, side);
     cudaStreamWaitEvent(st, e, 0);
     side_pending = false;
   };
+  // marker on the side stream after what has been issued there so far; wait_side(e) orders `st` after it (and nothing later)
+  auto side_marker = [&]() -> cudaEvent_t {
+    if (!live || !use_side || !side_pending) return nullptr;
+    cudaEvent_t e = next_sync_event();
+    cudaEventRecord(e, side);
+    return e;
+  };
+  auto wait_side = [&](cudaEvent_t e) { if (e && live) cudaStreamWaitEvent(st, e, 0); };
   auto run_tn = [&](const GemmTNArgs& gw) -> int {        // one weight-gradient GEMM, on the side stream when enabled
-    if (!live) return TULIP_OK;
+    if (!live || debug_skip_tn()) return TULIP_OK;
+    if (gemm_tn_groupable(gw)) {
+      if ((int)tn_pending.size() == TN_GROUP_MAX) flush_tn();
+      tn_pending.push_back(gw);
+      if ((int)tn_pending.size() >= tn_group_limit()) flush_tn();
+      return tn_rc;
+    }
+    flush_tn();
+    if (tn_rc != TULIP_OK) return tn_rc;
     if (!use_side) { RUN_TN(gw); return TULIP_OK; }
     fork();
     const int rc_ = gemm_tn(gw, side);
@@ -741,6 +812,11 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     side_pending = true;
     return TULIP_OK;
   };
+#define TN_FLUSH()                                  \
+  do {                                              \
+    flush_tn();                                     \
+    if (tn_rc != TULIP_OK) return tn_rc;            \
+  } while (0)
 #define TN_SIDE(g)                      \
   do {                                  \
     const int rc__ = run_tn(g);         \
@@ -778,6 +854,8 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   };
   // phase boundary: what the finished phase produced is complete on `st` (side stream joined, copies folded)
   auto enter_phase = [&](int ph) -> int {
+    flush_tn();
+    if (tn_rc != TULIP_OK) return tn_rc;
     if (live) {
       if (side_pending) { cudaEvent_t e = next_sync_event(); cudaEventRecord(e, side); cudaStreamWaitEvent(st, e, 0); side_pending = false; }
       const int rc_ = flush_sums();
@@ -873,6 +951,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     // dWe' += dh^T . xn_up (rows un-permuted on store); bias gradient = column sums of dh, same un-permutation
     GemmTNArgs gw = dw(l, dh, c.A(p.xn_up), T0);
     TN_SIDE(gw);
+    TN_FLUSH();
     // dxn_up = dh . We'          (A = dh [T0, E r^2], B = We'^T stored as Wt' [E, E r^2])
     GemmArgs gx = nt_args(dh, (long)E * r * r, c.Wt(l), (long)E * r * r, T0, E, E * r * r, nullptr, c.A(p.scr_dxn), E);
     want_scaled_for(dec_blocks[L - 2].back(), H0 * W0);
@@ -898,6 +977,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       gy = c.A(p.scr_gsm);
     }
     gsM_ready = false;
+    cudaEvent_t mlp_dw_done = nullptr;
     {
       const Linear& l2 = linears[b.fc2];
       const Linear& lf1 = linears[b.fc1];
@@ -914,6 +994,8 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       }
       const Linear& l1 = linears[b.fc1];
       TN_SIDE(dw(l1, c.A(p.scr_big), c.A(bb.xn2), T));
+      TN_FLUSH();                                         // fc2 + fc1 weight gradients: one launch beside the LayerNorm-backward GEMM
+      mlp_dw_done = side_marker();
       GemmArgs g1 = nt_args(c.A(p.scr_big), 4 * C, c.Wt(l1), 4 * C, T, C, 4 * C, nullptr, c.A(p.scr_dxn), C);
       if (ds1) { ln_dxs = c.A(p.scr_gs); ln_scale = ds1; ln_rps = Hs * Ws; }     // scaled copy for the attention branch
       GEMM_LN_BWD(g1, c.A(bb.xmid), b.n2w, b.n2b, c.F(bb.st2), c.A(p.scr_dxn), g_io, g_tmp, T, C, 0, 0, 0);   // g_tmp = dL/dx_mid
@@ -937,8 +1019,9 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       tag(K_ATTN_BWD, 160.0 * T * C, 16.0 * T * C);
       RUN(win_attn_bwd(a, st));
       const Linear& lq = linears[b.qkv];
-      join();                                             // the LayerNorm backward below overwrites g_io / the scaled copies
-      TN_SIDE(dw(lq, c.A(p.scr_dqkv), c.A(bb.xn1), T));   // reads neither: runs beside it
+      TN_SIDE(dw(lq, c.A(p.scr_dqkv), c.A(bb.xn1), T));
+      TN_FLUSH();                                         // proj + qkv weight gradients: one launch, reads neither buffer written below
+      wait_side(mlp_dw_done);                             // the LayerNorm backward below overwrites g_io / the scaled copies (fc2's dY)
       GemmArgs gq = nt_args(c.A(p.scr_dqkv), 3 * C, c.Wt(lq), 3 * C, T, C, 3 * C, nullptr, c.A(p.scr_dxn), C);
       want_scaled_for(bi_next, Hs * Ws);                  // next block in backward order lives on the same grid
       GEMM_LN_BWD(gq, x_in, b.n1w, b.n1b, c.F(bb.st1), c.A(p.scr_dxn), g_tmp, g_io, T, C, 0, 0, 0);            // g_io = dL/dx_in
@@ -1013,6 +1096,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       const bf16* x_stage_out = c.A(p.blocks[enc_blocks[s].back()].xout);
       join();
       TN_SIDE(dw(l, g_cur, c.A(p.xn_m[s]), T / 4));
+      TN_FLUSH();
       GemmArgs g = nt_args(g_cur, 2 * C, c.Wt(l), 2 * C, T / 4, 4 * C, 2 * C, nullptr, c.A(p.scr_big), 4 * C);
       RUN_NT(g, EPI_STORE);
       want_scaled_for(enc_blocks[s].back(), (Hs / 2) * (Ws / 2));       // rows here are merged (2x2) tokens
@@ -1048,6 +1132,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     RUN(patch_embed_bwd(e, st));
   }
   TULIP_REQUIRE(!gscr_overflow, "tulip_b200: gradient-copy scratch exhausted (grad_scratch_bytes() out of step with backward())");
+  TN_FLUSH();
   join();                                                 // the gradient fill and every weight-gradient GEMM precede the fold
   if (live) {
     rc = flush_sums();
@@ -1056,6 +1141,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
   join();                                                 // every gradient is complete on `st` when backward returns
   live = true;
 #undef TN_SIDE
+#undef TN_FLUSH
 #undef LN_BWD
 #undef GEMM_LN_BWD
   return TULIP_OK;

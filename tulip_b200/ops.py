@@ -33,6 +33,26 @@ def gemm_tn_ex(**fields):
     check(load_library().tulip_gemm_tn_ex(_C.byref(d), current_stream()), "tulip_gemm_tn_ex")
 
 
+def gemm_tn_group(problems):
+    """tulip_gemm_tn_group: up to 4 weight gradients dW_p += dY_p^T X_p (db_p += colsum dY_p) in one persistent launch.
+    problems: list of dicts with the tulip_gemm_tn_desc fields (tensors for the pointers)."""
+    arr = (GemmTNDesc * len(problems))()
+    for d, fields in zip(arr, problems):
+        for k, v in fields.items():
+            setattr(d, k, ptr(v) if isinstance(v, torch.Tensor) else v)
+    check(load_library().tulip_gemm_tn_group(arr, len(problems), current_stream()), "tulip_gemm_tn_group")
+
+
+def gemm_tn_group_plan(shapes, sms=148):
+    """Host-side work-item cut of a grouped launch: shapes = [(M, N, K), ...] -> (64-token blocks per item, items)."""
+    n = len(shapes)
+    I = _C.c_int * n
+    per, items = (_C.c_int * 4)(), _C.c_int(0)
+    check(load_library().tulip_gemm_tn_group_plan(I(*[s[0] for s in shapes]), I(*[s[1] for s in shapes]), I(*[s[2] for s in shapes]),
+                                                  n, sms, per, _C.byref(items)), "tulip_gemm_tn_group_plan")
+    return list(per)[:n], items.value
+
+
 def permute_rows_for_shuffle(w, R2, Cc):
     """Row order the PixelShuffle-feeding GEMMs use: destination row n' = ij*Cc + c holds source row c*R2 + ij."""
     return w.reshape(Cc, R2, *w.shape[1:]).transpose(0, 1).reshape(w.shape).contiguous()
