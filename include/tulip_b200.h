@@ -112,9 +112,13 @@ int tulip_net_backward_phases(tulip_net* net, int batch, const float* params, co
 int tulip_gemm_nt(const void* A, const void* W, const float* bias, void* out, void* out2, const void* aux,
                   const float* row_scale, int rows_per_sample, int M, int N, int K, int epilogue, int impl, void* stream);
 /* host-side tiling decision of tulip_gemm_nt for (M, N, K, epilogue) on the tcgen05 path -- no device work:
- * out10 = {tile width BN, resident-weight schedule (0/1), n_chunks, tiles per chunk, workers, A ring stages, K blocks,
+ * out10 = {tile width BN, schedule (0 tile-major, 1 resident-weight panels, 2 CTA pairs = cta_group::2 on 256-row tiles), n_chunks, tiles per chunk, workers, A ring stages, K blocks,
  *          MMA steps in the last K block, grid size, operand ring stages} */
 int tulip_gemm_nt_plan(int M, int N, int K, int epilogue, int save_pre, int* out10);
+/* CTA-pair schedule of the NT GEMM (cta_group::2: two CTAs of a cluster run one M = 256 MMA, each loads its own A rows and
+ * half of the B rows).  mode 0 = off (default: measured slower at this model's sizes), 1 = every eligible launch, 2 = launches
+ * with K >= 384; anything else only queries.  Returns the previous mode (-1: not decided yet, env TULIP_B200_CG2 or 0). */
+int tulip_gemm_nt_pairs_mode(int mode);
 int tulip_gemm_tn(const void* dY, const void* X, float* dW, float* db, int M, int N, int K, int impl, void* stream);
 
 /* The same two contractions with every operand mode and fused epilogue of the path spelled out (per-kernel parity tests of

@@ -132,7 +132,8 @@ def test_gemm_tiling_plan_host_logic():
     from tulip_b200._lib import load_library
     lib = load_library()
     keys = ("bn", "panel", "n_chunks", "npc", "nworkers", "nsa", "kb", "klast", "grid", "stages")
-    seen_panel = 0
+    seen_panel = seen_pairs = 0
+    prev_pairs = lib.tulip_gemm_nt_pairs_mode(2)               # the CTA-pair schedule is opt-in: plan it for K >= 384 here
     for tokens0, in ((32 * 16 * 256,), (16 * 32 * 512,)):
         for s in range(4):
             T, Cc = tokens0 >> (2 * s), 96 << s
@@ -143,7 +144,10 @@ def test_gemm_tiling_plan_host_logic():
                 assert p["bn"] in (96, 192) and N % p["bn"] == 0
                 assert p["kb"] == -(-K // 64) and 1 <= p["klast"] <= 4 and 16 * (p["klast"] - 1) < K - 64 * (p["kb"] - 1) <= 16 * p["klast"]
                 assert 1 <= p["grid"] <= 148 and 2 <= p["stages"] <= 8
-                if p["panel"]:
+                if p["panel"] == 2:                                                                # CTA pairs: deep K, whole pairs
+                    seen_pairs += 1
+                    assert K >= 384 and p["grid"] % 2 == 0 and epi in (0, 1, 2)
+                if p["panel"] == 1:
                     seen_panel += 1
                     assert p["n_chunks"] * p["npc"] * p["bn"] == N and p["grid"] == p["n_chunks"] * p["nworkers"]
                     assert p["nsa"] >= (p["kb"] + 1 if p["npc"] > 1 else 3) and p["nsa"] <= 8
@@ -151,6 +155,10 @@ def test_gemm_tiling_plan_host_logic():
                     assert p["npc"] * p["kb"] * p["bn"] * 128 + p["nsa"] * 128 * 64 * 2 <= area      # resident B + A ring fit the ring area
                     assert -(-T // 128) >= 4 * p["nworkers"]                                       # enough row panels per worker
     assert seen_panel >= 8                                                                         # the wide stages do use it
+    assert seen_pairs >= 4                                                                         # the deep-K GEMMs of stages 2-3 run as pairs
+    lib.tulip_gemm_nt_pairs_mode(max(prev_pairs, 0))
+    out = (C.c_int * 10)()
+    assert lib.tulip_gemm_nt_plan(2048, 768, 3072, 2, 0, out) == 0 and out[1] == (2 if prev_pairs > 0 else 0)   # default: no pairs
     out = (C.c_int * 10)()
     assert lib.tulip_gemm_nt_plan(1000, 100, 96, 0, 0, out) != 0                                   # N % 96: not a tcgen05 shape
     assert lib.tulip_gemm_nt_plan(131072, 384, 96, 1, 1, out) == 0 and out[0] == 96              # saved pre-activation: narrow tile
@@ -158,8 +166,9 @@ def test_gemm_tiling_plan_host_logic():
 
 def test_tn_group_plan_host_logic():
     """Work-item cut of the grouped weight-gradient launch (tulip_gemm_tn_group_plan, pure host logic): every token block of
-    every problem is covered exactly once, ranges keep >= 4 blocks where the problem has them, and the round-robin deal over
-    148 SMs is balanced for the half-block groups of BASELINE cfg2 (B = 32)."""
+    every problem is covered exactly once, ranges keep >= 4 blocks where the problem has them, and a round-robin deal over
+    148 SMs (the kernel hands items out dynamically; this is the planner's model) is balanced for the half-block groups of
+    BASELINE cfg2 (B = 32)."""
     from tulip_b200 import ops
     for T, C in [(131072, 96), (32768, 192), (8192, 384), (2048, 768)]:
         for shapes in ([(T, C, 4 * C), (T, 4 * C, C)], [(T, C, C), (T, 3 * C, C)]):
@@ -179,7 +188,7 @@ def test_tn_group_plan_host_logic():
                             idx += 1
             assert idx == items
             used = [v for v in loads if v > 0]
-            assert len(used) >= 140                                   # no launch of these leaves SMs without work
-            assert max(used) <= 1.25 * (sum(used) / len(used))         # and the longest SM is within 25 % of the mean
+            assert len(used) >= 100                                   # one wave may be smaller than the chip (an item pays a fixed
+            assert max(used) <= 1.25 * (sum(used) / len(used))         # cost), but the longest SM stays within 25 % of the mean
     with pytest.raises(RuntimeError):
         ops.gemm_tn_group_plan([(0, 96, 96)])

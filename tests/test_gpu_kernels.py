@@ -222,3 +222,46 @@ def test_l1_loss(ops):
     loss, pixel = ops.l1_loss(pred.cuda(), y.cuda(), True)
     assert abs(loss.item() - (pred - y).abs().mean().item()) <= 1e-6
     assert abs(pixel.item() - (torch.expm1(pred) - torch.expm1(y)).abs().mean().item()) <= 2e-6
+
+
+@pytest.mark.parametrize("M,N,K,epi", [
+    (8192, 384, 1536, "resid"),      # fc2, stage 2: BN = 96 pairs
+    (2048, 3072, 768, "gelu"),       # fc1, stage 3: BN = 192 pairs
+    (2048, 2304, 768, "store"),      # qkv, stage 3
+    (2048, 768, 3072, "resid"),      # fc2, stage 3: 48 K blocks per tile
+    (1152, 768, 768, "store"),       # 9 row tiles: the last pair has a phantom tile
+    (300, 192, 1536, "resid"),       # ragged rows inside the last real tile
+    (32768, 192, 768, "store"),      # dX of fc1, stage 1
+])
+def test_gemm_nt_cta_pairs(ops, M, N, K, epi):
+    """Deep-K launches run as CTA pairs (cta_group::2, schedule 2 of tulip_gemm_nt_plan): same tolerances as every
+    single-rounding GEMM epilogue, and the plan says pairs were used."""
+    import ctypes as C
+    code = {"store": ops.EPI_STORE, "gelu": ops.EPI_GELU, "resid": ops.EPI_RESID}[epi]
+    out = (C.c_int * 10)()
+    lib = ops.load_library()
+    prev = lib.tulip_gemm_nt_pairs_mode(1)                     # opt-in schedule (tulip_b200.h): switched on for this test only
+    try:
+        assert lib.tulip_gemm_nt_plan(M, N, K, code, 0, out) == 0 and out[1] == 2
+        _run_pairs_case(ops, M, N, K, epi)
+    finally:
+        lib.tulip_gemm_nt_pairs_mode(max(prev, 0))
+
+
+def _run_pairs_case(ops, M, N, K, epi):
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    pre = F.linear(x, w, b)
+    if epi == "store":
+        want = pre
+        got = ops.linear(x.cuda(), w.cuda(), b.cuda(), impl=2)
+    elif epi == "gelu":
+        want = F.gelu(pre)
+        got, _ = ops.linear(x.cuda(), w.cuda(), b.cuda(), epilogue=ops.EPI_GELU, impl=2, save_pre=False)
+    else:
+        res, rows_per = rnd(M, N, seed=4), 4
+        scale = torch.rand(-(-M // rows_per), generator=torch.Generator().manual_seed(5)) * 2
+        want = res + scale.repeat_interleave(rows_per)[:M, None] * pre
+        got = ops.linear(x.cuda(), w.cuda(), b.cuda(), epilogue=ops.EPI_RESID, aux=res.cuda(), row_scale=scale.cuda(),
+                         rows_per_sample=rows_per, impl=2)
+    got = got.float().cpu()
+    assert rel_l2(got, bf16r(want)) <= 1e-3 and ulp_frac(got, bf16r(want)) >= 0.99

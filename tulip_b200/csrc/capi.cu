@@ -308,6 +308,8 @@ int tulip_gemm_nt_plan(int M, int N, int K, int epilogue, int save_pre, int* out
   return rc;
 }
 
+int tulip_gemm_nt_pairs_mode(int mode) { return gemm_nt_pairs_mode(mode); }
+
 int tulip_gemm_tn(const void* dY, const void* X, float* dW, float* db, int M, int N, int K, int impl, void* stream) {
   GemmTNArgs g;
   memset(&g, 0, sizeof g);

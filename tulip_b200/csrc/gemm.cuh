@@ -74,6 +74,7 @@ int gemm_tn_mma(const GemmTNArgs& g, cudaStream_t st);
 int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st);   // returns TULIP_ERR_UNSUPPORTED for shapes it does not take
 int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st);
 int gemm_nt_tc05_plan(int M, int N, int K, int epi, int save_pre, int* out10);   // host-side tiling decision (tests, tooling)
+int gemm_nt_pairs_mode(int mode);                                // CTA-pair schedule: 0 off, 1 every eligible launch, 2 K >= 384; returns the previous mode
 int gemm_nt(const GemmArgs& g, int epi, cudaStream_t st);        // dispatch (env TULIP_B200_GEMM=mma forces the legacy path)
 int gemm_tn(const GemmTNArgs& g, cudaStream_t st);
 // Several independent weight gradients in ONE persistent launch (gemm_tn_group.cu).  Problems must be "plain" (no concat, no

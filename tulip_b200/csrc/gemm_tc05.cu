@@ -55,8 +55,17 @@ struct Sched {
   int klast;         // 16-column MMA steps in the last K block (1..4)
   int nsa;           // A ring stages (panel mode)
   int bres_bytes;    // resident B region (panel mode), the A ring follows it
+  int cg;            // 2: CTA pairs (cta_group::2) -- pair p walks 256-row x BN tiles, CTA rank r owns rows 128 r .. 128 r + 127
 };
 __device__ __forceinline__ bool tile_at(const Sched& sc, int it, int& mt, int& nt) {
+  if (sc.cg == 2) {
+    const int pt = (int)(blockIdx.x >> 1) + it * (int)(gridDim.x >> 1);
+    if (pt >= ((sc.tiles_m + 1) >> 1) * sc.tiles_n) return false;
+    const int mg = pt / sc.tiles_n;
+    nt = pt - mg * sc.tiles_n;
+    mt = 2 * mg + (int)(blockIdx.x & 1);                     // an odd tile count leaves one phantom tile: loaded as zeros, never stored
+    return true;
+  }
   if (!sc.panel) {
     const int tile = blockIdx.x + it * gridDim.x;
     if (tile >= sc.tiles_m * sc.tiles_n) return false;
@@ -188,7 +197,9 @@ __device__ __forceinline__ void epi_direct16(const GemmArgs& g, int m, int n, fl
 }
 
 // VAR = 1: head backward with two 96-channel groups (hd_E = 192): a second set of d(decoder_pred.weight) accumulators
-template <int BN, int EPI, int VAR = 0>
+// CG = 2: CTA pairs (tc05.cuh): tile-major schedule only; the even CTA issues M = 256 MMAs for both, each CTA loads its own A
+// rows and half of the B rows, so the deep-K GEMMs of stages 2-3 pull A + B/2 per K block over their SM's L2 port.
+template <int BN, int EPI, int VAR = 0, int CG = 1>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmArgs g, const __grid_constant__ Segments sg,
                     const __grid_constant__ Sched sc) {
@@ -209,18 +220,25 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxbar + 2 * EPI_WARPS);
 
   const int warp = tc::warp_idx_sync(), lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? (blockIdx.x & 1u) : 0u;   // cluster dims (2,1,1): rank in the pair
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSA_MAX; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
     tc::mbar_init(bfull, 1);
     for (int b = 0; b < 3; ++b) {                             // HEAD: one epilogue group (4 warps) drains a buffer
-      tc::mbar_init(tfull + b, 1); tc::mbar_init(tempty + b, EPI == EPI_HEAD ? 4 : EPI_WARPS);
+      tc::mbar_init(tfull + b, 1); tc::mbar_init(tempty + b, EPI == EPI_HEAD ? 4 : CG * EPI_WARPS);   // pairs: both CTAs' warps
     }
     for (int b = 0; b < 2 * EPI_WARPS; ++b) tc::mbar_init(auxbar + b, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
-  tc::fence_before_sync();
-  __syncthreads();
+  if (CG == 2) {
+    if (warp == 1) tc::tmem_alloc_cg2<TMEM_COLS>(tmem_slot);
+    tc::fence_before_sync();
+    tc::cluster_sync_all();                                   // the peer's barriers exist before anything arrives on them
+  } else {
+    if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc::fence_before_sync();
+    __syncthreads();
+  }
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                                               // set-up above overlapped the previous kernel's tail
@@ -311,6 +329,16 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         const int nb = (sg.len[s] + BK - 1) / BK;
         for (int kb = 0; kb < nb; ++kb) {
           tc::mbar_wait(empty + stage, phase ^ 1);
+          if (CG == 2) {
+            // both CTAs load (own A rows, own half of the B rows); the bytes of both are counted on the leader's barrier
+            if (tc::elect_one_sync()) {
+              unsigned char* a = smem + stage * CF::STAGE_BYTES;
+              unsigned char* b = a + CF::A_BYTES;
+              if (rank == 0) tc::mbar_expect_tx(full + stage, 2 * CF::A_BYTES + CF::B_BYTES);
+              tc::tma_load_2d_cg2(a, sg.amap[s] ? &maps.A2 : &maps.A, full + stage, kb * BK, m0);
+              tc::tma_load_2d_cg2(b, sg.bmap[s] ? &maps.B2 : &maps.B, full + stage, sg.bcol[s] + kb * BK, n0 + (int)rank * (BN / 2));
+            }
+          } else
           if (tc::elect_one_sync()) {
             unsigned char* a = smem + stage * CF::STAGE_BYTES;
             unsigned char* b = a + CF::A_BYTES;
@@ -328,9 +356,11 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         }
       }
     }
+  } else if (warp == 1 && CG == 2 && rank != 0) {
+    // the peer CTA of a pair issues nothing: its operands are read and its accumulator rows written by the leader's MMAs
   } else if (warp == 1) {
     // MMA issuer: same scheme; descriptors stay in uniform registers
-    constexpr uint32_t idesc = tc::make_idesc(BM, BN, 0, 0);
+    constexpr uint32_t idesc = tc::make_idesc(CG * BM, BN, 0, 0);
     constexpr uint32_t S16 = CF::STAGE_BYTES >> 4, A16 = CF::A_BYTES >> 4;
     const uint64_t d0 = tc::make_desc_kmajor_sw128(smem);
     uint64_t da = d0;                                       // A descriptor of `stage`; its B block follows A16 further
@@ -351,16 +381,21 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
           tc::fence_after_sync();
           if (tc::elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)               // +32 bytes per K=16 step inside the 128B swizzle atom
-              tc::umma_bf16(tmem_acc, da + 2 * k, da + A16 + 2 * k, idesc, (k > 0) ? 1u : ((started >> ac) & 1u));
-            tc::umma_commit(empty + stage);                 // smem slot free once these MMAs have read it
+            for (int k = 0; k < BK / 16; ++k) {             // +32 bytes per K=16 step inside the 128B swizzle atom
+              if (CG == 2) tc::umma_bf16_cg2(tmem_acc, da + 2 * k, da + A16 + 2 * k, idesc, (k > 0) ? 1u : ((started >> ac) & 1u));
+              else tc::umma_bf16(tmem_acc, da + 2 * k, da + A16 + 2 * k, idesc, (k > 0) ? 1u : ((started >> ac) & 1u));
+            }
+            if (CG == 2) tc::umma_commit_cg2(empty + stage);  // the slot is free in BOTH CTAs once these MMAs have read it
+            else tc::umma_commit(empty + stage);            // smem slot free once these MMAs have read it
           }
           __syncwarp();
           started |= 1u << ac;
           if (++stage == STAGES) { stage = 0; phase ^= 1; da = d0; } else { da += S16; }
         }
       }
-      if (tc::elect_one_sync()) tc::umma_commit(tfull + buf);   // accumulator complete
+      if (tc::elect_one_sync()) {                           // accumulator complete (pairs: in both CTAs)
+        if (CG == 2) tc::umma_commit_cg2(tfull + buf); else tc::umma_commit(tfull + buf);
+      }
       __syncwarp();
       if (++buf == NBUF) { buf = 0; tphase ^= 1; }
     }
@@ -518,7 +553,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         tc::fence_before_sync();
         tc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(tempty + buf);
+        if (lane == 0) { if (CG == 2) tc::mbar_arrive_cluster(tempty + buf, 0); else tc::mbar_arrive(tempty + buf); }
         if (tc::elect_one_sync()) {
           if (m0 + q * 32 < g.M) {
 #pragma unroll
@@ -603,7 +638,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         }
         tc::fence_before_sync();                             // accumulator consumed
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(tempty + buf);
+        if (lane == 0) { if (CG == 2) tc::mbar_arrive_cluster(tempty + buf, 0); else tc::mbar_arrive(tempty + buf); }
         float2* const red0 = red + (0 * 4 + q) * (EPI_GROUPS * 32);
         float2* const red1 = red + (1 * 4 + q) * (EPI_GROUPS * 32);
         red0[jgrp * 32 + lane].x = s;
@@ -783,7 +818,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         tc::fence_before_sync();
         tc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(tempty + buf);
+        if (lane == 0) { if (CG == 2) tc::mbar_arrive_cluster(tempty + buf, 0); else tc::mbar_arrive(tempty + buf); }
         if (tc::elect_one_sync()) {
           if (m0 + q * 32 < g.M) {                            // rows past M are clipped by the tensor map; skip all-out boxes
 #pragma unroll
@@ -816,7 +851,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         }
         tc::fence_before_sync();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(tempty + buf);
+        if (lane == 0) { if (CG == 2) tc::mbar_arrive_cluster(tempty + buf, 0); else tc::mbar_arrive(tempty + buf); }
         if (m < g.M) {
           float* p = g.pred + head_pixel(g, m, ij);
           if (g.hd_E == BN) *p = acc; else atomicAdd(p, acc);
@@ -835,7 +870,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         }
         tc::fence_before_sync();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(tempty + buf);
+        if (lane == 0) { if (CG == 2) tc::mbar_arrive_cluster(tempty + buf, 0); else tc::mbar_arrive(tempty + buf); }
       }
       if (++buf == NBUF) { buf = 0; tphase ^= 1; }
     }
@@ -865,8 +900,13 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
     }
   }
   tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (CG == 2) {
+    tc::cluster_sync_all();                                 // neither CTA of a pair retires while the other may still signal it
+    if (warp == 1) tc::tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
+  } else {
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
 }
 
 bool tc05_disabled() {
@@ -933,6 +973,25 @@ Sched choose_tiling(const GemmArgs& g, int epi, const Segments& sg, int* bn_out)
   return sc;
 }
 
+// CTA pairs (cta_group::2) for the tile-major launches with a deep K: the pair cuts the bytes an SM pulls per K block from
+// A + B to A + B/2.  MEASURED (scripts/time_nt.py, graph replay, B = 32): every eligible launch of the step is 0.1-1.0 us
+// SLOWER as a pair (fc1 stage 3: 13.1 -> 14.1 us, fc2 stage 2: 11.9 -> 12.0 us) -- at M <= 8192 rows these launches last
+// 5-18 us and are paced by fill / drain and the cluster hand-shakes, not by operand bytes -- so pairs are OFF by default.
+// TULIP_B200_CG2=2 enables them for K >= 384, =1 for every eligible launch (parity tests run them this way).
+int g_pairs_mode = -1;
+bool pairs_wanted(const GemmArgs& g, int epi, const Segments& sg, const Sched& sc, int bn) {
+  int& mode = g_pairs_mode;
+  if (mode < 0) {
+    const char* e = getenv("TULIP_B200_CG2");
+    mode = e ? atoi(e) : 0;
+  }
+  if (mode == 0 || sc.panel || sg.a5d || sg.n != 1) return false;
+  if (epi != EPI_STORE && epi != EPI_GELU && epi != EPI_RESID) return false;
+  if (epi == EPI_GELU && g.out2 != nullptr) return false;
+  if (sc.tiles_m < 2 || (bn != 96 && bn != 192)) return false;
+  return mode == 1 || g.K >= 384;
+}
+
 template <int BN, int EPI, int VAR = 0>
 int launch(const Maps& maps, const GemmArgs& g, const Segments& sg, const Sched& sc, cudaStream_t st) {
   using CF = Cfg<BN, EPI>;
@@ -947,8 +1006,41 @@ int launch(const Maps& maps, const GemmArgs& g, const Segments& sg, const Sched&
   return TULIP_OK;
 }
 
+// CTA-pair launch: clusters of two CTAs (one TPC), one pair per 256-row x BN tile in flight
+template <int BN, int EPI>
+int launch_pairs(const Maps& maps, const GemmArgs& g, const Segments& sg, const Sched& sc, cudaStream_t st) {
+  using CF = Cfg<BN, EPI>;
+  auto kern = gemm_nt_tc05_kernel<BN, EPI, 0, 2>;
+  static bool configured = false;
+  if (!configured) {
+    TULIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::TOTAL));
+    configured = true;
+  }
+  const int pair_tiles = ((sc.tiles_m + 1) / 2) * sc.tiles_n;
+  const int pairs = min(pair_tiles, tulip_num_sms() / 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = CF::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tulip_pdl_enabled() ? 2 : 1;
+  (void)cudaLaunchKernelEx(&cfg, kern, maps, g, sg, sc);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
 template <int EPI>
 int launch_bn(int bn, const Maps& maps, const GemmArgs& g, const Segments& sg, const Sched& sc, cudaStream_t st) {
+  if (sc.cg == 2) {
+    if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_RESID) {
+      if (bn == 192) return launch_pairs<192, EPI>(maps, g, sg, sc, st);
+      return launch_pairs<96, EPI>(maps, g, sg, sc, st);
+    }
+    return TULIP_ERR_UNSUPPORTED;
+  }
   if (bn == 192) return launch<192, EPI>(maps, g, sg, sc, st);
   return launch<96, EPI>(maps, g, sg, sc, st);
 }
@@ -1068,11 +1160,12 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
       sg.n = 2; sg.len[1] = g.K - K1; sg.amap[1] = 1; sg.bcol[1] = K1;
     }
   }
-  const Sched sc = choose_tiling(g, epi, sg, &bn);
+  Sched sc = choose_tiling(g, epi, sg, &bn);
+  sc.cg = pairs_wanted(g, epi, sg, sc, bn) ? 2 : 1;
   {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
     const uint64_t str[1] = {(uint64_t)g.ldb * 2};
-    const uint32_t box[2] = {64, (uint32_t)bn};
+    const uint32_t box[2] = {64, (uint32_t)(sc.cg == 2 ? bn / 2 : bn)};   // pairs: each CTA loads half of the B rows
     rc = tulip_make_tmap(&maps.B, g.B, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -1140,9 +1233,15 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
 }
 
 
+int gemm_nt_pairs_mode(int mode) {
+  const int prev = g_pairs_mode;
+  if (mode >= 0 && mode <= 2) g_pairs_mode = mode;
+  return prev;
+}
+
 int gemm_nt_tc05_plan(int M, int N, int K, int epi, int save_pre, int* out) {
   // host-side tiling decision for a plain (single-segment) launch, for tests and tooling:
-  // out = {bn, panel, n_chunks, npc, nworkers, nsa, kb, klast, grid, stages}
+  // out = {bn, schedule (0 tile-major, 1 B-stationary panels, 2 CTA pairs), n_chunks, npc, nworkers, nsa, kb, klast, grid, stages}
   GemmArgs g;
   memset(&g, 0, sizeof g);
   g.M = M; g.N = N; g.K = K; g.K1 = K;
@@ -1153,6 +1252,12 @@ int gemm_nt_tc05_plan(int M, int N, int K, int epi, int save_pre, int* out) {
   sg.n = 1; sg.len[0] = K;
   int bn = 96;
   const Sched sc = choose_tiling(g, epi, sg, &bn);
+  if (pairs_wanted(g, epi, sg, sc, bn)) {                  // schedule 2: CTA pairs on 256-row tiles
+    out[0] = bn; out[1] = 2; out[2] = 1; out[3] = sc.tiles_n; out[4] = 1; out[5] = 0; out[6] = sc.kb; out[7] = sc.klast;
+    out[8] = 2 * min(((sc.tiles_m + 1) / 2) * sc.tiles_n, tulip_num_sms() / 2);
+    out[9] = cfg_stages(bn, epi);
+    return TULIP_OK;
+  }
   out[0] = bn; out[1] = sc.panel; out[2] = sc.n_chunks; out[3] = sc.npc; out[4] = sc.nworkers; out[5] = sc.nsa; out[6] = sc.kb;
   out[7] = sc.klast; out[8] = sc.panel ? sc.n_chunks * sc.nworkers : min(sc.tiles_m * sc.tiles_n, tulip_num_sms());
   out[9] = cfg_stages(bn, epi);
