@@ -108,7 +108,9 @@ int tulip_net_backward_phases(tulip_net* net, int batch, const float* params, co
  * NT: out[M,N] = A[M,K] . W[N,K]^T (+bias) -- every nn.Linear / 1x1 Conv2d on the path
  *     (tulip.py:298 qkv, :318 proj, :195/:198 fc1/fc2, :105 reduction, :119 expand, :716 skip, :175 conv_expand)
  * epilogue: 0 store, 1 bias+GELU (out2 = pre-activation), 2 residual: out = aux + row_scale*(acc+bias)
- * TN: dW[N,K] += dY[M,N]^T . X[M,K]; db[N] += colsum(dY)   (autograd of the above) */
+ * TN: dW[N,K] += dY[M,N]^T . X[M,K]; db[N] += colsum(dY)   (autograd of the above)
+ * impl: 0 (2 is accepted as an alias).  There is ONE implementation, the tcgen05 / TMEM / TMA GEMM; N % 96 == 0, K % 8 == 0 and
+ * 16-byte aligned operands are required and anything else is an error (round 1's warp-MMA backend, impl 1, was removed). */
 int tulip_gemm_nt(const void* A, const void* W, const float* bias, void* out, void* out2, const void* aux,
                   const float* row_scale, int rows_per_sample, int M, int N, int K, int epilogue, int impl, void* stream);
 /* host-side tiling decision of tulip_gemm_nt for (M, N, K, epilogue) on the tcgen05 path -- no device work:

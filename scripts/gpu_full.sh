@@ -1,14 +1,16 @@
 #!/bin/bash
 # the driver's GPU gate in one process (python -m pytest tests -m gpu), smoke(), then the bench step; logs under gpurun_out/
 mkdir -p gpurun_out
+if [ -z "$SKIP_TESTS" ]; then
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -n 15 > gpurun_out/gputest_full.log
 echo "== pytest -m gpu: $(tail -n 1 gpurun_out/gputest_full.log)"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "== smoke rc=$? $(tail -n 2 gpurun_out/smoke.log)"
-B="python bench.py --steps ${STEPS:-60} --warmup 5 --no-cpu-baseline --no-eager-baseline --no-sustained"
+fi
+B="python bench.py --config ${CONFIG:-kitti32} --steps ${STEPS:-60} --warmup 5 --no-cpu-baseline --no-eager-baseline --no-sustained"
 for v in ${VARIANTS:-"X=1"}; do
   name="$(echo $v | tr '= ,' '___')"
-  env $(echo $v | tr ',' ' ') timeout 300 $B > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
-  python - "$name" <<'P'
+  env $(echo $v | tr ',' ' ') timeout 300 $B > gpurun_out/bench_${CONFIG:-kitti32}_$name.json 2> gpurun_out/bench_${CONFIG:-kitti32}_$name.err
+  python - "${CONFIG:-kitti32}_$name" <<'P'
 import json, sys
 n = sys.argv[1]
 try:

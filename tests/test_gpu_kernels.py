@@ -37,7 +37,7 @@ def rnd(*shape, seed=0, scale=1.0):
     return bf16r(torch.randn(*shape, generator=gen) * scale)
 
 
-IMPLS = [1, 0]      # 1 = legacy warp-MMA kernels, 0 = dispatcher (tcgen05 where the shape qualifies)
+IMPLS = [0]         # one GEMM implementation (tcgen05); the warp-MMA backend of round 1 is gone
 
 
 @pytest.mark.parametrize("impl", IMPLS)

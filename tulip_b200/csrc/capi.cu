@@ -34,31 +34,20 @@ bool tulip_pdl_enabled() {
   return v == 1;
 }
 
-static int gemm_impl_env() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TULIP_B200_GEMM");
-    v = (e && strcmp(e, "mma") == 0) ? 1 : 0;
-  }
-  return v;
-}
-
-bool gemm_forced_mma() { return gemm_impl_env() != 0; }
-
+// One GEMM implementation (tcgen05, gemm_tc05.cu).  A shape it does not take is an error for the caller, never a detour
+// through another kernel: every N on the TULIP path is a multiple of 96, every K a multiple of 8, operands 16-byte aligned.
 int gemm_nt(const GemmArgs& g, int epi, cudaStream_t st) {
-  if (!gemm_impl_env()) {
-    const int rc = gemm_nt_tc05(g, epi, st);
-    if (rc != TULIP_ERR_UNSUPPORTED) return rc;
-  }
-  return gemm_nt_mma(g, epi, st);
+  const int rc = gemm_nt_tc05(g, epi, st);
+  if (rc == TULIP_ERR_UNSUPPORTED)
+    tulip_set_error("gemm_nt: shape / operand layout not handled by the tcgen05 GEMM (N % 96, K % 8, 16-byte alignment, epilogue limits)");
+  return rc;
 }
 
 int gemm_tn(const GemmTNArgs& g, cudaStream_t st) {
-  if (!gemm_impl_env()) {
-    const int rc = gemm_tn_tc05(g, st);
-    if (rc != TULIP_ERR_UNSUPPORTED) return rc;
-  }
-  return gemm_tn_mma(g, st);
+  const int rc = gemm_tn_tc05(g, st);
+  if (rc == TULIP_ERR_UNSUPPORTED)
+    tulip_set_error("gemm_tn: shape / operand layout not handled by the tcgen05 GEMM (N % 8, K % 8, 16-byte alignment, gather geometry)");
+  return rc;
 }
 
 static bool graphs_enabled() {
@@ -296,8 +285,7 @@ int tulip_gemm_nt(const void* A, const void* W, const float* bias, void* out, vo
     tulip_set_error("tulip_gemm_nt: epilogue must be 0 (store), 1 (gelu), 2 (residual) or 5 (dgelu)");
     return TULIP_ERR_ARG;
   }
-  if (impl == 1) return gemm_nt_mma(g, epilogue, (cudaStream_t)stream);
-  if (impl == 2) return gemm_nt_tc05(g, epilogue, (cudaStream_t)stream);
+  if (impl != 0 && impl != 2) { tulip_set_error("tulip_gemm_nt: impl must be 0 (the warp-MMA backend, impl 1, was removed)"); return TULIP_ERR_ARG; }
   return gemm_nt(g, epilogue, (cudaStream_t)stream);
 }
 
@@ -319,8 +307,7 @@ int tulip_gemm_tn(const void* dY, const void* X, float* dW, float* db, int M, in
   int splits = tiles > 0 ? (2 * tulip_num_sms() + tiles - 1) / tiles : 1;
   const int max_splits = (M + 255) / 256;
   g.splits = splits > max_splits ? max_splits : (splits < 1 ? 1 : splits);
-  if (impl == 1) return gemm_tn_mma(g, (cudaStream_t)stream);
-  if (impl == 2) return gemm_tn_tc05(g, (cudaStream_t)stream);
+  if (impl != 0 && impl != 2) { tulip_set_error("tulip_gemm_tn: impl must be 0 (the warp-MMA backend, impl 1, was removed)"); return TULIP_ERR_ARG; }
   return gemm_tn(g, (cudaStream_t)stream);
 }
 

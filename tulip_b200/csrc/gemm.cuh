@@ -1,5 +1,4 @@
-// GEMM argument blocks + epilogue math shared by the tcgen05 (gemm_tc05.cu) and the
-// legacy warp-MMA (gemm_mma.cu) implementations.
+// GEMM argument blocks + epilogue math of the tcgen05 GEMMs (gemm_tc05.cu, gemm_tn_group.cu).
 //
 //   NT : out[M,N]  = A[M,K] . B[N,K]^T  (+bias, epilogue)      forward linears, dX = dY . Wt^T
 //   TN : dW[N,K]  += dY[M,N]^T . X[M,K], db[N] += colsum(dY)   weight gradients (split over M, fp32 atomics)
@@ -69,13 +68,11 @@ struct GemmTNArgs {
   int splits;
 };
 
-int gemm_nt_mma(const GemmArgs& g, int epi, cudaStream_t st);
-int gemm_tn_mma(const GemmTNArgs& g, cudaStream_t st);
 int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st);   // returns TULIP_ERR_UNSUPPORTED for shapes it does not take
 int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st);
 int gemm_nt_tc05_plan(int M, int N, int K, int epi, int save_pre, int* out10);   // host-side tiling decision (tests, tooling)
 int gemm_nt_pairs_mode(int mode);                                // CTA-pair schedule: 0 off, 1 every eligible launch, 2 K >= 384; returns the previous mode
-int gemm_nt(const GemmArgs& g, int epi, cudaStream_t st);        // dispatch (env TULIP_B200_GEMM=mma forces the legacy path)
+int gemm_nt(const GemmArgs& g, int epi, cudaStream_t st);        // the tcgen05 GEMM; an unsupported shape is an error (no second backend)
 int gemm_tn(const GemmTNArgs& g, cudaStream_t st);
 // Several independent weight gradients in ONE persistent launch (gemm_tn_group.cu).  Problems must be "plain" (no concat, no
 // PixelShuffle gather): gemm_tn_groupable() says so; per_out / items_out of the plan are for tests and tooling.
@@ -83,7 +80,6 @@ constexpr int TN_GROUP_MAX = 4;
 bool gemm_tn_groupable(const GemmTNArgs& g);
 int gemm_tn_group(const GemmTNArgs* gs, int n, cudaStream_t st);
 int gemm_tn_group_plan(const int* M, const int* N, const int* K, int n, int sms, int* per_out, int* items_out);
-bool gemm_forced_mma();                                          // env TULIP_B200_GEMM=mma
 bool gemm_nt_lnbwd_supported(int M, int N, int K);               // EPI_LNBWD takes this shape (else: EPI_STORE + layernorm_bwd)
 bool gemm_nt_lnfwd_supported(int M, int N, int K);               // EPI_STORE_LN / EPI_RESID_LN take this shape
 

@@ -909,15 +909,6 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
   }
 }
 
-bool tc05_disabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TULIP_B200_NO_TC05");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
 bool panel_disabled() {
   static int v = -1;
   if (v < 0) {
@@ -1062,7 +1053,7 @@ bool gemm_nt_lnbwd_supported(int M, int N, int K) {
     const char* e = getenv("TULIP_B200_NO_FUSED_LNBWD");
     off = (e && e[0] == '1') ? 1 : 0;
   }
-  return !off && !tc05_disabled() && !gemm_forced_mma() && M > 0 && (N == 96 || N == 192) && K % 8 == 0;
+  return !off && M > 0 && (N == 96 || N == 192) && K % 8 == 0;
 }
 
 bool gemm_nt_lnfwd_supported(int M, int N, int K) {
@@ -1071,7 +1062,7 @@ bool gemm_nt_lnfwd_supported(int M, int N, int K) {
     const char* e = getenv("TULIP_B200_NO_FUSED_LNFWD");
     off = (e && e[0] == '1') ? 1 : 0;
   }
-  return !off && !tc05_disabled() && !gemm_forced_mma() && M > 0 && (N == 96 || N == 192) && K % 8 == 0;
+  return !off && M > 0 && (N == 96 || N == 192) && K % 8 == 0;
 }
 
 tulip_tmap_encode_fn tulip_tmap_encoder() {
@@ -1107,7 +1098,6 @@ int tulip_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t
 }
 
 int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
-  if (tc05_disabled()) return TULIP_ERR_UNSUPPORTED;
   if (g.N % 96 || g.K % 8 || g.M <= 0) return TULIP_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15) || (g.lda % 8) || (g.ldb % 8))
     return TULIP_ERR_UNSUPPORTED;
@@ -1436,7 +1426,6 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
 }  // namespace
 
 int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st) {
-  if (tc05_disabled()) return TULIP_ERR_UNSUPPORTED;
   if (g.M <= 0) return TULIP_ERR_UNSUPPORTED;
   if (g.N % 8 || g.K % 8 || (g.ldy % 8) || (g.ldx % 8) || (g.lddw % 4) || (g.K % 4)) return TULIP_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(g.dY) & 15) || (reinterpret_cast<uintptr_t>(g.X) & 15) || (reinterpret_cast<uintptr_t>(g.dW) & 15))

@@ -239,9 +239,7 @@ bool group_disabled() {
 }  // namespace
 
 bool gemm_tn_groupable(const GemmTNArgs& g) {
-  if (group_disabled() || gemm_forced_mma()) return false;
-  const char* e = getenv("TULIP_B200_NO_TC05");
-  if (e && e[0] == '1') return false;
+  if (group_disabled()) return false;
   if (g.y_mode != A_PLAIN || g.K1 < g.K || g.M <= 0) return false;
   if (g.N % 8 || g.K % 8 || (g.ldy % 8) || (g.ldx % 8) || (g.lddw % 4) || (g.K % 4)) return false;
   if ((reinterpret_cast<uintptr_t>(g.dY) & 15) || (reinterpret_cast<uintptr_t>(g.X) & 15) || (reinterpret_cast<uintptr_t>(g.dW) & 15))

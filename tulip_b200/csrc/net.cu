@@ -253,7 +253,7 @@ int tulip_net::ensure_device() {
 
 Plan tulip_net::plan(int B) const {
   Plan p;
-  const bool save_pre = gemm_forced_mma();     // the legacy GEMM path keeps the saved-pre-activation GELU backward
+  const bool save_pre = false;                 // the GELU pre-activation is recomputed in the backward pass (EPI_DGELU2), never stored
   Bump bump;
   const long E = cfg.embed_dim;
   const long T0 = (long)B * H0 * W0;

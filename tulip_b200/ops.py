@@ -12,7 +12,7 @@ import ctypes as _C
 
 from ._lib import GemmDesc, GemmTNDesc, check, current_stream, load_library, ptr
 
-GEMM_AUTO, GEMM_MMA, GEMM_TC05 = 0, 1, 2
+GEMM_AUTO, GEMM_TC05 = 0, 2      # one implementation (tcgen05); 2 is kept as an alias of 0
 EPI_STORE, EPI_GELU, EPI_RESID, EPI_PIXSHUF, EPI_SPLIT2, EPI_DGELU, EPI_HEAD, EPI_HEAD_BWD, EPI_ROWSCALE, EPI_DGELU2, EPI_LNBWD, EPI_STORE_LN, EPI_RESID_LN = range(13)
 A_PLAIN, A_UNSHUFFLE = 0, 1
 
