@@ -39,6 +39,12 @@ typedef struct tulip_config {
   int mlp_ratio;              /* 4                                               */
   float ln_eps;               /* 1e-6, tulip.py:744                              */
   int log_transform;          /* second loss term in expm1 space, tulip.py:695-696 */
+  int patch_expanding;        /* 0: PatchUnmerging (--patch_unmerging, every shipped script); 1: PatchExpanding = Linear(C, 2C,
+                                 no bias) + '(P1 P2 C)' rearrange + LayerNorm(C/2) in the decoder and as first_patch_expanding
+                                 (patch_unmerging=False, tulip.py:126-141, 472, 565) */
+  int expanding_head;         /* 0: PixelShuffleHead (--pixel_shuffle); 1: FinalPatchExpanding = Linear(E, r^2 E, no bias) + '(P1 P2 C)'
+                                 rearrange + LayerNorm(E) per output pixel (pixel_shuffle=False, tulip.py:144-159, 582, 727-729);
+                                 embed_dim 96 only */
 } tulip_config;
 
 typedef struct tulip_net tulip_net;
@@ -154,6 +160,10 @@ typedef struct tulip_gemm_desc {
   /* epilogues 11 / 12 (= 0 / 2 on whole rows, N = 96 or 192, plus the LayerNorm that reads the output next): ln_w = gamma,
    * ln_b = beta, ln_y [M, N] bf16 = LayerNorm(out), ln_ystats [M, 2] = (mean, rstd) */
   const float* ln_b; void* ln_y; float* ln_ystats; float ln_eps;
+  /* epilogues 6 / 7 in their FinalPatchExpanding form (tulip.py:144-159; hd_E = 96, no bias): pred[pixel] = sum_c wd[c] *
+   * LayerNorm(acc row; ln_w, ln_b, ln_eps)[c]; 6 writes (mean, rstd) per pixel to ln_ystats [pixels, 2]; 7 reads them from
+   * ln_stats, out = d(acc) (bf16), ln_dw / ln_db / dwd += d(gamma) / d(beta) / d(decoder_pred.weight) */
+  int hd_ln;
 } tulip_gemm_desc;
 int tulip_gemm_nt_ex(const tulip_gemm_desc* d, int epilogue, void* stream);
 /* dW[N,K] += dY^T . [X | X2]; rows written un-permuted when perm_R2 > 1 (row n' = ij*Cc + c -> c*R2 + ij); y_mode 1 gathers

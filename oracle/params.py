@@ -35,6 +35,8 @@ class Cfg:
     drop_path_rate: float = 0.1
     log_transform: bool = True
     ln_eps: float = 1e-6
+    patch_unmerging: bool = True      # False: PatchExpanding (Linear + rearrange + LayerNorm, tulip.py:126-141) in the decoder
+    pixel_shuffle: bool = True        # False: FinalPatchExpanding head (tulip.py:144-159) instead of PixelShuffleHead
 
     @property
     def num_layers(self) -> int:
@@ -89,12 +91,21 @@ def param_shapes(cfg: Cfg) -> "OrderedDict[str, tuple]":
         C = E * 2 ** s
         for b in range(cfg.depths[s]):
             out += _block_shapes(f"layers_up.{u}.blocks.{b}", C, cfg.num_heads[s], cfg.window_size, cfg.mlp_ratio)
-        if u < Ls - 2:                                    # PatchUnmerging, tulip.py:109-115
+        if u < Ls - 2 and cfg.patch_unmerging:            # PatchUnmerging, tulip.py:109-115
             out += [(f"layers_up.{u}.upsample.expand.weight", (2 * C, C, 1, 1)),
                     (f"layers_up.{u}.upsample.expand.bias", (2 * C,))]
+        elif u < Ls - 2:                                  # PatchExpanding, tulip.py:126-132
+            out += [(f"layers_up.{u}.upsample.expand.weight", (2 * C, C)),
+                    (f"layers_up.{u}.upsample.norm.weight", (C // 2,)),
+                    (f"layers_up.{u}.upsample.norm.bias", (C // 2,))]
     Ctop = E * 2 ** (Ls - 1)
-    out += [("first_patch_expanding.expand.weight", (2 * Ctop, Ctop, 1, 1)),
-            ("first_patch_expanding.expand.bias", (2 * Ctop,))]
+    if cfg.patch_unmerging:
+        out += [("first_patch_expanding.expand.weight", (2 * Ctop, Ctop, 1, 1)),
+                ("first_patch_expanding.expand.bias", (2 * Ctop,))]
+    else:                                                 # tulip.py:565
+        out += [("first_patch_expanding.expand.weight", (2 * Ctop, Ctop)),
+                ("first_patch_expanding.norm.weight", (Ctop // 2,)),
+                ("first_patch_expanding.norm.bias", (Ctop // 2,))]
     for u in range(Ls - 1):                               # skip Linear(2C->C), tulip.py:682-688
         C = E * 2 ** (Ls - 2 - u)
         out += [(f"skip_connection_layers.{u}.weight", (C, 2 * C)),
@@ -105,8 +116,13 @@ def param_shapes(cfg: Cfg) -> "OrderedDict[str, tuple]":
             ("patch_embed.norm.weight", (E,)), ("patch_embed.norm.bias", (E,))]
     out += [("decoder_pred.weight", (cfg.in_chans, E, 1, 1))]
     r2 = cfg.upscale_factor ** 2
-    out += [("ps_head.conv_expand.0.weight", (E * r2, E, 1, 1)),
-            ("ps_head.conv_expand.0.bias", (E * r2,))]
+    if cfg.pixel_shuffle:
+        out += [("ps_head.conv_expand.0.weight", (E * r2, E, 1, 1)),
+                ("ps_head.conv_expand.0.bias", (E * r2,))]
+    else:                                                 # FinalPatchExpanding, tulip.py:144-150, 582
+        out += [("final_patch_expanding.expand.weight", (E * r2, E)),
+                ("final_patch_expanding.norm.weight", (E,)),
+                ("final_patch_expanding.norm.bias", (E,))]
     return OrderedDict(out)
 
 

@@ -157,6 +157,28 @@ def patch_unmerging(x, p, prefix):
     return y.reshape(B, 2 * H, 2 * W, C // 2)
 
 
+def patch_expanding(x, p, prefix, cfg):
+    """Linear(C -> 2C, no bias) -> 'B H W (P1 P2 C) -> B (H P1) (W P2) C' with P1 = P2 = 2 -> LayerNorm(C/2).
+    tulip.py:126-141.  out[b,2h+i,2w+j,:] = LN(x[b,h,w,:] . W[(2i+j)*C/2 : (2i+j+1)*C/2, :]^T)."""
+    B, H, W, C = x.shape
+    y = F.linear(x, p[f"{prefix}.expand.weight"])                      # (B,H,W,2C), columns (P1 P2 C)
+    y = y.view(B, H, W, 2, 2, C // 2).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, C // 2)
+    return layer_norm(y, p[f"{prefix}.norm.weight"], p[f"{prefix}.norm.bias"], cfg.ln_eps)
+
+
+def head_expanding(x, p, cfg):
+    """norm_up -> FinalPatchExpanding (Linear(E -> r^2 E, no bias) -> '(P1 P2 C)' rearrange -> LayerNorm(E)) -> decoder_pred.
+    tulip.py:720, 727-731, 144-159."""
+    B, H, W, E = x.shape
+    r = cfg.upscale_factor
+    x = layer_norm(x, p["norm_up.weight"], p["norm_up.bias"], cfg.ln_eps)
+    y = F.linear(x, p["final_patch_expanding.expand.weight"])
+    y = y.view(B, H, W, r, r, E).permute(0, 1, 3, 2, 4, 5).reshape(B, H * r, W * r, E)
+    y = layer_norm(y, p["final_patch_expanding.norm.weight"], p["final_patch_expanding.norm.bias"], cfg.ln_eps)
+    y = F.linear(y, p["decoder_pred.weight"].view(cfg.in_chans, E))
+    return y.permute(0, 3, 1, 2)
+
+
 def head(x, p, cfg):
     """norm_up -> 1x1 conv E->E*r^2 (+bias) -> LeakyReLU(0.01) -> PixelShuffle(r) -> 1x1 conv E->in_chans.
     tulip/model/tulip.py:720-731, 161-178, 574.  x: (B,H,W,E) -> (B,in_chans,H*r,W*r)."""
@@ -219,7 +241,8 @@ def forward(p: dict, cfg: Cfg, x, target=None, state=None, drop_scales=None, tap
         if s < Ls - 1:
             x = patch_merging(x, p, f"layers.{s}.downsample", cfg)
             tap(f"layers.{s}.downsample", x)
-    x = patch_unmerging(x, p, "first_patch_expanding")
+    up = patch_unmerging if cfg.patch_unmerging else (lambda x_, p_, pre_: patch_expanding(x_, p_, pre_, cfg))
+    x = up(x, p, "first_patch_expanding")
     tap("first_patch_expanding", x)
     for u in range(Ls - 1):
         s = Ls - u - 2
@@ -231,9 +254,9 @@ def forward(p: dict, cfg: Cfg, x, target=None, state=None, drop_scales=None, tap
             x = swin_block(x, p, pre, cfg.num_heads[s], win, b % 2 == 1, cfg, state, ds.get(pre, (None, None)))
             tap(pre, x)
         if u < Ls - 2:
-            x = patch_unmerging(x, p, f"layers_up.{u}.upsample")
+            x = up(x, p, f"layers_up.{u}.upsample")
             tap(f"layers_up.{u}.upsample", x)
-    pred = head(x, p, cfg)
+    pred = head(x, p, cfg) if cfg.pixel_shuffle else head_expanding(x, p, cfg)
     if target is None:
         return pred
     loss, pixel_loss = loss_fn(pred, target, cfg)

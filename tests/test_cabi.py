@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"libtulip_b200.so does not export {s}"
     assert sorted(SIGNATURES) == syms, "ctypes signature table and header disagree"
-    assert lib.tulip_abi_version() == 1
+    assert lib.tulip_abi_version() == 2
 
 
 def c_schema(cfg: Cfg):
@@ -46,6 +46,7 @@ def c_schema(cfg: Cfg):
     for i in range(cfg.num_layers):
         c.depths[i], c.num_heads[i] = cfg.depths[i], cfg.num_heads[i]
     c.mlp_ratio, c.ln_eps, c.log_transform = cfg.mlp_ratio, cfg.ln_eps, int(cfg.log_transform)
+    c.patch_expanding, c.expanding_head = int(not cfg.patch_unmerging), int(not cfg.pixel_shuffle)
     h = C.c_void_p()
     rc = lib.tulip_net_create(C.byref(c), C.byref(h))
     if rc != 0:
@@ -62,7 +63,9 @@ def c_schema(cfg: Cfg):
 
 
 @pytest.mark.parametrize("cfg,nblk", [(TULIP_BASE, 14), (TULIP_LARGE, 18),
-                                      (Cfg(img_size=(32, 2048), target_img_size=(128, 2048)), 14)])
+                                      (Cfg(img_size=(32, 2048), target_img_size=(128, 2048)), 14),
+                                      (Cfg(patch_unmerging=False), 14),           # PatchExpanding variant (tulip.py:126-141)
+                                      (Cfg(patch_unmerging=False, pixel_shuffle=False), 14)])   # + FinalPatchExpanding (:144-159)
 def test_c_schema_matches_reference_state_dict(cfg, nblk):
     schema, ws, n = c_schema(cfg)
     want = [(k, tuple(v)) for k, v in param_shapes(cfg).items() if not k.endswith("relative_position_index")]
@@ -76,11 +79,14 @@ def test_c_config_errors_are_reported_not_fatal():
     assert rc != 0 and "16 tokens" in msg
     rc, msg = c_schema(Cfg(target_img_size=(128, 1024)))          # BASELINE cfg5's 8x head: the reference cannot build it either
     assert rc != 0 and "upscale_factor" in msg
+    rc, msg = c_schema(Cfg(pixel_shuffle=False, embed_dim=192, num_heads=(6, 12, 24, 48)))   # FinalPatchExpanding: embed_dim 96 only
+    assert rc != 0 and "FinalPatchExpanding" in msg
 
 
-@pytest.mark.parametrize("factory,cfg", [(tulip_base, TULIP_BASE), (tulip_large, TULIP_LARGE)])
+@pytest.mark.parametrize("factory,cfg", [(tulip_base, TULIP_BASE), (tulip_large, TULIP_LARGE), (tulip_base, Cfg(patch_unmerging=False)),
+                                         (tulip_base, Cfg(patch_unmerging=False, pixel_shuffle=False))])
 def test_module_state_dict_schema(factory, cfg):
-    m = factory(**KW)
+    m = factory(**{**KW, "patch_unmerging": cfg.patch_unmerging, "pixel_shuffle": cfg.pixel_shuffle})
     sd = m.state_dict()
     want = param_shapes(cfg)
     assert list(sd.keys()) == list(want.keys())
@@ -88,7 +94,8 @@ def test_module_state_dict_schema(factory, cfg):
         assert tuple(v.shape) == tuple(want[k])
         assert v.dtype == (torch.int64 if k.endswith("relative_position_index") else torch.float32)
     assert [n for n, _ in m.named_children()] == ["pos_drop", "layers", "layers_up", "first_patch_expanding",
-                                                  "skip_connection_layers", "norm_up", "patch_embed", "decoder_pred", "ps_head"]
+                                                  "skip_connection_layers", "norm_up", "patch_embed", "decoder_pred",
+                                                  "ps_head" if cfg.pixel_shuffle else "final_patch_expanding"]
     assert m.upscale_factor == 4
     m._create_net()                      # C schema check against this module (raises on mismatch)
 
@@ -107,7 +114,7 @@ def test_module_contract_details():
     with pytest.raises(NotImplementedError):
         tulip_base(**{**KW, "swin_v2": True})
     with pytest.raises(NotImplementedError):
-        tulip_base(**{**KW, "pixel_shuffle": False})
+        tulip_base(**{**KW, "circular_padding": False})
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 1, 16, 1024), torch.zeros(1, 1, 64, 1024))
 

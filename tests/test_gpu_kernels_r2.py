@@ -235,3 +235,51 @@ def test_gemm_layernorm_forward_epilogue(M, C, K, resid):
     mean, var = xf.mean(-1), xf.var(-1, unbiased=False)
     assert torch.allclose(stats[:, 0], mean, rtol=1e-5, atol=1e-5)
     assert torch.allclose(stats[:, 1], torch.rsqrt(var + eps), rtol=1e-4, atol=0)
+
+
+def test_final_patch_expanding_head_fwd_bwd():
+    """FinalPatchExpanding + decoder_pred + L1 (tulip.py:144-159, 727-731, 692-693) as the head epilogues 6 / 7 with hd_ln:
+    Linear(E -> r^2 E, no bias) -> '(P1 P2 C)' rearrange -> LayerNorm(E) per output pixel -> 1x1 conv E -> 1.
+    Checked against the same math in fp32 torch from the same bf16 operands (tolerances as for the PixelShuffle head: pred 1e-5,
+    fp32 gradient accumulators 2e-3, d(acc) stored as bf16 3e-3)."""
+    from tulip_b200 import ops
+    B, H, W, E, r = 2, 4, 32, 96, 4
+    T, N = B * H * W, E * r * r
+    g = torch.Generator().manual_seed(5)
+    rb = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).bfloat16().float()
+    xn, we = rb(T, E), rb(N, E, sc=0.1)
+    gam, bet, wd = (1 + 0.1 * torch.randn(E, generator=g)), 0.1 * torch.randn(E, generator=g), 0.2 * torch.randn(E, generator=g)
+    target = rb(B, 1, H * r, W * r, sc=0.5)
+    cu = lambda t: t.cuda().contiguous()
+    xb, wb = cu(xn).bfloat16(), cu(we).bfloat16()
+    pred = torch.zeros((B, 1, H * r, W * r), dtype=torch.float32, device="cuda")
+    stats = torch.zeros((B * H * r * W * r, 2), dtype=torch.float32, device="cuda")
+    gam_c, bet_c, wd_c, tgt_c = cu(gam), cu(bet), cu(wd), cu(target)
+    ops.gemm_nt_ex(ops.EPI_HEAD, A=xb, lda=E, K1=E, B=wb, ldb=E, M=T, N=N, K=E, wd=wd_c, pred=pred, hd_H=H, hd_W=W, hd_r=r, hd_E=E,
+                   hd_ln=1, ln_w=gam_c, ln_b=bet_c, ln_eps=1e-6, ln_ystats=stats)
+    # fp32 torch on the same operands
+    xf, wf = xn.clone().requires_grad_(True), we.clone().requires_grad_(True)
+    gf, bf_, wdf = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True), wd.clone().requires_grad_(True)
+    y = torch.nn.functional.linear(xf, wf).view(B, H, W, r, r, E).permute(0, 1, 3, 2, 4, 5).reshape(B, H * r, W * r, E)
+    yn = torch.nn.functional.layer_norm(y, (E,), gf, bf_, 1e-6)
+    pred_t = (yn * wdf).sum(-1).unsqueeze(1)
+    assert rel_l2(pred, pred_t) <= 1e-5
+    mean_t = y.mean(-1).reshape(-1)
+    assert rel_l2(stats[:, 0], mean_t) <= 1e-5
+    assert rel_l2(stats[:, 1], (y.var(-1, unbiased=False) + 1e-6).rsqrt().reshape(-1)) <= 1e-5
+    dpred = torch.sign(pred.cpu() - target) / pred.numel()
+    pred_t.backward(dpred)
+    dh = torch.empty((T, N), dtype=torch.bfloat16, device="cuda")
+    dg, db, dwd = (torch.zeros(E, dtype=torch.float32, device="cuda") for _ in range(3))
+    gscale = torch.ones(1, dtype=torch.float32, device="cuda")
+    ops.gemm_nt_ex(ops.EPI_HEAD_BWD, A=xb, lda=E, K1=E, B=wb, ldb=E, M=T, N=N, K=E, wd=wd_c, pred=pred, target=tgt_c, gscale=gscale,
+                   dwd=dwd, out=dh, ldo=N, hd_H=H, hd_W=W, hd_r=r, hd_E=E, hd_ln=1, ln_w=gam_c, ln_b=bet_c, ln_eps=1e-6, ln_stats=stats,
+                   ln_dw=dg, ln_db=db)
+    assert rel_l2(dg, gf.grad) <= 2e-3 and rel_l2(db, bf_.grad) <= 2e-3 and rel_l2(dwd, wdf.grad) <= 2e-3
+    dWe = torch.zeros((N, E), dtype=torch.float32, device="cuda")
+    ops.gemm_tn_ex(dY=dh, ldy=N, X=xb, ldx=E, K1=E, M=T, N=N, K=E, dW=dWe, lddw=E)
+    dxn = torch.empty((T, E), dtype=torch.bfloat16, device="cuda")
+    wtb = cu(we.t()).bfloat16()
+    ops.gemm_nt_ex(ops.EPI_STORE, A=dh, lda=N, K1=N, B=wtb, ldb=N, M=T, N=E, K=N, out=dxn, ldo=E)
+    assert rel_l2(dWe, wf.grad) <= 3e-3
+    assert rel_l2(dxn.float(), xf.grad) <= 3e-3

@@ -27,6 +27,7 @@ KW = dict(patch_size=(1, 4), in_chans=1, window_size=[2, 8], swin_v2=False, pixe
 def build(cfg, large=False):
     from functools import partial
     from tulip_b200.model.tulip import TULIP, tulip_base, tulip_large
+    KW = {**globals()["KW"], "patch_unmerging": cfg.patch_unmerging, "pixel_shuffle": cfg.pixel_shuffle}
     if cfg.embed_dim != 96 or (tuple(cfg.depths) not in ((2, 2, 2, 2), (2, 2, 2, 2, 2))):
         # the TULIP constructor itself (tulip.py:531-584), as the BASELINE cfg5 surrogate needs it (SURVEY 8d option i)
         return TULIP(img_size=cfg.img_size, target_img_size=cfg.target_img_size, embed_dim=cfg.embed_dim, depths=cfg.depths,
@@ -42,7 +43,10 @@ def load_params(model, pn):
 
 
 TULIP_WIDE = Cfg(embed_dim=192, depths=(2, 2, 18, 2), num_heads=(6, 12, 24, 48))      # BASELINE cfg5 surrogate (SURVEY 8d option i)
-CASES = [("model_base_kitti_b2", TULIP_BASE, False), ("model_large_kitti_b1", TULIP_LARGE, True),
+EXPANDING = Cfg(patch_unmerging=False)              # PatchExpanding instead of PatchUnmerging (tulip.py:126-141, 472, 565)
+EXPANDING_HEAD = Cfg(patch_unmerging=False, pixel_shuffle=False)      # ... and FinalPatchExpanding instead of PixelShuffleHead (:144-159)
+CASES = [("model_base_kitti_b2", TULIP_BASE, False), ("model_large_kitti_b1", TULIP_LARGE, True), ("model_expanding_kitti_b1", EXPANDING, False),
+         ("model_expanding_head_kitti_b1", EXPANDING_HEAD, False),
          ("model_base_durlar_b1", Cfg(img_size=(32, 2048), target_img_size=(128, 2048)), False),
          ("model_wide_kitti_b1", TULIP_WIDE, False)]
 

@@ -102,6 +102,8 @@ MODEL_CASES = [
     ("model_base_kitti_b2", TULIP_BASE),
     ("model_large_kitti_b1", TULIP_LARGE),
     ("model_base_durlar_b1", Cfg(img_size=(32, 2048), target_img_size=(128, 2048))),
+    ("model_expanding_kitti_b1", Cfg(patch_unmerging=False)),                              # PatchExpanding, tulip.py:126-141
+    ("model_expanding_head_kitti_b1", Cfg(patch_unmerging=False, pixel_shuffle=False)),    # + FinalPatchExpanding, tulip.py:144-159
 ]
 
 

@@ -21,6 +21,7 @@ class TulipConfig(C.Structure):
         ("win_h", C.c_int), ("win_w", C.c_int), ("num_layers", C.c_int),
         ("depths", C.c_int * MAX_STAGES), ("num_heads", C.c_int * MAX_STAGES),
         ("mlp_ratio", C.c_int), ("ln_eps", C.c_float), ("log_transform", C.c_int),
+        ("patch_expanding", C.c_int), ("expanding_head", C.c_int),
     ]
 
 
@@ -37,7 +38,7 @@ class GemmDesc(C.Structure):                     # tulip_gemm_desc (include/tuli
                 ("hd_H", C.c_int), ("hd_W", C.c_int), ("hd_r", C.c_int), ("hd_E", C.c_int),
                 ("aux2", C.c_void_p), ("ldaux2", C.c_int64),
                 ("ln_w", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_dw", C.c_void_p), ("ln_db", C.c_void_p),
-                ("ln_b", C.c_void_p), ("ln_y", C.c_void_p), ("ln_ystats", C.c_void_p), ("ln_eps", C.c_float)]
+                ("ln_b", C.c_void_p), ("ln_y", C.c_void_p), ("ln_ystats", C.c_void_p), ("ln_eps", C.c_float), ("hd_ln", C.c_int)]
 
 
 class GemmTNDesc(C.Structure):                   # tulip_gemm_tn_desc

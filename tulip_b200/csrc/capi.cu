@@ -109,7 +109,7 @@ int tulip_net::run_graphed(GraphSlot& slot, const std::vector<uint64_t>& key, cu
 extern "C" {
 
 const char* tulip_last_error(void) { return g_error.c_str(); }
-int tulip_abi_version(void) { return 1; }
+int tulip_abi_version(void) { return 2; }   // 2: tulip_config.patch_expanding / expanding_head
 
 int tulip_net_create(const tulip_config* cfg, tulip_net** out) {
   if (!cfg || !out) { tulip_set_error("tulip_net_create: null argument"); return TULIP_ERR_ARG; }
@@ -330,6 +330,7 @@ int tulip_gemm_nt_ex(const tulip_gemm_desc* d, int epilogue, void* stream) {
   g.aux2 = (const bf16*)d->aux2; g.ldaux2 = d->ldaux2;
   g.ln_w = d->ln_w; g.ln_stats = d->ln_stats; g.ln_dw = d->ln_dw; g.ln_db = d->ln_db; g.ln_copies = 1;
   g.ln_b = d->ln_b; g.ln_y = (bf16*)d->ln_y; g.ln_ystats = d->ln_ystats; g.ln_eps = d->ln_eps;
+  g.hd_ln = d->hd_ln;
   return gemm_nt(g, epilogue, (cudaStream_t)stream);
 }
 

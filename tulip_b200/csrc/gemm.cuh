@@ -13,7 +13,8 @@ enum GemmEpi : int {
   EPI_SPLIT2 = 4,     // cols < split_col -> out, others -> out2            (skip-Linear backward: d[x | skip])
   EPI_DGELU = 5,      // out = acc * gelu'(aux)                             (backward through GELU)
   EPI_HEAD = 6,       // pred[m, ij] (+)= sum_c wd[c] * leaky(acc + bias)   (PixelShuffleHead + decoder_pred, tulip.py:174-178,731)
-  EPI_HEAD_BWD = 7,   // recompute pre; out = dh (bf16), dwd += colsum(dpred * leaky(pre))
+                      // hd_ln: pred[m, ij] = sum_c wd[c] * LayerNorm(acc)[c]      (FinalPatchExpanding, tulip.py:152-159)
+  EPI_HEAD_BWD = 7,   // recompute pre; out = dh (bf16), dwd += colsum(dpred * leaky(pre)); hd_ln: LayerNorm backward instead
   EPI_ROWSCALE = 8,   // out = row_scale[sample] * acc                      (DropPath backward on a branch dX)
   EPI_DGELU2 = 9,     // out = (A . B^T) * gelu'(A2 . B2^T + bias): the GELU pre-activation is RECOMPUTED by a second
                       // accumulator instead of being saved by the forward pass (tcgen05 path only)
@@ -48,6 +49,11 @@ struct GemmArgs {
   const float* wd; const float* target; float* pred; const float* gscale;
   float* dwd; int dwd_copies;              // EPI_HEAD_BWD: CTA b adds into copy b % dwd_copies (stride hd_E); 0/1 = in place
   int hd_H, hd_W, hd_r, hd_E; float hd_inv_npix;
+  // hd_ln = 1: FinalPatchExpanding head (tulip.py:144-159, 727-731) instead of PixelShuffleHead: no bias, no LeakyReLU;
+  // the hd_E channels of a pixel go through LayerNorm(ln_w, ln_b, ln_eps) before the decoder_pred dot product.
+  // EPI_HEAD also writes the pixel's (mean, rstd) to ln_ystats [pixels, 2]; EPI_HEAD_BWD reads them from ln_stats and
+  // accumulates d(gamma) -> ln_dw, d(beta) -> ln_db, d(decoder_pred.weight) -> dwd, all with ln_copies / ln_stride.
+  int hd_ln;
   // EPI_LNBWD
   const bf16* aux2; long ldaux2;           // residual-path gradient added to dx, or null
   const float* ln_w; const float* ln_stats;    // gamma [N], (mean, rstd) per row [M, 2]

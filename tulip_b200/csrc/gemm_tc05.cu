@@ -197,6 +197,8 @@ __device__ __forceinline__ void epi_direct16(const GemmArgs& g, int m, int n, fl
 }
 
 // VAR = 1: head backward with two 96-channel groups (hd_E = 192): a second set of d(decoder_pred.weight) accumulators
+// VAR = 2: the head epilogues in their FinalPatchExpanding form (GemmArgs::hd_ln, hd_E = 96): per-pixel LayerNorm over the
+//          tile's 96 columns instead of bias + LeakyReLU
 // CG = 2: CTA pairs (tc05.cuh): tile-major schedule only; the even CTA issues M = 256 MMAs for both, each CTA loads its own A
 // rows and half of the B rows, so the deep-K GEMMs of stages 2-3 pull A + B/2 per K block over their SM's L2 port.
 template <int BN, int EPI, int VAR = 0, int CG = 1>
@@ -440,6 +442,16 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       }
     };
     int mt, nt;
+    // FinalPatchExpanding head: bw = sum_c beta[c] wd[c] and mean_c(gamma[c] wd[c]) (per-thread constants, fixed order)
+    float hl_bw = 0.f, hl_mgw = 0.f, hl_dsum = 0.f;
+    if ((EPI == EPI_HEAD || EPI == EPI_HEAD_BWD) && VAR == 2) {
+      for (int cidx = 0; cidx < BN; ++cidx) {
+        const float wdc = g.wd[cidx];
+        hl_bw = fmaf(g.ln_b[cidx], wdc, hl_bw);
+        hl_mgw = fmaf(g.ln_w[cidx], wdc, hl_mgw);
+      }
+      hl_mgw *= 1.0f / (float)BN;
+    }
     if (EPI == EPI_LNBWD) {
       // ---- LayerNorm backward on whole output rows (tiles_n == 1).  Staging buffer 0: LN input rows x (-> scaled dx when a
       // second output is asked for), buffer 1: residual-path gradient (-> dx), both transformed in place.  Per row the three
@@ -716,14 +728,22 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       }
       // per-row scalars of the epilogue come from global memory: fetch them before the accumulator wait as well
       float dp = 0.f;
+      float hl_mean = 0.f, hl_rstd = 0.f, hl_s = 0.f;      // FinalPatchExpanding: the pixel's LayerNorm statistics, (pred - bw) / E
       int ij = 0, c0 = 0;
       if (EPI == EPI_HEAD_BWD) {
         ij = n0 / g.hd_E; c0 = n0 % g.hd_E;
         if (m < g.M) {
           const long px = head_pixel(g, m, ij);
-          const float d = g.pred[px] - g.target[px];
+          const float pr = g.pred[px];
+          const float d = pr - g.target[px];
           const float gs = g.gscale[0] * g.hd_inv_npix;
           dp = d > 0.f ? gs : (d < 0.f ? -gs : 0.f);
+          if (VAR == 2) {
+            const float2 ms = *reinterpret_cast<const float2*>(g.ln_stats + 2 * px);
+            hl_mean = ms.x; hl_rstd = ms.y;
+            hl_s = (pr - hl_bw) * (1.0f / (float)BN);
+            if (jgrp == 0) hl_dsum += dp;                    // one warp per lane quarter counts the row
+          }
         }
       }
       const float rs = (EPI == EPI_RESID && g.row_scale) ? g.row_scale[(m < g.M ? m : g.M - 1) / g.rows_per_sample] : 1.0f;
@@ -795,6 +815,21 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
             if (g.bias) add_bias32(g.bias, n, a);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad(a[i]);
+          } else if (EPI == EPI_HEAD_BWD && VAR == 2) {
+            // y = xhat gamma + beta, pred = sum_c wd[c] y[c]:  dv = rstd dp (gw[c] - mean(gw) - xhat (pred - bw) / E), gw = gamma wd;
+            // cwacc[c] += dp xhat[c] feeds d(gamma) and d(decoder_pred.weight) at the end of the CTA
+            float wdv[32], gam[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { wdv[i] = 0.f; gam[i] = 0.f; }
+            add_bias32(g.wd, j * BOXC, wdv);
+            add_bias32(g.ln_w, j * BOXC, gam);
+            const float rd = hl_rstd * dp;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float xh = (v[i] - hl_mean) * hl_rstd;
+              cwacc[jj][i] = fmaf(dp, xh, cwacc[jj][i]);
+              v[i] = rd * (fmaf(gam[i], wdv[i], -hl_mgw) - xh * hl_s);
+            }
           } else if (EPI == EPI_HEAD_BWD) {
             // dh = dpred * wd[c] * leaky'(pre);  dwd[c] += sum_rows dpred * leaky(pre)  (summed per thread across tiles)
             add_bias32(g.bias, n, v);
@@ -838,6 +873,39 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         // this thread sums the whole channel run of its pixel in a fixed order (bitwise reproducible, no cross-warp step)
         const int ij = n0 / g.hd_E, c0 = n0 % g.hd_E;
         float acc = 0.f;
+        float2 ln_ms = make_float2(0.f, 0.f);
+        if (VAR == 2) {
+          // FinalPatchExpanding: the tile's 96 columns are the pixel's whole channel run.  Two passes over the accumulator
+          // (mean, then centred squares and the gamma wd dot product), as layernorm_fwd does on rows.
+          float s1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < CF::NBOX; ++j) {
+            float v[32];
+            tc::tmem_ld32(taddr + j * BOXC, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s1 += v[i];
+          }
+          const float mean = s1 * (1.0f / (float)BN);
+          float s2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < CF::NBOX; ++j) {
+            float v[32], wdv[32], gam[32];
+            tc::tmem_ld32(taddr + j * BOXC, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { wdv[i] = 0.f; gam[i] = 0.f; }
+            add_bias32(g.wd, j * BOXC, wdv);
+            add_bias32(g.ln_w, j * BOXC, gam);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float d = v[i] - mean;
+              s2 = fmaf(d, d, s2);
+              acc = fmaf(d, gam[i] * wdv[i], acc);
+            }
+          }
+          const float rstd = rsqrtf(s2 * (1.0f / (float)BN) + g.ln_eps);
+          acc = fmaf(rstd, acc, hl_bw);
+          ln_ms = make_float2(mean, rstd);
+        } else {
 #pragma unroll
         for (int j = 0; j < CF::NBOX; ++j) {
           float v[32], wdv[32];
@@ -849,12 +917,15 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc = fmaf(wdv[i], leaky(v[i]), acc);
         }
+        }
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) { if (CG == 2) tc::mbar_arrive_cluster(tempty + buf, 0); else tc::mbar_arrive(tempty + buf); }
         if (m < g.M) {
-          float* p = g.pred + head_pixel(g, m, ij);
+          const long px = head_pixel(g, m, ij);
+          float* p = g.pred + px;
           if (g.hd_E == BN) *p = acc; else atomicAdd(p, acc);
+          if (VAR == 2) *reinterpret_cast<float2*>(g.ln_ystats + 2 * px) = ln_ms;
         }
         tphase ^= 1;                                          // this group's buffer completes one phase per tile it handles
         continue;
@@ -874,7 +945,27 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       }
       if (++buf == NBUF) { buf = 0; tphase ^= 1; }
     }
-    if (EPI == EPI_HEAD_BWD) {
+    if (EPI == EPI_HEAD_BWD && VAR == 2) {
+      // d(gamma)[c] = wd[c] A[c],  d(beta)[c] = wd[c] D,  d(wd)[c] = gamma[c] A[c] + beta[c] D  with A[c] = sum dp xhat[c], D = sum dp
+      const int copy_off = g.ln_copies > 1 ? (int)(blockIdx.x % g.ln_copies) * g.ln_stride : 0;
+#pragma unroll
+      for (int jj = 0; jj < (CF::NBOX + EPI_GROUPS - 1) / EPI_GROUPS; ++jj) {
+        const int j = jgrp + jj * EPI_GROUPS;
+        if (j < CF::NBOX) {
+          const float A = warp_colsum32(cwacc[jj], lane);
+          const int cc = j * BOXC + lane;
+          atomicAdd(g.ln_dw + copy_off + cc, g.wd[cc] * A);
+          atomicAdd(g.dwd + copy_off + cc, g.ln_w[cc] * A);
+        }
+      }
+      if (jgrp == 0) {
+        const float D = warp_sum(hl_dsum);
+        for (int cc = lane; cc < BN; cc += 32) {
+          atomicAdd(g.ln_db + copy_off + cc, g.wd[cc] * D);
+          atomicAdd(g.dwd + copy_off + cc, g.ln_b[cc] * D);
+        }
+      }
+    } else if (EPI == EPI_HEAD_BWD) {
       // hd_E is BN or 2 BN on this path (checked by the launcher): a tile covers channels c0 .. c0 + 95 with c0 = 0 or 96
       float* dwd = g.dwd + (g.dwd_copies > 1 ? (int)(blockIdx.x % g.dwd_copies) * g.hd_E : 0);
 #pragma unroll
@@ -1103,6 +1194,11 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     return TULIP_ERR_UNSUPPORTED;
   const bool head = (epi == EPI_HEAD || epi == EPI_HEAD_BWD);
   if (epi == EPI_HEAD_BWD && g.hd_E != 96 && g.hd_E != 192) return TULIP_ERR_UNSUPPORTED;   // dwd accumulators: one or two 96-channel groups
+  if (head && g.hd_ln) {                                   // FinalPatchExpanding: a tile must hold the pixel's whole channel run
+    if (g.hd_E != 96) return TULIP_ERR_UNSUPPORTED;
+    TULIP_REQUIRE(g.ln_w && g.ln_b && g.wd && g.pred && (epi == EPI_HEAD ? g.ln_ystats != nullptr : (g.ln_stats && g.ln_dw && g.ln_db && g.dwd && g.target && g.gscale)),
+                  "gemm_nt head (hd_ln): needs gamma, beta, decoder_pred.weight, pred and the statistics / gradient buffers");
+  }
   if (epi == EPI_LNBWD) {
     if (!gemm_nt_lnbwd_supported(g.M, g.N, g.K) || g.a_mode != A_PLAIN || g.K1 < g.K) return TULIP_ERR_UNSUPPORTED;
     TULIP_REQUIRE(g.aux && g.ln_w && g.ln_stats && g.ln_dw && g.ln_db && (!g.out2 || g.row_scale),
@@ -1215,8 +1311,9 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
     case EPI_LNBWD: return launch_bn<EPI_LNBWD>(bn, maps, g, sg, sc, st);
     case EPI_STORE_LN: return launch_bn<EPI_STORE_LN>(bn, maps, g, sg, sc, st);
     case EPI_RESID_LN: return launch_bn<EPI_RESID_LN>(bn, maps, g, sg, sc, st);
-    case EPI_HEAD: return launch<96, EPI_HEAD>(maps, g, sg, sc, st);
+    case EPI_HEAD: return g.hd_ln ? launch<96, EPI_HEAD, 2>(maps, g, sg, sc, st) : launch<96, EPI_HEAD>(maps, g, sg, sc, st);
     case EPI_HEAD_BWD:
+      if (g.hd_ln) return launch<96, EPI_HEAD_BWD, 2>(maps, g, sg, sc, st);
       return g.hd_E == 96 ? launch<96, EPI_HEAD_BWD>(maps, g, sg, sc, st) : launch<96, EPI_HEAD_BWD, 1>(maps, g, sg, sc, st);
   }
   return TULIP_ERR_UNSUPPORTED;

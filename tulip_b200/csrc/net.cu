@@ -106,6 +106,8 @@ int tulip_net::build() {
   TULIP_REQUIRE(c.embed_dim % 96 == 0 && c.embed_dim <= 192, "tulip_b200: embed_dim must be 96 or 192");
   TULIP_REQUIRE(c.mlp_ratio == 4, "tulip_b200: mlp_ratio must be 4");
   TULIP_REQUIRE(c.img_h % c.patch_h == 0 && c.img_w % c.patch_w == 0, "tulip: image not divisible by the patch size");
+  TULIP_REQUIRE(c.expanding_head == 0 || c.embed_dim == 96,
+                "tulip_b200: the FinalPatchExpanding head (pixel_shuffle=False, tulip.py:144-159) is built for embed_dim 96 only");
   L = c.num_layers;
   H0 = c.img_h / c.patch_h;
   W0 = c.img_w / c.patch_w;
@@ -175,6 +177,7 @@ int tulip_net::build() {
   dec_blocks.assign(L - 1, {});
   merge_nw.assign(L, -1); merge_nb.assign(L, -1); merge_lin.assign(L, -1);
   up_lin.assign(L - 1, -1);
+  up_nw.assign(L - 1, -1); up_nb.assign(L - 1, -1);
   skip_lin.assign(L - 1, -1);
   char buf[128];
   for (int s = 0; s < L; ++s) {                           // tulip.py:643-660
@@ -198,18 +201,31 @@ int tulip_net::build() {
       snprintf(buf, sizeof buf, "layers_up.%d.blocks.%d", u, b);
       dec_blocks[u].push_back(add_block(buf, s, b));
     }
-    if (u < L - 2) {
+    if (u < L - 2 && !c.patch_expanding) {                 // PatchUnmerging, tulip.py:109-115
       snprintf(buf, sizeof buf, "layers_up.%d.upsample.expand", u);
       const int w = add_param(std::string(buf) + ".weight", {2 * C, C, 1, 1});
       const int bb = add_param(std::string(buf) + ".bias", {2 * C});
       up_lin[u] = add_linear(w, bb, 2 * C, C, 4, C / 2);
+    } else if (u < L - 2) {                                // PatchExpanding, tulip.py:126-132: the Linear's columns are already
+      snprintf(buf, sizeof buf, "layers_up.%d.upsample", u); // in shuffle-slot order (P1 P2 C): no row permutation, no bias
+      const int w = add_param(std::string(buf) + ".expand.weight", {2 * C, C});
+      up_nw[u] = add_param(std::string(buf) + ".norm.weight", {C / 2});
+      up_nb[u] = add_param(std::string(buf) + ".norm.bias", {C / 2});
+      up_lin[u] = add_linear(w, -1, 2 * C, C, 1, 0);
     }
   }
   {
     const long C = c.embed_dim << (L - 1);
-    const int w = add_param("first_patch_expanding.expand.weight", {2 * C, C, 1, 1});
-    const int bb = add_param("first_patch_expanding.expand.bias", {2 * C});
-    fpe_lin = add_linear(w, bb, 2 * C, C, 4, C / 2);
+    if (!c.patch_expanding) {
+      const int w = add_param("first_patch_expanding.expand.weight", {2 * C, C, 1, 1});
+      const int bb = add_param("first_patch_expanding.expand.bias", {2 * C});
+      fpe_lin = add_linear(w, bb, 2 * C, C, 4, C / 2);
+    } else {                                               // tulip.py:565
+      const int w = add_param("first_patch_expanding.expand.weight", {2 * C, C});
+      fpe_nw = add_param("first_patch_expanding.norm.weight", {C / 2});
+      fpe_nb = add_param("first_patch_expanding.norm.bias", {C / 2});
+      fpe_lin = add_linear(w, -1, 2 * C, C, 1, 0);
+    }
   }
   for (int u = 0; u < L - 1; ++u) {                       // tulip.py:682-688
     const long C = c.embed_dim << (L - 2 - u);
@@ -226,10 +242,15 @@ int tulip_net::build() {
   slot_pe_nw = add_param("patch_embed.norm.weight", {E});
   slot_pe_nb = add_param("patch_embed.norm.bias", {E});
   slot_dec_w = add_param("decoder_pred.weight", {1, E, 1, 1});
-  {
+  if (!c.expanding_head) {
     const int w = add_param("ps_head.conv_expand.0.weight", {E * r * r, E, 1, 1});
     const int bb = add_param("ps_head.conv_expand.0.bias", {E * r * r});
     head_lin = add_linear(w, bb, E * r * r, E, r * r, E);
+  } else {                                                 // tulip.py:582; columns already in (P1 P2 C) = shuffle-slot order
+    const int w = add_param("final_patch_expanding.expand.weight", {E * r * r, E});
+    slot_fh_nw = add_param("final_patch_expanding.norm.weight", {E});
+    slot_fh_nb = add_param("final_patch_expanding.norm.bias", {E});
+    head_lin = add_linear(w, -1, E * r * r, E, 1, 0);
   }
 
   // bf16 weight arena + fp32 aux arena (permuted biases)
@@ -280,16 +301,20 @@ Plan tulip_net::plan(int B) const {
   {
     const long T = (long)B * (H0 >> (L - 1)) * (W0 >> (L - 1)), C = E << (L - 1);
     p.x_fpe = act(4 * T, C / 2);
+    if (fpe_nw >= 0) { p.x_fpe_pre = act(4 * T, C / 2); p.st_fpe = bump.take(4 * T * 8); }
   }
   p.x_skip.assign(L - 1, -1); p.x_up.assign(L - 1, -1);
+  p.x_up_pre.assign(L - 1, -1); p.st_upx.assign(L - 1, -1);
   for (int u = 0; u < L - 1; ++u) {
     const int s = L - u - 2;
     const long T = (long)B * (H0 >> s) * (W0 >> s), C = E << s;
     p.x_skip[u] = act(T, C);
     for (int bi : dec_blocks[u]) plan_block(bi);
     if (u < L - 2) p.x_up[u] = act(4 * T, C / 2);
+    if (u < L - 2 && up_nw[u] >= 0) { p.x_up_pre[u] = act(4 * T, C / 2); p.st_upx[u] = bump.take(4 * T * 8); }
   }
   p.xn_up = act(T0, E); p.st_up = bump.take(T0 * 8);
+  if (cfg.expanding_head) p.st_head = bump.take(T0 * r * r * 8);
   // backward scratch (T_s * C_s is largest at stage 0)
   p.gA = act(T0, E); p.gB = act(T0, E); p.scr_gs = act(T0, E); p.scr_gsm = act(T0, E);
   p.scr_dxn = act(T0, E); p.scr_do = act(T0, E); p.scr_dqkv = act(T0, 3 * E);
@@ -311,11 +336,14 @@ long tulip_net::grad_scratch_bytes() const {
   const int nbias = (2 * cfg.win_h - 1) * (2 * cfg.win_w - 1);
   auto take = [](long n) { return align_up(n * GRAD_COPIES, 64); };
   long fl = take(E) + take(2 * E) + take(11 * E);                  // decoder_pred.weight, norm_up, PatchEmbed
+  if (cfg.expanding_head) fl += take(3 * E);                        // FinalPatchExpanding: [d(gamma) | d(beta) | d(decoder_pred.weight)]
   for (const BlockDef& b : blocks) {
     const long C = E << b.stage;
     fl += 2 * take(2 * C) + take((long)nbias * cfg.num_heads[b.stage]);
   }
   for (int s = 0; s + 1 < L; ++s) fl += take(2 * 4 * (E << s));    // PatchMerging norms
+  if (cfg.patch_expanding)
+    for (int s = 1; s < L; ++s) fl += take(2 * ((E << s) / 2));     // PatchExpanding norms (one per upsampling site, C/2 wide)
   return fl * 4 + 1024;
 }
 
@@ -622,11 +650,13 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     return TULIP_OK;
   };
 
-  auto unmerge_fwd = [&](const Linear& l, const bf16* x, bf16* out, int Hs, int Ws, int C) -> int {
-    // 1x1 conv C -> 2C + PixelShuffle(2) as a GEMM with a scatter epilogue (tulip.py:117-123)
-    GemmArgs g = nt_args(x, C, c.W(l), C, B * Hs * Ws, 2 * C, C, c.bias(l), out, C / 2);
+  auto unmerge_fwd = [&](const Linear& l, const bf16* x, bf16* out, int Hs, int Ws, int C, int nw, int nb, long pre, long stats) -> int {
+    // 1x1 conv C -> 2C + PixelShuffle(2) as a GEMM with a scatter epilogue (tulip.py:117-123); PatchExpanding (nw >= 0,
+    // tulip.py:135-141) is the same scatter of an un-permuted, bias-free Linear into `pre`, followed by LayerNorm(C/2)
+    GemmArgs g = nt_args(x, C, c.W(l), C, B * Hs * Ws, 2 * C, C, c.bias(l), nw >= 0 ? c.A(pre) : out, C / 2);
     g.g_H = Hs; g.g_W = Ws; g.g_Cc = C / 2;
     RUN_NT(g, EPI_PIXSHUF);
+    if (nw >= 0) RUN(ln(c.A(pre), nw, nb, out, c.F(stats), 4 * B * Hs * Ws, C / 2, 0, 0, 0));
     return TULIP_OK;
   };
 
@@ -652,7 +682,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     }
   }
   at(L - 1, 0);
-  rc = unmerge_fwd(linears[fpe_lin], x, c.A(p.x_fpe), H0 >> (L - 1), W0 >> (L - 1), E << (L - 1));
+  rc = unmerge_fwd(linears[fpe_lin], x, c.A(p.x_fpe), H0 >> (L - 1), W0 >> (L - 1), E << (L - 1), fpe_nw, fpe_nb, p.x_fpe_pre, p.st_fpe);
   if (rc) return rc;
   x = c.A(p.x_fpe);
   for (int u = 0; u < L - 1; ++u) {
@@ -678,7 +708,7 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     }
     at(s, 0);
     if (u < L - 2) {
-      rc = unmerge_fwd(linears[up_lin[u]], x, c.A(p.x_up[u]), Hs, Ws, C);
+      rc = unmerge_fwd(linears[up_lin[u]], x, c.A(p.x_up[u]), Hs, Ws, C, up_nw[u], up_nb[u], p.x_up_pre[u], p.st_upx[u]);
       if (rc) return rc;
       x = c.A(p.x_up[u]);
     }
@@ -692,6 +722,9 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     if (E != 96) TULIP_CUDA(cudaMemsetAsync(pred, 0, (size_t)T0 * r * r * sizeof(float), st));   // partial sums over channel groups
     GemmArgs g = nt_args(c.A(p.xn_up), E, c.W(l), E, T0, E * r * r, E, c.bias(l), nullptr, 0);
     g.wd = c.P(slot_dec_w); g.pred = pred; g.hd_H = H0; g.hd_W = W0; g.hd_r = r; g.hd_E = E;
+    if (cfg.expanding_head) {                             // FinalPatchExpanding: LayerNorm per output pixel instead of bias + LeakyReLU
+      g.hd_ln = 1; g.ln_w = c.P(slot_fh_nw); g.ln_b = c.P(slot_fh_nb); g.ln_eps = cfg.ln_eps; g.ln_ystats = c.F(p.st_head);
+    }
     RUN_NT(g, EPI_HEAD);
   }
   tag(K_LOSS, 0, 8.0 * T0 * r * r);
@@ -946,6 +979,14 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       g.dwd = scr; g.dwd_copies = GRAD_COPIES;
       sum_to(c.G(slot_dec_w), scr, 0, E, E);
     }
+    if (cfg.expanding_head) {                             // per copy: [d(gamma) | d(beta) | d(decoder_pred.weight)]
+      float* scr = grad_scratch(3 * E);
+      g.hd_ln = 1; g.ln_w = c.P(slot_fh_nw); g.ln_b = c.P(slot_fh_nb); g.ln_eps = cfg.ln_eps; g.ln_stats = c.F(p.st_head);
+      g.ln_dw = scr; g.ln_db = scr + E; g.dwd = scr + 2 * E; g.ln_copies = GRAD_COPIES; g.ln_stride = 3 * E;
+      sum_to(c.G(slot_fh_nw), scr, 0, E, 3 * E);
+      sum_to(c.G(slot_fh_nb), scr, E, E, 3 * E);
+      sum_to(c.G(slot_dec_w), scr, 2 * E, E, 3 * E);
+    }
     g.hd_H = H0; g.hd_W = W0; g.hd_r = r; g.hd_E = E; g.hd_inv_npix = 1.0f / ((float)T0 * r * r);
     RUN_NT(g, EPI_HEAD_BWD);
     // dWe' += dh^T . xn_up (rows un-permuted on store); bias gradient = column sums of dh, same un-permutation
@@ -1029,10 +1070,15 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     return TULIP_OK;
   };
 
-  auto unmerge_bwd = [&](const Linear& l, const bf16* x_in, const bf16* g_out, bf16* g_in, int Hs, int Ws, int C) -> int {
+  auto unmerge_bwd = [&](const Linear& l, const bf16* x_in, const bf16* g_out, bf16* g_in, int Hs, int Ws, int C, int nw, int nb,
+                         long pre, long stats) -> int {
     // g_out: [B, 2Hs, 2Ws, C/2]; gathered view A[m, ij*C/2 + c] (PixelShuffle backward), then dX and dW
     const int T = B * Hs * Ws;
     join();
+    if (nw >= 0) {                                        // PatchExpanding: back through LayerNorm(C/2) first
+      LN_BWD(c.A(pre), nw, nb, c.F(stats), g_out, nullptr, c.A(p.scr_do), 4 * T, C / 2, 0, 0, 0);
+      g_out = c.A(p.scr_do);
+    }
     GemmTNArgs gw = dw(l, g_out, x_in, T);
     gw.ldy = C / 2; gw.y_mode = A_UNSHUFFLE; gw.g_H = Hs; gw.g_W = Ws; gw.g_Cc = C / 2;
     TN_SIDE(gw);
@@ -1049,7 +1095,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     at(s, 0);
     if (u < L - 2) {
       const bf16* x_before = c.A(p.blocks[dec_blocks[u].back()].xout);
-      rc = unmerge_bwd(linears[up_lin[u]], x_before, g_cur, g_alt, Hs, Ws, C);
+      rc = unmerge_bwd(linears[up_lin[u]], x_before, g_cur, g_alt, Hs, Ws, C, up_nw[u], up_nb[u], p.x_up_pre[u], p.st_upx[u]);
       if (rc) return rc;
       std::swap(g_cur, g_alt);
     }
@@ -1080,7 +1126,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     const int s = L - 1;
     at(s, 0);
     const bf16* x_top = c.A(p.blocks[enc_blocks[s].back()].xout);
-    rc = unmerge_bwd(linears[fpe_lin], x_top, g_cur, g_alt, H0 >> s, W0 >> s, E << s);
+    rc = unmerge_bwd(linears[fpe_lin], x_top, g_cur, g_alt, H0 >> s, W0 >> s, E << s, fpe_nw, fpe_nb, p.x_fpe_pre, p.st_fpe);
     if (rc) return rc;
     std::swap(g_cur, g_alt);
   }

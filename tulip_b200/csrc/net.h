@@ -58,7 +58,10 @@ struct Plan {
   std::vector<long> xn_m, st_m, x_merged;          // per encoder stage (valid for s < L-1)
   long x_fpe;
   std::vector<long> x_skip, x_up;                  // per decoder stage
+  long x_fpe_pre = -1, st_fpe = -1;                // PatchExpanding: rearranged rows before their LayerNorm, (mean, rstd) rows
+  std::vector<long> x_up_pre, st_upx;
   long xn_up, st_up;
+  long st_head = -1;                               // FinalPatchExpanding: (mean, rstd) of every output pixel
   long gA, gB, scr_gs, scr_gsm, scr_big, scr_dxn, scr_do, scr_dqkv;
   std::vector<long> g_save;
   long loss_acc;
@@ -81,9 +84,12 @@ struct tulip_net {
   std::vector<std::vector<int>> enc_blocks, dec_blocks;
   std::vector<int> merge_nw, merge_nb, merge_lin;  // per encoder stage
   std::vector<int> up_lin;                         // per decoder stage (-1: Identity)
+  std::vector<int> up_nw, up_nb;                   // PatchExpanding only: LayerNorm(C/2) after the rearrange (-1: PatchUnmerging)
+  int fpe_nw = -1, fpe_nb = -1;
   std::vector<int> skip_lin;
   int fpe_lin, head_lin;
   int slot_normup_w, slot_normup_b, slot_pe_w, slot_pe_b, slot_pe_nw, slot_pe_nb, slot_dec_w;
+  int slot_fh_nw = -1, slot_fh_nb = -1;            // FinalPatchExpanding.norm (expanding_head only)
   // device-side persistent state
   bf16* warena = nullptr; long warena_elems = 0;
   float* faux = nullptr; long faux_elems = 0;

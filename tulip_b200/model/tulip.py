@@ -12,9 +12,10 @@ but none of the reference's torch modules run.  The nn.Modules below only *own p
 the C++/CUDA executor in libtulip_b200.so (include/tulip_b200.h: tulip_net_forward / tulip_net_backward)
 through one `torch.autograd.Function`.  PyTorch supplies device memory, the stream and autograd glue only.
 
-Supported configuration = the one every shipped script uses (bash_scripts/tulip_upsampling_*.sh):
-`--pixel_shuffle --circular_padding --patch_unmerging`, patch (1,4), 16-token windows, in_chans 1,
-head_dim 32.  Anything else raises NotImplementedError -- there is no fallback path.
+Supported: `--circular_padding` (every shipped script), patch (1,4), 16-token windows, in_chans 1, head_dim 32, with either
+upsampling layer (`--patch_unmerging` = PatchUnmerging, without it PatchExpanding) and either head (`--pixel_shuffle` =
+PixelShuffleHead, without it FinalPatchExpanding at embed_dim 96).  Anything else raises NotImplementedError -- there is no
+fallback path.
 """
 from __future__ import annotations
 
@@ -84,6 +85,31 @@ class PatchUnmerging(nn.Module):
         super().__init__()
         self.dim = dim
         self.expand = nn.Conv2d(in_channels=dim, out_channels=dim * 2, kernel_size=(1, 1))
+
+    forward = _no_forward
+
+
+class PatchExpanding(nn.Module):
+    """reference tulip.py:126-141: Linear(C, 2C, bias=False), 'B H W (P1 P2 C) -> B (H P1) (W P2) C' (P1 = P2 = 2), LayerNorm(C/2)."""
+
+    def __init__(self, dim, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.expand = nn.Linear(dim, 2 * dim, bias=False)
+        self.norm = norm_layer(dim // 2)
+
+    forward = _no_forward
+
+
+class FinalPatchExpanding(nn.Module):
+    """reference tulip.py:144-159: Linear(E, r^2 E, bias=False), '(P1 P2 C)' rearrange with P1 = P2 = r, LayerNorm(E)."""
+
+    def __init__(self, dim, norm_layer=nn.LayerNorm, upscale_factor=4):
+        super().__init__()
+        self.dim = dim
+        self.expand = nn.Linear(dim, (upscale_factor ** 2) * dim, bias=False)
+        self.norm = norm_layer(dim)
+        self.upscale_factor = upscale_factor
 
     forward = _no_forward
 
@@ -189,7 +215,8 @@ class BasicBlock(nn.Module):
 class BasicBlockUp(nn.Module):
     """reference tulip.py:441-481 (stage index mirrored: index = len(depths) - index - 2, :447)."""
 
-    def __init__(self, index, embed_dim, window_size, depths, num_heads, mlp_ratio, drop_path, norm_layer, patch_expanding):
+    def __init__(self, index, embed_dim, window_size, depths, num_heads, mlp_ratio, drop_path, norm_layer, patch_expanding,
+                 patch_unmerging=True):
         super().__init__()
         index = len(depths) - index - 2
         dim = embed_dim * 2 ** index
@@ -197,7 +224,12 @@ class BasicBlockUp(nn.Module):
         self.blocks = nn.ModuleList([
             SwinTransformerBlock(dim, num_heads[index], window_size, shift=(i % 2 == 1), mlp_ratio=mlp_ratio,
                                  drop_path=rates[i], norm_layer=norm_layer) for i in range(depths[index])])
-        self.upsample = PatchUnmerging(dim=dim) if patch_expanding else nn.Identity()
+        if not patch_expanding:
+            self.upsample = nn.Identity()
+        elif patch_unmerging:                                                               # reference tulip.py:469-472
+            self.upsample = PatchUnmerging(dim=dim)
+        else:
+            self.upsample = PatchExpanding(dim=dim, norm_layer=norm_layer)
 
     forward = _no_forward
 
@@ -289,9 +321,10 @@ class TULIP(nn.Module):
         super().__init__()
         if swin_v2:
             raise NotImplementedError("swin_v2=True is dead code in the reference (AttributeError at tulip.py:602); not built")
-        if not (pixel_shuffle and circular_padding and patch_unmerging):
-            raise NotImplementedError("tulip_b200 builds the shipped configuration only: "
-                                      "pixel_shuffle=True, circular_padding=True, patch_unmerging=True")
+        if not circular_padding:
+            raise NotImplementedError("tulip_b200: circular_padding=False (plain patch conv) is not built; every shipped script pads")
+        if not pixel_shuffle and embed_dim != 96:
+            raise NotImplementedError("tulip_b200: the FinalPatchExpanding head (pixel_shuffle=False) is built for embed_dim 96")
         if drop_rate != 0. or attn_drop_rate != 0. or not qkv_bias or not patch_norm:
             raise NotImplementedError("tulip_b200: drop_rate/attn_drop_rate must be 0, qkv_bias and patch_norm True (both factories)")
         if not isinstance(window_size, collections.abc.Iterable):
@@ -319,8 +352,11 @@ class TULIP(nn.Module):
                        patch_merging=(i != L - 1)) for i in range(L)])
         self.layers_up = nn.ModuleList([
             BasicBlockUp(i, embed_dim, window_size, self.depths, self.num_heads, mlp_ratio, drop_path_rate, norm_layer,
-                         patch_expanding=(i < L - 2)) for i in range(L - 1)])
-        self.first_patch_expanding = PatchUnmerging(dim=embed_dim * 2 ** (L - 1))
+                         patch_expanding=(i < L - 2), patch_unmerging=patch_unmerging) for i in range(L - 1)])
+        if patch_unmerging:                                                                 # reference tulip.py:562-565
+            self.first_patch_expanding = PatchUnmerging(dim=embed_dim * 2 ** (L - 1))
+        else:
+            self.first_patch_expanding = PatchExpanding(dim=embed_dim * 2 ** (L - 1), norm_layer=norm_layer)
         self.skip_connection_layers = nn.ModuleList([
             nn.Linear(embed_dim * 2 ** (L - 2 - i) * 2, embed_dim * 2 ** (L - 2 - i)) for i in range(L - 1)])
         self.norm_up = norm_layer(embed_dim)
@@ -329,7 +365,10 @@ class TULIP(nn.Module):
         self.decoder_pred = nn.Conv2d(in_channels=embed_dim, out_channels=in_chans, kernel_size=(1, 1), bias=False)
         self.upscale_factor = int(((target_img_size[0] * target_img_size[1]) / (img_size[0] * img_size[1])) ** 0.5) * 2 * \
             int(((patch_size[0] * patch_size[1]) // 4) ** 0.5)                                     # reference tulip.py:577
-        self.ps_head = PixelShuffleHead(dim=embed_dim, upscale_factor=self.upscale_factor)
+        if pixel_shuffle:                                                                   # reference tulip.py:579-582
+            self.ps_head = PixelShuffleHead(dim=embed_dim, upscale_factor=self.upscale_factor)
+        else:
+            self.final_patch_expanding = FinalPatchExpanding(dim=embed_dim, norm_layer=norm_layer, upscale_factor=self.upscale_factor)
         self.apply(self.init_weights)
 
         self._net = None            # C handle, created lazily on the first CUDA forward
@@ -378,6 +417,8 @@ class TULIP(nn.Module):
             raise NotImplementedError("tulip_b200: mlp_ratio must be an integer")
         c.ln_eps = self.ln_eps
         c.log_transform = int(bool(self.log_transform))
+        c.patch_expanding = int(not self.patch_unmerging)
+        c.expanding_head = int(not self.pixel_shuffle)
         return c
 
     def _create_net(self):
