@@ -868,8 +868,12 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     if (gscr_used * 4 > p.gscr_bytes) { gscr_overflow = true; return c.F(p.gscr); }
     return ptr;
   };
+  bool sum_clash = false;                                 // two folds into one destination would race inside sum_copies
   auto sum_to = [&](float* dst, const float* scr, int off, int n, int stride) {
-    if (live) sum_items.push_back(SumCopiesItem{dst, scr + off, n, stride});
+    if (!live) return;
+    for (const SumCopiesItem& it : sum_items)
+      if (dst < it.dst + it.n && it.dst < dst + n) sum_clash = true;
+    sum_items.push_back(SumCopiesItem{dst, scr + off, n, stride});
   };
   // fold the gradient copies registered so far into the flat gradient (end of a phase / end of the pass)
   auto flush_sums = [&]() -> int {
@@ -975,9 +979,9 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     GemmArgs g = nt_args(c.A(p.xn_up), E, c.W(l), E, T0, E * r * r, E, c.bias(l), dh, (long)E * r * r);
     g.wd = c.P(slot_dec_w); g.pred = const_cast<float*>(pred); g.target = target; g.gscale = grad_loss;
     {
-      float* scr = grad_scratch(E);
+      float* scr = grad_scratch(E);                       // (handed out in both head forms: the scratch offsets that follow stay put)
       g.dwd = scr; g.dwd_copies = GRAD_COPIES;
-      sum_to(c.G(slot_dec_w), scr, 0, E, E);
+      if (!cfg.expanding_head) sum_to(c.G(slot_dec_w), scr, 0, E, E);   // one fold per destination: sum_copies items must not share one
     }
     if (cfg.expanding_head) {                             // per copy: [d(gamma) | d(beta) | d(decoder_pred.weight)]
       float* scr = grad_scratch(3 * E);
@@ -1178,6 +1182,7 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     RUN(patch_embed_bwd(e, st));
   }
   TULIP_REQUIRE(!gscr_overflow, "tulip_b200: gradient-copy scratch exhausted (grad_scratch_bytes() out of step with backward())");
+  TULIP_REQUIRE(!sum_clash, "tulip_b200: two gradient-copy folds share a destination (sum_copies items must be disjoint)");
   TN_FLUSH();
   join();                                                 // the gradient fill and every weight-gradient GEMM precede the fold
   if (live) {
