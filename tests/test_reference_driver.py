@@ -33,12 +33,12 @@ def write_frames(root, n_train=8, n_val=2):
             np.save(os.path.join(root, split, f"{i:08d}.npy"), a)
 
 
-def run_driver(extra, dropin, nproc=1, timeout=900):
+def run_driver(extra, dropin, nproc=1, timeout=900, args=None):
     cmd = [sys.executable]
     if nproc > 1:
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
                 "--master-port", "29533"]
-    cmd += ["main_lidar_upsampling.py"] + ARGS + extra
+    cmd += ["main_lidar_upsampling.py"] + (ARGS if args is None else args) + extra
     return subprocess.run(cmd, cwd=cenv.REF_TULIP, env=cenv.driver_env(dropin), capture_output=True, text=True, timeout=timeout)
 
 
@@ -89,6 +89,26 @@ def test_unmodified_driver_trains_resumes_and_evaluates_on_dropin(tmp_path):
     r3 = run_driver(common + ["--eval"], dropin=True)
     assert r3.returncode == 0, (r3.stdout[-3000:], r3.stderr[-3000:])
     assert os.path.exists(os.path.join(out, "results.txt"))
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_unmodified_driver_trains_the_expanding_variants(tmp_path):
+    """The same unmodified driver WITHOUT --pixel_shuffle / --patch_unmerging: PatchExpanding in the decoder and the
+    FinalPatchExpanding head (tulip.py:126-159) -- the configuration no shipped script selects."""
+    data, out = str(tmp_path / "KITTI"), str(tmp_path / "out")
+    write_frames(data, n_train=4, n_val=2)
+    common = ["--data_path_low_res", data, "--data_path_high_res", data, "--output_dir", out, "--log_dir", out]
+    args = [a for a in ARGS if a not in ("--pixel_shuffle", "--patch_unmerging")]
+    r = run_driver(common + ["--epochs", "1"], dropin=True, args=args)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    ck = torch.load(os.path.join(out, "checkpoint-0.pth"), map_location="cpu", weights_only=False)
+    keys = set(ck["model"])
+    assert {"final_patch_expanding.expand.weight", "final_patch_expanding.norm.bias", "first_patch_expanding.norm.weight",
+            "layers_up.0.upsample.expand.weight", "layers_up.1.upsample.norm.bias"} <= keys
+    assert not any(k.startswith("ps_head") or k.endswith("upsample.expand.bias") for k in keys)
+    log = [json.loads(l) for l in open(os.path.join(out, "log.txt"))]
+    assert len(log) == 1 and np.isfinite(log[0]["train_loss"])
 
 
 @needs_ref
