@@ -187,6 +187,16 @@ int tulip_gemm_tn_ex(const tulip_gemm_tn_desc* d, void* stream);
 int tulip_gemm_tn_group(const tulip_gemm_tn_desc* d, int n, void* stream);
 int tulip_gemm_tn_group_plan(const int* M, const int* N, const int* K, int n, int sms, int* per4, int* items);
 
+/* ---- fused head backward (PixelShuffleHead + decoder_pred + L1, tulip.py:161-178, 727-731, 692-693; embed_dim 96, r = 4):
+ * ONE launch for   dh[m, ij*E + c] = dpred[m, ij] * wd[c] * LeakyReLU'(xn[m,:] . we[ij*E + c, :] + bias[ij*E + c])   (bf16 out),
+ *                  dxn = dh . we  (bf16 [T, E]),   dwd[c] += sum_{m, ij} dpred[m, ij] * LeakyReLU(pre),
+ * dpred = sign(pred - target) * gscale[0] / (T r^2).  we [E r^2, E] bf16 with rows in shuffle-slot order n' = ij*E + c, wet = its
+ * transpose [E, E r^2]; pred / target fp32 [B, 1, H r, W r]; T = B H W. */
+int tulip_head_bwd_fused_supported(int E, int r);
+int tulip_head_bwd_fused(const void* xn, void* dxn, const void* we, const void* wet, const float* bias, const float* wd,
+                         const float* pred, const float* target, const float* gscale, void* dh, float* dwd, int T, int E, int H,
+                         int W, int r, void* stream);
+
 /* ---- fused W-MSA / SW-MSA half-block (SURVEY 8b tulip_wmsa_block_fwd): ONE launch for
  *   y = x + row_scale[b] * proj(attn(qkv(LayerNorm(x))))          tulip.py:338-346 with WindowAttention.forward :282-324
  * LayerNorm, cyclic shift, window partition / reverse, rel-pos bias, shift mask, softmax, both Linears and the residual; the

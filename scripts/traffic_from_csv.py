@@ -14,7 +14,7 @@ EPI = {"0": "store", "1": "gelu", "2": "resid", "3": "pixshuf", "4": "split2", "
 
 def tag(name):
     n = re.sub(r"^void |<unnamed>::|\(anonymous namespace\)::", "", name)
-    m = re.match(r"gemm_nt_(tc05|mma)_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)(?:, \(?(?:int\))?\d+)?>", n)
+    m = re.match(r"gemm_nt_(tc05|mma)_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)(?:, \(?(?:int\))?\d+)*>", n)
     if m:
         return f"gemm_nt<{EPI.get(m.group(3) if m.group(1) == 'tc05' else m.group(2), '?')}>"
     for k, t in (("gemm_tn_", "gemm_tn"), ("win_attn_fwd", "win_attn_fwd"), ("win_attn_bwd", "win_attn_bwd"),

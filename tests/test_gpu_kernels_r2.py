@@ -120,6 +120,19 @@ def test_head_fwd_bwd(mods, E):
     dxn = torch.empty((T, E), dtype=torch.bfloat16, device="cuda")
     wtb = bf(wep.t())
     ops.gemm_nt_ex(ops.EPI_STORE, A=dh, lda=N, K1=N, B=wtb, ldb=N, M=T, N=E, K=N, out=dxn, ldo=E)
+    if E == 96:
+        # the executor's path at embed_dim 96: ONE launch (fused head backward) for dh, dxn and dwd -- same operands, same
+        # roundings as the two GEMMs above (dh bf16, fp32 accumulation): everything within fp32 re-association
+        lib = ops.load_library()
+        assert lib.tulip_head_bwd_fused_supported(E, r) == 1
+        dh2, dxn2 = torch.empty_like(dh), torch.empty_like(dxn)
+        dwd2 = torch.zeros_like(dwd)
+        ops.check(lib.tulip_head_bwd_fused(ops.ptr(xn), ops.ptr(dxn2), ops.ptr(wb), ops.ptr(wtb), ops.ptr(bep), ops.ptr(wd), ops.ptr(pred),
+                                           ops.ptr(target), ops.ptr(gscale), ops.ptr(dh2), ops.ptr(dwd2), T, E, H, W, r,
+                                           ops.current_stream()), "tulip_head_bwd_fused")
+        assert rel_l2(dh2.float(), dh.float()) <= 1e-4          # (0.01 dp) wd against (dp wd) 0.01: one fp32 ulp before the bf16 store
+        assert rel_l2(dwd2, dwd) <= 1e-5
+        assert rel_l2(dxn2.float(), dxn.float()) <= 2e-3 and (dxn2.float() - dxn.float()).abs().max() <= 2 ** -7 * dxn.float().abs().max()
     gx, gnw, gnb = ops.layernorm_bwd(xb, nw, stats, dxn)
     # (1) kernel arithmetic: the same math in fp32 torch FROM THE SAME bf16 LayerNorm output and the kernel's own pred
     #     (LeakyReLU's slope jumps 100x at 0 and sign(pred - target) jumps at 0: both discontinuities are then evaluated on

@@ -85,6 +85,8 @@ SIGNATURES = {
     "tulip_gemm_tn_ex": (_i, [C.POINTER(GemmTNDesc), _vp]),
     "tulip_gemm_tn_group": (_i, [C.POINTER(GemmTNDesc), _i, _vp]),
     "tulip_gemm_tn_group_plan": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "tulip_head_bwd_fused_supported": (_i, [_i, _i]),
+    "tulip_head_bwd_fused": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _vp]),
     "tulip_wmsa_block_supported": (_i, [_i] * 7),
     "tulip_wmsa_block_fwd": (_i, [_vp, _vp, _fp, _fp, _vp, _fp, _vp, _fp, _fp, _fp] + [_i] * 12 + [C.c_float, _vp]),
     "tulip_mlp_block_supported": (_i, [_i, _i]),

@@ -378,6 +378,19 @@ int tulip_gemm_tn_group_plan(const int* M, const int* N, const int* K, int n, in
   return rc;
 }
 
+int tulip_head_bwd_fused_supported(int E, int r) { return head_bwd_fused_supported(E, r) ? 1 : 0; }
+
+int tulip_head_bwd_fused(const void* xn, void* dxn, const void* we, const void* wet, const float* bias, const float* wd,
+                         const float* pred, const float* target, const float* gscale, void* dh, float* dwd, int T, int E, int H,
+                         int W, int r, void* stream) {
+  HeadBwdArgs hb;
+  memset(&hb, 0, sizeof hb);
+  hb.xn = (const bf16*)xn; hb.dxn = (bf16*)dxn; hb.we = (const bf16*)we; hb.wet = (const bf16*)wet; hb.bias = bias; hb.wd = wd;
+  hb.pred = pred; hb.target = target; hb.gscale = gscale; hb.dh = (bf16*)dh; hb.dwd = dwd; hb.dwd_copies = 1;
+  hb.T = T; hb.E = E; hb.H = H; hb.W = W; hb.r = r;
+  return head_bwd_fused(hb, (cudaStream_t)stream);
+}
+
 int tulip_wmsa_block_supported(int B, int H, int W, int C, int heads, int Mh, int Mw) {
   return wmsa_block_supported(B, H, W, C, heads, Mh, Mw) ? 1 : 0;
 }

@@ -156,22 +156,6 @@ __device__ __forceinline__ void add_bias32(const float* __restrict__ bias, int n
   }
 }
 
-// Column sums over the 32 lanes of a warp for 32 per-lane values: recursive halving (31 shuffles), lane i returns the sum of
-// v[i] over all lanes.  Fixed tree, so the result does not depend on timing.  Destroys v.
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = up ? v[i] : v[i + off];
-      const float keep = up ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
-
 // direct-store epilogues (scatter destinations): 16 consecutive columns of one row
 template <int EPI>
 __device__ __forceinline__ void epi_direct16(const GemmArgs& g, int m, int n, float (&v)[16]) {

@@ -50,6 +50,22 @@ struct MlpBlockArgs {
 bool mlp_block_supported(int T, int C);
 int mlp_block_fwd(const MlpBlockArgs& a, cudaStream_t st);
 
+// fused head backward (mlp.cu, MODE 1) for PixelShuffleHead + decoder_pred + L1 at embed_dim 96, r = 4:
+//   dh [T, E r^2] (bf16, n' = ij*E + c order) = dpred[m, ij] * wd[c] * LeakyReLU'(xn . We'^T + bias'),  dxn = dh . We',
+//   dwd += colsum over (m, ij) of dpred * LeakyReLU(pre);  dpred = sign(pred - target) * gscale / (T r^2)
+struct HeadBwdArgs {
+  const bf16* xn; bf16* dxn;              // norm_up output [T, E], its gradient [T, E]
+  const bf16* we; const bf16* wet;        // We' [E r^2, E] (rows in shuffle-slot order) and its transpose [E, E r^2]
+  const float* bias;                      // bias' [E r^2], same order
+  const float* wd;                        // decoder_pred.weight [E]
+  const float* pred; const float* target; const float* gscale;
+  bf16* dh;                               // out: [T, E r^2], read by the weight-gradient GEMM
+  float* dwd; int dwd_copies;             // CTA b adds into copy b % dwd_copies (E floats apart)
+  int T, E, H, W, r;
+};
+bool head_bwd_fused_supported(int E, int r);
+int head_bwd_fused(const HeadBwdArgs& a, cudaStream_t st);
+
 struct LnArgs {
   const bf16* x;              // LN input rows [rows, C]; with gather: source tensor [B, 2*H2, 2*W2, C/4]
   const float* w; const float* b;

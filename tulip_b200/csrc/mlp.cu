@@ -16,6 +16,13 @@
 //   warp 3        weight-chunk loader (TMA ring)
 //   warps 4..7    LayerNorm: one thread per row, raw row -> K-major 64B-swizzled A tile (+ statistics in training)
 //   warps 8..19   GELU + epilogue: warp (q, j) owns rows 32q.. and columns 32j.. of every 96-column chunk / of the output
+//
+// MODE 1 of the same kernel is the HEAD BACKWARD (PixelShuffleHead + decoder_pred + L1, tulip.py:161-178, 727-731, 692-693, at
+// embed_dim 96): the head is an MLP with 16 "hidden" chunks -- chunk ij = the 96 channels of shuffle slot ij.  fc1 chunk =
+// recomputed pre-activation (xn_up . We'[96 ij.., :]^T), the GELU step becomes dh = dpred[m, ij] * wd[c] * LeakyReLU'(pre)
+// (+ the column sums for d(decoder_pred.weight)), fc2 accumulates d(xn_up) += dh_chunk . We'[chunk] over the 16 chunks, and the
+// dh chunks leave through the storer for the weight-gradient GEMM.  It replaces the recompute GEMM (epilogue 7) AND the dX GEMM
+// that re-read the 402 MB dh tensor.  The LayerNorm warps only copy the (already normalised) input rows into the A operand.
 #include "fused.cuh"
 #include "kernels.h"
 
@@ -26,8 +33,7 @@ namespace {
 using namespace fused;
 
 constexpr int MC = 96;                      // channels
-constexpr int MHID = 4 * MC;                // hidden units
-constexpr int NCH = MHID / MC;              // hidden chunks per tile
+constexpr int MAX_NCH = 16;                 // hidden chunks per tile: 4 (MLP, hidden 4C) or 16 (head backward, r^2 = 16 shuffle slots)
 constexpr int ML_WARPS = 20, ML_THREADS = 32 * ML_WARPS;
 constexpr int EP_WARPS = 12, LN_WARPS = 4, LN_WARP0 = 4, EP_WARP0 = 8;
 constexpr int REGS_ISSUER = 24, REGS_LN = 72, REGS_EP = 128;
@@ -39,11 +45,15 @@ constexpr int OFF_WR = 0;                                   // weight ring: 4 x 
 constexpr int OFF_A = OFF_WR + W_RING * W_SLOT;             // LayerNorm output, A operand of fc1
 constexpr int OFF_H = OFF_A + NKB * A_BLK;                  // 2 x activated hidden chunk, A operand of fc2
 constexpr int OFF_RAW = OFF_H + 2 * NKB * A_BLK;            // ring of raw x tiles: LayerNorm source, residual, then the y tile
-constexpr int OFF_PAR = OFF_RAW + RAW_RING * RAW_TILE;      // fp32: b1 [384] | b2 [96] | gamma [96] | beta [96]
-constexpr int OFF_BAR = OFF_PAR + (MHID + 3 * MC) * 4;
-constexpr int ML_SMEM = OFF_BAR + 512 + 1024;
+constexpr int OFF_PAR = OFF_RAW + RAW_RING * RAW_TILE;      // fp32: b1 [96 NCH] | b2 [96] (head: wd) | gamma [96] | beta [96]
+template <int NCH_>
+struct Lay {
+  static constexpr int NCH = NCH_, MHID = NCH_ * MC;
+  static constexpr int OFF_BAR = OFF_PAR + (MHID + 3 * MC) * 4;
+  static constexpr int SMEM = OFF_BAR + 512 + 1024;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
 constexpr int TM_ACC1 = 0, TM_ACC2 = 2 * MC;                // TMEM columns: two fc1 chunk buffers, two fc2 tile buffers
-static_assert(ML_SMEM <= 227 * 1024, "shared memory budget");
 
 struct MlpArgs {
   const float* ln_w; const float* ln_b; const float* b1; const float* b2;
@@ -52,18 +62,25 @@ struct MlpArgs {
   int T, ntiles;
   int save;                                 // training: LayerNorm output and activated hidden tensor are stored too
   float eps;
+  // MODE 1 (head backward): b1 = permuted conv_expand bias [1536], b2 = decoder_pred.weight [96]; dpred is formed from pred / target
+  const float* pred; const float* target; const float* gscale; float inv_npix;
+  float* dwd; int dwd_copies;               // CTA b adds its column sums into copy b % dwd_copies (96 floats apart)
+  int hd_H, hd_W, hd_r;
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(ML_THREADS, 1)
 mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                      const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
                      const __grid_constant__ CUtensorMap mapXn, const __grid_constant__ CUtensorMap mapHact,
                      const __grid_constant__ MlpArgs a) {
+  using LY = Lay<MODE == 0 ? 4 : MAX_NCH>;
+  constexpr int NCH = LY::NCH, MHID = LY::MHID;
   extern __shared__ unsigned char smem_raw[];
   pdl_trigger();
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* spar = reinterpret_cast<float*>(smem + OFF_PAR);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LY::OFF_BAR);
   uint64_t* w_full = bars;              // [4] weight chunk landed
   uint64_t* w_empty = bars + 4;         // [4] its MMAs have read it
   uint64_t* raw_full = bars + 8;        // [3]
@@ -80,14 +97,15 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
 
   const int warp = tc::warp_idx_sync(), lane = threadIdx.x & 31;
-  const int shared_readers = a.save ? 2 : 1;                // MMA commit (+ storer)
+  const bool save_xn = (MODE == 0) && a.save, save_h = a.save != 0;   // head backward: only the dh chunks are stored
+  const int a_readers = save_xn ? 2 : 1, h_readers = save_h ? 2 : 1;  // MMA commit (+ storer)
   if (threadIdx.x == 0) {
     for (int b = 0; b < W_RING; ++b) { tc::mbar_init(w_full + b, 1); tc::mbar_init(w_empty + b, 1); }
     for (int b = 0; b < RAW_RING; ++b) { tc::mbar_init(raw_full + b, 1); tc::mbar_init(raw_empty + b, 1); tc::mbar_init(y_full + b, EP_WARPS); }
-    tc::mbar_init(a_full, LN_WARPS); tc::mbar_init(a_empty, shared_readers);
+    tc::mbar_init(a_full, LN_WARPS); tc::mbar_init(a_empty, a_readers);
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(acc1_full + b, 1); tc::mbar_init(acc1_empty + b, EP_WARPS);
-      tc::mbar_init(h_full + b, EP_WARPS); tc::mbar_init(h_empty + b, shared_readers);
+      tc::mbar_init(h_full + b, EP_WARPS); tc::mbar_init(h_empty + b, h_readers);
       tc::mbar_init(acc2_full + b, 1); tc::mbar_init(acc2_empty + b, EP_WARPS);
     }
     tc::fence_barrier_init();
@@ -185,7 +203,7 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     if (tc::elect_one_sync()) { tc::prefetch_tensormap(&mapY); tc::prefetch_tensormap(&mapXn); tc::prefetch_tensormap(&mapHact); }
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
-      if (a.save) {
+      if (save_xn) {
         tc::mbar_wait(a_full, it & 1);
         if (tc::elect_one_sync()) {
           for (int kb = 0; kb < NKB; ++kb) tc::tma_store_2d(&mapXn, smem + OFF_A + kb * A_BLK, kb * KBLK, tile * 128);
@@ -194,6 +212,8 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
           tc::mbar_arrive(a_empty);
         }
         __syncwarp();
+      }
+      if (save_h) {
         for (int c = 0; c < NCH; ++c) {
           const int G = it * NCH + c, buf = G & 1;
           tc::mbar_wait(h_full + buf, (G >> 1) & 1);
@@ -235,7 +255,7 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     reg_dec<REGS_LN>();
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    for (int i = threadIdx.x - 32 * LN_WARP0; i < MHID + 3 * MC; i += 32 * LN_WARPS) {
+    for (int i = threadIdx.x - 32 * LN_WARP0; i < MHID + (MODE == 0 ? 3 : 1) * MC; i += 32 * LN_WARPS) {
       float v;
       if (i < MHID) v = a.b1[i];
       else if (i < MHID + MC) v = a.b2[i - MHID];
@@ -252,6 +272,21 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
       const unsigned char* src = smem + OFF_RAW + slot * RAW_TILE + r * ROWB;
       unsigned char* dst = smem + OFF_A;
       tc::mbar_wait(raw_full + slot, (it / RAW_RING) & 1);
+      if (MODE == 1) {
+        // head backward: the rows are LayerNorm output already; they only move into the swizzled A operand
+        if (it >= 1) tc::mbar_wait(a_empty, (it - 1) & 1);
+        int kk = rot;
+#pragma unroll 4
+        for (int c = 0; c < MC / 8; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src + kk * 16);
+          *reinterpret_cast<uint4*>(dst + (kk >> 2) * A_BLK + sw64_off(r, kk & 3)) = v;
+          kk = (kk == 11) ? 0 : kk + 1;
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(a_full);
+        continue;
+      }
       const float x0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(src)).x;
       float s1 = 0.f, s2 = 0.f;
       int k = rot;
@@ -334,7 +369,8 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = unpack_bf16(w4[e]);
-          o4[e] = pack_bf16(fmaf(rs, v[2 * e] + pp[2 * e], f.x), fmaf(rs, v[2 * e + 1] + pp[2 * e + 1], f.y));
+          if (MODE == 1) o4[e] = pack_bf16(v[2 * e], v[2 * e + 1]);             // d(xn_up): no bias, no residual
+          else o4[e] = pack_bf16(fmaf(rs, v[2 * e] + pp[2 * e], f.x), fmaf(rs, v[2 * e + 1] + pp[2 * e + 1], f.y));
         }
         *reinterpret_cast<uint4*>(xr + k * 16) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
       }
@@ -343,8 +379,34 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
       __syncwarp();
       if (lane == 0) { tc::mbar_arrive(acc2_empty + tb); tc::mbar_arrive(y_full + slot); }
     };
+    // head backward: dpred of (row, shuffle slot) = sign(pred - target) * gscale / npix, fetched one chunk ahead;
+    // cw[i] = this thread's part of the column sums sum_rows dpred * LeakyReLU(pre) for d(decoder_pred.weight)
+    float cw[32];
+    float hd_gs = 0.f, pn = 0.f, tn = 0.f;
+    auto hd_fetch = [&](int G_) {                            // pred / target of this thread's row for chunk G_
+      const int it_ = G_ / NCH, ij = G_ - it_ * NCH;
+      const int m = (blockIdx.x + it_ * gridDim.x) * 128 + r;
+      pn = tn = 0.f;
+      if (m < a.T) {
+        const int w = m % a.hd_W, bh = m / a.hd_W, hh = bh % a.hd_H, b_ = bh / a.hd_H, rr = a.hd_r;
+        const long px = ((long)(b_ * a.hd_H * rr + hh * rr + ij / rr) * (a.hd_W * rr) + w * rr + (ij % rr));
+        pn = a.pred[px]; tn = a.target[px];
+      }
+    };
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) cw[i] = 0.f;
+      hd_gs = a.gscale[0] * a.inv_npix;
+      if (NG > 0) hd_fetch(0);
+    }
     for (int G = 0; G < NG; ++G) {
       const int it = G / NCH, c = G - it * NCH, buf = G & 1;
+      float dp = 0.f;
+      if (MODE == 1) {
+        const float d = pn - tn;
+        dp = d > 0.f ? hd_gs : (d < 0.f ? -hd_gs : 0.f);
+        if (G + 1 < NG) hd_fetch(G + 1);
+      }
       tc::mbar_wait(acc1_full + buf, (G >> 1) & 1);
       tc::fence_after_sync();
       float v[32];
@@ -354,11 +416,32 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
       if (lane == 0) tc::mbar_arrive(acc1_empty + buf);       // the next-but-one fc1 chunk may overwrite the accumulator
       const float* bb = spar + c * MC + jg * 32;
       uint32_t h[16];
+      if (MODE == 1) {
+        const float* wdp = spar + MHID + jg * 32;             // decoder_pred.weight sits in the b2 slot
+        const float dp01 = 0.01f * dp;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * i);
+          const float4 w4 = *reinterpret_cast<const float4*>(wdp + 4 * i);
+          const float pre[4] = {v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w};
+          const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float t = pre[e] > 0.f ? dp : dp01;         // dpred * LeakyReLU'(pre)
+            cw[4 * i + e] = fmaf(t, pre[e], cw[4 * i + e]);    // dpred * LeakyReLU(pre)
+            o[e] = t * ww[e];
+          }
+          h[2 * i] = pack_bf16(o[0], o[1]);
+          h[2 * i + 1] = pack_bf16(o[2], o[3]);
+        }
+      } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * i);
         h[2 * i] = pack_bf16(gelu_erf(v[4 * i] + b4.x), gelu_erf(v[4 * i + 1] + b4.y));
         h[2 * i + 1] = pack_bf16(gelu_erf(v[4 * i + 2] + b4.z), gelu_erf(v[4 * i + 3] + b4.w));
+      }
       }
       tc::mbar_wait(h_empty + buf, ((G >> 1) & 1) ^ 1);        // fc2 of the chunk two back (and the storer) have read this H buffer
       unsigned char* hd = smem + OFF_H + buf * NKB * A_BLK + jg * A_BLK;
@@ -371,6 +454,12 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
       if (c == 1 && it > 0) epilogue(it - 1);                 // its last fc2 partial product was issued two chunks ago
     }
     if (my_tiles > 0) epilogue(my_tiles - 1);
+    if constexpr (MODE == 1) {
+      // column sums over the 32 rows of the warp (fixed tree), one atomic per column into this CTA's gradient copy
+      float* dwd = a.dwd + (a.dwd_copies > 1 ? (int)(blockIdx.x % a.dwd_copies) * MC : 0);
+      const float sum = warp_colsum32(cw, lane);
+      atomicAdd(dwd + jg * 32 + lane, sum);
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -406,12 +495,12 @@ int mlp_block_fwd(const MlpBlockArgs& m, cudaStream_t st) {
     if (rc) return rc;
     rc = tulip_make_tmap(&my, m.y, 2, dx, sx, brow, 0);
     if (rc) return rc;
-    const uint64_t d1[2] = {(uint64_t)MC, (uint64_t)MHID};
+    const uint64_t d1[2] = {(uint64_t)MC, (uint64_t)Lay<4>::MHID};
     const uint32_t bw[2] = {KBLK, MC};
     rc = tulip_make_tmap(&mw1, m.w1, 2, d1, sx, bw, 64);
     if (rc) return rc;
-    const uint64_t d2[2] = {(uint64_t)MHID, (uint64_t)MC};
-    const uint64_t s2[1] = {(uint64_t)MHID * 2};
+    const uint64_t d2[2] = {(uint64_t)Lay<4>::MHID, (uint64_t)MC};
+    const uint64_t s2[1] = {(uint64_t)Lay<4>::MHID * 2};
     rc = tulip_make_tmap(&mw2, m.w2, 2, d2, s2, bw, 64);
     if (rc) return rc;
     mxn = mx; mh = mx;
@@ -419,7 +508,7 @@ int mlp_block_fwd(const MlpBlockArgs& m, cudaStream_t st) {
       const uint32_t bk[2] = {KBLK, 128};                   // one 64B-swizzled K block of an operand tile
       rc = tulip_make_tmap(&mxn, m.xn, 2, dx, sx, bk, 64);
       if (rc) return rc;
-      const uint64_t dh[2] = {(uint64_t)MHID, (uint64_t)m.T};
+      const uint64_t dh[2] = {(uint64_t)Lay<4>::MHID, (uint64_t)m.T};
       rc = tulip_make_tmap(&mh, m.hact, 2, dh, s2, bk, 64);
       if (rc) return rc;
     }
@@ -432,11 +521,67 @@ int mlp_block_fwd(const MlpBlockArgs& m, cudaStream_t st) {
   a.T = m.T; a.ntiles = (m.T + 127) / 128; a.save = save ? 1 : 0; a.eps = m.eps;
   static bool configured = false;
   if (!configured) {
-    TULIP_CUDA(cudaFuncSetAttribute(mlp_block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM));
+    TULIP_CUDA(cudaFuncSetAttribute(mlp_block_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<4>::SMEM));
     configured = true;
   }
   const int grid = min(a.ntiles, tulip_num_sms());
-  tulip_launch(mlp_block_fwd_kernel, grid, ML_THREADS, ML_SMEM, st, mx, my, mw1, mw2, mxn, mh, a);
+  tulip_launch(mlp_block_fwd_kernel<0>, grid, ML_THREADS, Lay<4>::SMEM, st, mx, my, mw1, mw2, mxn, mh, a);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+bool head_bwd_fused_supported(int E, int r) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("TULIP_B200_NO_FUSED_HEAD_BWD");
+    off = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !off && E == MC && r * r == MAX_NCH;
+}
+
+int head_bwd_fused(const HeadBwdArgs& m, cudaStream_t st) {
+  TULIP_REQUIRE(head_bwd_fused_supported(m.E, m.r) && m.T >= 1, "fused head backward: needs embed_dim 96 and upscale factor 4");
+  auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  TULIP_REQUIRE(aligned(m.xn) && aligned(m.dxn) && aligned(m.we) && aligned(m.wet) && aligned(m.dh),
+                "fused head backward: 16-byte aligned activations and weights");
+  TULIP_REQUIRE(m.bias && m.wd && m.pred && m.target && m.gscale && m.dwd && m.dh, "fused head backward: null argument");
+  constexpr int HID = MAX_NCH * MC;
+  CUtensorMap mx, my, mw1, mw2, mh;
+  {
+    const uint64_t dx[2] = {(uint64_t)MC, (uint64_t)m.T};
+    const uint64_t sx[1] = {(uint64_t)MC * 2};
+    const uint32_t brow[2] = {MC, 128};
+    int rc = tulip_make_tmap(&mx, m.xn, 2, dx, sx, brow, 0);
+    if (rc) return rc;
+    rc = tulip_make_tmap(&my, m.dxn, 2, dx, sx, brow, 0);
+    if (rc) return rc;
+    const uint64_t d1[2] = {(uint64_t)MC, (uint64_t)HID};       // We' [E r^2, E]: rows 96 ij .. = shuffle slot ij
+    const uint32_t bw[2] = {KBLK, MC};
+    rc = tulip_make_tmap(&mw1, m.we, 2, d1, sx, bw, 64);
+    if (rc) return rc;
+    const uint64_t d2[2] = {(uint64_t)HID, (uint64_t)MC};       // We'^T [E, E r^2]: columns 96 ij ..
+    const uint64_t s2[1] = {(uint64_t)HID * 2};
+    rc = tulip_make_tmap(&mw2, m.wet, 2, d2, s2, bw, 64);
+    if (rc) return rc;
+    const uint32_t bk[2] = {KBLK, 128};
+    const uint64_t dh[2] = {(uint64_t)HID, (uint64_t)m.T};
+    rc = tulip_make_tmap(&mh, m.dh, 2, dh, s2, bk, 64);
+    if (rc) return rc;
+  }
+  MlpArgs a;
+  memset(&a, 0, sizeof a);
+  a.b1 = m.bias; a.b2 = m.wd;
+  a.rows_per_sample = 1;
+  a.T = m.T; a.ntiles = (m.T + 127) / 128; a.save = 1;
+  a.pred = m.pred; a.target = m.target; a.gscale = m.gscale; a.inv_npix = 1.0f / ((float)m.T * m.r * m.r);
+  a.dwd = m.dwd; a.dwd_copies = m.dwd_copies; a.hd_H = m.H; a.hd_W = m.W; a.hd_r = m.r;
+  static bool configured = false;
+  if (!configured) {
+    TULIP_CUDA(cudaFuncSetAttribute(mlp_block_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<MAX_NCH>::SMEM));
+    configured = true;
+  }
+  const int grid = min(a.ntiles, tulip_num_sms());
+  tulip_launch(mlp_block_fwd_kernel<1>, grid, ML_THREADS, Lay<MAX_NCH>::SMEM, st, mx, my, mw1, mw2, mx, mh, a);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }

@@ -992,15 +992,32 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       sum_to(c.G(slot_dec_w), scr, 2 * E, E, 3 * E);
     }
     g.hd_H = H0; g.hd_W = W0; g.hd_r = r; g.hd_E = E; g.hd_inv_npix = 1.0f / ((float)T0 * r * r);
-    RUN_NT(g, EPI_HEAD_BWD);
+    const bool fused_head = !cfg.expanding_head && head_bwd_fused_supported(E, r);
+    if (fused_head) {
+      // ONE launch (mlp.cu, MODE 1): recomputed pre-activation -> dh chunk in shared memory -> dxn accumulated over the 16
+      // shuffle slots; dh leaves once for the weight-gradient GEMM and is never read back by a dX GEMM
+      HeadBwdArgs hb;
+      memset(&hb, 0, sizeof hb);
+      hb.xn = c.A(p.xn_up); hb.dxn = c.A(p.scr_dxn); hb.we = c.W(l); hb.wet = c.Wt(l); hb.bias = c.bias(l); hb.wd = g.wd;
+      hb.pred = pred; hb.target = target; hb.gscale = grad_loss; hb.dh = dh; hb.dwd = g.dwd; hb.dwd_copies = g.dwd_copies;
+      hb.T = T0; hb.E = E; hb.H = H0; hb.W = W0; hb.r = r;
+      tag(K_NT_HEAD_BWD, 4.0 * T0 * E * r * r * E, 2.0 * T0 * E * (2.0 + r * r));
+      RUN(head_bwd_fused(hb, st));
+    } else {
+      RUN_NT(g, EPI_HEAD_BWD);
+    }
     // dWe' += dh^T . xn_up (rows un-permuted on store); bias gradient = column sums of dh, same un-permutation
     GemmTNArgs gw = dw(l, dh, c.A(p.xn_up), T0);
     TN_SIDE(gw);
     TN_FLUSH();
-    // dxn_up = dh . We'          (A = dh [T0, E r^2], B = We'^T stored as Wt' [E, E r^2])
-    GemmArgs gx = nt_args(dh, (long)E * r * r, c.Wt(l), (long)E * r * r, T0, E, E * r * r, nullptr, c.A(p.scr_dxn), E);
     want_scaled_for(dec_blocks[L - 2].back(), H0 * W0);
-    GEMM_LN_BWD(gx, x_last, slot_normup_w, slot_normup_b, c.F(p.st_up), c.A(p.scr_dxn), nullptr, g_cur, T0, E, 0, 0, 0);
+    if (fused_head) {
+      LN_BWD(x_last, slot_normup_w, slot_normup_b, c.F(p.st_up), c.A(p.scr_dxn), nullptr, g_cur, T0, E, 0, 0, 0);
+    } else {
+      // dxn_up = dh . We'          (A = dh [T0, E r^2], B = We'^T stored as Wt' [E, E r^2])
+      GemmArgs gx = nt_args(dh, (long)E * r * r, c.Wt(l), (long)E * r * r, T0, E, E * r * r, nullptr, c.A(p.scr_dxn), E);
+      GEMM_LN_BWD(gx, x_last, slot_normup_w, slot_normup_b, c.F(p.st_up), c.A(p.scr_dxn), nullptr, g_cur, T0, E, 0, 0, 0);
+    }
   }
 
   auto block_bwd = [&](int bi, const bf16* x_in, bf16* g_io, bf16* g_tmp, int bi_next) -> int {
