@@ -12,9 +12,4 @@ timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
   --log-file gpurun_out/final_traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-sustained > gpurun_out/final_ncu_traffic.log 2>&1
 echo "== traffic rc=$?"
 timeout 300 python scripts/launch_table.py 32 > gpurun_out/final_launch_table.md 2> gpurun_out/final_launch_table.err; echo "== table rc=$? $(head -n 1 gpurun_out/final_launch_table.md)"
-bash scripts/ncu_step_kernel.sh final_full_tn_group_s0 gemm_tn_group 6
-bash scripts/ncu_step_kernel.sh final_full_tn_group_s3 gemm_tn_group 20
-bash scripts/ncu_step_kernel.sh final_full_mlp_fwd mlp_block_fwd 5
-bash scripts/ncu_step_kernel.sh final_full_lnbwd "gemm_nt_tc05_kernel<96, 10" 4
-timeout 200 python scripts/time_tn.py 32 > gpurun_out/final_time_tn.md 2>&1
-timeout 200 python scripts/time_nt.py 32 96 > gpurun_out/final_time_nt.md 2>&1
+bash scripts/ncu_step_kernel.sh final_full_head_bwd "mlp_block_fwd_kernel<1>" 1
