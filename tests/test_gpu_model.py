@@ -86,11 +86,12 @@ def test_model_vs_reference_fixture(golden_dir, name, cfg, large):
     assert np.median(heads) <= 2e-2
 
 
-def test_model_vs_oracle_full_gradients():
-    """Every gradient tensor in full against the oracle's autograd (tulip_base, KITTI shape, B=1)."""
-    cfg = TULIP_BASE
+@pytest.mark.parametrize("cfg,B", [(TULIP_BASE, 1), (EXPANDING, 2), (EXPANDING_HEAD, 2)], ids=["base", "expanding", "expanding_head"])
+def test_model_vs_oracle_full_gradients(cfg, B):
+    """Every gradient tensor in full against the oracle's autograd (tulip_base, KITTI shape): the shipped configuration and the
+    PatchExpanding / FinalPatchExpanding variants (tulip.py:126-159)."""
     pn = make_params(cfg, 11)
-    lo, hi = make_inputs(cfg, 1, 12)
+    lo, hi = make_inputs(cfg, B, 12)
     p = O.to_torch(pn, requires_grad=True)
     pred_o, loss_o, pixel_o = O.forward(p, cfg, torch.from_numpy(lo), torch.from_numpy(hi), state={})
     loss_o.backward()
@@ -106,8 +107,8 @@ def test_model_vs_oracle_full_gradients():
     assert rel_l2(pred, pred_o) <= 1e-2 and med <= 2e-2 and errs[worst] <= 0.3
 
 
-def test_train_mode_droppath_and_state_dict_roundtrip():
-    cfg = TULIP_BASE
+@pytest.mark.parametrize("cfg", [TULIP_BASE, EXPANDING_HEAD], ids=["base", "expanding_head"])
+def test_train_mode_droppath_and_state_dict_roundtrip(cfg):
     pn = make_params(cfg, 21)
     lo, hi = make_inputs(cfg, 4, 22)
     model = build(cfg)
