@@ -383,13 +383,21 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     // cw[i] = this thread's part of the column sums sum_rows dpred * LeakyReLU(pre) for d(decoder_pred.weight)
     float cw[32];
     float hd_gs = 0.f, pn = 0.f, tn = 0.f;
-    auto hd_fetch = [&](int G_) {                            // pred / target of this thread's row for chunk G_
-      const int it_ = G_ / NCH, ij = G_ - it_ * NCH;
-      const int m = (blockIdx.x + it_ * gridDim.x) * 128 + r;
+    long hd_base = -1;                                       // pixel (b, 4h, 4w) of this thread's row in the current tile, -1: row past T
+    const int hd_Wr = a.hd_W * 4;                            // r = 4 in this mode (16 shuffle slots)
+    auto hd_fetch = [&](int G_) {                            // pred / target of this thread's row for chunk G_ (slot ij = G_ mod 16)
+      const int ij = G_ & (NCH - 1);
+      if (ij == 0) {                                         // first slot of a tile: the row's base pixel (the only divisions)
+        const int m = (blockIdx.x + (G_ / NCH) * gridDim.x) * 128 + r;
+        hd_base = -1;
+        if (m < a.T) {
+          const int w = m % a.hd_W, bh = m / a.hd_W, hh = bh % a.hd_H, b_ = bh / a.hd_H;
+          hd_base = (long)(b_ * a.hd_H + hh) * 4 * hd_Wr + w * 4;
+        }
+      }
       pn = tn = 0.f;
-      if (m < a.T) {
-        const int w = m % a.hd_W, bh = m / a.hd_W, hh = bh % a.hd_H, b_ = bh / a.hd_H, rr = a.hd_r;
-        const long px = ((long)(b_ * a.hd_H * rr + hh * rr + ij / rr) * (a.hd_W * rr) + w * rr + (ij % rr));
+      if (hd_base >= 0) {
+        const long px = hd_base + (ij >> 2) * hd_Wr + (ij & 3);
         pn = a.pred[px]; tn = a.target[px];
       }
     };
@@ -409,33 +417,43 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
       }
       tc::mbar_wait(acc1_full + buf, (G >> 1) & 1);
       tc::fence_after_sync();
+      const float* bb = spar + c * MC + jg * 32;
+      uint32_t h[16];
+      if constexpr (MODE == 1) {
+        // two 16-column halves: next to the 32 column-sum accumulators a whole 32-column load does not fit the register budget
+        const float* wdp = spar + MHID + jg * 32;             // decoder_pred.weight sits in the b2 slot
+        const float dp01 = 0.01f * dp;
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC1 + buf * MC + jg * 32;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float v16[16];
+          tc::tmem_ld16(ta + 16 * hf, v16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bb + 16 * hf + 4 * i);
+            const float4 w4 = *reinterpret_cast<const float4*>(wdp + 16 * hf + 4 * i);
+            const float pre[4] = {v16[4 * i] + b4.x, v16[4 * i + 1] + b4.y, v16[4 * i + 2] + b4.z, v16[4 * i + 3] + b4.w};
+            const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float t = pre[e] > 0.f ? dp : dp01;       // dpred * LeakyReLU'(pre)
+              cw[16 * hf + 4 * i + e] = fmaf(t, pre[e], cw[16 * hf + 4 * i + e]);   // dpred * LeakyReLU(pre)
+              o[e] = t * ww[e];
+            }
+            h[8 * hf + 2 * i] = pack_bf16(o[0], o[1]);
+            h[8 * hf + 2 * i + 1] = pack_bf16(o[2], o[3]);
+          }
+        }
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(acc1_empty + buf);     // the next-but-one fc1 chunk may overwrite the accumulator
+      } else {
       float v[32];
       tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC1 + buf * MC + jg * 32, v);
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(acc1_empty + buf);       // the next-but-one fc1 chunk may overwrite the accumulator
-      const float* bb = spar + c * MC + jg * 32;
-      uint32_t h[16];
-      if (MODE == 1) {
-        const float* wdp = spar + MHID + jg * 32;             // decoder_pred.weight sits in the b2 slot
-        const float dp01 = 0.01f * dp;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * i);
-          const float4 w4 = *reinterpret_cast<const float4*>(wdp + 4 * i);
-          const float pre[4] = {v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w};
-          const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float t = pre[e] > 0.f ? dp : dp01;         // dpred * LeakyReLU'(pre)
-            cw[4 * i + e] = fmaf(t, pre[e], cw[4 * i + e]);    // dpred * LeakyReLU(pre)
-            o[e] = t * ww[e];
-          }
-          h[2 * i] = pack_bf16(o[0], o[1]);
-          h[2 * i + 1] = pack_bf16(o[2], o[3]);
-        }
-      } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * i);
