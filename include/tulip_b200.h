@@ -306,6 +306,10 @@ int tulip_grad_norm(const float* grads, const tulip_adamw_segment* segments_dev,
                     void* stream);
 int tulip_l1_loss(const float* pred, const float* target, int64_t n, int log_transform, float* scratch2, float* out2,
                   void* stream);
+/* inputs of a step (low-res frames, targets, DropPath scales; any pair may be NULL) copied into persistent buffers by ONE launch:
+ * a host that keeps its buffers gets tulip_net_forward / _backward replayed as CUDA graphs (stable pointers) */
+int tulip_stage_inputs(const float* lo, float* lo_dst, int64_t n_lo, const float* hi, float* hi_dst, int64_t n_hi, const float* drop,
+                       float* drop_dst, int64_t n_drop, void* stream);
 
 /* ---- stand-alone index ops (bit-exact; the same device functions the fused kernels use) ----
  * window_partition (tulip.py:248-252) composed with torch.roll(-sh,-sw) (tulip.py:290); reverse = tulip.py:320,323 */

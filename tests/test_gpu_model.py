@@ -373,3 +373,52 @@ def test_backward_in_three_phases_equals_one_pass(cfg, large):
     errs = {n: rel_l2(q.grad, want[n]) for n, q in model.named_parameters()}
     worst = max(errs, key=errs.get)
     assert errs[worst] <= 1e-4, (worst, errs[worst])
+
+
+def test_predrawn_droppath_scales_are_reproducible_and_invalidate():
+    """The DropPath scales of the next training forward are drawn right after the current forward is launched (off the host's
+    critical path when the loop reads the loss every step).  Same seed -> same sequence of scale sets; a reseed or any other
+    CUDA random op in between discards the pre-drawn set instead of using stale numbers."""
+    cfg = TULIP_BASE
+    pn = make_params(cfg, 41)
+    lo, hi = make_inputs(cfg, 2, 42)
+    lo_t, hi_t = torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda()
+    model = build(cfg)
+    load_params(model, pn)
+    model.cuda().train()
+
+    def run(n, disturb=False):
+        torch.manual_seed(7)
+        out = []
+        for i in range(n):
+            if disturb and i == 1:
+                torch.rand(3, device="cuda")                  # moves the generator: the pre-drawn set must not be used
+            _, loss, _ = model(lo_t, hi_t)
+            loss.item()
+            (bufs,) = [b for b in model._step_bufs.values()]
+            out.append(bufs["drop"].clone())                  # the scales this forward ran with
+        return out
+
+    a = run(8)
+    hits = model._predraw_hits
+    assert hits == 7 and "_predrawn" in model.__dict__        # every call after the first used the set drawn behind its predecessor
+    b = run(8)
+    assert all(torch.equal(x, y) for x, y in zip(a, b)) and model._predraw_hits == hits + 7   # reseed: waiting set discarded, same replay
+    c = run(8, disturb=True)
+    assert torch.equal(c[0], a[0]) and not all(torch.equal(x, y) for x, y in zip(a[1:], c[1:]))   # the stream moved: nothing stale reused
+    assert model._predraw_hits == hits + 7 + 6
+    assert not all(torch.equal(a[0], x) for x in a[1:])       # masks do change from step to step
+
+
+def test_stage_inputs_one_launch_copy():
+    from tulip_b200._lib import check, current_stream, load_library, ptr
+    lib = load_library()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for sizes in ((32 * 16 * 1024, 32 * 64 * 1024, 28 * 32), (1027, 0, 5), (4, 8, 0)):
+        src = [torch.rand(n, device="cuda", generator=g) if n else None for n in sizes]
+        dst = [torch.full((n + 4,), -1.0, device="cuda") if n else None for n in sizes]
+        check(lib.tulip_stage_inputs(ptr(src[0]), ptr(dst[0]), sizes[0], ptr(src[1]), ptr(dst[1]), sizes[1], ptr(src[2]), ptr(dst[2]),
+                                     sizes[2], current_stream()), "tulip_stage_inputs")
+        for s_, d_, n in zip(src, dst, sizes):
+            if n:
+                assert torch.equal(d_[:n], s_) and bool((d_[n:] == -1).all())

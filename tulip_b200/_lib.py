@@ -109,6 +109,7 @@ SIGNATURES = {
     "tulip_adamw_step": (_i, [_fp, _fp, _fp, _fp, _vp, _i, _i64, _vp, _vp]),
     "tulip_grad_norm": (_i, [_fp, _vp, _i, _i64, _vp, _fp, _vp]),
     "tulip_l1_loss": (_i, [_fp, _fp, _i64, _i, _fp, _fp, _vp]),
+    "tulip_stage_inputs": (_i, [_fp, _fp, _i64, _fp, _fp, _i64, _fp, _fp, _i64, _vp]),
     "tulip_window_partition": (_i, [_vp, _vp] + [_i] * 8 + [_vp]),
     "tulip_window_reverse": (_i, [_vp, _vp] + [_i] * 8 + [_vp]),
     "tulip_shift_mask": (_i, [_fp] + [_i] * 6 + [_vp]),

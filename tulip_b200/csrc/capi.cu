@@ -553,6 +553,14 @@ int tulip_grad_norm(const float* grads, const tulip_adamw_segment* segments_dev,
   return grad_norm(grads, reinterpret_cast<const AdamwSegment*>(segments_dev), n_segments, (long)span, scratch, out, (cudaStream_t)stream);
 }
 
+int tulip_stage_inputs(const float* lo, float* lo_dst, int64_t n_lo, const float* hi, float* hi_dst, int64_t n_hi, const float* drop,
+                       float* drop_dst, int64_t n_drop, void* stream) {
+  const float* src[3] = {lo, hi, drop};
+  float* dst[3] = {lo_dst, hi_dst, drop_dst};
+  const long n[3] = {(long)n_lo, (long)n_hi, (long)n_drop};
+  return stage_inputs(src, dst, n, (cudaStream_t)stream);
+}
+
 int tulip_l1_loss(const float* pred, const float* target, int64_t n, int log_transform, float* scratch2, float* out2, void* stream) {
   return l1_loss(pred, target, (long)n, log_transform, scratch2, out2, (cudaStream_t)stream);
 }

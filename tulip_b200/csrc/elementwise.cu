@@ -920,6 +920,39 @@ int scale_rows_bf16(bf16* dst, const bf16* src, const float* row_scale, int rows
   return TULIP_OK;
 }
 
+// Inputs of a step into the module's persistent buffers (stable addresses let the step replay as a CUDA graph): low-res
+// frames, targets and DropPath scales in ONE launch instead of three copy launches on the host's critical path.
+namespace {
+struct Stage3 { const float* src[3]; float* dst[3]; long n[3]; };
+__global__ void stage_inputs_kernel(const Stage3 s) {
+  pdl_sync();
+  const long stride = (long)gridDim.x * blockDim.x;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const long n4 = s.n[k] >> 2;
+    const float4* a = reinterpret_cast<const float4*>(s.src[k]);
+    float4* b = reinterpret_cast<float4*>(s.dst[k]);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) b[i] = a[i];
+    for (long i = (n4 << 2) + (long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n[k]; i += stride) s.dst[k][i] = s.src[k][i];
+  }
+}
+}  // namespace
+
+int stage_inputs(const float* const* src, float* const* dst, const long* n, cudaStream_t st) {
+  Stage3 s;
+  long total = 0;
+  for (int k = 0; k < 3; ++k) {
+    s.src[k] = src[k]; s.dst[k] = dst[k]; s.n[k] = (src[k] && dst[k]) ? n[k] : 0;
+    TULIP_REQUIRE(s.n[k] == 0 || (((reinterpret_cast<uintptr_t>(src[k]) | reinterpret_cast<uintptr_t>(dst[k])) & 15) == 0),
+                  "stage_inputs: 16-byte aligned buffers");
+    total += s.n[k];
+  }
+  if (total == 0) return TULIP_OK;
+  tulip_launch(stage_inputs_kernel, ew_grid((total + 3) / 4, 256), 256, 0, st, s);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
 int l1_loss(const float* pred, const float* target, long n, int log_transform, float* acc2, float* out2, cudaStream_t st) {
   TULIP_CUDA(cudaMemsetAsync(acc2, 0, 2 * sizeof(float), st));
   tulip_launch(l1_loss_kernel, ew_grid(n, 256), 256, 0, st, pred, target, n, log_transform, acc2);

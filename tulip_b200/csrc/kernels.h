@@ -120,6 +120,7 @@ int eval_postprocess(const float* pred, const float* lo, const float* hi, float*
 // Monte-Carlo-dropout aggregation (engine_upsampling.py:423-427): preds [n, npix] -> out [npix] (mean, zeroed where std > threshold * mean)
 int mc_aggregate(const float* preds, float* out, float* std_out, int n, long npix, float threshold, cudaStream_t st);
 int l1_loss(const float* pred, const float* target, long n, int log_transform, float* acc2, float* out2, cudaStream_t st);
+int stage_inputs(const float* const* src, float* const* dst, const long* n, cudaStream_t st);   // up to three fp32 copies, one launch
 
 // stand-alone index ops (bit-exact tests of the index arithmetic used inside the fused kernels)
 int window_gather(const bf16* x, bf16* out, int B, int H, int W, int C, int Mh, int Mw, int sh, int sw, cudaStream_t st);

@@ -309,6 +309,11 @@ class _TulipFunction(torch.autograd.Function):
         return (None,) * n_fixed + grads
 
 
+def _stageable(*tensors):
+    """fp32, contiguous, 16-byte aligned CUDA tensors (or None): what tulip_stage_inputs copies in one launch."""
+    return all(t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.data_ptr() % 16 == 0) for t in tensors)
+
+
 class TULIP(nn.Module):
     """Same constructor signature as the reference TULIP (tulip.py:531-535)."""
 
@@ -507,7 +512,7 @@ class TULIP(nn.Module):
     # runtime state that must not travel with copy.deepcopy / pickle / torch.save(model): the C handle and raw ctypes pointers
     # (not picklable), buffers tied to that handle, and weak references.  A copy re-creates all of it lazily on its first forward.
     _RUNTIME_STATE = ("_net", "_flat", "_grad_bufs", "_views", "_param_list", "_offsets", "_offsets_p", "_ws_bytes", "_step_bufs",
-                      "_persistent_owner", "_win_modes_cache", "_keep_cache", "_schema", "_grad_mode_hint")
+                      "_persistent_owner", "_win_modes_cache", "_keep_cache", "_schema", "_grad_mode_hint", "_predrawn", "_predraw_hits")
 
     def __getstate__(self):
         state = dict(self.__dict__)
@@ -546,15 +551,18 @@ class TULIP(nn.Module):
         pers = self._step_buffers(B, dev) if self._persistent_free() else None
         if pers is not None:
             ws, xin, pred_w, losses_w = pers["ws"], pers["lo"], pers["pred"], pers["losses"]
-            xin.copy_(x)
-            tin = None
-            if target is not None:
-                tin = pers["hi"]
-                tin.copy_(target)
-            din = None
-            if drop_scales is not None:
-                din = pers["drop"]
-                din.copy_(drop_scales)
+            tin = pers["hi"] if target is not None else None
+            din = pers["drop"] if drop_scales is not None else None
+            if _stageable(x, target, drop_scales):                 # one launch instead of three copy_ calls (host critical path)
+                check(lib.tulip_stage_inputs(ptr(x), ptr(xin), x.numel(), ptr(target), ptr(tin), 0 if target is None else target.numel(),
+                                             ptr(drop_scales), ptr(din), 0 if drop_scales is None else drop_scales.numel(),
+                                             current_stream()), "tulip_stage_inputs")
+            else:
+                xin.copy_(x)
+                if target is not None:
+                    tin.copy_(target)
+                if drop_scales is not None:
+                    din.copy_(drop_scales)
         else:
             ws = torch.empty(self._workspace_bytes(B), dtype=torch.uint8, device=dev)
             xin, tin, din = x, target, drop_scales
@@ -650,8 +658,29 @@ class TULIP(nn.Module):
             keep = 1.0 - torch.tensor([r for r in rates for _ in (0, 1)], dtype=torch.float32, device=device).unsqueeze(1)
             cached = self._keep_cache = (key, keep)
         keep = cached[1]
+        # The scales of the NEXT training forward are drawn right after this forward has been launched (_predraw_drop_scales),
+        # so the four small launches queue behind the running step instead of in front of it (the host path between reading
+        # the loss and launching the next forward is what the GPU idles on).  A pre-drawn set is used only if the CUDA
+        # generator is exactly where the pre-draw left it (no reseed, no other random op since): same stream, drawn earlier.
+        pre = self.__dict__.pop("_predrawn", None)
+        if pre is not None and pre[0] == (key, B) and pre[1] == self._rng_position(device):
+            self._predraw_hits = getattr(self, "_predraw_hits", 0) + 1
+            return pre[2]
         u = torch.rand((keep.shape[0], B), dtype=torch.float32, device=device)
         return u.add_(keep).floor_().div_(keep)
+
+    @staticmethod
+    def _rng_position(device):
+        gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+        return (gen.initial_seed(), gen.get_offset())
+
+    def _predraw_drop_scales(self, B, device):
+        cached = getattr(self, "_keep_cache", None)
+        if not self.training or cached is None:
+            return
+        keep = cached[1]
+        u = torch.rand((keep.shape[0], B), dtype=torch.float32, device=device)
+        self._predrawn = ((cached[0], B), self._rng_position(device), u.add_(keep).floor_().div_(keep))
 
     def kernel_launches(self) -> int:
         return 0 if self._net is None else int(load_library().tulip_net_kernel_launches(self._net))
@@ -691,6 +720,8 @@ class TULIP(nn.Module):
             self._ensure_flat(x.device)
             self._params_version = -1
             launched = self._launch_forward(x, tgt, drop, self._window_modes())
+        if _drop_scales is None and drop is not None and self._grad_mode_hint:
+            self._predraw_drop_scales(B, x.device)          # behind the forward that is already running
         pred, loss, pixel = _TulipFunction.apply(self, launched, tgt is not None, win_mode, *self._param_list)
         if mc_drop:
             return pred
