@@ -83,6 +83,7 @@ static bool debug_skip_tn() {
   if (v < 0) {
     const char* e = getenv("TULIP_B200_DEBUG_SKIP_TN");
     v = (e && e[0] == '1') ? 1 : 0;
+    if (v) fprintf(stderr, "tulip_b200: TULIP_B200_DEBUG_SKIP_TN=1 -- weight-gradient GEMMs are NOT launched, gradients are WRONG (timing only)\n");
   }
   return v == 1;
 }
