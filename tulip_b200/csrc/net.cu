@@ -88,46 +88,6 @@ static bool debug_skip_tn() {
   return v == 1;
 }
 
-// EXPERIMENT (TULIP_B200_L2_WINDOWS=1): L2 access-policy windows.  A tensor that one kernel writes and the next ones read
-// (qkv, the GELU-backward output, dqkv) is marked persisting for the launches that touch it, so at stages 0-1 -- where those
-// tensors are 25-100 MB and L2 holds 126 MB -- the re-reads can be served by L2 instead of HBM.
-static size_t l2_persist_bytes() {
-  static long v = -1;
-  if (v < 0) {
-    v = 0;
-    const char* e = getenv("TULIP_B200_L2_WINDOWS");
-    if (e && e[0] == '1') {
-      int dev = 0;
-      cudaDeviceProp prop;
-      if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-        size_t want = (size_t)prop.persistingL2CacheMaxSize;
-        const char* f = getenv("TULIP_B200_L2_WINDOW_MB");
-        if (f && atoi(f) > 0) want = std::min(want, (size_t)atoi(f) << 20);
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) v = (long)want;
-        fprintf(stderr, "tulip_b200: L2 windows on, persisting set-aside %.1f MB (max %.1f MB, window max %.1f MB)\n", v / 1048576.0,
-                prop.persistingL2CacheMaxSize / 1048576.0, prop.accessPolicyMaxWindowSize / 1048576.0);
-      }
-      cudaGetLastError();
-    }
-  }
-  return (size_t)v;
-}
-static void l2_window(cudaStream_t st, const void* p, size_t bytes) {
-  const size_t cap = l2_persist_bytes();
-  if (!cap || !st) return;
-  cudaStreamAttrValue v;
-  memset(&v, 0, sizeof v);
-  if (p && bytes) {
-    v.accessPolicyWindow.base_ptr = const_cast<void*>(p);
-    v.accessPolicyWindow.num_bytes = bytes;
-    v.accessPolicyWindow.hitRatio = bytes <= cap ? 1.0f : (float)((double)cap / (double)bytes);
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  }
-  cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
-  cudaGetLastError();
-}
-
 static bool side_stream_disabled() {
   static int v = -1;
   if (v < 0) {
@@ -617,7 +577,6 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
     }
     if (!xn1_ready) RUN(ln(x_in, b.n1w, b.n1b, c.A(bb.xn1), c.F(bb.st1), T, C, 0, 0, 0));
     join_pack();
-    l2_window(st, c.A(bb.qkv), (size_t)T * 3 * C * 2);
     {
       const Linear& l = linears[b.qkv];
       GemmArgs g = nt_args(c.A(bb.xn1), C, c.W(l), C, T, 3 * C, C, c.bias(l), c.A(bb.qkv), 3 * C);
@@ -629,7 +588,6 @@ int tulip_net::forward(int B, const float* params_, const int64_t* offs, const f
       tag(K_ATTN_FWD, 64.0 * T * C, 8.0 * T * C);
       RUN(win_attn_fwd(a, st));
     }
-    l2_window(st, nullptr, 0);
     {
       const Linear& l = linears[b.proj];
       GemmArgs g = nt_args(c.A(bb.ao), C, c.W(l), C, T, C, C, c.bias(l), c.A(bb.xmid), C);
@@ -1087,8 +1045,6 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       const Linear& l2 = linears[b.fc2];
       const Linear& lf1 = linears[b.fc1];
       TN_SIDE(dw(l2, gy, c.A(bb.hact), T));
-      l2_window(st, c.A(p.scr_big), (size_t)T * 4 * C * 2);
-      l2_window(side, c.A(p.scr_big), (size_t)T * 4 * C * 2);
       GemmArgs g = nt_args(gy, C, c.Wt(l2), C, T, 4 * C, C, nullptr, c.A(p.scr_big), 4 * C);   // dh = (gy . W2) o gelu'(pre)
       if (bb.hpre >= 0) {
         g.aux = c.A(bb.hpre); g.ldaux = 4 * C;
@@ -1109,8 +1065,6 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
     }
     // ---- attention half: x_mid = x_in + s1 * proj(attn(qkv(LN1(x_in)))) ----
     at(b.stage, 1);
-    l2_window(st, c.A(p.scr_dqkv), (size_t)T * 3 * C * 2);
-    l2_window(side, c.A(p.scr_dqkv), (size_t)T * 3 * C * 2);
     gy = ds1 ? c.A(p.scr_gs) : g_tmp;
     {
       const Linear& lp = linears[b.proj];
@@ -1135,8 +1089,6 @@ int tulip_net::backward(int B, const float* params_, const int64_t* offs, float*
       want_scaled_for(bi_next, Hs * Ws);                  // next block in backward order lives on the same grid
       GEMM_LN_BWD(gq, x_in, b.n1w, b.n1b, c.F(bb.st1), c.A(p.scr_dxn), g_tmp, g_io, T, C, 0, 0, 0);            // g_io = dL/dx_in
     }
-    l2_window(st, nullptr, 0);
-    l2_window(side, nullptr, 0);
     return TULIP_OK;
   };
 
