@@ -8,7 +8,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 fi
 B="python bench.py --config ${CONFIG:-kitti32} --steps ${STEPS:-60} --warmup 5 --no-cpu-baseline --no-eager-baseline --no-sustained"
 for v in ${VARIANTS:-"X=1"}; do
-  name="$(echo $v | tr '= ,' '___')"
+  name="$(echo $v | tr '= ,/.' '_____')"
   env $(echo $v | tr ',' ' ') timeout 300 $B > gpurun_out/bench_${CONFIG:-kitti32}_$name.json 2> gpurun_out/bench_${CONFIG:-kitti32}_$name.err
   python - "${CONFIG:-kitti32}_$name" <<'P'
 import json, sys

@@ -143,7 +143,10 @@ __device__ __forceinline__ void load_window_rows(const AttnArgs& a, bf16* sq, co
     const bf16* src = qkv + (long)tok[k] * 3 * a.C + hg * HG * HD + lc8;
     bf16* dst = sq + (li + 8 * k) * QLD + lc8;
 #pragma unroll
-    for (int seg = 0; seg < 3; ++seg) cp_async16(dst + seg * HG * HD, src + seg * a.C, 16);
+    for (int seg = 0; seg < 3; ++seg) {
+      if (a.hint) cp_async16_pol(dst + seg * HG * HD, src + seg * a.C, l2_evict_first_policy());
+      else cp_async16(dst + seg * HG * HD, src + seg * a.C, 16);
+    }
   }
 }
 
@@ -262,7 +265,8 @@ __global__ void __launch_bounds__(96) win_attn_bwd_kernel(const AttnArgs a) {
     load_window_rows(a, q, a.qkv, tok, li, lc8, hg);
 #pragma unroll
     for (int k = 0; k < 2; ++k)
-      cp_async16(d + (li + 8 * k) * OLD + lc8, a.dout + (long)tok[k] * a.C + hg * HG * HD + lc8, 16);
+      if (a.hint) cp_async16_pol(d + (li + 8 * k) * OLD + lc8, a.dout + (long)tok[k] * a.C + hg * HG * HD + lc8, l2_evict_first_policy());
+      else cp_async16(d + (li + 8 * k) * OLD + lc8, a.dout + (long)tok[k] * a.C + hg * HG * HD + lc8, 16);
   };
   // The kernel is bound by loads in flight (5 CTAs of ~120 registers per SM): each CTA keeps the rows of the next TWO
   // windows on their way (cp.async groups) while it works on the current one.
@@ -450,7 +454,9 @@ int win_attn_fwd(const AttnArgs& a, cudaStream_t st) {
   static int per_sm = 0;
   if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, win_attn_fwd_kernel, 96, 0) != cudaSuccess || per_sm < 1)) per_sm = 8;
   const int slots = max(1, min(nwin, per_sm * tulip_num_sms() / hgn));      // one full wave; grid stays a multiple of hgn
-  tulip_launch(win_attn_fwd_kernel, slots * hgn, 96, 0, st, a);
+  AttnArgs ah = a;
+  ah.hint = (tulip_hints() & 32) ? 1 : 0;
+  tulip_launch(win_attn_fwd_kernel, slots * hgn, 96, 0, st, ah);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }
@@ -465,6 +471,7 @@ int win_attn_bwd(const AttnArgs& a_in, cudaStream_t st) {
   static int per_sm = 0;
   if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, win_attn_bwd_kernel, 96, smem) != cudaSuccess || per_sm < 1)) per_sm = 4;
   const int slots = max(1, min(nwin, per_sm * tulip_num_sms() / hgn));
+  a.hint = (tulip_hints() & 32) ? 1 : 0;
   tulip_launch(win_attn_bwd_kernel, slots * hgn, 96, smem, st, a);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;

@@ -25,6 +25,15 @@ int tulip_num_sms() {
   return g_num_sms;
 }
 
+int tulip_hints() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TULIP_B200_HINTS");
+    v = e ? atoi(e) : 127;
+  }
+  return v;
+}
+
 bool tulip_pdl_enabled() {
   static int v = -1;
   if (v < 0) {

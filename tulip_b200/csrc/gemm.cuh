@@ -72,6 +72,7 @@ struct GemmTNArgs {
   float* db;                             // [N] or null
   int perm_R2, perm_Cc;                  // row n' = ij*Cc + c is written to row c*R2 + ij (R2 == 1: identity)
   int splits;
+  int hint;                              // set by the launcher: operand loads carry the L2 evict_first priority (tulip_hints() & 1)
 };
 
 int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st);   // returns TULIP_ERR_UNSUPPORTED for shapes it does not take

@@ -55,6 +55,7 @@ struct Sched {
   int klast;         // 16-column MMA steps in the last K block (1..4)
   int nsa;           // A ring stages (panel mode)
   int bres_bytes;    // resident B region (panel mode), the A ring follows it
+  int hints;         // tulip_hints(): L2 eviction priorities of the operand / auxiliary loads
   int cg;            // 2: CTA pairs (cta_group::2) -- pair p walks 256-row x BN tiles, CTA rank r owns rows 128 r .. 128 r + 127
 };
 __device__ __forceinline__ bool tile_at(const Sched& sc, int it, int& mt, int& nt) {
@@ -234,13 +235,16 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
   if (warp == 0 && sc.panel) {
     // ---- TMA producer, B-stationary panels ----
     const int worker = blockIdx.x / sc.n_chunks, chunk = blockIdx.x - worker * sc.n_chunks;
+    // one instruction form on the issue path whatever the hint mask says: the policy is chosen once, outside the loops
+    const uint64_t polA = (sc.hints & 2) ? tc::l2_policy_evict_first() : tc::l2_policy_evict_normal();
+    const uint64_t polB = (sc.hints & 64) ? tc::l2_policy_evict_last() : tc::l2_policy_evict_normal();
     if (tc::elect_one_sync()) {
       tc::prefetch_tensormap(&maps.A);
       tc::prefetch_tensormap(&maps.B);
       tc::mbar_expect_tx(bfull, sc.bres_bytes);
       for (int ni = 0; ni < sc.npc; ++ni)
         for (int kbi = 0; kbi < sc.kb; ++kbi)
-          tc::tma_load_2d(smem + (ni * sc.kb + kbi) * CF::B_BYTES, &maps.B, bfull, kbi * BK, (chunk * sc.npc + ni) * BN);
+          tc::tma_load_2d_hint(smem + (ni * sc.kb + kbi) * CF::B_BYTES, &maps.B, bfull, kbi * BK, (chunk * sc.npc + ni) * BN, polB);
     }
     __syncwarp();
     int stage = 0; uint32_t phase = 0;
@@ -249,7 +253,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
         tc::mbar_wait(empty + stage, phase ^ 1);
         if (tc::elect_one_sync()) {
           tc::mbar_expect_tx(full + stage, CF::A_BYTES);
-          tc::tma_load_2d(smem + sc.bres_bytes + stage * CF::A_BYTES, &maps.A, full + stage, kbi * BK, mt * BM);
+          tc::tma_load_2d_hint(smem + sc.bres_bytes + stage * CF::A_BYTES, &maps.A, full + stage, kbi * BK, mt * BM, polA);
         }
         __syncwarp();
         if (++stage == sc.nsa) { stage = 0; phase ^= 1; }
@@ -307,6 +311,8 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       tc::prefetch_tensormap(&maps.A);
       tc::prefetch_tensormap(&maps.B);
     }
+    const uint64_t polA = (sc.hints & 4) ? tc::l2_policy_evict_first() : tc::l2_policy_evict_normal();
+    const uint64_t polB = (sc.hints & 64) ? tc::l2_policy_evict_last() : tc::l2_policy_evict_normal();
     int stage = 0; uint32_t phase = 0;
     int mt, nt;
     for (int it = 0; tile_at(sc, it, mt, nt); ++it) {
@@ -333,9 +339,9 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
               const int bh0 = m0 / sg.gW, w0 = m0 % sg.gW;
               tc::tma_load_5d(a, &maps.A, full + stage, kb * BK, sg.sj[s], w0, sg.si[s], bh0);
             } else {
-              tc::tma_load_2d(a, sg.amap[s] ? &maps.A2 : &maps.A, full + stage, kb * BK, m0);
+              tc::tma_load_2d_hint(a, sg.amap[s] ? &maps.A2 : &maps.A, full + stage, kb * BK, m0, polA);
             }
-            tc::tma_load_2d(b, sg.bmap[s] ? &maps.B2 : &maps.B, full + stage, sg.bcol[s] + kb * BK, n0);
+            tc::tma_load_2d_hint(b, sg.bmap[s] ? &maps.B2 : &maps.B, full + stage, sg.bcol[s] + kb * BK, n0, polB);
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -386,6 +392,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       if (++buf == NBUF) { buf = 0; tphase ^= 1; }
     }
   } else {
+    const uint64_t aux_pol = (sc.hints & 8) ? tc::l2_policy_evict_first() : tc::l2_policy_evict_normal();   // auxiliary tiles are read once here
     const int q = warp & 3;                                   // TMEM lane quarter this warp may access
     const int jgrp = (warp - 2) >> 2;                         // which column boxes of the tile this warp handles
     const int r = q * 32 + lane;                              // row inside the tile
@@ -422,7 +429,8 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
       for (int jj = 0; jj < MYBOX; ++jj) {
         const int j = jgrp + jj * EPI_GROUPS;
         if (j < CF::NBOX)
-          tc::tma_load_2d(smem + CF::OUT_OFF + ob_a * CF::TILE_BYTES + j * BOX_BYTES + q * 2048, &maps.aux, mybar + ob_a, n0a + j * BOXC, m0a);
+          tc::tma_load_2d_hint(smem + CF::OUT_OFF + ob_a * CF::TILE_BYTES + j * BOX_BYTES + q * 2048, &maps.aux, mybar + ob_a, n0a + j * BOXC, m0a,
+                               aux_pol);
       }
     };
     int mt, nt;
@@ -459,8 +467,8 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
 #pragma unroll
         for (int jj = 0; jj < MYBOX; ++jj) {
           const int j = jgrp + jj * EPI_GROUPS;
-          tc::tma_load_2d(bx + j * BOX_BYTES + q * 2048, &maps.aux, mybar, j * BOXC, m0a);
-          if (has_res) tc::tma_load_2d(br + j * BOX_BYTES + q * 2048, &maps.aux2, mybar, j * BOXC, m0a);
+          tc::tma_load_2d_hint(bx + j * BOX_BYTES + q * 2048, &maps.aux, mybar, j * BOXC, m0a, aux_pol);
+          if (has_res) tc::tma_load_2d_hint(br + j * BOX_BYTES + q * 2048, &maps.aux2, mybar, j * BOXC, m0a, aux_pol);
         }
       };
       if (tile_at(sc, 0, mt, nt)) {
@@ -597,7 +605,7 @@ gemm_nt_tc05_kernel(const __grid_constant__ Maps maps, const __grid_constant__ G
 #pragma unroll
         for (int jj = 0; jj < MYBOX; ++jj) {
           const int j = jgrp + jj * EPI_GROUPS;
-          tc::tma_load_2d(b0 + j * BOX_BYTES + q * 2048, &maps.aux, mybar, j * BOXC, m0a);
+          tc::tma_load_2d_hint(b0 + j * BOX_BYTES + q * 2048, &maps.aux, mybar, j * BOXC, m0a, aux_pol);
         }
       };
       if (RES && tile_at(sc, 0, mt, nt)) {
@@ -1232,6 +1240,7 @@ int gemm_nt_tc05(const GemmArgs& g, int epi, cudaStream_t st) {
   }
   Sched sc = choose_tiling(g, epi, sg, &bn);
   sc.cg = pairs_wanted(g, epi, sg, sc, bn) ? 2 : 1;
+  sc.hints = tulip_hints();
   {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
     const uint64_t str[1] = {(uint64_t)g.ldb * 2};
@@ -1418,6 +1427,8 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
   if (warp == 0) {
     // TMA producer: whole warp walks the loop, one elected lane issues (see tc::elect_one_sync)
     int stage = 0; uint32_t phase = 0;
+    const uint64_t pol_first = tc::l2_policy_evict_first();
+    const bool hint = g.hint != 0;                               // operands are streamed once: L2 evict_first
     for (int tb = tb_begin; tb < tb_end; ++tb) {
       tc::mbar_wait(empty + stage, phase ^ 1);
       if (tc::elect_one_sync()) {
@@ -1431,11 +1442,11 @@ gemm_tn_tc05_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_const
           tc::tma_load_5d(a, &mapY, full + stage, c0, seg & 1, w0, seg >> 1, bh0);
           tc::tma_load_5d(a + TN_BOX, &mapY, full + stage, c0 + 64, seg & 1, w0, seg >> 1, bh0);
         } else {
-          tc::tma_load_2d(a, &mapY, full + stage, n0, tb * TN_TOK);
-          tc::tma_load_2d(a + TN_BOX, &mapY, full + stage, n0 + 64, tb * TN_TOK);
+          tc::tma_load_2d_pol(a, &mapY, full + stage, n0, tb * TN_TOK, pol_first, hint);
+          tc::tma_load_2d_pol(a + TN_BOX, &mapY, full + stage, n0 + 64, tb * TN_TOK, pol_first, hint);
         }
         for (int j = 0; j < nbx; ++j)
-          tc::tma_load_2d(a + (2 + j) * TN_BOX, x2 ? &mapX2 : &mapX, full + stage, (x2 ? k0 - g.K1 : k0) + 64 * j, tb * TN_TOK);
+          tc::tma_load_2d_pol(a + (2 + j) * TN_BOX, x2 ? &mapX2 : &mapX, full + stage, (x2 ? k0 - g.K1 : k0) + 64 * j, tb * TN_TOK, pol_first, hint);
       }
       __syncwarp();
       if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
@@ -1577,7 +1588,9 @@ int gemm_tn_tc05(const GemmTNArgs& g, cudaStream_t st) {
   const int per = ceil_div(tb_total, splits);
   splits = ceil_div(tb_total, per);
   dim3 grid(n_tiles, k_tiles, splits);
-  tulip_launch(gemm_tn_tc05_kernel, grid, TN_THREADS, TN_SMEM, st, mY, mX, mX2, g, kcols, per, row_seg_len, row_tiles_per_seg, y5d);
+  GemmTNArgs gh = g;
+  gh.hint = (tulip_hints() & 1) ? 1 : 0;
+  tulip_launch(gemm_tn_tc05_kernel, grid, TN_THREADS, TN_SMEM, st, mY, mX, mX2, gh, kcols, per, row_seg_len, row_tiles_per_seg, y5d);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }

@@ -16,6 +16,7 @@ struct AttnArgs {
   int masked;                 // 1 for shifted blocks (mask is built even when a shift component is 0)
   int bMh, bMw, nbias;        // window the bias index buffer was built for (never rebuilt, tulip.py:228-240)
   float scale;
+  int hint;                   // set by the launcher: q|k|v / dO rows are read once here, load them with the L2 evict_first priority
 };
 int win_attn_fwd(const AttnArgs& a, cudaStream_t st);
 int win_attn_bwd(const AttnArgs& a, cudaStream_t st);

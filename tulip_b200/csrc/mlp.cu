@@ -66,6 +66,7 @@ struct MlpArgs {
   const float* pred; const float* target; const float* gscale; float inv_npix;
   float* dwd; int dwd_copies;               // CTA b adds its column sums into copy b % dwd_copies (96 floats apart)
   int hd_H, hd_W, hd_r;
+  int hints;                                // tulip_hints(): 16 input tile + by-product stores evict_first, 64 weight chunks evict_last
 };
 
 template <int MODE>
@@ -176,7 +177,8 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
       if (it >= RAW_RING) tc::mbar_wait(raw_empty + slot, ((it / RAW_RING) - 1) & 1);
       if (tc::elect_one_sync()) {
         tc::mbar_expect_tx(raw_full + slot, RAW_TILE);        // rows past T are zero-filled by the TMA unit and still count
-        tc::tma_load_2d(smem + OFF_RAW + slot * RAW_TILE, &mapX, raw_full + slot, 0, tile * 128);
+        tc::tma_load_2d_pol(smem + OFF_RAW + slot * RAW_TILE, &mapX, raw_full + slot, 0, tile * 128, tc::l2_policy_evict_first(),
+                            (a.hints & 16) != 0);
       }
       __syncwarp();
     }
@@ -189,7 +191,9 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
       if (wn >= W_RING) tc::mbar_wait(w_empty + slot, ((wn / W_RING) - 1) & 1);
       if (tc::elect_one_sync()) {
         tc::mbar_expect_tx(w_full + slot, W_SLOT);
-        for (int kb = 0; kb < NKB; ++kb) tc::tma_load_2d(smem + OFF_WR + slot * W_SLOT + kb * W_BLK, map, w_full + slot, col0 + kb * KBLK, row0);
+        for (int kb = 0; kb < NKB; ++kb)
+          tc::tma_load_2d_pol(smem + OFF_WR + slot * W_SLOT + kb * W_BLK, map, w_full + slot, col0 + kb * KBLK, row0,
+                              tc::l2_policy_evict_last(), (a.hints & 64) != 0);
       }
       __syncwarp();
       ++wn;
@@ -206,7 +210,8 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
       if (save_xn) {
         tc::mbar_wait(a_full, it & 1);
         if (tc::elect_one_sync()) {
-          for (int kb = 0; kb < NKB; ++kb) tc::tma_store_2d(&mapXn, smem + OFF_A + kb * A_BLK, kb * KBLK, tile * 128);
+          for (int kb = 0; kb < NKB; ++kb)
+            tc::tma_store_2d_pol(&mapXn, smem + OFF_A + kb * A_BLK, kb * KBLK, tile * 128, tc::l2_policy_evict_first(), (a.hints & 16) != 0);
           tc::tma_store_commit();
           tc::tma_store_wait_read<0>();
           tc::mbar_arrive(a_empty);
@@ -219,7 +224,8 @@ mlp_block_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
           tc::mbar_wait(h_full + buf, (G >> 1) & 1);
           if (tc::elect_one_sync()) {
             for (int kb = 0; kb < NKB; ++kb)
-              tc::tma_store_2d(&mapHact, smem + OFF_H + buf * NKB * A_BLK + kb * A_BLK, c * MC + kb * KBLK, tile * 128);
+              tc::tma_store_2d_pol(&mapHact, smem + OFF_H + buf * NKB * A_BLK + kb * A_BLK, c * MC + kb * KBLK, tile * 128,
+                                   tc::l2_policy_evict_first(), (a.hints & 16) != 0);
             tc::tma_store_commit();
             tc::tma_store_wait_read<0>();
             tc::mbar_arrive(h_empty + buf);
@@ -537,6 +543,7 @@ int mlp_block_fwd(const MlpBlockArgs& m, cudaStream_t st) {
   a.rows_per_sample = m.rows_per_sample > 0 ? m.rows_per_sample : 1;
   a.stats = save ? m.stats : nullptr;
   a.T = m.T; a.ntiles = (m.T + 127) / 128; a.save = save ? 1 : 0; a.eps = m.eps;
+  a.hints = tulip_hints();
   static bool configured = false;
   if (!configured) {
     TULIP_CUDA(cudaFuncSetAttribute(mlp_block_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<4>::SMEM));
@@ -593,6 +600,7 @@ int head_bwd_fused(const HeadBwdArgs& m, cudaStream_t st) {
   a.T = m.T; a.ntiles = (m.T + 127) / 128; a.save = 1;
   a.pred = m.pred; a.target = m.target; a.gscale = m.gscale; a.inv_npix = 1.0f / ((float)m.T * m.r * m.r);
   a.dwd = m.dwd; a.dwd_copies = m.dwd_copies; a.hd_H = m.H; a.hd_W = m.W; a.hd_r = m.r;
+  a.hints = tulip_hints();
   static bool configured = false;
   if (!configured) {
     TULIP_CUDA(cudaFuncSetAttribute(mlp_block_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<MAX_NCH>::SMEM));
