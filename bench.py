@@ -415,7 +415,10 @@ def run_ours(args, rank, world, local_rank):
         consumed[i].record(cur)
         prefetch(i ^ 1)
         slot[0] = i ^ 1
-        return loss.item()
+        # the module's own loss read-back: (total, pixel) copied to pinned host memory behind the forward on a side stream, so
+        # the host sync waits for this step's forward, as `loss.item()` does in the reference loop where it comes BEFORE
+        # backward (engine_upsampling.py:84-93) -- not for the backward pass this loop has already queued
+        return model.loss_item() if not args.e2e_item else loss.item()
     prefetch(0)
     for _ in range(2):
         e2e_step()
@@ -590,9 +593,11 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "activation working set of a step is GBs >> 126 MB L2 (no flush needed)", "train_mode": True},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4),
-                "h2d_bytes_per_step": int(lo_pin.numel() * 4 + hi_pin.numel() * 4), "d2h_bytes_per_step": 4,
+                "h2d_bytes_per_step": int(lo_pin.numel() * 4 + hi_pin.numel() * 4),
+                "d2h_bytes_per_step": 4 if args.e2e_item else 8,
                 "pipeline": "pinned host batch -> copy stream (double-buffered, uploads batch i+1 during step i) -> model(lo, hi); "
-                            "loss.backward(); loss.item() every step"},
+                            "loss.backward(); " + ("loss.item()" if args.e2e_item else "model.loss_item() (losses copied to pinned "
+                            "host memory behind the forward; the host waits for that copy)") + " every step"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "step_split": step_split,
@@ -619,6 +624,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU (default: the config's batch)")
     ap.add_argument("--allreduce", default="flat", choices=["flat", "overlap"],
                     help="N > 1: one flat all-reduce after backward, or the same bytes in 4 slices launched under the backward phases")
+    ap.add_argument("--e2e-item", action="store_true",
+                    help="end-to-end loop reads the loss with loss.item() on the compute stream (waits for the queued backward) "
+                         "instead of model.loss_item()")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the reference's GPU torch-eager arm (gpu_eager_baseline)")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2.5 s sustained reading")

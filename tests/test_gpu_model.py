@@ -422,3 +422,23 @@ def test_stage_inputs_one_launch_copy():
         for s_, d_, n in zip(src, dst, sizes):
             if n:
                 assert torch.equal(d_[:n], s_) and bool((d_[n:] == -1).all())
+
+
+def test_loss_item_reads_behind_the_forward_only():
+    """TULIP.loss_item(): the pinned-host copy of (total, pixel) queued behind the forward equals `.item()` on the returned
+    tensors, step after step on the persistent buffers, also when a backward pass is queued before the read."""
+    cfg = TULIP_BASE
+    torch.manual_seed(0)
+    model = build(cfg).cuda().train()
+    with pytest.raises(RuntimeError):
+        model.loss_item()
+    for it in range(4):
+        lo, hi = make_inputs(cfg, 2, 60 + it)
+        _, total_loss, pixel_loss = model(torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda())
+        total_loss.backward()
+        got, got_pixel = model.loss_item(), model.loss_item(pixel=True)
+        assert got == total_loss.item() and got_pixel == pixel_loss.item()
+        model.zero_grad(set_to_none=True)
+    import copy
+    clone = copy.deepcopy(model)                               # streams / events are runtime state, not module state
+    assert "_loss_rb" not in clone.__dict__

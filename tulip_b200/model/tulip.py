@@ -512,7 +512,7 @@ class TULIP(nn.Module):
     # runtime state that must not travel with copy.deepcopy / pickle / torch.save(model): the C handle and raw ctypes pointers
     # (not picklable), buffers tied to that handle, and weak references.  A copy re-creates all of it lazily on its first forward.
     _RUNTIME_STATE = ("_net", "_flat", "_grad_bufs", "_views", "_param_list", "_offsets", "_offsets_p", "_ws_bytes", "_step_bufs",
-                      "_persistent_owner", "_win_modes_cache", "_keep_cache", "_schema", "_grad_mode_hint", "_predrawn", "_predraw_hits")
+                      "_persistent_owner", "_win_modes_cache", "_keep_cache", "_schema", "_grad_mode_hint", "_predrawn", "_predraw_hits", "_loss_rb")
 
     def __getstate__(self):
         state = dict(self.__dict__)
@@ -549,6 +549,9 @@ class TULIP(nn.Module):
         dev = x.device
         Ht, Wt = self.target_img_size
         pers = self._step_buffers(B, dev) if self._persistent_free() else None
+        rb = self.__dict__.get("_loss_rb")
+        if rb is not None and rb["dev"] == dev:
+            torch.cuda.current_stream(dev).wait_event(rb["done"])   # the loss buffer is not overwritten before it was read back
         if pers is not None:
             ws, xin, pred_w, losses_w = pers["ws"], pers["lo"], pers["pred"], pers["losses"]
             tin = pers["hi"] if target is not None else None
@@ -575,7 +578,33 @@ class TULIP(nn.Module):
         check(lib.tulip_net_forward(self._net, B, ptr(self._flat), self._offsets_p, ptr(xin), ptr(tin), ptr(din),
                                     win_mode.ctypes.data_as(C.c_void_p), ptr(ws), ptr(pred_w), ptr(losses_w), current_stream()),
               "tulip_net_forward")
+        if target is not None and self._grad_mode_hint:
+            self._post_loss_readback(losses_w, dev)
         return (pers, ws, xin, tin, din, pred_w, losses_w, B)
+
+    def _post_loss_readback(self, losses_w, dev):
+        """Queue the copy of (total_loss, pixel_loss) into pinned host memory on a side stream that waits for the forward just
+        launched and for nothing after it.  `loss_item()` then costs the host one event wait; a `.item()` on the returned
+        loss tensor would run on the caller's stream, i.e. behind a backward pass that is already queued there."""
+        rb = self.__dict__.get("_loss_rb")
+        if rb is None or rb["dev"] != dev:
+            rb = self._loss_rb = {"dev": dev, "stream": torch.cuda.Stream(device=dev), "host": torch.zeros(2).pin_memory(),
+                                  "fwd": torch.cuda.Event(), "done": torch.cuda.Event()}
+        cur = torch.cuda.current_stream(dev)
+        rb["fwd"].record(cur)
+        with torch.cuda.stream(rb["stream"]):
+            rb["stream"].wait_event(rb["fwd"])
+            rb["host"].copy_(losses_w, non_blocking=True)
+            rb["done"].record(rb["stream"])
+
+    def loss_item(self, pixel: bool = False) -> float:
+        """Python float of the last training forward's total loss (or pixel loss): what the reference loop reads with
+        `total_loss.item()` (engine_upsampling.py:84), waiting only for that forward."""
+        rb = self.__dict__.get("_loss_rb")
+        if rb is None:
+            raise RuntimeError("tulip_b200: loss_item() needs a training forward (target given, grad mode on) before it")
+        rb["done"].synchronize()
+        return float(rb["host"][1 if pixel else 0])
 
     def _persistent_free(self) -> bool:
         owner = getattr(self, "_persistent_owner", None)
