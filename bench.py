@@ -333,7 +333,8 @@ def run_ours(args, rank, world, local_rank):
     model = build_model(tb_model).to(dev).train()          # train mode: DropPath masks are drawn every step, as in the reference
     torch.manual_seed(0 + rank)                            # per-rank RNG stream for the DropPath masks (reference: seed + rank, main:155)
     if world > 1 and args.allreduce == "overlap":
-        overlap_gradient_allreduce(model)                  # slices of the flat buffer are reduced under the rest of backward
+        # slices of the flat buffer are reduced under the rest of backward, which leaves NCCL's SMs alone (--reserve-sms)
+        overlap_gradient_allreduce(model, reserve_sms=args.reserve_sms)
     lo_h, hi_h = synth_inputs(B, 1 + rank)
     lo_pin, hi_pin = lo_h.pin_memory(), hi_h.pin_memory()
     lo_d, hi_d = lo_pin.to(dev), hi_pin.to(dev)
@@ -624,6 +625,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU (default: the config's batch)")
     ap.add_argument("--allreduce", default="flat", choices=["flat", "overlap"],
                     help="N > 1: one flat all-reduce after backward, or the same bytes in 4 slices launched under the backward phases")
+    ap.add_argument("--reserve-sms", type=int, default=0,
+                    help="with --allreduce overlap: SMs left to NCCL (NCCL_MAX_CTAS) while the backward pass runs beside it")
     ap.add_argument("--e2e-item", action="store_true",
                     help="end-to-end loop reads the loss with loss.item() on the compute stream (waits for the queued backward) "
                          "instead of model.loss_item()")
@@ -646,6 +649,8 @@ def main():
         if args.allreduce == "overlap":
             # NCCL's kernels must win SM slots against the persistent 148-CTA kernels of the backward pass they run under
             os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
+            if args.reserve_sms > 0:
+                os.environ.setdefault("NCCL_MAX_CTAS", str(args.reserve_sms))
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:

@@ -127,6 +127,12 @@ int tulip_gemm_nt_plan(int M, int N, int K, int epilogue, int save_pre, int* out
  * half of the B rows).  mode 0 = off (default: measured slower at this model's sizes), 1 = every eligible launch, 2 = launches
  * with K >= 384; anything else only queries.  Returns the previous mode (-1: not decided yet, env TULIP_B200_CG2 or 0). */
 int tulip_gemm_nt_pairs_mode(int mode);
+/* SM budget of the persistent kernels (GEMMs, fused half-block kernels, grouped weight gradients): n > 0 sizes their grids for
+ * n SMs instead of the whole device, n <= 0 lifts the limit.  The data-parallel exchange uses it: while NCCL reduces the finished
+ * gradient slices under the rest of the backward pass (the reference's DDP buckets, main_lidar_upsampling.py:277), the pass runs
+ * on the SMs NCCL's CTAs leave free instead of queueing a second wave behind them.  Returns the previous budget (0 = none).
+ * Launch sequences captured as CUDA graphs keep the budget they were captured under. */
+int tulip_set_sm_budget(int n);
 int tulip_gemm_tn(const void* dY, const void* X, float* dW, float* db, int M, int N, int K, int impl, void* stream);
 
 /* The same two contractions with every operand mode and fused epilogue of the path spelled out (per-kernel parity tests of

@@ -80,6 +80,7 @@ SIGNATURES = {
     "tulip_gemm_nt": (_i, [_vp, _vp, _fp, _vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
     "tulip_gemm_nt_plan": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i)]),
     "tulip_gemm_nt_pairs_mode": (_i, [_i]),
+    "tulip_set_sm_budget": (_i, [_i]),
     "tulip_gemm_tn": (_i, [_vp, _vp, _fp, _fp, _i, _i, _i, _i, _vp]),
     "tulip_gemm_nt_ex": (_i, [C.POINTER(GemmDesc), _i, _vp]),
     "tulip_gemm_tn_ex": (_i, [C.POINTER(GemmTNDesc), _vp]),

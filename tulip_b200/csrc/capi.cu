@@ -10,6 +10,7 @@
 namespace {
 thread_local std::string g_error;
 int g_num_sms = 0;
+int g_sm_budget = 0;     // > 0: persistent kernels size their grids for this many SMs (tulip_set_sm_budget)
 }  // namespace
 
 void tulip_set_error(const char* msg) { g_error = msg ? msg : "unknown error"; }
@@ -21,8 +22,10 @@ int tulip_num_sms() {
       g_num_sms = n;
     else
       g_num_sms = 148;
+    const char* e = getenv("TULIP_B200_SM_BUDGET");      // measurement knob: the whole process under a budget
+    if (e && atoi(e) > 0) g_sm_budget = atoi(e);
   }
-  return g_num_sms;
+  return (g_sm_budget > 0 && g_sm_budget < g_num_sms) ? g_sm_budget : g_num_sms;
 }
 
 int tulip_hints() {
@@ -306,6 +309,12 @@ int tulip_gemm_nt_plan(int M, int N, int K, int epilogue, int save_pre, int* out
 }
 
 int tulip_gemm_nt_pairs_mode(int mode) { return gemm_nt_pairs_mode(mode); }
+
+int tulip_set_sm_budget(int n) {
+  const int prev = g_sm_budget;
+  g_sm_budget = n > 0 ? n : 0;
+  return prev;
+}
 
 int tulip_gemm_tn(const void* dY, const void* X, float* dW, float* db, int M, int N, int K, int impl, void* stream) {
   GemmTNArgs g;

@@ -291,12 +291,18 @@ class _TulipFunction(torch.autograd.Function):
             group = None if sync is True else sync
             slices = phase_slices(model._schema, model._views, model.num_layers)
             works = []
+            reserve = int(getattr(model, "_grad_sync_reserve_sms", 0)) if dist_on else 0
             for ph in range(3):
                 check(lib.tulip_net_backward_phases(model._net, ctx.B, ptr(model._flat), model._offsets_p, ptr(gbuf), ptr(x), ptr(target),
                                                     ptr(pred), ptr(g_loss), ptr(drop_scales), ctx.win_mode.ctypes.data_as(C.c_void_p),
                                                     ptr(ws), current_stream(), ph, ph), "tulip_net_backward_phases")
                 if dist_on:
                     works += launch_slice_allreduce(gbuf, slices[ph], group)
+                    if reserve > 0 and ph == 0:
+                        # NCCL's CTAs now hold SMs: the persistent kernels of the remaining phases are sized for the rest
+                        lib.tulip_set_sm_budget(_device_sms(gbuf.device) - reserve)
+            if reserve > 0:
+                lib.tulip_set_sm_budget(0)
             model._grad_sync_pending = works if dist_on else None
         else:
             check(lib.tulip_net_backward(model._net, ctx.B, ptr(model._flat), model._offsets_p, ptr(gbuf), ptr(x), ptr(target),
@@ -307,6 +313,10 @@ class _TulipFunction(torch.autograd.Function):
         # fresh views every time: autograd only adopts an incoming gradient as `.grad` (no copy) if nothing else references it
         grads = tuple(gbuf[o:o + n].view(s) for o, n, s in model._views)
         return (None,) * n_fixed + grads
+
+
+def _device_sms(device) -> int:
+    return torch.cuda.get_device_properties(device).multi_processor_count
 
 
 def _stageable(*tensors):

@@ -87,13 +87,16 @@ def phase_slices(names, views, num_layers: int):
     return out
 
 
-def overlap_gradient_allreduce(model, group=None, enabled: bool = True):
+def overlap_gradient_allreduce(model, group=None, enabled: bool = True, reserve_sms: int = 0):
     """Exchange the gradients INSIDE backward(): the pass runs as three phases (head + decoder, top encoder stage, the rest) and
     the all-reduce of each finished slice of the flat buffer is launched on NCCL's stream under the remaining phases -- what the
     reference gets from DDP's bucketed reduce (main_lidar_upsampling.py:277).  Same arithmetic as one flat all-reduce (mean over
     ranks of every element), 4 collectives instead of 1.  Call `allreduce_gradients(model)` after backward() as before: it then
-    only joins the NCCL stream.  Do not combine with DistributedDataParallel or with gradient accumulation across backward() calls."""
+    only joins the NCCL stream.  Do not combine with DistributedDataParallel or with gradient accumulation across backward() calls.
+    `reserve_sms` > 0: once the first reduce is in flight the persistent kernels of the remaining phases are launched for
+    (SMs - reserve_sms) SMs (tulip_set_sm_budget), so their CTAs do not queue behind NCCL's; pair it with NCCL_MAX_CTAS."""
     model._grad_sync = (group if group is not None else True) if enabled else None
+    model._grad_sync_reserve_sms = int(reserve_sms) if enabled else 0
     model._grad_sync_pending = None
     return model
 
