@@ -296,3 +296,27 @@ def test_final_patch_expanding_head_fwd_bwd():
     ops.gemm_nt_ex(ops.EPI_STORE, A=dh, lda=N, K1=N, B=wtb, ldb=N, M=T, N=E, K=N, out=dxn, ldo=E)
     assert rel_l2(dWe, wf.grad) <= 3e-3
     assert rel_l2(dxn.float(), xf.grad) <= 3e-3
+
+
+@pytest.mark.parametrize("M,C", [(4096, 96), (128 * 160, 96), (128 * 152 + 77, 96), (128 * 150, 192), (9000, 384)],
+                         ids=["c96", "c96_full_waves", "c96_ragged", "c192", "c384"])
+def test_gemm_nt_dgelu2_recompute(M, C):
+    """EPI_DGELU2 (Mlp backward through GELU, tulip.py:195-199 differentiated): out = (dY . W2^T-packed) * gelu'(xn . W1^T + b1),
+    both products in one launch (two TMEM accumulators per tile), incl. a ragged last row tile and more tiles than CTAs.
+    One bf16 rounding after fp32 accumulation: rel-L2 <= 1e-3 against the fp32 torch reference rounded to bf16."""
+    from tulip_b200 import ops
+    N = 4 * C
+    g = torch.Generator(device="cuda").manual_seed(M + C)
+    dy = bf(torch.randn(M, C, device="cuda", generator=g))
+    xn = bf(torch.randn(M, C, device="cuda", generator=g))
+    w2t = bf(torch.randn(N, C, device="cuda", generator=g) / C ** 0.5)      # fc2.weight^T: [4C, C]
+    w1 = bf(torch.randn(N, C, device="cuda", generator=g) / C ** 0.5)       # fc1.weight:   [4C, C]
+    b1 = (0.2 * torch.randn(N, device="cuda", generator=g)).contiguous()
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_nt_ex(ops.EPI_DGELU2, A=dy, lda=C, K1=C, B=w2t, ldb=C, A2=xn, lda2=C, B2=w1, ldb2=C, K2=C, M=M, N=N, K=C,
+                   bias=b1, out=out, ldo=N)
+    pre = xn.float() @ w1.float().t() + b1
+    gp = 0.5 * (1 + torch.erf(pre / 2 ** 0.5)) + pre * torch.exp(-0.5 * pre * pre) / (2 * torch.pi) ** 0.5
+    ref = bf16r((dy.float() @ w2t.float().t()) * gp)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out.float(), ref) <= 1e-3
