@@ -589,10 +589,10 @@ class TULIP(nn.Module):
                                     win_mode.ctypes.data_as(C.c_void_p), ptr(ws), ptr(pred_w), ptr(losses_w), current_stream()),
               "tulip_net_forward")
         if target is not None and self._grad_mode_hint:
-            self._post_loss_readback(losses_w, dev)
+            self._post_loss_readback(losses_w, dev, transient=pers is None)
         return (pers, ws, xin, tin, din, pred_w, losses_w, B)
 
-    def _post_loss_readback(self, losses_w, dev):
+    def _post_loss_readback(self, losses_w, dev, transient=False):
         """Queue the copy of (total_loss, pixel_loss) into pinned host memory on a side stream that waits for the forward just
         launched and for nothing after it.  `loss_item()` then costs the host one event wait; a `.item()` on the returned
         loss tensor would run on the caller's stream, i.e. behind a backward pass that is already queued there."""
@@ -605,6 +605,8 @@ class TULIP(nn.Module):
         with torch.cuda.stream(rb["stream"]):
             rb["stream"].wait_event(rb["fwd"])
             rb["host"].copy_(losses_w, non_blocking=True)
+            if transient:
+                losses_w.record_stream(rb["stream"])       # a per-call buffer: the allocator must not hand it out before the copy ran
             rb["done"].record(rb["stream"])
 
     def loss_item(self, pixel: bool = False) -> float:
