@@ -293,6 +293,11 @@ int tulip_chamfer_distance(const float* a, const float* b, int na, int nb, float
  * (DownsampleTensor :120-128, DownsampleTensorWidth :130-138). */
 int tulip_preprocess_range(const float* raw, int channels, float scale, int filter, float min_range, float max_range, int row_factor,
                            int col_factor, int log_transform, float* hi, float* lo, int B, int H, int W, void* stream);
+/* The CARLA `.rimg` container (rimg_loader, tulip/util/datasets.py:181-193): a file is two native unsigned longs (size[0], size[1])
+ * followed by size[1] rows of size[0] float16 values; the loader returns flip(transpose(rows)) widened to float32.
+ * rows_f16: the payloads of B files back to back (device, header stripped); frames [B, size0, size1] fp32:
+ * frames[b][i][j] = rows[b][size1 - 1 - j][size0 - 1 - i] -- what tulip_preprocess_range takes as `raw` with channels = 1. */
+int tulip_rimg_decode(const void* rows_f16, float* frames, int B, int size0, int size1, void* stream);
 /* ---- optimizer step over the flat buffers: torch.optim.AdamW(param_groups_layer_decay(...), betas=(0.9, 0.95))
  * (main_lidar_upsampling.py:281-283) and get_grad_norm_ (util/misc.py:317-329) as one launch each ----
  * segments (device array, sorted by offset): parameter i occupies [offset, offset + numel) of the flat fp32 buffers and belongs to

@@ -1,10 +1,11 @@
 """TEST INFRASTRUCTURE ONLY -- torch (CPU, fp32) restatement of the reference's per-frame input transforms
-(tulip/util/datasets.py: npy_loader :187-191, ToTensor, ScaleTensor :140-144, FilterInvalidPixels :146-154, DownsampleTensor
+(tulip/util/datasets.py: npy_loader :187-191, rimg_loader :181-193 [the CARLA .rimg container], ToTensor, ScaleTensor :140-144, FilterInvalidPixels :146-154, DownsampleTensor
 :120-128, DownsampleTensorWidth :130-138, LogTransform :73-75) chained as build_{kitti,durlar,carla}_upsampling_dataset do
 (:244-369).  Only tests/, smoke() and bench.py's cpu_baseline may import this module.
 
 Pinned: `python -m oracle.make_golden_input` (build container only) composes the UNMODIFIED reference transform classes the way the
 three builders do and checks this file bit for bit, writing tests/golden/input_pipeline.npz."""
+import numpy as np
 import torch
 
 # (scale, filter min or None) per dataset: datasets.py:249-250 (durlar), :285-286 (kitti), :322-323 (carla)
@@ -30,3 +31,16 @@ def preprocess(raw, dataset, h_low, w_low=None, log_transform=True):
     if log_transform:
         lo, hi = torch.log1p(lo), torch.log1p(hi)                # LogTransform
     return lo.contiguous(), hi.contiguous()
+
+
+def rimg_decode(buf: bytes):
+    """The CARLA `.rimg` container (datasets.py:181-193): two native unsigned longs (size[0], size[1]), then size[0] * size[1]
+    float16 values stored as `size[1]` rows of `size[0]`; the loader transposes, flips BOTH axes and widens to float32.
+    -> (frame (size[0], size[1]) float32, payload (size[1], size[0]) float16 as stored)."""
+    size = np.frombuffer(buf, dtype=np.uint64, count=2)          # np.uint is the platform's unsigned long: 8 bytes on Linux
+    s0, s1 = int(size[0]), int(size[1])
+    payload = np.frombuffer(buf, dtype=np.float16, offset=16).reshape(s1, s0)
+    frame = np.empty((s0, s1), dtype=np.float32)
+    for i in range(s0):                                          # F[i, j] = payload[s1 - 1 - j, s0 - 1 - i]
+        frame[i, :] = payload[::-1, s0 - 1 - i].astype(np.float32)
+    return frame, payload

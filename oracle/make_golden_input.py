@@ -58,9 +58,31 @@ def main():
         lo_o, hi_o = P.preprocess(raw, dataset, in_size[0], in_size[1], True)
         out[f"{dataset}_hi"] = hi_o.numpy()[:, :, ::8, ::16].copy()
         out[f"{dataset}_lo_sum"] = np.array([float(lo_o.double().sum())])
+    # the CARLA .rimg container: the reference's own loader on files written here (datasets.py:181-193)
+    import tempfile
+    for name, (s0, s1) in (("rimg_a", (16, 48)), ("rimg_b", (64, 1024))):
+        payload = (rng.random((s1, s0), dtype=np.float32) * 90.0).astype(np.float16)
+        payload[rng.random(payload.shape) < 0.05] = 0
+        buf = np.array([s0, s1], dtype=np.uint64).tobytes() + payload.tobytes()
+        with tempfile.NamedTemporaryFile(suffix=".rimg") as f:
+            f.write(buf); f.flush()
+            ref = D.rimg_loader(f.name)
+        got, stored = P.rimg_decode(buf)
+        assert ref.dtype == np.float32 and ref.shape == (s0, s1) and np.array_equal(ref, got), name
+        assert np.array_equal(stored, payload)
+        if name == "rimg_a":
+            out["rimg_a_file"] = np.frombuffer(buf, dtype=np.uint8).copy()
+            out["rimg_a_frame"] = ref.copy()
+        else:
+            out["rimg_b_seed"] = np.array([s0, s1], dtype=np.int64)
+            out["rimg_b_frame_sum"] = np.array([float(ref.astype(np.float64).sum()), float(ref[3, 17]), float(ref[-1, 0])])
+            lo_o, hi_o = P.preprocess(ref[None, :, :, None], "carla", 16, 1024, True)
+            out["rimg_b_hi_sum"] = np.array([float(hi_o.double().sum()), float(lo_o.double().sum())])
+            out["rimg_b_file"] = np.frombuffer(buf, dtype=np.uint8).copy()
     os.makedirs(GOLDEN, exist_ok=True)
     np.savez_compressed(os.path.join(GOLDEN, "input_pipeline.npz"), **out)
-    print("input pipeline oracle pinned bit for bit against the reference transform chains (kitti, durlar, carla; log and linear)")
+    print("input pipeline oracle pinned bit for bit against the reference transform chains (kitti, durlar, carla; log and linear) "
+          "and rimg_loader")
 
 
 if __name__ == "__main__":

@@ -38,3 +38,34 @@ def test_preprocess_single_channel_and_errors():
         preprocess(raw, "kitti", (15, 1024))
     with pytest.raises(NotImplementedError):
         preprocess(raw, "nuscenes", (16, 1024))
+
+
+def test_rimg_decode_kernel_bit_exact(tmp_path):
+    """CARLA .rimg payloads -> fp32 frames (rimg_loader, datasets.py:181-193): bit-exact against the reference loader's output
+    kept in the fixture and against the oracle on ragged sizes (tiles of 32 cut both ways), batched; then the carla chain."""
+    import os
+    from tulip_b200.input_pipeline import decode_rimg, preprocess, read_rimg
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "input_pipeline.npz"))
+    file_a, file_b = g["rimg_a_file"].tobytes(), g["rimg_b_file"].tobytes()
+    got = read_rimg([file_a])
+    assert got.dtype == torch.float32 and np.array_equal(got[0].cpu().numpy(), g["rimg_a_frame"])
+    path = tmp_path / "frame.rimg"
+    path.write_bytes(file_b)
+    frames = read_rimg([str(path), file_b])
+    want, _ = P.rimg_decode(file_b)
+    assert np.array_equal(frames[0].cpu().numpy(), want) and torch.equal(frames[0], frames[1])
+    lo, hi = preprocess(frames[:, :, :, None].contiguous(), "carla", (16, 1024), True)
+    lo_o, hi_o = P.preprocess(want[None, :, :, None], "carla", 16, 1024, True)
+    np.testing.assert_allclose(hi[0].cpu().numpy(), hi_o[0].numpy(), rtol=2e-7, atol=0)
+    np.testing.assert_allclose(lo[0].cpu().numpy(), lo_o[0].numpy(), rtol=2e-7, atol=0)
+    rng = np.random.Generator(np.random.PCG64(5))
+    for s0, s1, B in ((1, 1, 1), (33, 70, 3), (128, 2048, 2), (7, 31, 1)):
+        rows = (rng.random((B, s1, s0), dtype=np.float32) * 100).astype(np.float16)
+        out = decode_rimg(torch.from_numpy(rows).cuda().view(B, -1), (s0, s1)).cpu().numpy()
+        for b in range(B):
+            buf = np.array([s0, s1], dtype=np.uint64).tobytes() + rows[b].tobytes()
+            assert np.array_equal(out[b], P.rimg_decode(buf)[0]), (s0, s1, b)
+    with pytest.raises(ValueError):
+        read_rimg([file_a, file_b])
+    with pytest.raises(TypeError):
+        decode_rimg(torch.zeros(4, device="cuda"), (2, 2))

@@ -30,3 +30,17 @@ def test_input_pipeline_oracle_matches_reference_fixture():
         assert abs(float(lo.double().sum()) - g[f"{dataset}_lo_sum"][0]) == 0
         if dataset != "kitti":
             assert (hi == 0).any()                                  # the range filter removed something
+
+
+def test_rimg_decode_oracle_matches_reference_fixture():
+    """oracle rimg_decode against what the reference's rimg_loader (datasets.py:181-193) returned for the same file bytes."""
+    g = np.load(GOLDEN)
+    frame, rows = P.rimg_decode(g["rimg_a_file"].tobytes())
+    assert frame.dtype == np.float32 and np.array_equal(frame, g["rimg_a_frame"])
+    assert rows.shape == frame.shape[::-1]
+    assert frame[0, 0] == np.float32(rows[-1, -1]) and frame[-1, 0] == np.float32(rows[-1, 0])       # both axes flipped
+    frame_b, _ = P.rimg_decode(g["rimg_b_file"].tobytes())
+    assert frame_b.shape == tuple(g["rimg_b_seed"])
+    assert [float(frame_b.astype(np.float64).sum()), float(frame_b[3, 17]), float(frame_b[-1, 0])] == list(g["rimg_b_frame_sum"])
+    lo, hi = P.preprocess(frame_b[None, :, :, None], "carla", 16, 1024, True)
+    assert [float(hi.double().sum()), float(lo.double().sum())] == list(g["rimg_b_hi_sum"])

@@ -107,6 +107,7 @@ SIGNATURES = {
     "tulip_voxel_metrics_f64": (_i, [_vp, _vp, _i, C.c_double, _vp, _vp, _vp]),
     "tulip_chamfer_distance": (_i, [_fp, _fp, _i, _i, _fp, _fp, _fp, _vp]),
     "tulip_preprocess_range": (_i, [_fp, _i, C.c_float, _i, C.c_float, C.c_float, _i, _i, _i, _fp, _fp, _i, _i, _i, _vp]),
+    "tulip_rimg_decode": (_i, [_vp, _fp, _i, _i, _i, _vp]),
     "tulip_adamw_step": (_i, [_fp, _fp, _fp, _fp, _vp, _i, _i64, _vp, _vp]),
     "tulip_grad_norm": (_i, [_fp, _vp, _i, _i64, _vp, _fp, _vp]),
     "tulip_l1_loss": (_i, [_fp, _fp, _i64, _i, _fp, _fp, _vp]),

@@ -555,6 +555,11 @@ int tulip_preprocess_range(const float* raw, int channels, float scale, int filt
                           (cudaStream_t)stream);
 }
 
+int tulip_rimg_decode(const void* rows_f16, float* frames, int B, int size0, int size1, void* stream) {
+  if (!rows_f16 || !frames) { tulip_set_error("tulip_rimg_decode: null argument"); return TULIP_ERR_ARG; }
+  return rimg_decode(rows_f16, frames, B, size0, size1, (cudaStream_t)stream);
+}
+
 int tulip_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const tulip_adamw_segment* segments_dev,
                      int n_segments, int64_t span, const tulip_adamw_hyper* hyper_host, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || !segments_dev || !hyper_host) { tulip_set_error("tulip_adamw_step: null argument"); return TULIP_ERR_ARG; }

@@ -1,6 +1,8 @@
 // HBM-bound kernels of the TULIP path: LayerNorm (+ PatchMerging gather), PatchEmbed, weight repack,
 // loss, small element-wise helpers and the stand-alone index ops.  All of them move each byte once,
 // with 16-byte vector accesses and grids sized in multiples of the SM count.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "window_index.cuh"
@@ -1096,6 +1098,37 @@ int preprocess_range(const float* raw, int channels, float scale, int filter, fl
   const long n = (long)B * H * W;
   tulip_launch(preprocess_range_kernel, ew_grid(n, 256), 256, 0, st, raw, channels, scale, filter, min_range, max_range, row_factor,
                col_factor, log_transform, hi, lo, n, H, W);
+  TULIP_CHECK_LAUNCH();
+  return TULIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CARLA `.rimg` frames (reference rimg_loader, tulip/util/datasets.py:181-193): the file stores size[1] rows of size[0] float16
+// values; the loader returns flip(transpose(rows)) as float32, i.e. frame[i][j] = rows[size1 - 1 - j][size0 - 1 - i].
+// 32 x 32 tiles through shared memory so both the fp16 reads and the fp32 writes are coalesced.
+__global__ void __launch_bounds__(256) rimg_decode_kernel(const __half* __restrict__ rows, float* __restrict__ frame, int s0, int s1) {
+  pdl_sync();
+  __shared__ float tile[32][33];
+  const long fb = (long)blockIdx.z * s0 * s1;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int r = r0 + threadIdx.y + k, c = c0 + threadIdx.x;
+    if (r < s1 && c < s0) tile[threadIdx.y + k][threadIdx.x] = __half2float(rows[fb + (long)r * s0 + c]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int c = c0 + threadIdx.y + k, r = r0 + threadIdx.x;
+    if (r < s1 && c < s0) frame[fb + (long)(s0 - 1 - c) * s1 + (s1 - 1 - r)] = tile[threadIdx.x][threadIdx.y + k];
+  }
+}
+
+int rimg_decode(const void* rows_f16, float* frame, int B, int size0, int size1, cudaStream_t st) {
+  TULIP_REQUIRE(B > 0 && size0 > 0 && size1 > 0, "rimg_decode: empty input");
+  TULIP_REQUIRE(B <= 65535 && ceil_div(size1, 32) <= 65535, "rimg_decode: batch / frame width beyond the launch grid");
+  tulip_launch(rimg_decode_kernel, dim3(ceil_div(size0, 32), ceil_div(size1, 32), B), dim3(32, 8), 0, st,
+               reinterpret_cast<const __half*>(rows_f16), frame, size0, size1);
   TULIP_CHECK_LAUNCH();
   return TULIP_OK;
 }

@@ -142,6 +142,9 @@ int chamfer_distance(const float* a, const float* b, int na, int nb, float* dist
 int preprocess_range(const float* raw, int channels, float scale, int filter, float min_range, float max_range, int row_factor,
                      int col_factor, int log_transform, float* hi, float* lo, int B, int H, int W, cudaStream_t st);
 
+// CARLA .rimg payload (size1 rows of size0 fp16 values per frame) -> frames [B, size0, size1] fp32 (datasets.py:181-193)
+int rimg_decode(const void* rows_f16, float* frame, int B, int size0, int size1, cudaStream_t st);
+
 // fused AdamW / gradient norm over the flat buffers (layout mirrored by tulip_adamw_segment / tulip_adamw_hyper in the C header)
 struct AdamwSegment { long offset; long numel; int group; int pad; };
 struct AdamwHyper {

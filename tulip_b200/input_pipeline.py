@@ -3,6 +3,7 @@
 both model inputs.  The DataLoader then only has to deliver raw frames (e.g. pinned (B,H,W,2) float32 batches)."""
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from ._lib import check, current_stream, load_library, ptr
@@ -30,3 +31,39 @@ def preprocess(raw: torch.Tensor, dataset: str, img_size_low_res, log_transform:
     check(load_library().tulip_preprocess_range(ptr(x), channels, float(scale), int(fmin is not None), float(fmin or 0.0), 1.0, H // h, W // w,
                                                 int(log_transform), ptr(hi), ptr(lo), B, H, W, current_stream()), "tulip_preprocess_range")
     return lo, hi
+
+
+def read_rimg(paths, device="cuda"):
+    """CARLA `.rimg` files (rimg_loader, datasets.py:181-193) -> frames [B, size0, size1] fp32 on the GPU, metres.  The host only
+    strips the 16-byte headers and uploads the float16 payloads; transpose, flip and widening run in one kernel.  All files of a
+    batch must have the same size (they do per resolution folder)."""
+    if isinstance(paths, (str, bytes)) or hasattr(paths, "__fspath__"):
+        paths = [paths]
+    size, rows = None, []
+    for p in paths:
+        buf = p if isinstance(p, (bytes, bytearray, memoryview)) else open(p, "rb").read()
+        s = tuple(int(v) for v in np.frombuffer(buf, dtype=np.uint64, count=2))
+        if size is None:
+            size = s
+        elif s != size:
+            raise ValueError(f"rimg files of one batch differ in size: {s} vs {size}")
+        body = np.frombuffer(buf, dtype=np.float16, offset=16)
+        if body.size != s[0] * s[1]:
+            raise ValueError(f"rimg payload holds {body.size} values, header says {s[0]} x {s[1]}")
+        rows.append(body)
+    host = torch.from_numpy(np.stack(rows))
+    dev = host.pin_memory().to(device, non_blocking=True) if torch.device(device).type == "cuda" else host
+    return decode_rimg(dev, size)
+
+
+def decode_rimg(rows: torch.Tensor, size):
+    """rows [B, size1 * size0] float16 CUDA (file payloads as stored) -> frames [B, size0, size1] fp32."""
+    if not rows.is_cuda:
+        raise RuntimeError("tulip_b200.input_pipeline runs on CUDA only")
+    if rows.dtype != torch.float16:
+        raise TypeError("rimg payloads are float16")
+    s0, s1 = int(size[0]), int(size[1])
+    rows = rows.contiguous().view(-1, s1 * s0)
+    out = torch.empty((rows.shape[0], s0, s1), dtype=torch.float32, device=rows.device)
+    check(load_library().tulip_rimg_decode(ptr(rows), ptr(out), rows.shape[0], s0, s1, current_stream()), "tulip_rimg_decode")
+    return out
