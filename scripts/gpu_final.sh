@@ -8,3 +8,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 echo "== reference arm rc=$? $(head -c 300 gpurun_out/final_bench_ref.json)"
 ( time timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err ) 2>&1 | grep real
 echo "== bench rc=$? $(head -c 600 gpurun_out/final_bench.json)"
+for c in durlar16 large8; do
+  timeout 900 python bench.py --config $c --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/final_bench_$c.json 2> gpurun_out/final_bench_$c.err
+  echo "== bench $c rc=$? $(head -c 260 gpurun_out/final_bench_$c.json)"
+done
