@@ -439,6 +439,10 @@ def test_loss_item_reads_behind_the_forward_only():
         got, got_pixel = model.loss_item(), model.loss_item(pixel=True)
         assert got == total_loss.item() and got_pixel == pixel_loss.item()
         model.zero_grad(set_to_none=True)
+    with torch.no_grad():                                      # a forward-only call in between invalidates the read-back
+        model(torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda())
+    with pytest.raises(RuntimeError):
+        model.loss_item()
     import copy
     clone = copy.deepcopy(model)                               # streams / events are runtime state, not module state
     assert "_loss_rb" not in clone.__dict__

@@ -590,6 +590,8 @@ class TULIP(nn.Module):
               "tulip_net_forward")
         if target is not None and self._grad_mode_hint:
             self._post_loss_readback(losses_w, dev, transient=pers is None)
+        elif rb is not None:
+            rb["valid"] = False                              # a forward-only call: loss_item() must not answer with an older loss
         return (pers, ws, xin, tin, din, pred_w, losses_w, B)
 
     def _post_loss_readback(self, losses_w, dev, transient=False):
@@ -608,12 +610,13 @@ class TULIP(nn.Module):
             if transient:
                 losses_w.record_stream(rb["stream"])       # a per-call buffer: the allocator must not hand it out before the copy ran
             rb["done"].record(rb["stream"])
+        rb["valid"] = True
 
     def loss_item(self, pixel: bool = False) -> float:
         """Python float of the last training forward's total loss (or pixel loss): what the reference loop reads with
         `total_loss.item()` (engine_upsampling.py:84), waiting only for that forward."""
         rb = self.__dict__.get("_loss_rb")
-        if rb is None:
+        if rb is None or not rb.get("valid"):
             raise RuntimeError("tulip_b200: loss_item() needs a training forward (target given, grad mode on) before it")
         rb["done"].synchronize()
         return float(rb["host"][1 if pixel else 0])
