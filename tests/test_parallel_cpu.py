@@ -84,3 +84,16 @@ def test_phase_slices_partition_the_flat_buffer():
             ph = [i for i in range(3) if any(lo <= o and o + k <= hi for lo, hi in sl[i])]
             want = 2 if n.startswith("patch_embed.") else (1 if n.startswith(top) else (2 if n.startswith("layers.") else 0))
             assert ph == [want], n
+
+
+def test_overlap_switch_records_group_and_sm_reserve():
+    """overlap_gradient_allreduce only flips host-side switches the autograd node reads (tulip_b200/model/tulip.py backward):
+    the process group (True = default group), the SM reserve handed to tulip_set_sm_budget, and no pending work."""
+    import types
+    from tulip_b200.parallel import overlap_gradient_allreduce
+    m = types.SimpleNamespace()
+    assert overlap_gradient_allreduce(m) is m and m._grad_sync is True and m._grad_sync_reserve_sms == 0
+    overlap_gradient_allreduce(m, group="g", reserve_sms=8)
+    assert m._grad_sync == "g" and m._grad_sync_reserve_sms == 8 and m._grad_sync_pending is None
+    overlap_gradient_allreduce(m, enabled=False, reserve_sms=8)
+    assert m._grad_sync is None and m._grad_sync_reserve_sms == 0
