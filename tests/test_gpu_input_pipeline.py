@@ -69,3 +69,23 @@ def test_rimg_decode_kernel_bit_exact(tmp_path):
         read_rimg([file_a, file_b])
     with pytest.raises(TypeError):
         decode_rimg(torch.zeros(4, device="cuda"), (2, 2))
+
+
+def test_read_npy_feeds_preprocess(tmp_path):
+    """`.npy` frames as the KITTI / DurLAR folders hold them ((H, W, 2) float32, npy_loader datasets.py:187-191) -> read_npy ->
+    preprocess == the oracle chain on np.load(f)[..., 0]."""
+    from tulip_b200.input_pipeline import preprocess, read_npy
+    raw = raw_frames()["durlar"]
+    paths = []
+    for b in range(raw.shape[0]):
+        paths.append(str(tmp_path / f"{b:08d}.npy"))
+        np.save(paths[-1], raw[b])
+    batch = read_npy(paths)
+    assert batch.is_cuda and tuple(batch.shape) == raw.shape and torch.equal(batch.cpu(), torch.from_numpy(raw))
+    out_size, in_size = SIZES["durlar"]
+    lo, hi = preprocess(batch, "durlar", in_size, False)
+    lo_o, hi_o = P.preprocess(np.stack([np.load(p)[..., 0].astype(np.float32) for p in paths]), "durlar", in_size[0], in_size[1], False)
+    assert torch.equal(hi.cpu(), hi_o) and torch.equal(lo.cpu(), lo_o)
+    np.save(str(tmp_path / "odd.npy"), raw[0, :8])
+    with pytest.raises(ValueError):
+        read_npy([paths[0], str(tmp_path / "odd.npy")])

@@ -33,6 +33,21 @@ def preprocess(raw: torch.Tensor, dataset: str, img_size_low_res, log_transform:
     return lo, hi
 
 
+def read_npy(paths, device="cuda"):
+    """KITTI / DurLAR `.npy` frames (npy_loader, datasets.py:187-191: `np.load(f)[..., 0].astype(float32)`) -> one pinned upload of
+    the raw (B, H, W, C) float32 batch; `preprocess` picks channel 0 on the GPU, so the host touches no pixel."""
+    if isinstance(paths, str) or hasattr(paths, "__fspath__"):
+        paths = [paths]
+    frames = [np.load(p) for p in paths]
+    shape = frames[0].shape
+    if any(f.shape != shape for f in frames):
+        raise ValueError("npy frames of one batch differ in shape")
+    if frames[0].ndim not in (2, 3):
+        raise ValueError(f"expected (H, W) or (H, W, C) range frames, got {shape}")
+    host = torch.from_numpy(np.stack(frames).astype(np.float32, copy=False))
+    return host.pin_memory().to(device, non_blocking=True) if torch.device(device).type == "cuda" else host
+
+
 def read_rimg(paths, device="cuda"):
     """CARLA `.rimg` files (rimg_loader, datasets.py:181-193) -> frames [B, size0, size1] fp32 on the GPU, metres.  The host only
     strips the 16-byte headers and uploads the float16 payloads; transpose, flip and widening run in one kernel.  All files of a
